@@ -1,0 +1,122 @@
+"""Pins the CPU restatement (oracle/oracle.cpp): known answers, golden vectors made by the
+unmodified reference, and -- where oracle/_ref exists -- the live reference on random inputs."""
+import math
+
+import numpy as np
+import pytest
+
+import golden_util
+import orc
+
+
+class PortEngine:
+    def __init__(self, o):
+        self.o = o
+
+    def simulate(self, p, rid, params, k, tol):
+        return self.o.simulate(p, rid, params, k, tol)
+
+    def apply_modifier(self, p, mid, params):
+        return self.o.apply_modifier(p, mid, params)
+
+
+def test_default_hasher_known_answers(port):
+    # libstdc++ std::hash<string_view>, g++ 13.3 in this image
+    z = orc.Packed.from_objects([b"\0" * 12, bytes([1, 0, 0, 0]), bytes([1, 1, 0, 0])], [1, 1, 1])
+    h = port.hash_objects(z, orc.RULE_HADAMARD, [0])
+    assert [hex(x) for x in h] == ["0xabfb1a4626dbb342", "0x1e194d667accaf15", "0x3046654aacfd7af4"]
+
+
+def test_qcgd_fresh_graph_known_answers(port):
+    # make_graph with all bits 0
+    for n, size, want in ((1, 24, 0x59572c1820095bfc), (3, 64, 0xe4556617d0d779a7), (12, 244, 0xbed7c6ba66b86de0)):
+        g = port.qcgd_random_state(n, 1, 0, 1.0)
+        fresh = bytearray(g.objects()[0])
+        fresh[2:2 + 2 * n] = bytes(2 * n)
+        st = orc.Packed.from_objects([bytes(fresh)], [1])
+        assert st.sizes[0] == size
+        assert int(port.hash_objects(st, orc.RULE_ERASE_CREATE, [0, 0, 0])[0]) == want
+
+
+def test_hadamard_known_answer(port):
+    st = orc.Packed.from_objects([bytes([1, 1, 0, 0])], [0.5 + 0.25j])
+    nxt, nc, nu = port.simulate(st, orc.RULE_HADAMARD, [1])
+    assert (nc, nu, nxt.n) == (2, 2, 2)
+    f = math.sqrt(nxt.total_proba)
+    got = dict(zip(nxt.objects(), (nxt.cmags * f).tolist()))
+    assert got[bytes([1, 0, 0, 0])] == complex(0.35355339059327373, 0.17677669529663687)
+    assert got[bytes([1, 1, 0, 0])] == -complex(0.35355339059327373, 0.17677669529663687)
+
+
+def test_split_merge_known_answer(port):
+    g = bytearray(port.qcgd_random_state(3, 1, 0, 1.0).objects()[0])
+    g[2:5], g[5:8] = bytes([1, 1, 0]), bytes([1, 0, 1])
+    st = orc.Packed.from_objects([bytes(g)], [1])
+    nxt, nc, nu = port.simulate(st, orc.RULE_SPLIT_MERGE, [0.25, 0.25, 0.25])
+    assert sorted(nxt.sizes.tolist()) == [64, 76, 116, 128]
+    want = {0x09ae092a706239a2, 0xc67ae82883b35ab6, 0xf08a12507a782496, 0x2ed3a638b2767827}
+    assert set(port.hash_objects(nxt, orc.RULE_SPLIT_MERGE, [0, 0, 0]).tolist()) == want
+
+
+@pytest.mark.parametrize("name", golden_util.fixtures())
+def test_port_reproduces_golden(port, name):
+    assert golden_util.replay(name, PortEngine(port), port) > 0
+
+
+def test_zero_max_num_object_is_refused(port):
+    st = orc.Packed.from_objects([bytes(4)], [1])
+    with pytest.raises(AssertionError):
+        port.simulate(st, orc.RULE_HADAMARD, [0], max_num_object=0)
+
+
+def test_empty_state(port):
+    st = orc.Packed.from_objects([], [])
+    nxt, nc, nu = port.simulate(st, orc.RULE_HADAMARD, [0])
+    assert (nxt.n, nc, nu) == (0, 0, 0)
+    assert nxt.total_proba == 0.0  # quids.hpp:986-992
+
+
+@pytest.mark.parametrize("rule_id", orc.QCGD_RULES)
+@pytest.mark.parametrize("n_node,n_graphs,seed", [(1, 3, 5), (2, 6, 6), (8, 20, 7), (11, 4, 8)])
+def test_port_matches_live_reference(port, reference, rule_id, n_node, n_graphs, seed):
+    params = [0.37, 0.21, -0.4]
+    a = reference.qcgd_random_state(n_node, n_graphs, seed)
+    b = port.qcgd_random_state(n_node, n_graphs, seed)
+    assert [orc.canonical_qcgd(o) for o in a.objects()] == [orc.canonical_qcgd(o) for o in b.objects()]
+    state = b
+    for it in range(2):
+        ra, nca, nua = reference.simulate(state, rule_id, params, tolerance=1e-18)
+        rb, ncb, nub = port.simulate(state, rule_id, params, tolerance=1e-18)
+        assert (nca, nua) == (ncb, nub)
+        orc.assert_same_state(rb, port.hash_objects(rb, rule_id, params), ra, reference.hash_objects(ra, rule_id, params), True,
+                              what=f"rule {rule_id} it {it}")
+        state = port.apply_modifier(rb, orc.MOD_STEP)
+        ref_state = reference.apply_modifier(rb, orc.MOD_STEP)
+        assert state.objects() == ref_state.objects()
+        if state.n > 3000:
+            break
+
+
+def test_port_matches_live_reference_hadamard_ragged(port, reference):
+    rng = np.random.default_rng(3)
+    objs = [bytes(rng.integers(0, 2, size=int(l), dtype=np.uint8)) for l in rng.integers(3, 40, size=50)]
+    objs = list(dict.fromkeys(objs))
+    mags = rng.normal(size=len(objs)) + 1j * rng.normal(size=len(objs))
+    st = orc.Packed.from_objects(objs, mags)
+    for bit in (0, 2, 1, 2):
+        ra, nca, nua = reference.simulate(st, orc.RULE_HADAMARD, [bit])
+        rb, ncb, nub = port.simulate(st, orc.RULE_HADAMARD, [bit])
+        assert (nca, nua) == (ncb, nub)
+        orc.assert_same_state(rb, port.hash_objects(rb, 1, [0]), ra, reference.hash_objects(ra, 1, [0]), False)
+        st = rb
+
+
+def test_modifiers_match_live_reference(port, reference):
+    rng = np.random.default_rng(4)
+    objs = [bytes(rng.integers(0, 2, size=6, dtype=np.uint8)) for _ in range(20)]
+    st = orc.Packed.from_objects(objs, rng.normal(size=20) + 1j * rng.normal(size=20))
+    for mid, params in ((orc.MOD_CNOT, [1, 3]), (orc.MOD_XGATE, [2]), (orc.MOD_YGATE, [0]), (orc.MOD_ZGATE, [3]), (orc.MOD_PHASE, [0.3])):
+        a, b = port.apply_modifier(st, mid, params), reference.apply_modifier(st, mid, params)
+        assert a.objects() == b.objects()
+        assert np.array_equal(a.mags, b.mags)
+        st = a
