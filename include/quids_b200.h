@@ -1,0 +1,161 @@
+/*
+ * quids_b200.h -- C ABI of the B200-native QuIDS rule-application step (libquids_b200.so).
+ *
+ * The reference (jolatechno/QuIDS) has no FFI: its boundary is the header-only C++ API of
+ * src/quids.hpp / src/quids_mpi.hpp.  The drop-in headers of this repository (the .hpp files under include/quids)
+ * keep that C++ surface and call the functions below; every entry point names the reference
+ * interface it stands behind (file:line into /root/reference/src).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative qb_status otherwise; qb_last_error() gives
+ *     the message (thread local).  The C++ layer turns non-zero into std::runtime_error, the only
+ *     exception the reference itself throws (utils/vector.hpp:126-127).
+ *   - one qb_ctx <-> one GPU <-> one host thread.  Calls are synchronous at the API: counters are
+ *     valid on return (quids.hpp:152-154,344-346 are plain public members in the reference).
+ *   - plain pointers and sizes only.  Magnitudes cross as interleaved (re, im) doubles, layout
+ *     identical to std::complex<double> (PROBA_TYPE = double, quids.hpp:21-23,78).
+ *   - states cross in the reference's own storage layout (quids.hpp:266-276, appendix A.1 of
+ *     SURVEY.md): `objects` = object bytes padded to the caller's alignment, object_begin[n+1],
+ *     object_size[n], magnitude[n].
+ *   - there is NO CPU fallback: every compute entry point fails with QB_ERR_CUDA when no device
+ *     is usable.
+ */
+#ifndef QUIDS_B200_H
+#define QUIDS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum qb_status {
+	QB_OK = 0,
+	QB_ERR_CUDA = -1,        /* a CUDA runtime call failed (includes "no device") */
+	QB_ERR_ARG = -2,         /* invalid argument */
+	QB_ERR_UNKNOWN_RULE = -3,
+	QB_ERR_UNSUPPORTED = -4, /* e.g. max_num_object == 0 (auto memory budget, quids.hpp:459-485): SURVEY 8(f) */
+	QB_ERR_CAPACITY = -5,    /* an internal limit was exceeded (child index >= 2^40, object >= 16 MiB, table full) */
+	QB_ERR_COMM = -6         /* NCCL failure on the distributed path */
+} qb_status;
+
+typedef struct qb_ctx qb_ctx;   /* device context: stream, workspace              */
+typedef struct qb_iter qb_iter; /* quids::iteration (quids.hpp:149-335) in HBM     */
+typedef struct qb_sym qb_sym;   /* quids::symbolic_iteration (quids.hpp:338-429)   */
+typedef struct qb_comm qb_comm; /* stands where MPI_Comm stands in quids_mpi.hpp   */
+
+#define QB_NO_TRUNCATION UINT64_MAX /* max_num_object = -1 in the reference (quids.hpp:445) */
+
+/* the mutable namespace globals of the reference that influence one call (quids.hpp:60-75) */
+typedef struct qb_options {
+	double tolerance;          /* quids::tolerance, strict > on re^2+im^2 (quids.hpp:62,821)        */
+	uint32_t align_byte_length; /* quids::align_byte_length (quids.hpp:60,93-102)                    */
+	int32_t simple_truncation; /* quids::simple_truncation; only 1 is supported */
+	double table_load;         /* engine knob: max load factor of the interference table, 0 = default */
+	int32_t profile;           /* 1: record CUDA events at the phase boundaries (qb_sym_phase_ms)     */
+	int32_t reserved;
+} qb_options;
+
+void qb_options_default(qb_options *opt);
+
+/* phase callback = quids::debug_t mid_step_function (quids.hpp:90); labels and order of SURVEY
+ * section 5 are kept.  Called on the calling thread, after the stream has been drained. */
+typedef void (*qb_step_cb)(const char *label, void *user);
+
+const char *qb_last_error(void);
+int qb_version(void);
+int qb_device_count(void); /* 0 when no CUDA device is usable */
+
+int qb_ctx_create(int device, qb_ctx **out);
+int qb_ctx_destroy(qb_ctx *ctx);
+int qb_ctx_synchronize(qb_ctx *ctx);
+/* cudaStream_t every kernel of this context is launched on (for CUDA-event timing by the caller) */
+void *qb_ctx_stream(qb_ctx *ctx);
+/* number of kernels this context has launched so far */
+uint64_t qb_ctx_launch_count(const qb_ctx *ctx);
+
+/* pinned host memory for fast transfers (plain cudaHostAlloc / cudaFreeHost) */
+int qb_host_alloc(size_t bytes, void **out);
+int qb_host_free(void *p);
+
+/* ---- quids::iteration --------------------------------------------------------------------- */
+int qb_iter_create(qb_ctx *ctx, qb_iter **out); /* iteration() quids.hpp:157-161 */
+int qb_iter_destroy(qb_iter *it);
+/* replaces the state (what append() builds on the host, quids.hpp:174-188) */
+int qb_iter_upload(qb_iter *it, uint64_t num_object, const uint8_t *objects, uint64_t num_bytes,
+                   const uint64_t *object_begin, const uint32_t *object_size, const double *magnitude,
+                   double total_proba);
+/* num_object, total_proba (quids.hpp:152-154) and the padded byte length object_begin[num_object] */
+int qb_iter_counts(const qb_iter *it, uint64_t *num_object, uint64_t *num_bytes, double *total_proba);
+/* copies the state out (what get_object() reads, quids.hpp:242-258); any pointer may be NULL */
+int qb_iter_download(const qb_iter *it, uint8_t *objects, uint64_t *object_begin, uint32_t *object_size, double *magnitude);
+/* device pointers of the four arrays (for zero-copy consumers; valid until the next call that writes `it`) */
+int qb_iter_device_ptrs(const qb_iter *it, void **objects, void **object_begin, void **object_size, void **magnitude);
+/* pop(n, normalize) quids.hpp:194-203 */
+int qb_iter_pop(qb_iter *it, uint64_t n, int normalize);
+/* normalize() quids.hpp:985-1017 */
+int qb_iter_normalize(qb_iter *it);
+
+/* ---- quids::symbolic_iteration ------------------------------------------------------------- */
+int qb_sym_create(qb_ctx *ctx, qb_sym **out);
+int qb_sym_destroy(qb_sym *sym);
+/* num_object, num_object_after_interferences (quids.hpp:344-346) */
+int qb_sym_counts(const qb_sym *sym, uint64_t *num_object, uint64_t *num_object_after_interferences);
+
+/* per-phase device times of the last qb_simulate (needs options.profile = 1) */
+enum {
+	QB_PHASE_NUM_CHILD = 0, /* get_num_child kernel + scan           quids.hpp:548-569        */
+	QB_PHASE_PRE_TRUNCATE,  /* parent top-k                          quids.hpp:613-642        */
+	QB_PHASE_TABLE_CLEAR,   /* interference table reset                                       */
+	QB_PHASE_SYMBOLIC,      /* children -> (hash, mag) -> table      quids.hpp:647-721,785-809 */
+	QB_PHASE_COMPACT,       /* tolerance filter + compaction         quids.hpp:819-823        */
+	QB_PHASE_TRUNCATE,      /* child top-k                           quids.hpp:866-900        */
+	QB_PHASE_FINALIZE,      /* sizes, scan, populate_child_simple    quids.hpp:905-968        */
+	QB_PHASE_NORMALIZE,     /* quids.hpp:985-1017                                             */
+	QB_PHASE_COUNT
+};
+int qb_sym_phase_ms(const qb_sym *sym, float *ms /* [QB_PHASE_COUNT] */);
+/* bytes of HBM currently held by the symbolic workspace */
+uint64_t qb_sym_device_bytes(const qb_sym *sym);
+
+/* ---- rules and modifiers -------------------------------------------------------------------- */
+/* registry lookups; built in: rules "hadamard", "erase_create", "coin", "split_merge" (+ "_generic"
+ * variants that run the four reference methods without the fused symbolic hook);
+ * modifiers "cnot", "xgate", "ygate", "zgate", "step", "reversed_step", "phase".
+ * Parameters are passed as an array of doubles, in the order of the reference constructors:
+ *   hadamard(bit) quantum_computer.hpp:35 | erase_create/coin/split_merge(theta, phi, xi) qcgd.hpp:466,541,614
+ *   cnot(control, target) :25 | xgate/ygate/zgate(bit) :52,58,68 | phase(theta) */
+int qb_rule_id(const char *name);     /* >= 1, or QB_ERR_UNKNOWN_RULE */
+int qb_modifier_id(const char *name); /* >= 1, or QB_ERR_UNKNOWN_RULE */
+
+/* quids::simulate(it_t&, modifier_t)  quids.hpp:436-438 / apply_modifier :973-980 */
+int qb_apply_modifier(qb_iter *it, int modifier_id, const double *params, uint32_t num_params);
+
+/* quids::simulate(it_t&, rule_t const*, it_t&, sy_it_t&, size_t max_num_object, debug_t)  quids.hpp:448-543 */
+int qb_simulate(qb_iter *it, int rule_id, const double *params, uint32_t num_params, qb_iter *next,
+                qb_sym *sym, uint64_t max_num_object, const qb_options *opt, qb_step_cb cb, void *user);
+
+/* rule->hasher over every object of a state (quids.hpp:143-145, qcgd.hpp:472-474) */
+int qb_hash_objects(const qb_iter *it, int rule_id, const double *params, uint32_t num_params, uint64_t *hashes);
+
+/* ---- distributed path (quids::mpi, quids_mpi.hpp) ------------------------------------------- */
+/* 128-byte NCCL unique id, created on one rank and shared by the caller (torch.distributed, MPI, files...) */
+int qb_comm_unique_id(uint8_t id[128]);
+/* stands for the MPI_Comm argument of quids::mpi::simulate (quids_mpi.hpp:423) */
+int qb_comm_create(qb_ctx *ctx, int world_size, int rank, const uint8_t id[128], qb_comm **out);
+int qb_comm_destroy(qb_comm *comm);
+/* quids::mpi::simulate quids_mpi.hpp:423-598: hash-ownership interference over NCCL all-to-allv,
+ * global top-k, global normalisation.  next->total_proba is the global sum; node_total_proba is
+ * this rank's share (quids_mpi.hpp:67,892). */
+int qb_simulate_dist(qb_iter *it, int rule_id, const double *params, uint32_t num_params, qb_iter *next,
+                     qb_sym *sym, qb_comm *comm, uint64_t max_num_object, const qb_options *opt,
+                     qb_step_cb cb, void *user, double *node_total_proba);
+/* get_total_num_object / get_total_num_symbolic_object style all-reduced counters (quids_mpi.hpp:77-99,322-339) */
+int qb_comm_allreduce_u64(qb_comm *comm, uint64_t *values, uint32_t n, int op_max);
+int qb_comm_allreduce_f64(qb_comm *comm, double *values, uint32_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

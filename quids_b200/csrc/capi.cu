@@ -1,0 +1,806 @@
+// capi.cu -- implementation of the C ABI of include/quids_b200.h: contexts, states in HBM, and the
+// orchestration of one rule iteration (the GPU counterpart of quids::simulate, quids.hpp:448-543).
+#include <cmath>
+#include <complex>
+#include <mutex>
+#include <vector>
+
+#include "engine.cuh"
+#include "pipeline.cuh"
+
+using namespace qb;
+
+// ---- error reporting ----------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+template <class F>
+static int guarded(F &&f) {
+	try {
+		f();
+		return QB_OK;
+	} catch (const qb::error &e) {
+		g_last_error = e.what();
+		return e.status;
+	} catch (const std::exception &e) {
+		g_last_error = e.what();
+		return QB_ERR_ARG;
+	}
+}
+
+// ---- registry -----------------------------------------------------------------------------------------
+namespace qb {
+static std::vector<rule_ops> &rule_registry() {
+	static std::vector<rule_ops> r;
+	return r;
+}
+static std::vector<modifier_ops> &modifier_registry() {
+	static std::vector<modifier_ops> r;
+	return r;
+}
+int register_rule(const rule_ops &ops) {
+	rule_registry().push_back(ops);
+	return (int)rule_registry().size();
+}
+int register_modifier(const modifier_ops &ops) {
+	modifier_registry().push_back(ops);
+	return (int)modifier_registry().size();
+}
+const rule_ops *find_rule(int id) { return id >= 1 && id <= (int)rule_registry().size() ? &rule_registry()[id - 1] : nullptr; }
+const modifier_ops *find_modifier(int id) { return id >= 1 && id <= (int)modifier_registry().size() ? &modifier_registry()[id - 1] : nullptr; }
+} // namespace qb
+
+// ---- objects behind the opaque handles ----------------------------------------------------------------
+enum { // u64 words of the small device scratch
+	DS_MAX_CHILD_SIZE = 0,
+	DS_COUNT = 1,
+	DS_OVERFLOW = 2,
+	DS_TOTAL = 3,
+	DS_WORDS = 8
+};
+
+struct qb_ctx {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	int sm_count = 0;
+	uint64_t launches = 0;
+	uint64_t *h_small = nullptr; // pinned mirror of d_small
+	dev_buf d_small;
+	dev_buf scan_ws;
+	dev_buf partials;
+	dev_buf select;
+
+	void use() const { QB_CUDA(cudaSetDevice(device)); }
+	void sync() const { QB_CUDA(cudaStreamSynchronize(stream)); }
+
+	// zeroed look-back workspace for a scan over `tiles` tiles
+	scan_state scan(uint64_t tiles) {
+		const size_t bytes = (tiles + 2) * sizeof(uint64_t);
+		scan_ws.ensure(bytes, stream);
+		QB_CUDA(cudaMemsetAsync(scan_ws.ptr, 0, bytes, stream));
+		scan_state st;
+		st.status = scan_ws.as<uint64_t>() + 1;
+		st.ticket = scan_ws.as<unsigned int>();
+		return st;
+	}
+	uint64_t *small(int word) { return d_small.as<uint64_t>() + word; }
+	void fetch_small() {
+		QB_CUDA(cudaMemcpyAsync(h_small, d_small.ptr, DS_WORDS * sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+		sync();
+	}
+	int grid_cap() const { return sm_count * 8; }
+};
+
+struct qb_iter {
+	qb_ctx *ctx;
+	uint64_t n = 0, n_bytes = 0;
+	double total_proba = 1; // quids.hpp:154
+	dev_buf objects, begin, size, mag, num_childs, child_begin;
+
+	iter_view view() const { return iter_view{objects.as<uint8_t>(), begin.as<uint64_t>(), size.as<uint32_t>(), mag.as<cplx>(), n}; }
+};
+
+struct qb_sym {
+	qb_ctx *ctx;
+	uint64_t n_children = 0, n_unique = 0; // quids.hpp:344-346
+	dev_buf table, ukey, uslot, sslot, kept, scratch, survivor_parent, survivor_child, padded;
+	cudaEvent_t ev[2 * QB_PHASE_COUNT] = {};
+	bool ev_used[QB_PHASE_COUNT] = {};
+	float phase_ms[QB_PHASE_COUNT] = {};
+
+	uint64_t device_bytes() const {
+		return table.cap + ukey.cap + uslot.cap + sslot.cap + kept.cap + scratch.cap + survivor_parent.cap + survivor_child.cap + padded.cap;
+	}
+};
+
+struct qb_comm {
+	qb_ctx *ctx;
+	int world = 1, rank = 0;
+	void *nccl = nullptr;
+};
+
+// ---- helpers --------------------------------------------------------------------------------------------
+namespace {
+
+struct phase_timer {
+	qb_sym *sym;
+	bool on;
+	phase_timer(qb_sym *s, bool on_) : sym(s), on(on_) {
+		for (int p = 0; p < QB_PHASE_COUNT; ++p) {
+			sym->ev_used[p] = false;
+			sym->phase_ms[p] = 0;
+		}
+	}
+	bool started[QB_PHASE_COUNT] = {};
+	void begin(int phase) { // a phase may be entered several times: it spans first begin .. last end
+		if (!on || started[phase]) return;
+		started[phase] = true;
+		if (!sym->ev[2 * phase]) {
+			QB_CUDA(cudaEventCreate(&sym->ev[2 * phase]));
+			QB_CUDA(cudaEventCreate(&sym->ev[2 * phase + 1]));
+		}
+		QB_CUDA(cudaEventRecord(sym->ev[2 * phase], sym->ctx->stream));
+	}
+	void end(int phase) {
+		if (!on) return;
+		QB_CUDA(cudaEventRecord(sym->ev[2 * phase + 1], sym->ctx->stream));
+		sym->ev_used[phase] = true;
+	}
+	void collect() {
+		if (!on) return;
+		sym->ctx->sync();
+		for (int p = 0; p < QB_PHASE_COUNT; ++p)
+			if (sym->ev_used[p])
+				QB_CUDA(cudaEventElapsedTime(&sym->phase_ms[p], sym->ev[2 * p], sym->ev[2 * p + 1]));
+	}
+};
+
+struct stepper { // mid_step_function: the stream is drained before the driver's callback runs
+	qb_ctx *ctx;
+	qb_step_cb cb;
+	void *user;
+	void operator()(const char *label) const {
+		if (cb) {
+			ctx->sync();
+			cb(label, user);
+		}
+	}
+};
+
+template <class F>
+void exclusive_scan(qb_ctx *ctx, F f, uint64_t *out, uint64_t n) {
+	if (n == 0) {
+		QB_CUDA(cudaMemsetAsync(out, 0, sizeof(uint64_t), ctx->stream));
+		return;
+	}
+	const uint64_t tiles = div_up<uint64_t>(n, SCAN_TILE);
+	scan_state st = ctx->scan(tiles);
+	exclusive_scan_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, ctx->stream>>>(f, out, n, st);
+	++ctx->launches;
+	QB_CUDA(cudaGetLastError());
+}
+
+// k-th largest key: leaves threshold / count_gt / need in ctx->select (device)
+template <class KeyFn>
+void radix_select(qb_ctx *ctx, KeyFn key_of, uint64_t n, uint64_t k) {
+	ctx->select.ensure(sizeof(select_state), ctx->stream);
+	select_state init;
+	memset(&init, 0, sizeof init);
+	init.k = k;
+	QB_CUDA(cudaMemcpyAsync(ctx->select.ptr, &init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+	ctx->sync(); // `init` lives on this stack frame
+	const int grid = grid_for(n, 256, ctx->grid_cap());
+	int shift = 64;
+	while (shift > 0) {
+		const int bits = shift >= SELECT_MAX_BITS ? SELECT_MAX_BITS : shift;
+		shift -= bits;
+		select_histogram_kernel<<<grid, 256, 0, ctx->stream>>>(key_of, n, ctx->select.as<select_state>(), shift, bits);
+		select_pick_kernel<<<1, SCAN_THREADS, 0, ctx->stream>>>(ctx->select.as<select_state>(), shift, bits);
+		ctx->launches += 2;
+	}
+	QB_CUDA(cudaGetLastError());
+}
+
+template <class KeyFn, class OutFn>
+void select_compact(qb_ctx *ctx, KeyFn key_of, uint64_t n, OutFn out) {
+	const uint64_t tiles = div_up<uint64_t>(n, COMPACT_TILE);
+	for (int pass = 0; pass < 2; ++pass) {
+		scan_state st = ctx->scan(tiles);
+		select_compact_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, ctx->stream>>>(key_of, n, ctx->select.as<select_state>(), pass, out, st);
+		++ctx->launches;
+	}
+	QB_CUDA(cudaGetLastError());
+}
+
+struct key_from_mag {
+	const cplx *mag;
+	__device__ uint64_t operator()(uint64_t i) const { return key_of_norm(cnorm(mag[i])); }
+};
+struct key_from_array {
+	const uint64_t *key;
+	__device__ uint64_t operator()(uint64_t i) const { return key[i]; }
+};
+struct out_index {
+	uint64_t *dst;
+	__device__ void operator()(uint64_t rank, uint64_t i) const { dst[rank] = i; }
+};
+struct out_gather_u32 {
+	uint32_t *dst;
+	const uint32_t *src;
+	__device__ void operator()(uint64_t rank, uint64_t i) const { dst[rank] = src[i]; }
+};
+struct counts_through {
+	const uint32_t *num_childs;
+	const uint64_t *kept;
+	__device__ uint64_t operator()(uint64_t j) const { return num_childs[kept ? kept[j] : j]; }
+};
+struct widen_u32 {
+	const uint32_t *v;
+	__device__ uint64_t operator()(uint64_t j) const { return v[j]; }
+};
+
+double reduce_norm_total(qb_ctx *ctx, const cplx *mag, uint64_t n) {
+	const int grid = grid_for(n, SCAN_THREADS, ctx->grid_cap());
+	ctx->partials.ensure(sizeof(double) * (size_t)ctx->grid_cap(), ctx->stream);
+	norm_partial_kernel<<<grid, SCAN_THREADS, 0, ctx->stream>>>(mag, n, ctx->partials.as<double>());
+	norm_total_kernel<<<1, SCAN_THREADS, 0, ctx->stream>>>(ctx->partials.as<double>(), grid, reinterpret_cast<double *>(ctx->small(DS_TOTAL)));
+	ctx->launches += 2;
+	ctx->fetch_small();
+	double total;
+	memcpy(&total, &ctx->h_small[DS_TOTAL], sizeof total);
+	return total;
+}
+
+void scale_state(qb_ctx *ctx, cplx *mag, uint64_t n, double total) {
+	const double factor = std::sqrt(total);
+	if (n == 0 || factor == 1) // quids.hpp:1010
+		return;
+	scale_kernel<<<grid_for(n, SCAN_THREADS, ctx->grid_cap()), SCAN_THREADS, 0, ctx->stream>>>(mag, n, factor);
+	++ctx->launches;
+}
+
+void resolve_options(const qb_options *in, qb_options &opt) {
+	qb_options_default(&opt);
+	if (in)
+		opt = *in;
+	if (!(opt.table_load > 0 && opt.table_load <= 0.95))
+		opt.table_load = 0.75;
+	QB_REQUIRE(opt.simple_truncation != 0, QB_ERR_UNSUPPORTED,
+	           "probabilistic truncation (quids::simple_truncation = false) is not supported: set simple_truncation (SURVEY 8f)");
+}
+
+// ======================================================================================================
+// one rule iteration on one GPU
+// ======================================================================================================
+void simulate(qb_iter *it, const rule_ops *ops, const void *rule, qb_iter *next, qb_sym *sym, uint64_t max_num_object, const qb_options &opt,
+              qb_step_cb cb, void *user) {
+	qb_ctx *ctx = it->ctx;
+	QB_REQUIRE(next->ctx == ctx && sym->ctx == ctx, QB_ERR_ARG, "iteration, next iteration and symbolic iteration belong to different contexts");
+	QB_REQUIRE(next != it, QB_ERR_ARG, "next_iteration must be a different object from iteration");
+	QB_REQUIRE(max_num_object != 0, QB_ERR_UNSUPPORTED,
+	           "max_num_object = 0 (automatic memory budget, quids.hpp:459-485) is not supported: pass an explicit maximum or QB_NO_TRUNCATION");
+	ctx->use();
+	cudaStream_t stream = ctx->stream;
+	stepper step{ctx, cb, user};
+	phase_timer timer(sym, opt.profile != 0);
+
+	engine_launch L;
+	memset(&L, 0, sizeof L);
+	L.stream = stream;
+	L.sm_count = ctx->sm_count;
+	L.launch_counter = &ctx->launches;
+	L.it = it->view();
+
+	auto finish_empty = [&](int from) { // the label sequences of the reference's early outs (quids.hpp:650-651,729-731,908-909,989-990)
+		static const char *labels[] = {"prepare_index", "symbolic_iteration", "compute_collisions - prepare", "compute_collisions - insert",
+		                               "compute_collisions - finalize", "truncate - prepare", "truncate", "prepare_final", "final", "normalize", "end"};
+		for (int i = from; i < 11; ++i)
+			step(labels[i]);
+		next->n = 0;
+		next->n_bytes = 0;
+		next->total_proba = 0;
+		next->begin.ensure(sizeof(uint64_t), stream);
+		QB_CUDA(cudaMemsetAsync(next->begin.ptr, 0, sizeof(uint64_t), stream));
+		ctx->sync();
+	};
+
+	// ---- 1. number of children per parent (quids.hpp:548-569) --------------------------------------
+	step("num_child");
+	sym->n_children = sym->n_unique = 0;
+	if (it->n == 0) {
+		step("truncate_symbolic - prepare");
+		step("truncate_symbolic");
+		finish_empty(0);
+		return;
+	}
+	timer.begin(QB_PHASE_NUM_CHILD);
+	it->num_childs.ensure(sizeof(uint32_t) * it->n, stream);
+	QB_CUDA(cudaMemsetAsync(ctx->d_small.ptr, 0, DS_WORDS * sizeof(uint64_t), stream));
+	L.num_childs = it->num_childs.as<uint32_t>();
+	L.max_child_size = reinterpret_cast<unsigned int *>(ctx->small(DS_MAX_CHILD_SIZE));
+	ops->launch_num_child(rule, L);
+	timer.end(QB_PHASE_NUM_CHILD);
+
+	// ---- 2. parent pre-truncation: the max_num_object most probable parents (quids.hpp:613-642) ------
+	step("truncate_symbolic - prepare");
+	step("truncate_symbolic");
+	uint64_t n_parents = it->n;
+	const uint64_t *kept = nullptr;
+	if (max_num_object < it->n) {
+		timer.begin(QB_PHASE_PRE_TRUNCATE);
+		n_parents = max_num_object;
+		sym->kept.ensure(sizeof(uint64_t) * n_parents, stream);
+		key_from_mag keys{it->mag.as<cplx>()};
+		radix_select(ctx, keys, it->n, n_parents);
+		select_compact(ctx, keys, it->n, out_index{sym->kept.as<uint64_t>()});
+		kept = sym->kept.as<uint64_t>();
+		timer.end(QB_PHASE_PRE_TRUNCATE);
+	}
+
+	// ---- 3. child index ranges (quids.hpp:666-671: a serial loop in the reference) --------------------
+	step("prepare_index");
+	timer.begin(QB_PHASE_NUM_CHILD);
+	it->child_begin.ensure(sizeof(uint64_t) * (n_parents + 1), stream);
+	exclusive_scan(ctx, counts_through{it->num_childs.as<uint32_t>(), kept}, it->child_begin.as<uint64_t>(), n_parents);
+	QB_CUDA(cudaMemcpyAsync(&ctx->h_small[DS_COUNT], it->child_begin.as<uint64_t>() + n_parents, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+	QB_CUDA(cudaMemcpyAsync(&ctx->h_small[DS_MAX_CHILD_SIZE], ctx->small(DS_MAX_CHILD_SIZE), sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+	timer.end(QB_PHASE_NUM_CHILD);
+	ctx->sync();
+	const uint64_t n_children = ctx->h_small[DS_COUNT];
+	const uint32_t max_child_size = (uint32_t)ctx->h_small[DS_MAX_CHILD_SIZE];
+	sym->n_children = n_children;
+	if (n_children == 0) {
+		finish_empty(1);
+		return;
+	}
+	QB_REQUIRE(n_children <= REP_MAX_INDEX, QB_ERR_CAPACITY, "more than 2^40 children in one iteration");
+	QB_REQUIRE(max_child_size <= REP_MAX_SIZE, QB_ERR_CAPACITY, "child objects of 16 MiB or more are not supported");
+
+	// ---- 4. interference table ----------------------------------------------------------------------
+	timer.begin(QB_PHASE_TABLE_CLEAR);
+	uint64_t capacity = (uint64_t)std::ceil((double)n_children / opt.table_load);
+	if (capacity < 1024)
+		capacity = 1024;
+	QB_REQUIRE(capacity + 1 <= 0xffffffffull, QB_ERR_CAPACITY, "interference table would need more than 2^32 slots");
+	const size_t table_bytes = (capacity + 1) * sizeof(table_slot);
+	sym->table.ensure(table_bytes, stream);
+	QB_CUDA(cudaMemsetAsync(sym->table.ptr, 0, table_bytes, stream));
+	table_view table{sym->table.as<table_slot>(), capacity, reinterpret_cast<unsigned int *>(ctx->small(DS_OVERFLOW))};
+	timer.end(QB_PHASE_TABLE_CLEAR);
+
+	// ---- 5. children -> (hash, magnitude) -> table (quids.hpp:705-719 fused with :785-809) ------------
+	step("symbolic_iteration");
+	timer.begin(QB_PHASE_SYMBOLIC);
+	L.child_begin = it->child_begin.as<uint64_t>();
+	L.kept = kept;
+	L.n_parents = n_parents;
+	L.n_children = n_children;
+	L.table = table;
+	if (ops->needs_scratch) {
+		L.scratch_stride = (max_child_size + 15u) & ~15u;
+		if (L.scratch_stride == 0)
+			L.scratch_stride = 16;
+		sym->scratch.ensure((size_t)ops->symbolic_grid(ctx->sm_count) * ENGINE_THREADS * L.scratch_stride, stream);
+		L.scratch = sym->scratch.as<uint8_t>();
+	}
+	ops->launch_symbolic(rule, L);
+	QB_CUDA(cudaGetLastError());
+	timer.end(QB_PHASE_SYMBOLIC);
+	step("compute_collisions - prepare");
+	step("compute_collisions - insert");
+
+	// ---- 6. unique children above the tolerance (quids.hpp:819-823) ------------------------------------
+	step("compute_collisions - finalize");
+	timer.begin(QB_PHASE_COMPACT);
+	sym->ukey.ensure(sizeof(uint64_t) * n_children, stream);
+	sym->uslot.ensure(sizeof(uint32_t) * n_children, stream);
+	{
+		const uint64_t tiles = div_up<uint64_t>(capacity + 1, COMPACT_TILE);
+		scan_state st = ctx->scan(tiles);
+		table_compact_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, stream>>>(table, opt.tolerance, sym->ukey.as<uint64_t>(), sym->uslot.as<uint32_t>(),
+		                                                                    reinterpret_cast<unsigned long long *>(ctx->small(DS_COUNT)), st);
+		++ctx->launches;
+		QB_CUDA(cudaGetLastError());
+	}
+	timer.end(QB_PHASE_COMPACT);
+	ctx->fetch_small();
+	QB_REQUIRE(ctx->h_small[DS_OVERFLOW] == 0, QB_ERR_CAPACITY, "interference table overflow");
+	const uint64_t n_unique = ctx->h_small[DS_COUNT];
+	sym->n_unique = n_unique;
+
+	// ---- 7. child truncation: the max_num_object most probable (quids.hpp:866-900) ---------------------
+	step("truncate - prepare");
+	step("truncate");
+	uint64_t n_survivors = n_unique;
+	const uint32_t *survivor_slot = sym->uslot.as<uint32_t>();
+	if (max_num_object < n_unique) {
+		timer.begin(QB_PHASE_TRUNCATE);
+		n_survivors = max_num_object;
+		sym->sslot.ensure(sizeof(uint32_t) * n_survivors, stream);
+		key_from_array keys{sym->ukey.as<uint64_t>()};
+		radix_select(ctx, keys, n_unique, n_survivors);
+		select_compact(ctx, keys, n_unique, out_gather_u32{sym->sslot.as<uint32_t>(), sym->uslot.as<uint32_t>()});
+		survivor_slot = sym->sslot.as<uint32_t>();
+		timer.end(QB_PHASE_TRUNCATE);
+	}
+	if (n_survivors == 0) {
+		finish_empty(7);
+		return;
+	}
+
+	// ---- 8. finalisation (quids.hpp:905-968) ------------------------------------------------------------
+	step("prepare_final");
+	timer.begin(QB_PHASE_FINALIZE);
+	next->n = n_survivors;
+	next->size.ensure(sizeof(uint32_t) * n_survivors, stream);
+	next->mag.ensure(sizeof(cplx) * n_survivors, stream);
+	next->begin.ensure(sizeof(uint64_t) * (n_survivors + 1), stream);
+	sym->padded.ensure(sizeof(uint32_t) * n_survivors, stream);
+	sym->survivor_parent.ensure(sizeof(uint64_t) * n_survivors, stream);
+	sym->survivor_child.ensure(sizeof(uint32_t) * n_survivors, stream);
+	ctx->partials.ensure(sizeof(double) * (size_t)ctx->grid_cap(), stream);
+	const int meta_grid = grid_for(n_survivors, SCAN_THREADS, ctx->grid_cap());
+	{
+		finalize_args a;
+		a.table = table;
+		a.survivor_slot = survivor_slot;
+		a.n_survivors = n_survivors;
+		a.child_begin = it->child_begin.as<uint64_t>();
+		a.kept = kept;
+		a.n_parents = n_parents;
+		a.align = opt.align_byte_length;
+		a.next_size = next->size.as<uint32_t>();
+		a.next_padded = sym->padded.as<uint32_t>();
+		a.next_mag = next->mag.as<cplx>();
+		a.survivor_parent = sym->survivor_parent.as<uint64_t>();
+		a.survivor_child = sym->survivor_child.as<uint32_t>();
+		a.partial_norm = ctx->partials.as<double>();
+		finalize_meta_kernel<<<meta_grid, SCAN_THREADS, 0, stream>>>(a);
+		norm_total_kernel<<<1, SCAN_THREADS, 0, stream>>>(ctx->partials.as<double>(), meta_grid, reinterpret_cast<double *>(ctx->small(DS_TOTAL)));
+		ctx->launches += 2;
+	}
+	exclusive_scan(ctx, widen_u32{sym->padded.as<uint32_t>()}, next->begin.as<uint64_t>(), n_survivors);
+	QB_CUDA(cudaMemcpyAsync(&ctx->h_small[DS_COUNT], next->begin.as<uint64_t>() + n_survivors, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+	QB_CUDA(cudaMemcpyAsync(&ctx->h_small[DS_TOTAL], ctx->small(DS_TOTAL), sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+	ctx->sync();
+	next->n_bytes = ctx->h_small[DS_COUNT];
+	double total;
+	memcpy(&total, &ctx->h_small[DS_TOTAL], sizeof total);
+	next->objects.ensure(next->n_bytes + 16, stream);
+
+	step("final");
+	L.n_survivors = n_survivors;
+	L.survivor_parent = sym->survivor_parent.as<uint64_t>();
+	L.survivor_child = sym->survivor_child.as<uint32_t>();
+	L.next_objects = next->objects.as<uint8_t>();
+	L.next_begin = next->begin.as<uint64_t>();
+	L.next_size = next->size.as<uint32_t>();
+	ops->launch_populate(rule, L);
+	QB_CUDA(cudaGetLastError());
+	timer.end(QB_PHASE_FINALIZE);
+
+	// ---- 9. normalisation (quids.hpp:985-1017); total_proba keeps the pre-normalisation sum -------------
+	step("normalize");
+	timer.begin(QB_PHASE_NORMALIZE);
+	next->total_proba = total;
+	scale_state(ctx, next->mag.as<cplx>(), n_survivors, total);
+	timer.end(QB_PHASE_NORMALIZE);
+	ctx->sync();
+	QB_CUDA(cudaGetLastError());
+	timer.collect();
+	step("end");
+}
+
+} // namespace
+
+// ======================================================================================================
+// C ABI
+// ======================================================================================================
+extern "C" {
+
+void qb_options_default(qb_options *opt) {
+	memset(opt, 0, sizeof *opt);
+	opt->tolerance = 1e-30;     // TOLERANCE, quids.hpp:30-32
+	opt->align_byte_length = 8; // ALIGNMENT_BYTE_LENGTH, quids.hpp:27-29
+	opt->simple_truncation = 1;
+	opt->table_load = 0;
+	opt->profile = 0;
+}
+
+const char *qb_last_error(void) { return g_last_error.c_str(); }
+int qb_version(void) { return 100; }
+
+int qb_device_count(void) {
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	return n;
+}
+
+int qb_ctx_create(int device, qb_ctx **out) {
+	return guarded([&] {
+		QB_REQUIRE(out, QB_ERR_ARG, "qb_ctx_create: null output");
+		int count = 0;
+		QB_CUDA(cudaGetDeviceCount(&count));
+		QB_REQUIRE(device >= 0 && device < count, QB_ERR_CUDA, "qb_ctx_create: no such CUDA device (there is no CPU fallback)");
+		QB_CUDA(cudaSetDevice(device));
+		qb_ctx *ctx = new qb_ctx();
+		ctx->device = device;
+		QB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+		QB_CUDA(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
+		QB_CUDA(cudaHostAlloc((void **)&ctx->h_small, DS_WORDS * sizeof(uint64_t), cudaHostAllocDefault));
+		ctx->d_small.ensure(DS_WORDS * sizeof(uint64_t), ctx->stream);
+		QB_CUDA(cudaMemsetAsync(ctx->d_small.ptr, 0, DS_WORDS * sizeof(uint64_t), ctx->stream));
+		ctx->sync();
+		*out = ctx;
+	});
+}
+
+int qb_ctx_destroy(qb_ctx *ctx) {
+	return guarded([&] {
+		if (!ctx) return;
+		cudaSetDevice(ctx->device);
+		cudaStreamSynchronize(ctx->stream);
+		if (ctx->h_small) cudaFreeHost(ctx->h_small);
+		ctx->d_small.release();
+		ctx->scan_ws.release();
+		ctx->partials.release();
+		ctx->select.release();
+		cudaStreamDestroy(ctx->stream);
+		delete ctx;
+	});
+}
+
+int qb_ctx_synchronize(qb_ctx *ctx) {
+	return guarded([&] {
+		QB_REQUIRE(ctx, QB_ERR_ARG, "null context");
+		ctx->sync();
+	});
+}
+void *qb_ctx_stream(qb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+uint64_t qb_ctx_launch_count(const qb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int qb_host_alloc(size_t bytes, void **out) {
+	return guarded([&] { QB_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault)); });
+}
+int qb_host_free(void *p) {
+	return guarded([&] {
+		if (p) QB_CUDA(cudaFreeHost(p));
+	});
+}
+
+// ---- iteration ---------------------------------------------------------------------------------------
+int qb_iter_create(qb_ctx *ctx, qb_iter **out) {
+	return guarded([&] {
+		QB_REQUIRE(ctx && out, QB_ERR_ARG, "qb_iter_create: null argument");
+		ctx->use();
+		qb_iter *it = new qb_iter();
+		it->ctx = ctx;
+		it->begin.ensure(sizeof(uint64_t), ctx->stream);
+		QB_CUDA(cudaMemsetAsync(it->begin.ptr, 0, sizeof(uint64_t), ctx->stream)); // object_begin[0] = 0, quids.hpp:160
+		ctx->sync();
+		*out = it;
+	});
+}
+
+int qb_iter_destroy(qb_iter *it) {
+	return guarded([&] {
+		if (!it) return;
+		it->ctx->use();
+		it->ctx->sync();
+		delete it;
+	});
+}
+
+int qb_iter_upload(qb_iter *it, uint64_t n, const uint8_t *objects, uint64_t num_bytes, const uint64_t *object_begin, const uint32_t *object_size,
+                   const double *magnitude, double total_proba) {
+	return guarded([&] {
+		QB_REQUIRE(it, QB_ERR_ARG, "null iteration");
+		QB_REQUIRE(n == 0 || (object_begin && object_size && magnitude), QB_ERR_ARG, "qb_iter_upload: null array");
+		QB_REQUIRE(num_bytes == 0 || objects, QB_ERR_ARG, "qb_iter_upload: null objects");
+		qb_ctx *ctx = it->ctx;
+		ctx->use();
+		cudaStream_t s = ctx->stream;
+		it->objects.ensure(num_bytes + 16, s);
+		it->begin.ensure(sizeof(uint64_t) * (n + 1), s);
+		it->size.ensure(sizeof(uint32_t) * (n ? n : 1), s);
+		it->mag.ensure(sizeof(cplx) * (n ? n : 1), s);
+		if (num_bytes) QB_CUDA(cudaMemcpyAsync(it->objects.ptr, objects, num_bytes, cudaMemcpyHostToDevice, s));
+		if (n) {
+			QB_CUDA(cudaMemcpyAsync(it->begin.ptr, object_begin, sizeof(uint64_t) * (n + 1), cudaMemcpyHostToDevice, s));
+			QB_CUDA(cudaMemcpyAsync(it->size.ptr, object_size, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, s));
+			QB_CUDA(cudaMemcpyAsync(it->mag.ptr, magnitude, sizeof(cplx) * n, cudaMemcpyHostToDevice, s));
+		} else {
+			QB_CUDA(cudaMemsetAsync(it->begin.ptr, 0, sizeof(uint64_t), s));
+		}
+		ctx->sync();
+		it->n = n;
+		it->n_bytes = num_bytes;
+		it->total_proba = total_proba;
+	});
+}
+
+int qb_iter_counts(const qb_iter *it, uint64_t *num_object, uint64_t *num_bytes, double *total_proba) {
+	return guarded([&] {
+		QB_REQUIRE(it, QB_ERR_ARG, "null iteration");
+		if (num_object) *num_object = it->n;
+		if (num_bytes) *num_bytes = it->n_bytes;
+		if (total_proba) *total_proba = it->total_proba;
+	});
+}
+
+int qb_iter_download(const qb_iter *it, uint8_t *objects, uint64_t *object_begin, uint32_t *object_size, double *magnitude) {
+	return guarded([&] {
+		QB_REQUIRE(it, QB_ERR_ARG, "null iteration");
+		qb_ctx *ctx = it->ctx;
+		ctx->use();
+		cudaStream_t s = ctx->stream;
+		if (objects && it->n_bytes) QB_CUDA(cudaMemcpyAsync(objects, it->objects.ptr, it->n_bytes, cudaMemcpyDeviceToHost, s));
+		if (object_begin) QB_CUDA(cudaMemcpyAsync(object_begin, it->begin.ptr, sizeof(uint64_t) * (it->n + 1), cudaMemcpyDeviceToHost, s));
+		if (object_size && it->n) QB_CUDA(cudaMemcpyAsync(object_size, it->size.ptr, sizeof(uint32_t) * it->n, cudaMemcpyDeviceToHost, s));
+		if (magnitude && it->n) QB_CUDA(cudaMemcpyAsync(magnitude, it->mag.ptr, sizeof(cplx) * it->n, cudaMemcpyDeviceToHost, s));
+		ctx->sync();
+	});
+}
+
+int qb_iter_device_ptrs(const qb_iter *it, void **objects, void **object_begin, void **object_size, void **magnitude) {
+	return guarded([&] {
+		QB_REQUIRE(it, QB_ERR_ARG, "null iteration");
+		if (objects) *objects = it->objects.ptr;
+		if (object_begin) *object_begin = it->begin.ptr;
+		if (object_size) *object_size = it->size.ptr;
+		if (magnitude) *magnitude = it->mag.ptr;
+	});
+}
+
+int qb_iter_normalize(qb_iter *it) {
+	return guarded([&] {
+		QB_REQUIRE(it, QB_ERR_ARG, "null iteration");
+		qb_ctx *ctx = it->ctx;
+		ctx->use();
+		it->total_proba = 0; // quids.hpp:986
+		if (it->n == 0) return;
+		it->total_proba = reduce_norm_total(ctx, it->mag.as<cplx>(), it->n);
+		scale_state(ctx, it->mag.as<cplx>(), it->n, it->total_proba);
+		ctx->sync();
+	});
+}
+
+int qb_iter_pop(qb_iter *it, uint64_t n, int normalize) {
+	int rc = guarded([&] {
+		QB_REQUIRE(it, QB_ERR_ARG, "null iteration");
+		QB_REQUIRE(n <= it->n, QB_ERR_ARG, "qb_iter_pop: more objects than the state holds");
+		if (n < 1) return; // quids.hpp:195-196
+		qb_ctx *ctx = it->ctx;
+		ctx->use();
+		it->n -= n;
+		QB_CUDA(cudaMemcpyAsync(&ctx->h_small[DS_COUNT], it->begin.as<uint64_t>() + it->n, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+		ctx->sync();
+		it->n_bytes = ctx->h_small[DS_COUNT];
+	});
+	if (rc == QB_OK && n >= 1 && normalize)
+		rc = qb_iter_normalize(it);
+	return rc;
+}
+
+// ---- symbolic iteration --------------------------------------------------------------------------------
+int qb_sym_create(qb_ctx *ctx, qb_sym **out) {
+	return guarded([&] {
+		QB_REQUIRE(ctx && out, QB_ERR_ARG, "qb_sym_create: null argument");
+		qb_sym *sym = new qb_sym();
+		sym->ctx = ctx;
+		*out = sym;
+	});
+}
+
+int qb_sym_destroy(qb_sym *sym) {
+	return guarded([&] {
+		if (!sym) return;
+		sym->ctx->use();
+		sym->ctx->sync();
+		for (cudaEvent_t e : sym->ev)
+			if (e) cudaEventDestroy(e);
+		delete sym;
+	});
+}
+
+int qb_sym_counts(const qb_sym *sym, uint64_t *num_object, uint64_t *num_object_after_interferences) {
+	return guarded([&] {
+		QB_REQUIRE(sym, QB_ERR_ARG, "null symbolic iteration");
+		if (num_object) *num_object = sym->n_children;
+		if (num_object_after_interferences) *num_object_after_interferences = sym->n_unique;
+	});
+}
+
+int qb_sym_phase_ms(const qb_sym *sym, float *ms) {
+	return guarded([&] {
+		QB_REQUIRE(sym && ms, QB_ERR_ARG, "null argument");
+		for (int p = 0; p < QB_PHASE_COUNT; ++p)
+			ms[p] = sym->phase_ms[p];
+	});
+}
+
+uint64_t qb_sym_device_bytes(const qb_sym *sym) { return sym ? sym->device_bytes() : 0; }
+
+// ---- rules, modifiers ------------------------------------------------------------------------------------
+int qb_rule_id(const char *name) {
+	if (name)
+		for (size_t i = 0; i < rule_registry().size(); ++i)
+			if (!strcmp(rule_registry()[i].name, name))
+				return (int)i + 1;
+	g_last_error = std::string("unknown rule: ") + (name ? name : "(null)");
+	return QB_ERR_UNKNOWN_RULE;
+}
+
+int qb_modifier_id(const char *name) {
+	if (name)
+		for (size_t i = 0; i < modifier_registry().size(); ++i)
+			if (!strcmp(modifier_registry()[i].name, name))
+				return (int)i + 1;
+	g_last_error = std::string("unknown modifier: ") + (name ? name : "(null)");
+	return QB_ERR_UNKNOWN_RULE;
+}
+
+int qb_apply_modifier(qb_iter *it, int modifier_id, const double *params, uint32_t num_params) {
+	return guarded([&] {
+		QB_REQUIRE(it, QB_ERR_ARG, "null iteration");
+		const modifier_ops *ops = find_modifier(modifier_id);
+		QB_REQUIRE(ops, QB_ERR_UNKNOWN_RULE, "unknown modifier id");
+		alignas(16) unsigned char storage[RULE_STORAGE_BYTES];
+		int rc = ops->make(params, num_params, storage);
+		QB_REQUIRE(rc == QB_OK, rc, std::string("bad parameters for modifier ") + ops->name);
+		qb_ctx *ctx = it->ctx;
+		ctx->use();
+		if (it->n == 0) return;
+		ops->launch(storage, it->view(), ctx->stream, ctx->sm_count);
+		++ctx->launches;
+		QB_CUDA(cudaGetLastError());
+		ctx->sync();
+	});
+}
+
+int qb_simulate(qb_iter *it, int rule_id, const double *params, uint32_t num_params, qb_iter *next, qb_sym *sym, uint64_t max_num_object,
+                const qb_options *opt_in, qb_step_cb cb, void *user) {
+	return guarded([&] {
+		QB_REQUIRE(it && next && sym, QB_ERR_ARG, "qb_simulate: null handle");
+		const rule_ops *ops = find_rule(rule_id);
+		QB_REQUIRE(ops, QB_ERR_UNKNOWN_RULE, "unknown rule id");
+		alignas(16) unsigned char storage[RULE_STORAGE_BYTES];
+		int rc = ops->make(params, num_params, storage);
+		QB_REQUIRE(rc == QB_OK, rc, std::string("bad parameters for rule ") + ops->name);
+		qb_options opt;
+		resolve_options(opt_in, opt);
+		simulate(it, ops, storage, next, sym, max_num_object, opt, cb, user);
+	});
+}
+
+int qb_hash_objects(const qb_iter *it, int rule_id, const double *params, uint32_t num_params, uint64_t *hashes) {
+	return guarded([&] {
+		QB_REQUIRE(it && (hashes || it->n == 0), QB_ERR_ARG, "qb_hash_objects: null argument");
+		const rule_ops *ops = find_rule(rule_id);
+		QB_REQUIRE(ops, QB_ERR_UNKNOWN_RULE, "unknown rule id");
+		alignas(16) unsigned char storage[RULE_STORAGE_BYTES];
+		int rc = ops->make(params, num_params, storage);
+		QB_REQUIRE(rc == QB_OK, rc, std::string("bad parameters for rule ") + ops->name);
+		if (it->n == 0) return;
+		qb_ctx *ctx = it->ctx;
+		ctx->use();
+		dev_buf out;
+		out.ensure(sizeof(uint64_t) * it->n, ctx->stream);
+		engine_launch L;
+		memset(&L, 0, sizeof L);
+		L.stream = ctx->stream;
+		L.sm_count = ctx->sm_count;
+		L.launch_counter = &ctx->launches;
+		L.it = it->view();
+		L.hashes = out.as<uint64_t>();
+		ops->launch_hash(storage, L);
+		QB_CUDA(cudaGetLastError());
+		QB_CUDA(cudaMemcpyAsync(hashes, out.ptr, sizeof(uint64_t) * it->n, cudaMemcpyDeviceToHost, ctx->stream));
+		ctx->sync();
+	});
+}
+
+// ---- distributed path: see dist.cu ---------------------------------------------------------------------
+}

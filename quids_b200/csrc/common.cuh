@@ -1,0 +1,146 @@
+// common.cuh -- error handling, device buffers and small device helpers shared by all kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+#include "../../include/quids_b200.h"
+
+namespace qb {
+
+// ---- errors --------------------------------------------------------------------------------
+struct error : std::runtime_error {
+	int status;
+	error(int status_, const std::string &what) : std::runtime_error(what), status(status_) {}
+};
+
+#define QB_CUDA(call)                                                                                        \
+	do {                                                                                                     \
+		cudaError_t qb_err_ = (call);                                                                        \
+		if (qb_err_ != cudaSuccess)                                                                          \
+			throw ::qb::error(QB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(qb_err_) + " (" +  \
+			                                   __FILE__ + ":" + std::to_string(__LINE__) + ")");            \
+	} while (0)
+
+#define QB_REQUIRE(cond, status, msg)          \
+	do {                                       \
+		if (!(cond))                           \
+			throw ::qb::error((status), (msg)); \
+	} while (0)
+
+// ---- complex magnitude: layout identical to std::complex<double> (quids.hpp:78) ---------------
+struct __align__(16) cplx {
+	double re, im;
+};
+
+// complex product with every operation rounded separately, i.e. what g++ -O3 emits on x86-64 for
+// std::complex<double>::operator*= (no FMA contraction) -- keeps child magnitudes bit-identical to
+// the reference before the interference sums
+__device__ __forceinline__ cplx cmul(cplx a, cplx b) {
+	cplx r;
+	r.re = __dsub_rn(__dmul_rn(a.re, b.re), __dmul_rn(a.im, b.im));
+	r.im = __dadd_rn(__dmul_rn(a.re, b.im), __dmul_rn(a.im, b.re));
+	return r;
+}
+__device__ __forceinline__ cplx cscale(cplx a, double f) { return cplx{__dmul_rn(a.re, f), __dmul_rn(a.im, f)}; }
+__device__ __forceinline__ double cnorm(cplx a) { return __dadd_rn(__dmul_rn(a.re, a.re), __dmul_rn(a.im, a.im)); }
+
+// ---- integer helpers --------------------------------------------------------------------------
+constexpr uint64_t MURMUR_MUL = 0xc6a4a7935bd1e995ull;
+
+__host__ __device__ __forceinline__ uint64_t shift_mix(uint64_t v) { return v ^ (v >> 47); }
+
+// slot mixer of the interference table (NOT part of any reference hash: the reference hashes are
+// only compared for equality, this spreads them over the table)
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
+	x ^= x >> 32;
+	x *= 0xd6e8feb86659fd93ull;
+	x ^= x >> 32;
+	x *= 0xd6e8feb86659fd93ull;
+	x ^= x >> 32;
+	return x;
+}
+
+template <class T>
+__host__ __device__ __forceinline__ T div_up(T a, T b) {
+	return (a + b - 1) / b;
+}
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }
+
+__device__ __forceinline__ uint64_t warp_sum(uint64_t v) {
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+		v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+		v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+
+// first index i in [0, n) with a[i] > v (a ascending); the classic upper bound
+__device__ __forceinline__ uint64_t upper_bound_u64(const uint64_t *a, uint64_t n, uint64_t v) {
+	uint64_t lo = 0, hi = n;
+	while (lo < hi) {
+		uint64_t mid = (lo + hi) >> 1;
+		if (a[mid] <= v)
+			lo = mid + 1;
+		else
+			hi = mid;
+	}
+	return lo;
+}
+
+// ---- growable device buffer (stands for utils::fast_vector, utils/vector.hpp:36-160) -----------
+// Grows geometrically (upsize policy 1.1 like the reference), never shrinks implicitly; content is
+// NOT preserved by ensure() unless keep = true.
+struct dev_buf {
+	void *ptr = nullptr;
+	size_t cap = 0;
+
+	dev_buf() = default;
+	dev_buf(const dev_buf &) = delete;
+	dev_buf &operator=(const dev_buf &) = delete;
+	~dev_buf() { release(); }
+
+	void release() {
+		if (ptr)
+			cudaFree(ptr);
+		ptr = nullptr;
+		cap = 0;
+	}
+	void ensure(size_t bytes, cudaStream_t stream, bool keep = false, size_t keep_bytes = 0) {
+		if (bytes <= cap)
+			return;
+		size_t want = bytes + bytes / 10 + 256;
+		void *fresh = nullptr;
+		cudaError_t err = cudaMalloc(&fresh, want);
+		if (err != cudaSuccess) { // retry without slack before giving up
+			cudaGetLastError();
+			want = bytes + 256;
+			err = cudaMalloc(&fresh, want);
+		}
+		if (err != cudaSuccess)
+			throw error(QB_ERR_CUDA, std::string("cudaMalloc of ") + std::to_string(want) + " bytes: " + cudaGetErrorString(err));
+		if (keep && ptr && keep_bytes)
+			QB_CUDA(cudaMemcpyAsync(fresh, ptr, keep_bytes, cudaMemcpyDeviceToDevice, stream));
+		if (ptr) {
+			QB_CUDA(cudaStreamSynchronize(stream));
+			cudaFree(ptr);
+		}
+		ptr = fresh;
+		cap = want;
+	}
+	template <class T>
+	T *as() const { return reinterpret_cast<T *>(ptr); }
+};
+
+} // namespace qb

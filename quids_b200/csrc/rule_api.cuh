@@ -1,0 +1,129 @@
+// rule_api.cuh -- what a rule is on the device, and how rules reach the engine.
+//
+// The reference's plug-in interface is the abstract class quids::rule (quids.hpp:105-146) with four
+// virtual methods called from OpenMP loops.  Host objects with vtables cannot be called from a
+// kernel, so here a rule is a trivially copyable struct passed BY VALUE to the kernels, carrying
+// its parameters and implementing the same four methods as __device__ members (static dispatch:
+// the engine's kernels are templates instantiated per rule type):
+//
+//     get_num_child(parent, parent_size, num_child&, max_child_size&)        quids.hpp:115
+//     populate_child(parent, parent_size, child, child_id, size&, mag&)      quids.hpp:124
+//     populate_child_simple(parent, parent_size, child, child_id)            quids.hpp:131-136 (optional)
+//     hasher(object, size)                                                   quids.hpp:143-145 (optional, default = libstdc++ murmur)
+//
+// plus two OPTIONAL hooks that only exist on the GPU path:
+//     prepare(parent, parent_size, ctx&)   per-parent precomputation shared by all its children
+//     symbolic(parent, parent_size, ctx, child_id, scratch, size&, mag&) -> hash
+//                                          size, magnitude and hash of a child WITHOUT writing its
+//                                          bytes; the default materialises the child into `scratch`
+//                                          with populate_child and calls hasher on it, exactly like
+//                                          the symbolic loop of the reference (quids.hpp:705-719)
+//
+// QB_REGISTER_RULE(name, type, make) instantiates the engine kernels for `type` in the translation
+// unit where it appears and adds the rule to the registry looked up by qb_rule_id().
+#pragma once
+
+#include "common.cuh"
+
+namespace qb {
+
+// ---- default hasher: libstdc++ std::hash<std::string_view> = _Hash_bytes (64-bit murmur variant,
+// gcc libsupc++/hash_bytes.cc, seed 0xc70f6907); the byte source is a functor so that rules can hash
+// a child that only exists as "parent with one byte changed"
+template <class ByteAt>
+__device__ __forceinline__ uint64_t murmur_bytes(ByteAt at, uint32_t len) {
+	uint64_t h = 0xc70f6907ull ^ ((uint64_t)len * MURMUR_MUL);
+	const uint32_t whole = len & ~7u;
+	for (uint32_t i = 0; i < whole; i += 8) {
+		uint64_t w = 0;
+#pragma unroll
+		for (int b = 7; b >= 0; --b)
+			w = (w << 8) | (uint64_t)at(i + b);
+		h ^= shift_mix(w * MURMUR_MUL) * MURMUR_MUL;
+		h *= MURMUR_MUL;
+	}
+	if (len & 7u) {
+		uint64_t w = 0;
+		for (uint32_t b = len & 7u; b-- > 0;)
+			w = (w << 8) + (uint64_t)at(whole + b);
+		h ^= w;
+		h *= MURMUR_MUL;
+	}
+	h = shift_mix(h) * MURMUR_MUL;
+	return shift_mix(h);
+}
+
+__device__ __forceinline__ uint64_t murmur_bytes(const uint8_t *p, uint32_t len) {
+	return murmur_bytes([p](uint32_t i) { return p[i]; }, len);
+}
+
+struct no_ctx {};
+
+template <class Derived>
+struct rule_base {
+	typedef no_ctx ctx_t;
+	// true: `symbolic` needs a scratch buffer of max_child_size bytes per thread
+	static constexpr bool needs_scratch = true;
+
+	__device__ const Derived &self() const { return *static_cast<const Derived *>(this); }
+
+	__device__ void prepare(const uint8_t *, uint32_t, no_ctx &) const {}
+
+	__device__ uint64_t hasher(const uint8_t *object, uint32_t size) const { return murmur_bytes(object, size); }
+
+	__device__ void populate_child_simple(const uint8_t *parent, uint32_t parent_size, uint8_t *child, uint32_t child_id) const {
+		uint32_t size;
+		cplx mag{1, 0};
+		self().populate_child(parent, parent_size, child, child_id, size, mag);
+	}
+
+	template <class Ctx>
+	__device__ uint64_t symbolic(const uint8_t *parent, uint32_t parent_size, const Ctx &, uint32_t child_id, uint8_t *scratch,
+	                             uint32_t &size, cplx &mag) const {
+		self().populate_child(parent, parent_size, scratch, child_id, size, mag);
+		return self().hasher(scratch, size);
+	}
+};
+
+// ---- modifiers: f(begin, end, mag&) in place (quids.hpp:86,973-980) as a device functor
+//     __device__ void operator()(uint8_t *object, uint32_t size, cplx &mag) const
+
+// ---- views handed to the kernels ----------------------------------------------------------------
+struct iter_view {
+	uint8_t *objects;
+	const uint64_t *begin;
+	const uint32_t *size;
+	cplx *mag;
+	uint64_t n;
+};
+
+struct table_view;
+struct engine_launch; // defined in engine.cuh
+
+// what the engine needs from one rule type (filled by the template in engine.cuh)
+struct rule_ops {
+	const char *name;
+	// builds the device rule (<= 256 bytes, trivially copyable) from the ABI parameter doubles
+	int (*make)(const double *params, uint32_t num_params, void *rule_storage);
+	void (*launch_num_child)(const void *rule, const engine_launch &L);
+	void (*launch_symbolic)(const void *rule, const engine_launch &L);
+	void (*launch_populate)(const void *rule, const engine_launch &L);
+	void (*launch_hash)(const void *rule, const engine_launch &L);
+	bool needs_scratch;
+	int (*symbolic_grid)(int sm_count); // CTAs the symbolic kernel is launched with at most (sizes the scratch)
+};
+
+struct modifier_ops {
+	const char *name;
+	int (*make)(const double *params, uint32_t num_params, void *storage);
+	void (*launch)(const void *modifier, const iter_view &it, cudaStream_t stream, int sm_count);
+};
+
+constexpr size_t RULE_STORAGE_BYTES = 256;
+
+int register_rule(const rule_ops &ops);
+int register_modifier(const modifier_ops &ops);
+const rule_ops *find_rule(int id);
+const modifier_ops *find_modifier(int id);
+
+} // namespace qb

@@ -1,0 +1,291 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU checker and the golden vectors.
+
+Bar (BASELINE.json north_star): surviving set of object byte strings and hashes bit-exact
+(sub_node padding masked), magnitudes within 1e-12 relative, total_proba within 1e-12; truncating
+steps through the documented tie band."""
+import math
+
+import numpy as np
+import pytest
+
+import golden_util
+import orc
+
+pytestmark = pytest.mark.gpu
+
+PI = math.pi
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import quids_b200 as qb
+    if qb.lib().qb_device_count() < 1:
+        pytest.fail("no CUDA device: the CUDA path has no fallback")
+    from gpu_engine import GpuEngine
+    return GpuEngine
+
+
+@pytest.mark.parametrize("suffix", ["", "_generic"])
+@pytest.mark.parametrize("name", golden_util.fixtures())
+def test_golden_vectors(gpu, port, name, suffix):
+    assert golden_util.replay(name, gpu(suffix), port) > 0
+
+
+@pytest.mark.parametrize("align", [0, 4, 8, 16])
+def test_golden_vectors_other_alignments(gpu, port, align):
+    for name in ("qc_example", "qcgd_example_seed1", "qcgd_truncate_children"):
+        if align == 0 and name.startswith("qcgd"):
+            pass  # QCGD object sizes are multiples of 4, so unpadded storage stays 4-byte aligned
+        golden_util.replay(name, gpu("", align=align), port)
+
+
+def test_hashers_match(gpu, port):
+    rng = np.random.default_rng(0)
+    objs = [bytes(rng.integers(0, 256, size=l, dtype=np.uint8)) for l in range(0, 80)]
+    st = orc.Packed.from_objects(objs, [1] * len(objs))
+    for align in (0, 8):
+        assert np.array_equal(gpu("", align=align).hash_objects(st, orc.RULE_HADAMARD, [0]), port.hash_objects(st, orc.RULE_HADAMARD, [0]))
+    g = port.qcgd_random_state(9, 300, 4)
+    grown, _, _ = port.simulate(g, orc.RULE_SPLIT_MERGE, [0.3, 0.2, 0.1], tolerance=1e-18)
+    for rid in orc.QCGD_RULES:
+        assert np.array_equal(gpu().hash_objects(grown, rid), port.hash_objects(grown, rid, [0, 0, 0]))
+
+
+@pytest.mark.parametrize("suffix", ["", "_generic"])
+@pytest.mark.parametrize("rule_id", orc.QCGD_RULES)
+def test_qcgd_random_graphs_vs_oracle(gpu, port, rule_id, suffix):
+    params = [0.37, 0.21, -0.4]
+    eng = gpu(suffix)
+    state = port.qcgd_random_state(8, 400, 9)
+    for it in range(2):
+        want, nc, nu = port.simulate(state, rule_id, params, tolerance=1e-18)
+        got, gc, gu = eng.simulate(state, rule_id, params, tol=1e-18)
+        assert (gc, gu) == (nc, nu)
+        orc.assert_same_state(got, port.hash_objects(got, rule_id, params), want, port.hash_objects(want, rule_id, params), True,
+                              what=f"rule {rule_id}{suffix} iteration {it}")
+        state = port.apply_modifier(want, orc.MOD_STEP)
+        assert eng.apply_modifier(want, orc.MOD_STEP).objects() == state.objects()
+        if state.n > 60000:
+            break
+
+
+def test_qcgd_wide_graphs_vs_oracle(gpu, port):
+    # more than 64 nodes: the bit-mask fast path of erase_create / coin does not apply
+    base = port.qcgd_random_state(70, 2, 1, 1.0)
+    objs = []
+    for o in base.objects():
+        a = bytearray(o)
+        n = 70
+        for i in range(n):  # keep the fan-out small: only 6 eligible nodes per rule
+            a[2 + i] = 1 if i < 6 else (i & 1)
+            a[2 + n + i] = 1 if i < 6 else 1 - (i & 1)
+        a[2 + 3] ^= 1
+        objs.append(bytes(a))
+    objs[1] = objs[1][:2 + 8] + bytes([1 - objs[1][2 + 8]]) + objs[1][2 + 9:]
+    st = orc.Packed.from_objects(objs, [0.6, 0.8j])
+    for rid in (orc.RULE_ERASE_CREATE, orc.RULE_COIN):
+        want, nc, nu = port.simulate(st, rid, [0.3, 0.1, 0.2], tolerance=1e-18)
+        got, gc, gu = gpu().simulate(st, rid, [0.3, 0.1, 0.2], tol=1e-18)
+        assert (gc, gu) == (nc, nu)
+        orc.assert_same_state(got, port.hash_objects(got, rid), want, port.hash_objects(want, rid), True, what=f"wide rule {rid}")
+
+
+def test_hadamard_ragged_vs_oracle(gpu, port):
+    rng = np.random.default_rng(3)
+    objs = [bytes(rng.integers(0, 2, size=int(l), dtype=np.uint8)) for l in rng.integers(3, 40, size=300)]
+    objs = list(dict.fromkeys(objs))
+    st = orc.Packed.from_objects(objs, rng.normal(size=len(objs)) + 1j * rng.normal(size=len(objs)))
+    for align in (0, 8):
+        eng = gpu("", align=align)
+        cur = st
+        for bit in (0, 2, 1, 2, 0):
+            want, nc, nu = port.simulate(cur, orc.RULE_HADAMARD, [bit])
+            got, gc, gu = eng.simulate(cur, orc.RULE_HADAMARD, [bit])
+            assert (gc, gu) == (nc, nu)
+            orc.assert_same_state(got, port.hash_objects(got, 1, [0]), want, port.hash_objects(want, 1, [0]), False, what=f"H({bit}) align {align}")
+            cur = want
+
+
+def test_modifiers_vs_oracle(gpu, port):
+    rng = np.random.default_rng(4)
+    objs = [bytes(rng.integers(0, 2, size=6, dtype=np.uint8)) for _ in range(1000)]
+    st = orc.Packed.from_objects(objs, rng.normal(size=1000) + 1j * rng.normal(size=1000))
+    eng = gpu("", align=0)
+    for mid, params in ((orc.MOD_CNOT, [1, 3]), (orc.MOD_XGATE, [2]), (orc.MOD_YGATE, [0]), (orc.MOD_ZGATE, [3]), (orc.MOD_PHASE, [0.3])):
+        want, got = port.apply_modifier(st, mid, params), eng.apply_modifier(st, mid, params)
+        assert got.objects() == want.objects()
+        assert np.array_equal(got.mags, want.mags), mid  # modifiers are exact: no reassociation anywhere
+        st = want
+    g = port.qcgd_random_state(7, 500, 2)
+    for mid in (orc.MOD_STEP, orc.MOD_REVERSED_STEP, orc.MOD_STEP):
+        want, got = port.apply_modifier(g, mid), gpu().apply_modifier(g, mid)
+        assert got.objects() == want.objects()
+        g = want
+
+
+def test_truncation_band_vs_oracle(gpu, port):
+    base = port.qcgd_random_state(7, 300, 13, 1.0)
+    rng = np.random.default_rng(6)
+    mags = rng.normal(size=(300, 2))
+    mags /= np.sqrt((mags ** 2).sum())
+    st = orc.Packed(base.sizes, mags, base.data)
+    params = [PI / 4, 0.1, 0.2]
+    for rid, k in ((orc.RULE_ERASE_CREATE, 1000), (orc.RULE_COIN, 777), (orc.RULE_SPLIT_MERGE, 400)):  # k >= number of parents: only the children are truncated here
+        full, _, nu = port.simulate(st, rid, params, tolerance=1e-18)
+        want, wc, wu = port.simulate(st, rid, params, k, 1e-18)
+        got, gc, gu = gpu().simulate(st, rid, params, k, 1e-18)
+        assert (gc, gu) == (wc, wu) and nu == wu
+        orc.assert_same_truncated(got, port.hash_objects(got, rid), want, port.hash_objects(want, rid), full, port.hash_objects(full, rid),
+                                  min(k, full.n), True, what=f"truncated rule {rid}")
+
+
+def test_truncation_with_exact_ties(gpu, port):
+    # equal magnitudes everywhere: any k objects of the tied set are a legal answer, the count is not negotiable
+    st = port.qcgd_random_state(6, 64, 3)
+    k = 500
+    full, _, nu = port.simulate(st, orc.RULE_ERASE_CREATE, [PI / 4, 0, 0], tolerance=1e-18)
+    got, gc, gu = gpu().simulate(st, orc.RULE_ERASE_CREATE, [PI / 4, 0, 0], k, 1e-18)
+    assert gu == nu and got.n == min(k, nu)
+    kf = orc.keyed(full, port.hash_objects(full, orc.RULE_ERASE_CREATE), True)
+    f, ff = math.sqrt(got.total_proba), math.sqrt(full.total_proba)
+    probs = np.sort(np.abs(full.cmags) ** 2)[::-1]
+    for h, (o, m) in orc.keyed(got, port.hash_objects(got, orc.RULE_ERASE_CREATE), True).items():
+        assert h in kf and kf[h][0] == o
+        assert abs(m * f - kf[h][1] * ff) <= 1e-12 * abs(m * f)
+        assert abs(kf[h][1]) ** 2 >= probs[k - 1] * (1 - 1e-12)
+
+
+def test_parent_pretruncation(gpu, port):
+    st0 = port.qcgd_random_state(6, 200, 17, 1.0)
+    rng = np.random.default_rng(8)
+    mags = rng.normal(size=(200, 2))
+    mags /= np.sqrt((mags ** 2).sum())
+    st = orc.Packed(st0.sizes, mags, st0.data)
+    k = 50  # < number of parents: the 50 most probable parents are expanded, then 50 children kept
+    want, wc, wu = port.simulate(st, orc.RULE_COIN, [0.3, 0.2, 0.1], k, 1e-18)
+    got, gc, gu = gpu().simulate(st, orc.RULE_COIN, [0.3, 0.2, 0.1], k, 1e-18)
+    assert (gc, gu) == (wc, wu)
+    order = np.argsort(-(np.abs(st.cmags) ** 2), kind="stable")[:k]
+    objs = st.objects()
+    sub = orc.Packed.from_objects([objs[j] for j in np.sort(order)], st.cmags[np.sort(order)])
+    full, _, _ = port.simulate(sub, orc.RULE_COIN, [0.3, 0.2, 0.1], tolerance=1e-18)
+    orc.assert_same_truncated(got, port.hash_objects(got, 3), want, port.hash_objects(want, 3), full, port.hash_objects(full, 3), k, True)
+
+
+def test_empty_and_degenerate_states(gpu, port):
+    eng = gpu()
+    empty = orc.Packed.from_objects([], [])
+    got, nc, nu = eng.simulate(empty, orc.RULE_HADAMARD, [0])
+    assert (got.n, nc, nu, got.total_proba) == (0, 0, 0, 0.0)
+    assert eng.apply_modifier(empty, orc.MOD_XGATE, [0]).n == 0
+    # everything cancels: H on (|0> - |1>)/sqrt2 ... then a tolerance that removes all children
+    st = orc.Packed.from_objects([bytes([0, 0])], [1])
+    got, nc, nu = eng.simulate(st, orc.RULE_HADAMARD, [0], tol=10.0)
+    assert (got.n, nc, nu, got.total_proba) == (0, 2, 0, 0.0)
+    # a single object
+    got, nc, nu = eng.simulate(st, orc.RULE_HADAMARD, [1])
+    assert (got.n, nc, nu) == (2, 2, 2) and abs(got.total_proba - 1) < 1e-15
+
+
+def test_phase_labels_in_reference_order(gpu):
+    import quids_b200 as qb
+    it, nxt, sym = qb.Iteration(), qb.Iteration(), qb.SymbolicIteration()
+    qb.config.align_byte_length = 0
+    it.append(bytes([0, 1, 0]), 1.0)
+    labels = []
+    qb.simulate(it, qb.Rule("hadamard", 1), nxt, sym, qb.NO_TRUNCATION, labels.append)
+    assert labels == ["num_child", "truncate_symbolic - prepare", "truncate_symbolic", "prepare_index", "symbolic_iteration",
+                      "compute_collisions - prepare", "compute_collisions - insert", "compute_collisions - finalize", "truncate - prepare",
+                      "truncate", "prepare_final", "final", "normalize", "end"]
+    assert nxt.num_object == 2
+    qb.config.align_byte_length = 8
+
+
+def test_unsupported_requests_fail_loudly(gpu):
+    import quids_b200 as qb
+    it, nxt, sym = qb.Iteration(), qb.Iteration(), qb.SymbolicIteration()
+    it.append(bytes([0, 1, 0]), 1.0)
+    with pytest.raises(qb.QuidsError):
+        qb.simulate(it, qb.Rule("hadamard", 1), nxt, sym, 0)  # auto memory budget: SURVEY 8(f), not silently ignored
+    with pytest.raises(qb.QuidsError):
+        qb.simulate(it, qb.Rule("hadamard", 1), it, sym)
+    with pytest.raises(qb.QuidsError):
+        qb.Rule("not_a_rule")
+
+
+# ---- size-independent properties at sizes the CPU checker would not finish in seconds ---------------------
+def test_register_to_full_superposition_and_back(gpu):
+    """SURVEY 8(d) C3 shape at 20 qubits: 1 -> 2^20 objects -> 1, exact cancellation, P = 1."""
+    import quids_b200 as qb
+    nq = 20
+    qb.config.align_byte_length = 0
+    qb.config.tolerance = 1e-30
+    a, b, sym = qb.Iteration(), qb.Iteration(), qb.SymbolicIteration()
+    a.append(bytes(nq), 1.0)
+    for bit in range(nq):
+        qb.simulate(a, qb.Rule("hadamard", bit), b, sym)
+        assert sym.num_object == 2 ** (bit + 1) and b.num_object == 2 ** (bit + 1)
+        a, b = b, a
+    sizes, mags, data = a.download_packed()
+    assert len(set(bytes(r) for r in data.reshape(-1, nq))) == 2 ** nq
+    s = 1 / math.sqrt(2.)
+    amp = 1.0
+    for _ in range(nq):
+        amp *= s
+    np.testing.assert_allclose(mags[:, 0], amp, rtol=1e-12)
+    assert np.all(mags[:, 1] == 0)
+    for bit in reversed(range(nq)):
+        qb.simulate(a, qb.Rule("hadamard", bit), b, sym)
+        assert sym.num_object == 2 ** (bit + 2) and sym.num_object_after_interferences == 2 ** bit
+        a, b = b, a
+    obj, mag = a.get_object(0)
+    assert a.num_object == 1 and obj == bytes(nq)
+    assert abs(mag - 1) < 1e-12 and abs(a.total_proba - 1) < 1e-12
+    qb.config.align_byte_length = 8
+
+
+def test_qcgd_reversibility_large(gpu, port):
+    """examples/qcgd_test.cpp property on a wider graph: forward then reversed rules return the
+    single initial graph with magnitude 1 (interference of ~1e5-1e6 children down to one object)."""
+    import quids_b200 as qb
+    init = port.qcgd_random_state(9, 1, 5, 1.0)
+    qb.config.align_byte_length = 8
+    qb.config.tolerance = 1e-15
+    a, b, sym = qb.Iteration(), qb.Iteration(), qb.SymbolicIteration()
+    a.upload_packed(init.sizes, init.mags, init.data)
+    ec, sm, rsm = qb.Rule("erase_create", 0.3333), qb.Rule("split_merge", 0.25, 0.25, 0.25), qb.Rule("split_merge", 0.25, 0.25, -0.25)
+    step, rstep = qb.Modifier("step"), qb.Modifier("reversed_step")
+    qb.simulate(a, step)
+    qb.simulate(a, ec, b, sym)
+    qb.simulate(b, sm, a, sym)
+    qb.simulate(a, step)
+    qb.simulate(a, sm, b, sym)
+    grown = b.num_object
+    assert grown > 1000
+    qb.simulate(b, rsm, a, sym)
+    qb.simulate(a, rstep)
+    qb.simulate(a, rsm, b, sym)
+    qb.simulate(b, ec, a, sym)
+    qb.simulate(a, rstep)
+    assert a.num_object == 1
+    obj, mag = a.get_object(0)
+    assert orc.canonical_qcgd(obj) == orc.canonical_qcgd(init.objects()[0])
+    assert abs(abs(mag) - 1) < 1e-9 and abs(a.total_proba - 1) < 1e-9
+    qb.config.tolerance = 1e-30
+
+
+def test_probability_is_conserved_without_truncation(gpu, port):
+    import quids_b200 as qb
+    init = port.qcgd_random_state(10, 2000, 5)
+    init = orc.Packed.from_objects(list(dict.fromkeys(init.objects())), [1] * len(dict.fromkeys(init.objects())))
+    init.mags /= math.sqrt(init.n)
+    qb.config.tolerance = 1e-18
+    a, b, sym = qb.Iteration(), qb.Iteration(), qb.SymbolicIteration()
+    a.upload_packed(init.sizes, init.mags, init.data)
+    for rule in (qb.Rule("erase_create", PI / 4), qb.Rule("split_merge", PI / 4, PI / 4, PI / 4)):
+        qb.simulate(a, rule, b, sym)
+        assert abs(b.total_proba - 1) < 1e-11
+        h = b.hashes(rule)
+        assert len(np.unique(h)) == b.num_object == sym.num_object_after_interferences
+        a, b = b, a
+    qb.config.tolerance = 1e-30
