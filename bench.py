@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- children/sec per rule iteration on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one rule iteration (quids::simulate, quids.hpp:448-543) over one resident batch of
+synthetic input.  Workload at N = 1 (BASELINE.json configs[3]): QCGD erase_create
+(theta = pi/4) on 1e7 random density-1/2 12-node graphs (244-byte objects), max_num_object = 1e7,
+simple truncation, tolerance 1e-18.  At N > 1 every rank holds the same number of parents (weak
+scaling) and the interference step is hash-sharded over NCCL (qb_simulate_dist).
+
+One JSON line is printed by rank 0; see the task contract for the keys.  `value` is measured with
+the state resident in HBM (CUDA events on the library's stream); `e2e` goes through the same C-ABI
+calls with HOST buffers: upload of the input state and download of the result are inside the timed
+region.  `cpu_baseline` / `--impl reference` time the reference's own CPU implementation
+(oracle/_ref, all host threads) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_NODE = 12
+THETA = math.pi / 4
+TOLERANCE = 1e-18
+METRIC = "children_per_sec_per_rule_iteration"
+UNIT = "children/s"
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_parents(n_parents, seed):
+    from quids_b200 import qcgd
+    sizes, data = qcgd.random_graphs(N_NODE, n_parents, seed=seed)
+    mags = np.zeros((n_parents, 2))
+    mags[:, 0] = qcgd.read_state_magnitude(n_parents)[0]
+    return sizes, mags, data
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)"""
+    FIELDS = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device):
+        self.device = device
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes(n_p, s_p, n_c, n_u, n_s, s_s):
+    """compulsory payload traffic of one rule iteration"""
+    return n_p * (s_p + 16) + 48 * n_c + 40 * n_u + n_s * (s_p + s_s + 16)
+
+
+def cpu_reference_rate(sample_parents, seed, repeats=1):
+    """children/s of the reference's own CPU implementation (oracle/_ref, else the port) on a bounded sample"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import orc
+    if orc.have_reference():
+        o = orc.Oracle(orc.REF_SO)
+    else:
+        if not os.path.exists(orc.PORT_SO):
+            orc.build()
+        o = orc.Oracle(orc.PORT_SO)
+    sizes, mags, data = make_parents(sample_parents, seed)
+    st = orc.Packed(sizes, mags, data)
+    best = None
+    for _ in range(repeats):
+        _, nc, nu = o.simulate(st, orc.RULE_ERASE_CREATE, [THETA, 0, 0], sample_parents, TOLERANCE)
+        rate = nc / o.last_seconds
+        best = rate if best is None else max(best, rate)
+    return best, o, nc, o.last_seconds
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path, all host threads, same metric and config"""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # calibrate on a small sample, then size each step to a few seconds
+    rate, o, _, _ = cpu_reference_rate(20000, seed=0)
+    budget_s = 150.0 / max(1, args.steps + args.warmup)
+    parents = int(min(1e6, max(2e4, rate * min(8.0, budget_s) / 129.7)))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import orc
+    sizes, mags, data = make_parents(parents, 0)
+    st = orc.Packed(sizes, mags, data)
+    times, nc = [], 0
+    for i in range(args.warmup + args.steps):
+        _, nc, nu = o.simulate(st, orc.RULE_ERASE_CREATE, [THETA, 0, 0], parents, TOLERANCE)
+        if i >= args.warmup:
+            times.append(o.last_seconds)
+    ms = 1e3 * sum(times) / len(times)
+    value = nc / (ms / 1e3)
+    sample = f"{parents} random 12-node parents ({nc} children) per step, erase_create(pi/4), max_num_object={parents}"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": o.num_threads, "kind": o.kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus, parents_per_gpu=None):
+    return {"workload": "QCGD erase_create(theta=pi/4) on random density-1/2 12-node graphs (244 B objects), max_num_object = parents, "
+                        "simple truncation, tolerance 1e-18 (BASELINE.json configs[3]; configs[4] when hash-sharded over several GPUs)",
+            "parents_per_gpu": parents_per_gpu, "n_node": N_NODE, "rule": "erase_create", "theta": THETA,
+            "l2": "inputs larger than L2 (2.6 GB state, GB-scale interference table rewritten every step)",
+            "parallelism": "1 GPU" if n_gpus == 1 else f"hash-sharded interference over {n_gpus} GPUs (NCCL all-to-allv)"}
+
+
+def run_ours(args):
+    import torch
+    import quids_b200 as qb
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the CUDA path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    parents = args.parents
+    qb.config.tolerance = TOLERANCE
+    qb.config.align_byte_length = 8
+    qb.config.profile = True
+    ctx = qb.default_context()
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+
+    sizes, mags, data = make_parents(parents, seed=rank)
+    a, b, sym = qb.Iteration(ctx), qb.Iteration(ctx), qb.SymbolicIteration(ctx)
+    a.upload_packed(sizes, mags, data)
+    rule = qb.Rule("erase_create", THETA, 0.0, 0.0)
+    comm = None
+    if world > 1:
+        comm = qb.Communicator.from_torch(ctx, dist)
+    k_total = parents * world
+
+    def step():
+        if comm is None:
+            qb.simulate(a, rule, b, sym, parents)
+        else:
+            qb.mpi_simulate(a, rule, b, sym, comm, k_total)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    launches0 = ctx.launch_count
+    sampler = ClockSampler(local)
+    phase_sum = {}
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+        for name, ms in sym.phase_ms.items():
+            phase_sum[name] = phase_sum.get(name, 0.0) + ms
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    launches = ctx.launch_count - launches0
+    elapsed_ms = e0.elapsed_time(e1)
+    n_c, n_u, n_s = sym.num_object, sym.num_object_after_interferences, b.num_object
+    if dist is not None:
+        t = torch.tensor([elapsed_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+        c = torch.tensor([n_c, n_u, n_s], device="cuda", dtype=torch.int64)
+        dist.all_reduce(c)
+        n_c_total = int(c[0].item())
+    else:
+        n_c_total = n_c
+    ms_per_step = elapsed_ms / args.steps
+    value = n_c_total / (ms_per_step / 1e3)
+
+    # ---- end to end through the C ABI with host buffers: upload + simulate + download per step ----------
+    objects, begin, size, mag = a.download()
+    h2d = objects.nbytes + begin.nbytes + size.nbytes + mag.nbytes
+    pinned = [torch.from_numpy(x.copy()).pin_memory() for x in (objects, begin, size, mag)]
+    host = [p.numpy() for p in pinned]
+    a2, b2 = qb.Iteration(ctx), qb.Iteration(ctx)
+    out_host = None
+    e2e_steps = max(1, min(args.steps, 3))
+    d2h = 0
+    for it in range(1 + e2e_steps):
+        if it == 1:
+            barrier()
+            t0 = time.perf_counter()
+        a2.upload(host[0], host[1], host[2], host[3].reshape(-1, 2))
+        if comm is None:
+            qb.simulate(a2, rule, b2, sym, parents)
+        else:
+            qb.mpi_simulate(a2, rule, b2, sym, comm, k_total)
+        if out_host is None:
+            n2, nb2, _ = b2._counts_noflush()
+            cap = int(nb2 * 1.05) + 4096
+            out_host = [torch.empty(cap, dtype=torch.uint8).pin_memory().numpy(), torch.empty(n2 + 1 + 4096, dtype=torch.int64).pin_memory().numpy().view(np.uint64),
+                        torch.empty(n2 + 4096, dtype=torch.int32).pin_memory().numpy().view(np.uint32), torch.empty((n2 + 4096) * 2, dtype=torch.float64).pin_memory().numpy()]
+        n2, nb2, _ = b2._counts_noflush()
+        assert nb2 <= out_host[0].nbytes and n2 + 1 <= out_host[1].shape[0]
+        qb._check(qb.lib().qb_iter_download(b2.handle, out_host[0].ctypes.data, out_host[1].ctypes.data, out_host[2].ctypes.data, out_host[3].ctypes.data))
+        d2h = nb2 + 8 * (n2 + 1) + 4 * n2 + 16 * n2
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    if dist is not None:
+        t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = n_c_total / (e2e_ms / 1e3)
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel (symbolic_kernel: children -> (hash, magnitude) -> table) --------
+    peak, peak_src = measured_peak_gbs()
+    s_p = 4 + 20 * N_NODE + 4  # 244 B padded to 248
+    phase_ms = {k: v / args.steps for k, v in phase_sum.items()}
+    dominant = max(phase_ms, key=phase_ms.get)
+    sym_ms = phase_ms["symbolic"]
+    sym_bytes = parents * (s_p + 16) + 48 * n_c  # parents read once + 48 B per child (hash 8 + mag 16, written once, read once)
+    achieved = sym_bytes / (sym_ms / 1e3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if tj.get("parents") == parents and tj.get("kernel") == "symbolic_kernel":
+            traffic = tj.get("dram_bytes_per_launch")
+    total_bytes = algorithmic_bytes(parents, s_p, n_c, n_u, n_s, s_p)
+    roofline = {"bound": "hbm", "kernel": "symbolic_kernel<erase_create> (child generation fused with interference-table insert)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": sym_bytes, "kernel_ms": sym_ms, "kernel_share_of_step": sym_ms / ms_per_step,
+                "dominant_phase": dominant, "phase_ms": phase_ms,
+                "whole_iteration": {"algorithmic_bytes": total_bytes, "achieved": total_bytes / (ms_per_step / 1e3) / 1e9,
+                                    "frac": total_bytes / (ms_per_step / 1e3) / 1e9 / peak}}
+
+    # ---- CPU baseline beside it (bounded sample, rank 0, N = 1 only) ----------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        rate, o, _, _ = cpu_reference_rate(20000, seed=0)
+        sample_parents = int(min(1e6, max(2e4, rate * 12.0 / 129.7)))
+        rate, o, nc_cpu, secs = cpu_reference_rate(sample_parents, seed=0)
+        cpu = {"value": rate, "unit": UNIT, "cores": o.num_threads, "kind": o.kind,
+               "sample": f"{sample_parents} parents of the same generator ({nc_cpu} children, {secs:.1f} s), erase_create(pi/4), max_num_object={sample_parents}"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(world, parents),
+            "counts": {"N_p": parents * world, "N_c": n_c_total, "N_u_rank0": n_u, "N_s_rank0": n_s},
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches)}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--parents", type=int, default=10**7, help="parents per GPU")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

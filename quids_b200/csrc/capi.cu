@@ -2,11 +2,13 @@
 // orchestration of one rule iteration (the GPU counterpart of quids::simulate, quids.hpp:448-543).
 #include <cmath>
 #include <complex>
+#include <map>
 #include <mutex>
 #include <vector>
 
 #include "engine.cuh"
 #include "pipeline.cuh"
+#include "sort.cuh"
 
 using namespace qb;
 
@@ -55,6 +57,7 @@ enum { // u64 words of the small device scratch
 	DS_COUNT = 1,
 	DS_OVERFLOW = 2,
 	DS_TOTAL = 3,
+	DS_USED = 4,
 	DS_WORDS = 8
 };
 
@@ -94,7 +97,7 @@ struct qb_iter {
 	qb_ctx *ctx;
 	uint64_t n = 0, n_bytes = 0;
 	double total_proba = 1; // quids.hpp:154
-	dev_buf objects, begin, size, mag, num_childs, child_begin;
+	dev_buf objects, begin, size, mag, num_childs, child_begin, num_groups, group_begin, locality;
 
 	iter_view view() const { return iter_view{objects.as<uint8_t>(), begin.as<uint64_t>(), size.as<uint32_t>(), mag.as<cplx>(), n}; }
 };
@@ -102,13 +105,16 @@ struct qb_iter {
 struct qb_sym {
 	qb_ctx *ctx;
 	uint64_t n_children = 0, n_unique = 0; // quids.hpp:344-346
-	dev_buf table, ukey, uslot, sslot, kept, scratch, survivor_parent, survivor_child, padded;
+	dev_buf table, ukey, uslot, sslot, kept, scratch, survivor_parent, survivor_child, padded, chunk_parent, sort_keys, sort_vals, sort_hist, sort_base;
 	cudaEvent_t ev[2 * QB_PHASE_COUNT] = {};
 	bool ev_used[QB_PHASE_COUNT] = {};
 	float phase_ms[QB_PHASE_COUNT] = {};
+	std::map<int, double> unique_ratio; // per rule id: slots created / children of the last call (sizes the next table)
+	uint64_t table_capacity = 0;        // of the last call
+	int table_attempts = 0;
 
 	uint64_t device_bytes() const {
-		return table.cap + ukey.cap + uslot.cap + sslot.cap + kept.cap + scratch.cap + survivor_parent.cap + survivor_child.cap + padded.cap;
+		return table.cap + ukey.cap + uslot.cap + sslot.cap + kept.cap + scratch.cap + survivor_parent.cap + survivor_child.cap + padded.cap + chunk_parent.cap + sort_keys.cap + sort_vals.cap + sort_hist.cap + sort_base.cap;
 	}
 };
 
@@ -238,6 +244,41 @@ struct widen_u32 {
 	__device__ uint64_t operator()(uint64_t j) const { return v[j]; }
 };
 
+// keys[j] = locality[kept ? kept[j] : j], vals[j] = that object id
+__global__ void __launch_bounds__(256) sort_init_kernel(const uint32_t *locality, const uint64_t *kept, uint64_t n, uint32_t *keys, uint64_t *vals) {
+	const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (j < n) {
+		const uint64_t oid = kept ? kept[j] : j;
+		keys[j] = locality[oid];
+		vals[j] = oid;
+	}
+}
+
+// orders the kept parents by locality key; returns the sorted object ids (device)
+const uint64_t *sort_parents_by_locality(qb_ctx *ctx, qb_sym *sym, const uint32_t *locality, const uint64_t *kept, uint64_t n) {
+	cudaStream_t stream = ctx->stream;
+	const uint64_t tiles = div_up<uint64_t>(n, SORT_TILE);
+	sym->sort_keys.ensure(2 * sizeof(uint32_t) * n, stream);
+	sym->sort_vals.ensure(2 * sizeof(uint64_t) * n, stream);
+	sym->sort_hist.ensure(sizeof(uint32_t) * SORT_BINS * tiles, stream);
+	sym->sort_base.ensure(sizeof(uint64_t) * (SORT_BINS * tiles + 1), stream);
+	uint32_t *keys[2] = {sym->sort_keys.as<uint32_t>(), sym->sort_keys.as<uint32_t>() + n};
+	uint64_t *vals[2] = {sym->sort_vals.as<uint64_t>(), sym->sort_vals.as<uint64_t>() + n};
+	sort_init_kernel<<<(unsigned)div_up<uint64_t>(n, 256), 256, 0, stream>>>(locality, kept, n, keys[0], vals[0]);
+	++ctx->launches;
+	int src = 0;
+	for (int shift = 0; shift < 32; shift += 8, src ^= 1) {
+		radix_histogram_kernel<<<(unsigned)tiles, SORT_THREADS, 0, stream>>>(keys[src], n, shift, sym->sort_hist.as<uint32_t>(), tiles);
+		++ctx->launches;
+		exclusive_scan(ctx, widen_u32{sym->sort_hist.as<uint32_t>()}, sym->sort_base.as<uint64_t>(), SORT_BINS * tiles);
+		radix_scatter_kernel<<<(unsigned)tiles, SORT_THREADS, 0, stream>>>(keys[src], vals[src], n, shift, sym->sort_base.as<uint64_t>(), tiles,
+		                                                                   keys[src ^ 1], vals[src ^ 1]);
+		++ctx->launches;
+	}
+	QB_CUDA(cudaGetLastError());
+	return vals[src];
+}
+
 double reduce_norm_total(qb_ctx *ctx, const cplx *mag, uint64_t n) {
 	const int grid = grid_for(n, SCAN_THREADS, ctx->grid_cap());
 	ctx->partials.ensure(sizeof(double) * (size_t)ctx->grid_cap(), ctx->stream);
@@ -271,7 +312,7 @@ void resolve_options(const qb_options *in, qb_options &opt) {
 // ======================================================================================================
 // one rule iteration on one GPU
 // ======================================================================================================
-void simulate(qb_iter *it, const rule_ops *ops, const void *rule, qb_iter *next, qb_sym *sym, uint64_t max_num_object, const qb_options &opt,
+void simulate(qb_iter *it, int rule_id, const rule_ops *ops, const void *rule, qb_iter *next, qb_sym *sym, uint64_t max_num_object, const qb_options &opt,
               qb_step_cb cb, void *user) {
 	qb_ctx *ctx = it->ctx;
 	QB_REQUIRE(next->ctx == ctx && sym->ctx == ctx, QB_ERR_ARG, "iteration, next iteration and symbolic iteration belong to different contexts");
@@ -301,6 +342,7 @@ void simulate(qb_iter *it, const rule_ops *ops, const void *rule, qb_iter *next,
 		next->begin.ensure(sizeof(uint64_t), stream);
 		QB_CUDA(cudaMemsetAsync(next->begin.ptr, 0, sizeof(uint64_t), stream));
 		ctx->sync();
+		timer.collect();
 	};
 
 	// ---- 1. number of children per parent (quids.hpp:548-569) --------------------------------------
@@ -316,6 +358,16 @@ void simulate(qb_iter *it, const rule_ops *ops, const void *rule, qb_iter *next,
 	it->num_childs.ensure(sizeof(uint32_t) * it->n, stream);
 	QB_CUDA(cudaMemsetAsync(ctx->d_small.ptr, 0, DS_WORDS * sizeof(uint64_t), stream));
 	L.num_childs = it->num_childs.as<uint32_t>();
+	if (ops->warp_groups) {
+		it->num_groups.ensure(sizeof(uint32_t) * it->n, stream);
+		L.num_groups = it->num_groups.as<uint32_t>();
+	}
+	// ordering the parents only pays when the table cannot stay in L2 anyway
+	const bool order_parents = ops->has_locality_key && opt.locality_sort != 0 && it->n >= (opt.locality_sort > 1 ? 2u : 1u << 17);
+	if (order_parents) {
+		it->locality.ensure(sizeof(uint32_t) * it->n, stream);
+		L.locality = it->locality.as<uint32_t>();
+	}
 	L.max_child_size = reinterpret_cast<unsigned int *>(ctx->small(DS_MAX_CHILD_SIZE));
 	ops->launch_num_child(rule, L);
 	timer.end(QB_PHASE_NUM_CHILD);
@@ -336,16 +388,30 @@ void simulate(qb_iter *it, const rule_ops *ops, const void *rule, qb_iter *next,
 		timer.end(QB_PHASE_PRE_TRUNCATE);
 	}
 
+	if (order_parents) {
+		timer.begin(QB_PHASE_PRE_TRUNCATE);
+		kept = sort_parents_by_locality(ctx, sym, it->locality.as<uint32_t>(), kept, n_parents);
+		timer.end(QB_PHASE_PRE_TRUNCATE);
+	}
+
 	// ---- 3. child index ranges (quids.hpp:666-671: a serial loop in the reference) --------------------
 	step("prepare_index");
 	timer.begin(QB_PHASE_NUM_CHILD);
 	it->child_begin.ensure(sizeof(uint64_t) * (n_parents + 1), stream);
 	exclusive_scan(ctx, counts_through{it->num_childs.as<uint32_t>(), kept}, it->child_begin.as<uint64_t>(), n_parents);
+	const uint64_t *group_begin = it->child_begin.as<uint64_t>();
+	if (ops->warp_groups) { // children are produced in groups that share work: a second index space
+		it->group_begin.ensure(sizeof(uint64_t) * (n_parents + 1), stream);
+		exclusive_scan(ctx, counts_through{it->num_groups.as<uint32_t>(), kept}, it->group_begin.as<uint64_t>(), n_parents);
+		group_begin = it->group_begin.as<uint64_t>();
+	}
 	QB_CUDA(cudaMemcpyAsync(&ctx->h_small[DS_COUNT], it->child_begin.as<uint64_t>() + n_parents, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+	QB_CUDA(cudaMemcpyAsync(&ctx->h_small[DS_USED], group_begin + n_parents, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
 	QB_CUDA(cudaMemcpyAsync(&ctx->h_small[DS_MAX_CHILD_SIZE], ctx->small(DS_MAX_CHILD_SIZE), sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
 	timer.end(QB_PHASE_NUM_CHILD);
 	ctx->sync();
 	const uint64_t n_children = ctx->h_small[DS_COUNT];
+	const uint64_t n_groups = ctx->h_small[DS_USED];
 	const uint32_t max_child_size = (uint32_t)ctx->h_small[DS_MAX_CHILD_SIZE];
 	sym->n_children = n_children;
 	if (n_children == 0) {
@@ -355,57 +421,78 @@ void simulate(qb_iter *it, const rule_ops *ops, const void *rule, qb_iter *next,
 	QB_REQUIRE(n_children <= REP_MAX_INDEX, QB_ERR_CAPACITY, "more than 2^40 children in one iteration");
 	QB_REQUIRE(max_child_size <= REP_MAX_SIZE, QB_ERR_CAPACITY, "child objects of 16 MiB or more are not supported");
 
-	// ---- 4. interference table ----------------------------------------------------------------------
-	timer.begin(QB_PHASE_TABLE_CLEAR);
-	uint64_t capacity = (uint64_t)std::ceil((double)n_children / opt.table_load);
-	if (capacity < 1024)
-		capacity = 1024;
-	QB_REQUIRE(capacity + 1 <= 0xffffffffull, QB_ERR_CAPACITY, "interference table would need more than 2^32 slots");
-	const size_t table_bytes = (capacity + 1) * sizeof(table_slot);
-	sym->table.ensure(table_bytes, stream);
-	QB_CUDA(cudaMemsetAsync(sym->table.ptr, 0, table_bytes, stream));
-	table_view table{sym->table.as<table_slot>(), capacity, reinterpret_cast<unsigned int *>(ctx->small(DS_OVERFLOW))};
-	timer.end(QB_PHASE_TABLE_CLEAR);
-
-	// ---- 5. children -> (hash, magnitude) -> table (quids.hpp:705-719 fused with :785-809) ------------
-	step("symbolic_iteration");
-	timer.begin(QB_PHASE_SYMBOLIC);
+	// ---- 4-6. interference: table sized from the last call of this rule, full size as fallback -------------
+	// Capacity: enough for every child to be unique at the configured load (safe), unless the previous
+	// call of the same rule showed how many slots are really created: then 2.6x that prediction.  An
+	// insert that probes too long raises `overflow` and the whole step is redone at full size.
+	const uint64_t full_capacity = std::max<uint64_t>(1024, (uint64_t)std::ceil((double)n_children / opt.table_load));
+	uint64_t capacity = full_capacity;
+	{
+		auto hint = sym->unique_ratio.find(rule_id);
+		if (hint != sym->unique_ratio.end())
+			capacity = std::min<uint64_t>(full_capacity, std::max<uint64_t>(1024, (uint64_t)((hint->second * (double)n_children * 1.3 + 1024) / 0.5)));
+	}
 	L.child_begin = it->child_begin.as<uint64_t>();
+	L.group_begin = group_begin;
 	L.kept = kept;
 	L.n_parents = n_parents;
 	L.n_children = n_children;
-	L.table = table;
+	L.n_groups = n_groups;
+	sym->chunk_parent.ensure(sizeof(uint64_t) * (ops->symbolic_chunks(n_groups) + 2), stream);
+	L.chunk_parent = sym->chunk_parent.as<uint64_t>();
 	if (ops->needs_scratch) {
 		L.scratch_stride = (max_child_size + 15u) & ~15u;
 		if (L.scratch_stride == 0)
 			L.scratch_stride = 16;
-		sym->scratch.ensure((size_t)ops->symbolic_grid(ctx->sm_count) * ENGINE_THREADS * L.scratch_stride, stream);
+		sym->scratch.ensure((size_t)ops->symbolic_grid(ctx->sm_count) * SYMBOLIC_THREADS * L.scratch_stride, stream);
 		L.scratch = sym->scratch.as<uint8_t>();
 	}
-	ops->launch_symbolic(rule, L);
-	QB_CUDA(cudaGetLastError());
-	timer.end(QB_PHASE_SYMBOLIC);
-	step("compute_collisions - prepare");
-	step("compute_collisions - insert");
+	table_view table;
+	uint64_t n_unique = 0;
+	step("symbolic_iteration");
+	for (sym->table_attempts = 1;; ++sym->table_attempts) {
+		QB_REQUIRE(capacity + 1 <= 0xffffffffull, QB_ERR_CAPACITY, "interference table would need more than 2^32 slots");
+		timer.begin(QB_PHASE_TABLE_CLEAR);
+		const size_t table_bytes = (capacity + 1) * sizeof(table_slot);
+		sym->table.ensure(table_bytes, stream);
+		QB_CUDA(cudaMemsetAsync(sym->table.ptr, 0, table_bytes, stream));
+		QB_CUDA(cudaMemsetAsync(ctx->small(DS_COUNT), 0, 4 * sizeof(uint64_t), stream)); // count, overflow, total, used
+		table = table_view{sym->table.as<table_slot>(), capacity, reinterpret_cast<unsigned int *>(ctx->small(DS_OVERFLOW)),
+		                   reinterpret_cast<unsigned long long *>(ctx->small(DS_USED))};
+		timer.end(QB_PHASE_TABLE_CLEAR);
 
-	// ---- 6. unique children above the tolerance (quids.hpp:819-823) ------------------------------------
-	step("compute_collisions - finalize");
-	timer.begin(QB_PHASE_COMPACT);
-	sym->ukey.ensure(sizeof(uint64_t) * n_children, stream);
-	sym->uslot.ensure(sizeof(uint32_t) * n_children, stream);
-	{
+		// children -> (hash, magnitude) -> table (quids.hpp:705-719 fused with :785-809)
+		timer.begin(QB_PHASE_SYMBOLIC);
+		L.table = table;
+		ops->launch_symbolic(rule, L);
+		QB_CUDA(cudaGetLastError());
+		timer.end(QB_PHASE_SYMBOLIC);
+
+		// unique children above the tolerance (quids.hpp:819-823)
+		timer.begin(QB_PHASE_COMPACT);
+		const uint64_t bound = std::min<uint64_t>(n_children, capacity + 1);
+		sym->ukey.ensure(sizeof(uint64_t) * bound, stream);
+		sym->uslot.ensure(sizeof(uint32_t) * bound, stream);
 		const uint64_t tiles = div_up<uint64_t>(capacity + 1, COMPACT_TILE);
 		scan_state st = ctx->scan(tiles);
 		table_compact_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, stream>>>(table, opt.tolerance, sym->ukey.as<uint64_t>(), sym->uslot.as<uint32_t>(),
 		                                                                    reinterpret_cast<unsigned long long *>(ctx->small(DS_COUNT)), st);
 		++ctx->launches;
 		QB_CUDA(cudaGetLastError());
+		timer.end(QB_PHASE_COMPACT);
+		ctx->fetch_small();
+		if (ctx->h_small[DS_OVERFLOW] == 0)
+			break;
+		QB_REQUIRE(capacity < full_capacity, QB_ERR_CAPACITY, "interference table overflow at full size");
+		capacity = full_capacity; // the prediction was too small: redo at the safe size
 	}
-	timer.end(QB_PHASE_COMPACT);
-	ctx->fetch_small();
-	QB_REQUIRE(ctx->h_small[DS_OVERFLOW] == 0, QB_ERR_CAPACITY, "interference table overflow");
-	const uint64_t n_unique = ctx->h_small[DS_COUNT];
+	n_unique = ctx->h_small[DS_COUNT];
 	sym->n_unique = n_unique;
+	sym->table_capacity = capacity;
+	sym->unique_ratio[rule_id] = (double)ctx->h_small[DS_USED] / (double)n_children;
+	step("compute_collisions - prepare");
+	step("compute_collisions - insert");
+	step("compute_collisions - finalize");
 
 	// ---- 7. child truncation: the max_num_object most probable (quids.hpp:866-900) ---------------------
 	step("truncate - prepare");
@@ -504,6 +591,7 @@ void qb_options_default(qb_options *opt) {
 	opt->simple_truncation = 1;
 	opt->table_load = 0;
 	opt->profile = 0;
+	opt->locality_sort = 0;
 }
 
 const char *qb_last_error(void) { return g_last_error.c_str(); }
@@ -527,6 +615,9 @@ int qb_ctx_create(int device, qb_ctx **out) {
 		QB_CUDA(cudaSetDevice(device));
 		qb_ctx *ctx = new qb_ctx();
 		ctx->device = device;
+		// the interference table is hit at random, one 32-byte slot at a time: do not let L2 widen the fills
+		cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
+		cudaGetLastError();
 		QB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
 		QB_CUDA(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
 		QB_CUDA(cudaHostAlloc((void **)&ctx->h_small, DS_WORDS * sizeof(uint64_t), cudaHostAllocDefault));
@@ -771,7 +862,7 @@ int qb_simulate(qb_iter *it, int rule_id, const double *params, uint32_t num_par
 		QB_REQUIRE(rc == QB_OK, rc, std::string("bad parameters for rule ") + ops->name);
 		qb_options opt;
 		resolve_options(opt_in, opt);
-		simulate(it, ops, storage, next, sym, max_num_object, opt, cb, user);
+		simulate(it, rule_id, ops, storage, next, sym, max_num_object, opt, cb, user);
 	});
 }
 

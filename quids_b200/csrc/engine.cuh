@@ -25,13 +25,18 @@ struct engine_launch {
 
 	// num_child
 	uint32_t *num_childs;
+	uint32_t *num_groups; // only for rules with warp_groups
+	uint32_t *locality;   // only for rules with has_locality_key
 	unsigned int *max_child_size;
 
 	// symbolic
 	const uint64_t *child_begin; // exclusive scan of num_childs over the kept parents, n_parents + 1 entries
 	const uint64_t *kept;        // object ids of the kept parents, or nullptr = all parents in order
+	const uint64_t *group_begin; // same over the group counts (== child_begin for rules without groups)
+	const uint64_t *chunk_parent; // parent holding the first group of every chunk of the symbolic kernel (+ one sentinel)
 	uint64_t n_parents;
 	uint64_t n_children;
+	uint64_t n_groups;
 	table_view table;
 	uint8_t *scratch;        // needs_scratch rules: scratch_stride bytes per resident thread
 	uint32_t scratch_stride;
@@ -49,8 +54,7 @@ struct engine_launch {
 };
 
 constexpr int ENGINE_THREADS = 256;
-constexpr int SYMBOLIC_CHUNK = 2048;      // children handled by one CTA per loop iteration
-constexpr int SYMBOLIC_GROUP = ENGINE_THREADS; // parents whose contexts are resident at once
+constexpr int SYMBOLIC_CHUNK = 128; // groups of children handled by one warp per loop iteration
 
 inline int resident_grid(const void *kernel, int threads, int sm_count) {
 	int per_sm = 0;
@@ -61,7 +65,8 @@ inline int resident_grid(const void *kernel, int threads, int sm_count) {
 }
 
 template <class Rule>
-__global__ void __launch_bounds__(ENGINE_THREADS) num_child_kernel(const Rule rule, iter_view it, uint32_t *num_childs, unsigned int *max_child_size) {
+__global__ void __launch_bounds__(ENGINE_THREADS) num_child_kernel(const Rule rule, iter_view it, uint32_t *num_childs, uint32_t *num_groups,
+                                                                 uint32_t *locality, unsigned int *max_child_size) {
 	__shared__ unsigned int s_max;
 	if (threadIdx.x == 0)
 		s_max = 0;
@@ -70,8 +75,14 @@ __global__ void __launch_bounds__(ENGINE_THREADS) num_child_kernel(const Rule ru
 	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
 	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < it.n; i += stride) {
 		uint32_t count, bound;
-		rule.get_num_child(it.objects + it.begin[i], it.size[i], count, bound);
+		const uint8_t *parent = it.objects + it.begin[i];
+		const uint32_t size = it.size[i];
+		rule.get_num_child(parent, size, count, bound);
 		num_childs[i] = count;
+		if (Rule::warp_groups)
+			num_groups[i] = rule.get_num_group(parent, size, count);
+		if (Rule::has_locality_key && locality)
+			locality[i] = rule.locality_key(parent, size);
 		local_max = max(local_max, bound);
 	}
 	atomicMax(&s_max, local_max);
@@ -80,60 +91,131 @@ __global__ void __launch_bounds__(ENGINE_THREADS) num_child_kernel(const Rule ru
 		atomicMax(max_child_size, s_max);
 }
 
-// One CTA takes SYMBOLIC_CHUNK consecutive children at a time (balanced whatever the fan-out), finds
-// the parents they belong to, prepares those parents' contexts in shared memory (one thread per
-// parent), then every thread produces children: symbolic() -> table_insert().
+// children -> interference table, straight from registers
+struct table_emitter {
+	const table_view &table;
+	uint64_t first_child; // index of child 0 of this parent in the symbolic order
+	uint32_t created = 0;
+	__device__ table_emitter(const table_view &t, uint64_t first) : table(t), first_child(first) {}
+	__device__ void operator()(uint32_t child_id, uint64_t hash, uint32_t size, cplx mag) {
+		created += table_insert(table, hash, mag, rep_pack(first_child + child_id, size));
+	}
+	// batch<N>(count, hash[N], size, child_id_of(i), mag_of(i)): up to N children of the same size at once
+	template <int N, class ChildOf, class MagOf>
+	__device__ void batch(int count, const uint64_t (&hash)[N], uint32_t size, ChildOf child_of, MagOf mag_of) {
+		const uint64_t first = first_child;
+		created += table_insert_batch<N>(table, count, hash, mag_of, [=](int i) { return rep_pack(first + child_of(i), size); });
+	}
+};
+
+constexpr int SYMBOLIC_THREADS = 128; // per-warp shared-memory slices: 4 warps keep the CTA under the 48 KB static limit
+constexpr int ENGINE_WARPS = SYMBOLIC_THREADS / 32;
+
+// Every WARP works on its own: it takes SYMBOLIC_CHUNK consecutive groups of children at a time
+// (balanced whatever the fan-out), finds the parents they belong to, prepares those parents' contexts
+// in its slice of shared memory (one lane per parent), then produces the groups -- one child per lane
+// (symbolic()), or, for rules with warp_groups, one group at a time with all lanes (symbolic_warp()).
+// No CTA-wide barrier: an insert is a DRAM round trip of very variable length, and a barrier would
+// make every warp wait for the slowest lane of the CTA.
 template <class Rule>
-__global__ void __launch_bounds__(ENGINE_THREADS) symbolic_kernel(const Rule rule, const engine_launch L) {
+__global__ void __launch_bounds__(SYMBOLIC_THREADS, 5) symbolic_kernel(const Rule rule, const engine_launch L) {
 	typedef typename Rule::ctx_t ctx_t;
-	__shared__ ctx_t s_ctx[SYMBOLIC_GROUP];
-	__shared__ uint64_t s_child_begin[SYMBOLIC_GROUP + 1];
-	__shared__ uint64_t s_object[SYMBOLIC_GROUP]; // byte offset of the parent
-	__shared__ uint32_t s_size[SYMBOLIC_GROUP];
-	__shared__ cplx s_mag[SYMBOLIC_GROUP];
-	__shared__ uint64_t s_parent_range[2];
+	constexpr int CHUNK = Rule::warp_groups ? 32 : SYMBOLIC_CHUNK;
+	struct warp_slice {
+		ctx_t ctx[32];
+		uint64_t group_begin[33];
+		uint64_t child_begin[32];
+		uint64_t object[32]; // byte offset of the parent
+		cplx mag[32];
+		uint32_t size[32];
+		typename Rule::group_ctx_t group_ctx[32];
+	};
+	__shared__ warp_slice s_slices[ENGINE_WARPS];
+	__shared__ typename Rule::workspace_t s_workspace[ENGINE_WARPS];
+	warp_slice &s = s_slices[threadIdx.x >> 5];
+	const unsigned lane = lane_id();
 
-	uint8_t *scratch = Rule::needs_scratch ? L.scratch + ((size_t)blockIdx.x * ENGINE_THREADS + threadIdx.x) * L.scratch_stride : nullptr;
+	uint8_t *scratch = Rule::needs_scratch ? L.scratch + ((size_t)blockIdx.x * SYMBOLIC_THREADS + threadIdx.x) * L.scratch_stride : nullptr;
+	uint32_t created = 0;
 
-	const uint64_t num_chunks = div_up<uint64_t>(L.n_children, SYMBOLIC_CHUNK);
-	for (uint64_t chunk = blockIdx.x; chunk < num_chunks; chunk += gridDim.x) {
-		const uint64_t c0 = chunk * SYMBOLIC_CHUNK;
-		const uint64_t c1 = min(c0 + (uint64_t)SYMBOLIC_CHUNK, L.n_children);
-		if (threadIdx.x < 2) // parent of child c = last p with child_begin[p] <= c
-			s_parent_range[threadIdx.x] = upper_bound_u64(L.child_begin, L.n_parents + 1, threadIdx.x == 0 ? c0 : c1 - 1) - 1;
-		__syncthreads();
-		const uint64_t p_lo = s_parent_range[0], p_hi = s_parent_range[1];
+	const uint64_t num_chunks = div_up<uint64_t>(L.n_groups, CHUNK);
+	const uint64_t warp_stride = (uint64_t)gridDim.x * ENGINE_WARPS;
+	for (uint64_t chunk = (uint64_t)blockIdx.x * ENGINE_WARPS + (threadIdx.x >> 5); chunk < num_chunks; chunk += warp_stride) {
+		const uint64_t c0 = chunk * CHUNK;
+		const uint64_t c1 = min(c0 + (uint64_t)CHUNK, L.n_groups);
+		// parents of this chunk: from the one holding group c0 to the one holding group c1 - 1
+		const uint64_t p_lo = L.chunk_parent[chunk];
+		uint64_t p_hi = L.chunk_parent[chunk + 1];
+		if (p_hi > p_lo && L.group_begin[p_hi] == c1)
+			--p_hi;
 
-		for (uint64_t g0 = p_lo; g0 <= p_hi; g0 += SYMBOLIC_GROUP) {
-			const uint32_t count = (uint32_t)min((uint64_t)SYMBOLIC_GROUP, p_hi + 1 - g0);
-			if (threadIdx.x < count) {
-				const uint64_t p = g0 + threadIdx.x;
+		for (uint64_t g0 = p_lo; g0 <= p_hi; g0 += 32) {
+			const uint32_t count = (uint32_t)min((uint64_t)32, p_hi + 1 - g0);
+			if (lane < count) {
+				const uint64_t p = g0 + lane;
 				const uint64_t oid = L.kept ? L.kept[p] : p;
 				const uint64_t off = L.it.begin[oid];
 				const uint32_t sz = L.it.size[oid];
-				s_child_begin[threadIdx.x] = L.child_begin[p];
-				s_object[threadIdx.x] = off;
-				s_size[threadIdx.x] = sz;
-				s_mag[threadIdx.x] = L.it.mag[oid];
-				if (L.child_begin[p + 1] > L.child_begin[p]) // childless parents need no context
-					rule.prepare(L.it.objects + off, sz, s_ctx[threadIdx.x]);
+				const uint64_t gb = L.group_begin[p];
+				s.group_begin[lane] = gb;
+				s.child_begin[lane] = L.child_begin[p];
+				s.object[lane] = off;
+				s.size[lane] = sz;
+				s.mag[lane] = L.it.mag[oid];
+				if (L.group_begin[p + 1] > gb) // childless parents need no context
+					rule.prepare(L.it.objects + off, sz, s.ctx[lane]);
 			}
-			if (threadIdx.x == 0)
-				s_child_begin[count] = L.child_begin[g0 + count];
-			__syncthreads();
+			if (lane == 0)
+				s.group_begin[count] = L.group_begin[g0 + count];
+			__syncwarp();
 
-			const uint64_t lo = max(c0, s_child_begin[0]), hi = min(c1, s_child_begin[count]);
-			for (uint64_t c = lo + threadIdx.x; c < hi; c += ENGINE_THREADS) {
-				const uint32_t j = (uint32_t)upper_bound_u64(s_child_begin, count + 1, c) - 1;
-				const uint32_t child_id = (uint32_t)(c - s_child_begin[j]);
-				cplx mag = s_mag[j];
-				uint32_t size;
-				const uint64_t hash = rule.symbolic(L.it.objects + s_object[j], s_size[j], s_ctx[j], child_id, scratch, size, mag);
-				table_insert(L.table, hash, mag, rep_pack(c, size));
+			const uint64_t lo = max(c0, s.group_begin[0]), hi = min(c1, s.group_begin[count]);
+			if constexpr (Rule::warp_groups) {
+				// at most 32 groups here: one lane per group prepares what the whole group shares ...
+				if (lo + lane < hi) {
+					const uint32_t j = (uint32_t)upper_bound_u64(s.group_begin, count + 1, lo + lane) - 1;
+					rule.prepare_group(s.ctx[j], (uint32_t)(lo + lane - s.group_begin[j]), s.mag[j], s.group_ctx[lane]);
+				}
+				__syncwarp();
+				// ... then all lanes together produce one group after the other
+				uint32_t j = 0;
+				for (uint64_t c = lo; c < hi; ++c) {
+					while (s.group_begin[j + 1] <= c)
+						++j;
+					table_emitter emit(L.table, s.child_begin[j]);
+					rule.symbolic_warp(L.it.objects + s.object[j], s.size[j], s.ctx[j], (uint32_t)(c - s.group_begin[j]), s.group_ctx[c - lo],
+					                   s_workspace[threadIdx.x >> 5], emit);
+					created += emit.created;
+				}
+			} else {
+				for (uint64_t c = lo + lane; c < hi; c += 32) { // one child per lane: the loop body of quids.hpp:705-719
+					const uint32_t j = (uint32_t)upper_bound_u64(s.group_begin, count + 1, c) - 1;
+					table_emitter emit(L.table, s.child_begin[j]);
+					cplx mag = s.mag[j];
+					uint32_t size;
+					const uint64_t hash = rule.symbolic(L.it.objects + s.object[j], s.size[j], s.ctx[j], (uint32_t)(c - s.group_begin[j]), scratch, size, mag);
+					emit((uint32_t)(c - s.group_begin[j]), hash, size, mag);
+					created += emit.created;
+				}
 			}
-			__syncthreads();
+			__syncwarp();
 		}
 	}
+	// slots created -> one global atomic per warp (sizes the next call's table)
+	created = (uint32_t)warp_sum((uint64_t)created);
+	if (lane == 0 && created)
+		atomicAdd(L.table.used, (unsigned long long)created);
+}
+
+// parent holding the first group of every chunk (one binary search per chunk, all in parallel, instead of
+// a chain of dependent loads at the head of every chunk of the symbolic kernel)
+static __global__ void __launch_bounds__(ENGINE_THREADS) chunk_parent_kernel(const uint64_t *group_begin, uint64_t n_parents, uint64_t n_groups, uint32_t chunk,
+                                                                    uint64_t num_chunks, uint64_t *chunk_parent) {
+	const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (c < num_chunks)
+		chunk_parent[c] = upper_bound_u64(group_begin, n_parents + 1, c * chunk) - 1;
+	else if (c == num_chunks)
+		chunk_parent[c] = n_parents - 1;
 }
 
 // v1 finalisation: one thread rebuilds one surviving child in place (populate_child_simple) and
@@ -183,13 +265,19 @@ struct rule_glue {
 
 	static void num_child(const void *rule, const engine_launch &L) {
 		int grid = grid_for(L.it.n, ENGINE_THREADS, resident_grid((const void *)num_child_kernel<Rule>, ENGINE_THREADS, L.sm_count));
-		num_child_kernel<Rule><<<grid, ENGINE_THREADS, 0, L.stream>>>(*static_cast<const Rule *>(rule), L.it, L.num_childs, L.max_child_size);
+		num_child_kernel<Rule><<<grid, ENGINE_THREADS, 0, L.stream>>>(*static_cast<const Rule *>(rule), L.it, L.num_childs, L.num_groups, L.locality, L.max_child_size);
 		++*L.launch_counter;
 	}
-	static int symbolic_grid(int sm_count) { return resident_grid((const void *)symbolic_kernel<Rule>, ENGINE_THREADS, sm_count); }
+	static uint64_t symbolic_chunks(uint64_t n_groups) { return div_up<uint64_t>(n_groups, Rule::warp_groups ? 32 : SYMBOLIC_CHUNK); }
+	static int symbolic_grid(int sm_count) { return resident_grid((const void *)symbolic_kernel<Rule>, SYMBOLIC_THREADS, sm_count); }
 	static void symbolic(const void *rule, const engine_launch &L) {
-		int grid = grid_for(div_up<uint64_t>(L.n_children, SYMBOLIC_CHUNK) * ENGINE_THREADS, ENGINE_THREADS, symbolic_grid(L.sm_count));
-		symbolic_kernel<Rule><<<grid, ENGINE_THREADS, 0, L.stream>>>(*static_cast<const Rule *>(rule), L);
+		constexpr int chunk = Rule::warp_groups ? 32 : SYMBOLIC_CHUNK;
+		const uint64_t warps = div_up<uint64_t>(L.n_groups, chunk);
+		chunk_parent_kernel<<<(unsigned)div_up<uint64_t>(warps + 1, ENGINE_THREADS), ENGINE_THREADS, 0, L.stream>>>(
+		    L.group_begin, L.n_parents, L.n_groups, chunk, warps, const_cast<uint64_t *>(L.chunk_parent));
+		++*L.launch_counter;
+		int grid = grid_for(warps * 32, SYMBOLIC_THREADS, symbolic_grid(L.sm_count));
+		symbolic_kernel<Rule><<<grid, SYMBOLIC_THREADS, 0, L.stream>>>(*static_cast<const Rule *>(rule), L);
 		++*L.launch_counter;
 	}
 	static void populate(const void *rule, const engine_launch &L) {
@@ -211,7 +299,10 @@ struct rule_glue {
 		o.launch_populate = populate;
 		o.launch_hash = hash;
 		o.needs_scratch = Rule::needs_scratch;
+		o.warp_groups = Rule::warp_groups;
+		o.has_locality_key = Rule::has_locality_key;
 		o.symbolic_grid = symbolic_grid;
+		o.symbolic_chunks = symbolic_chunks;
 		return o;
 	}
 };

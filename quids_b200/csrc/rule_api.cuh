@@ -18,6 +18,13 @@
 //                                          bytes; the default materialises the child into `scratch`
 //                                          with populate_child and calls hasher on it, exactly like
 //                                          the symbolic loop of the reference (quids.hpp:705-719)
+//     get_num_group(parent, parent_size, num_child) / symbolic_warp(..., group, ..., workspace, emit)
+//                                          children of one parent may be produced in GROUPS by a whole
+//                                          warp that shares work between siblings (e.g. expands the
+//                                          binary tree of their choices level by level in shared memory,
+//                                          reusing the common prefix of hash and magnitude); a group
+//                                          must emit each of its children exactly once.  Default: one
+//                                          child per group, one lane per child.
 //
 // QB_REGISTER_RULE(name, type, make) instantiates the engine kernels for `type` in the translation
 // unit where it appears and adds the rule to the registry looked up by qb_rule_id().
@@ -83,6 +90,32 @@ struct rule_base {
 		self().populate_child(parent, parent_size, scratch, child_id, size, mag);
 		return self().hasher(scratch, size);
 	}
+
+	// false: a group is a single child handled by one lane (the engine calls symbolic() itself and
+	// skips the second prefix sum).  true: the rule provides
+	//     workspace_t                                  per-warp shared memory it needs
+	//     get_num_group(parent, parent_size, num_child) -> number of groups
+	//     group_ctx_t, prepare_group(ctx, group, parent_mag, group_ctx&)   one lane per group
+	//     symbolic_warp(parent, parent_size, ctx, group, group_ctx, workspace&, emit)
+	// symbolic_warp is called by all 32 lanes of a warp with identical arguments; every child of the
+	// group must be emitted exactly once, by any lane: emit(child_id, hash, size, mag) or
+	// emit.batch<N>(count, hash[N], size, child_id_of(i), mag_of(i)).
+	static constexpr bool warp_groups = false;
+	struct workspace_t {};
+	// per-group precomputation done by ONE lane per group, 32 groups at a time (whatever is the same
+	// for all children of the group and would otherwise be recomputed identically by all 32 lanes)
+	struct group_ctx_t {};
+	template <class Ctx>
+	__device__ void prepare_group(const Ctx &, uint32_t, cplx, group_ctx_t &) const {}
+
+	__device__ uint32_t get_num_group(const uint8_t *, uint32_t, uint32_t num_child) const { return num_child; }
+
+	// optional: a 32-bit key such that parents producing the same children have equal keys.  The
+	// engine then generates children in key order, so that all contributions to one object reach
+	// the interference table close together in time (L2 hits instead of DRAM round trips).  Purely a
+	// performance hint: any key gives correct results.
+	static constexpr bool has_locality_key = false;
+	__device__ uint32_t locality_key(const uint8_t *, uint32_t) const { return 0; }
 };
 
 // ---- modifiers: f(begin, end, mag&) in place (quids.hpp:86,973-980) as a device functor
@@ -110,7 +143,10 @@ struct rule_ops {
 	void (*launch_populate)(const void *rule, const engine_launch &L);
 	void (*launch_hash)(const void *rule, const engine_launch &L);
 	bool needs_scratch;
+	bool warp_groups;
+	bool has_locality_key;
 	int (*symbolic_grid)(int sm_count); // CTAs the symbolic kernel is launched with at most (sizes the scratch)
+	uint64_t (*symbolic_chunks)(uint64_t n_groups); // work chunks of the symbolic kernel (sizes chunk_parent)
 };
 
 struct modifier_ops {

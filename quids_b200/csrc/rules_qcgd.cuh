@@ -33,6 +33,13 @@ __host__ __device__ __forceinline__ uint64_t hash_combine(uint64_t seed, uint64_
 	return seed + 0xe6546b64ull;
 }
 
+// same function for a value below 2^47 (a node index): `seed ^= v >> 47` is then a no-op and the
+// first two multiplications merge into one by MURMUR_MUL^2 (mod 2^64)
+__host__ __device__ __forceinline__ uint64_t hash_combine_index(uint64_t seed, uint32_t index) {
+	constexpr uint64_t MUL2 = MURMUR_MUL * MURMUR_MUL;
+	return ((seed * MUL2) ^ (uint64_t)index) * MURMUR_MUL + 0xe6546b64ull;
+}
+
 struct atom {
 	int hmlz; // "has most-left zero" flag / element + 1   (qcgd.hpp:36,40-42)
 	int kind;
@@ -93,7 +100,12 @@ struct amplitudes {
 		f[2] = cplx{go.real(), go.imag()};
 		f[3] = cplx{go.real(), -go.imag()};
 	}
-	__device__ cplx get(bool taken, bool conjugated) const { return f[(taken ? 2 : 0) + (conjugated ? 1 : 0)]; }
+	// selects instead of an indexed load: the rule lives in the kernel parameters (constant bank), a
+	// dynamic index would force a local-memory copy of the table
+	__device__ cplx get(bool taken, bool conjugated) const {
+		const cplx a = conjugated ? f[1] : f[0], b = conjugated ? f[3] : f[2];
+		return taken ? b : a;
+	}
 };
 
 // ===================================================================================================
@@ -102,10 +114,28 @@ struct amplitudes {
 // coin: eligible = left != right.  Size unchanged, names untouched.  In both rules the amplitude is
 // conjugated exactly when the left particle is present.
 // ===================================================================================================
+constexpr int FLIP_LEVELS = 8;               // tree levels one warp expands in shared memory
+constexpr int FLIP_BLOCK = 1 << FLIP_LEVELS; // children per group (at most)
+
 struct flip_ctx {
 	uint64_t left, right; // particle masks (only when n <= 64)
 	uint64_t names_hash;  // fold of the first-atom hashes: the same for every child
 	uint32_t n;
+	uint8_t eligible;             // number of eligible nodes k: the parent has 2^k children
+	uint8_t levels;               // min(k, FLIP_LEVELS): tree levels of one group
+	uint8_t pos[FLIP_LEVELS + 1]; // node index of the last `levels` eligible nodes, then n
+};
+
+// per-warp tree states: after level l, state i (i < 2^l) = fold of hash_graph's left/right hashes and
+// the magnitude product over every node before the next tree node, for the choice bits i
+struct flip_root { // state before the first tree level of one group
+	uint64_t hl, hr;
+	cplx mag;
+};
+
+struct flip_workspace {
+	uint64_t hl[FLIP_BLOCK], hr[FLIP_BLOCK];
+	double re[FLIP_BLOCK], im[FLIP_BLOCK];
 };
 
 template <bool WANT_EQUAL>
@@ -148,70 +178,206 @@ struct flip_rule : rule_base<flip_rule<WANT_EQUAL>> {
 template <bool WANT_EQUAL>
 struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 	typedef flip_ctx ctx_t;
+	typedef flip_workspace workspace_t;
+	typedef flip_root group_ctx_t;
 	static constexpr bool needs_scratch = false;
+	static constexpr bool warp_groups = true;
+	static constexpr bool has_locality_key = true;
+
+	// Two parents produce the same children exactly when they have the same eligible nodes, the same
+	// particles on the other nodes and the same names: each of them reaches all 2^k settings of the
+	// eligible nodes.  The key folds the first two (names are left out: grouping a few unrelated
+	// parents together costs nothing).
+	__device__ uint32_t locality_key(const uint8_t *parent, uint32_t) const {
+		graph g(parent);
+		uint64_t key = g.n;
+		for (uint32_t i = 0; i < g.n; ++i) {
+			const bool l = g.left(i), r = g.right(i);
+			const uint64_t code = ((l == r) == WANT_EQUAL) ? 2 : (l ? 1 : 0);
+			key = key * 3 + code;
+			if ((i & 31) == 31)
+				key = mix64(key);
+		}
+		return (uint32_t)(mix64(key) >> 32);
+	}
+
+	// The 2^k children of a parent are the leaves of a binary tree over its k eligible nodes, and
+	// hash_graph folds the nodes in index order: two children share the fold (and the magnitude
+	// product) up to the first eligible node where their choices differ.  A warp therefore produces
+	// children in groups of up to 2^FLIP_LEVELS: the group index fixes the choices of the FIRST
+	// k - levels eligible nodes (the low bits of child_id); the tree over the last `levels` ones is
+	// expanded level by level in shared memory, one lane per tree node.  ~2 fold steps per child
+	// instead of n, and all lanes run the same control flow because they share the parent.
+	// Graphs wider than the 64-bit masks: groups of 32 children, one per lane, walking the bytes.
+	__device__ uint32_t get_num_group(const uint8_t *parent, uint32_t, uint32_t num_child) const {
+		const uint32_t n = *reinterpret_cast<const uint16_t *>(parent);
+		if (n > 64)
+			return (num_child + 31) / 32;
+		return num_child > (uint32_t)FLIP_BLOCK ? num_child >> FLIP_LEVELS : 1;
+	}
 
 	__device__ void prepare(const uint8_t *parent, uint32_t, flip_ctx &ctx) const {
 		graph g(parent);
 		ctx.n = g.n;
 		uint64_t l = 0, r = 0, hn = 0;
+		uint32_t eligible = 0;
 		for (uint32_t i = 0; i < g.n; ++i) {
+			const bool li = g.left(i), ri = g.right(i);
 			if (i < 64) {
-				l |= (uint64_t)g.left(i) << i;
-				r |= (uint64_t)g.right(i) << i;
+				l |= (uint64_t)li << i;
+				r |= (uint64_t)ri << i;
 			}
+			eligible += (li == ri) == WANT_EQUAL;
 			hn = hash_combine(hn, g.atom_hash(g.name_begin(i)));
 		}
 		ctx.left = l;
 		ctx.right = r;
 		ctx.names_hash = hn;
+		ctx.eligible = (uint8_t)eligible;
+		const uint32_t levels = min(eligible, (uint32_t)FLIP_LEVELS);
+		ctx.levels = (uint8_t)levels;
+		if (g.n <= 64) {
+			uint32_t seen = 0;
+			for (uint32_t i = 0; i < g.n; ++i)
+				if ((((l ^ r) >> i) & 1) != (uint64_t)WANT_EQUAL) {
+					if (seen + levels >= eligible)
+						ctx.pos[seen + levels - eligible] = (uint8_t)i;
+					++seen;
+				}
+			ctx.pos[levels] = (uint8_t)g.n;
+		}
 	}
 
-	__device__ uint64_t symbolic(const uint8_t *parent, uint32_t parent_size, const flip_ctx &ctx, uint32_t child_id, uint8_t *, uint32_t &size,
+	// one child on its own (also the symbolic hook of the one-child-per-lane path)
+	__device__ uint64_t symbolic(const uint8_t *parent, uint32_t parent_size, const flip_ctx &, uint32_t child_id, uint8_t *, uint32_t &size,
 	                             cplx &mag) const {
 		size = parent_size;
-		uint64_t hl = 0, hr = 0;
-		if (ctx.n <= 64) {
-			const uint64_t all = ctx.n == 64 ? ~0ull : ((1ull << ctx.n) - 1);
-			uint64_t eligible = (WANT_EQUAL ? ~(ctx.left ^ ctx.right) : (ctx.left ^ ctx.right)) & all;
-			uint64_t toggled = 0;
-			while (eligible) {
-				const uint64_t lowest = eligible & (0 - eligible);
-				eligible ^= lowest;
+		graph g(parent);
+		uint64_t hl = 0, hr = 0, hn = 0;
+		for (uint32_t i = 0; i < g.n; ++i) {
+			bool l = g.left(i), r = g.right(i);
+			if ((l == r) == WANT_EQUAL) {
 				const bool taken = child_id & 1;
 				child_id >>= 1;
-				mag = cmul(mag, this->amp.get(taken, ctx.left & lowest));
-				if (taken)
-					toggled |= lowest;
+				mag = cmul(mag, this->amp.get(taken, l));
+				l ^= taken;
+				r ^= taken;
 			}
-			uint64_t l = ctx.left ^ toggled, r = ctx.right ^ toggled;
-			while (l) {
-				hl = hash_combine(hl, (uint64_t)(__ffsll((long long)l) - 1));
-				l &= l - 1;
-			}
-			while (r) {
-				hr = hash_combine(hr, (uint64_t)(__ffsll((long long)r) - 1));
-				r &= r - 1;
-			}
-		} else { // wide graphs: same walk on the bytes
-			graph g(parent);
-			for (uint32_t i = 0; i < g.n; ++i) {
-				bool l = g.left(i), r = g.right(i);
-				if ((l == r) == WANT_EQUAL) {
-					const bool taken = child_id & 1;
-					child_id >>= 1;
+			if (l) hl = hash_combine_index(hl, i);
+			if (r) hr = hash_combine_index(hr, i);
+			hn = hash_combine(hn, g.atom_hash(g.name_begin(i)));
+		}
+		return hash_combine(hash_combine(hn, hl), hr);
+	}
+
+	// root of a group: everything before the first tree node, choices taken from the group index
+	__device__ void prepare_group(const flip_ctx &ctx, uint32_t group, cplx mag, flip_root &root) const {
+		uint64_t hl = 0, hr = 0;
+		if (ctx.n <= 64) {
+			const uint64_t left = ctx.left, right = ctx.right;
+			const uint64_t eligible = WANT_EQUAL ? ~(left ^ right) : (left ^ right);
+			uint32_t bits = group;
+			const uint32_t first = ctx.pos[0];
+			for (uint32_t i = 0; i < first; ++i) {
+				bool l = (left >> i) & 1, r = (right >> i) & 1;
+				if ((eligible >> i) & 1) {
+					const bool taken = bits & 1;
+					bits >>= 1;
 					mag = cmul(mag, this->amp.get(taken, l));
-					if (taken) {
-						l = !l;
-						r = !r;
-					}
+					l ^= taken;
+					r ^= taken;
 				}
-				if (l)
-					hl = hash_combine(hl, i);
-				if (r)
-					hr = hash_combine(hr, i);
+				if (l) hl = hash_combine_index(hl, i);
+				if (r) hr = hash_combine_index(hr, i);
 			}
 		}
-		return hash_combine(hash_combine(ctx.names_hash, hl), hr);
+		root.hl = hl;
+		root.hr = hr;
+		root.mag = mag;
+	}
+
+	template <class Emit>
+	__device__ void symbolic_warp(const uint8_t *parent, uint32_t parent_size, const flip_ctx &ctx, uint32_t group, const flip_root &root,
+	                              flip_workspace &ws, Emit &emit) const {
+		const uint32_t lane = lane_id();
+		if (ctx.n > 64) { // wide graph: 32 children per group, one per lane
+			const uint32_t child_id = group * 32 + lane;
+			if (ctx.eligible < 32 && child_id < (1u << ctx.eligible)) {
+				uint32_t size;
+				cplx mag = root.mag;
+				const uint64_t hash = symbolic(parent, parent_size, ctx, child_id, nullptr, size, mag);
+				emit(child_id, hash, size, mag);
+			}
+			return;
+		}
+		const uint64_t left = ctx.left, right = ctx.right;
+		const uint32_t levels = ctx.levels;
+		if (lane == 0) {
+			ws.hl[0] = root.hl;
+			ws.hr[0] = root.hr;
+			ws.re[0] = root.mag.re;
+			ws.im[0] = root.mag.im;
+		}
+		__syncwarp();
+
+		// level l: tree node pos[l] with both choices, then the non-eligible nodes up to the next tree
+		// node.  State i keeps choice 0 in place; choice 1 becomes state i + 2^l (bit l of the leaf index).
+		for (uint32_t l = 0; l < levels; ++l) {
+			const uint32_t e = ctx.pos[l], end = ctx.pos[l + 1];
+			const bool pl = (left >> e) & 1, pr = (right >> e) & 1;
+			const cplx stay = this->amp.get(false, pl), go = this->amp.get(true, pl);
+			const uint32_t width = 1u << l;
+			for (uint32_t i = lane; i < width; i += 32) {
+				uint64_t hl0 = ws.hl[i], hr0 = ws.hr[i];
+				const cplx m{ws.re[i], ws.im[i]};
+				uint64_t hl1 = hl0, hr1 = hr0;
+				// choice 0 keeps the parent's particles, choice 1 toggles both
+				if (pl) hl0 = hash_combine_index(hl0, e); else hl1 = hash_combine_index(hl1, e);
+				if (pr) hr0 = hash_combine_index(hr0, e); else hr1 = hash_combine_index(hr1, e);
+				for (uint32_t j = e + 1; j < end; ++j) {
+					if ((left >> j) & 1) {
+						hl0 = hash_combine_index(hl0, j);
+						hl1 = hash_combine_index(hl1, j);
+					}
+					if ((right >> j) & 1) {
+						hr0 = hash_combine_index(hr0, j);
+						hr1 = hash_combine_index(hr1, j);
+					}
+				}
+				const cplx m0 = cmul(m, stay), m1 = cmul(m, go);
+				ws.hl[i] = hl0;
+				ws.hr[i] = hr0;
+				ws.re[i] = m0.re;
+				ws.im[i] = m0.im;
+				ws.hl[i + width] = hl1;
+				ws.hr[i + width] = hr1;
+				ws.re[i + width] = m1.re;
+				ws.im[i + width] = m1.im;
+			}
+			__syncwarp();
+		}
+
+		// leaves: finish the hash and insert, four per lane at a time (four table loads in flight);
+		// magnitudes stay in shared memory until their entry is resolved
+		const uint32_t leaves = 1u << levels;
+		const uint32_t shift = ctx.eligible - levels; // child_id = group | leaf << shift
+		const uint64_t names_hash = ctx.names_hash;
+		for (uint32_t base = lane; base < leaves; base += 128) {
+			uint64_t hash[4];
+			int count = 0;
+#pragma unroll
+			for (int q = 0; q < 4; ++q) {
+				const uint32_t leaf = base + q * 32;
+				if (leaf < leaves) {
+					hash[q] = hash_combine(hash_combine(names_hash, ws.hl[leaf]), ws.hr[leaf]);
+					count = q + 1;
+				}
+			}
+			emit.template batch<4>(
+			    count, hash, parent_size, [=](int q) { return group | ((base + q * 32) << shift); },
+			    [&ws, base](int q) { return cplx{ws.re[base + q * 32], ws.im[base + q * 32]}; });
+		}
+		__syncwarp();
 	}
 };
 

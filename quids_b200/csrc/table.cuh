@@ -33,39 +33,116 @@ __host__ __device__ __forceinline__ uint32_t rep_size(uint64_t rep) { return (ui
 struct table_view {
 	table_slot *slots;     // capacity + 1 slots
 	uint64_t capacity;     // regular slots
-	unsigned int *overflow; // set to 1 if an insert found no free slot
+	unsigned int *overflow; // set to 1 if an insert gave up probing
+	unsigned long long *used; // number of slots created (counted per CTA)
 };
 
 __device__ __forceinline__ uint64_t table_home(uint64_t hash, uint64_t capacity) { return __umul64hi(mix64(hash), capacity); }
 
-__device__ __forceinline__ void table_insert(const table_view &t, uint64_t hash, cplx mag, uint64_t rep) {
+constexpr uint32_t TABLE_MAX_PROBES = 4096; // longer probe sequences mean the table was sized too small: the host retries larger
+
+// the probe loop, entered with the key already observed in slot `i` (0 = the slot looked empty).
+// Returns true when this call created the slot (first child with that hash).
+__device__ __forceinline__ bool table_insert_from(const table_view &t, uint64_t hash, cplx mag, uint64_t rep, uint64_t i, unsigned long long seen) {
 	table_slot *s;
-	if (hash == 0) {
-		s = t.slots + t.capacity;
-		atomicCAS(&s->rep, 0ull, (unsigned long long)rep);
-	} else {
-		uint64_t i = table_home(hash, t.capacity);
-		uint64_t probes = 0;
-		while (true) {
-			s = t.slots + i;
-			unsigned long long seen = atomicCAS(&s->key, 0ull, (unsigned long long)hash);
+	bool created = false;
+	uint32_t probes = 0;
+	while (true) {
+		s = t.slots + i;
+		// keys never change once set, so a plain L2 load that sees a key is final; only an empty slot
+		// needs the compare-and-swap.  Most children of a grown state find their key present.
+		if (seen == 0) {
+			seen = atomicCAS(&s->key, 0ull, (unsigned long long)hash);
 			if (seen == 0) { // this child created the slot: it is the representative
 				s->rep = rep;
+				created = true;
 				break;
-			}
-			if (seen == hash)
-				break;
-			if (++i == t.capacity)
-				i = 0;
-			if (++probes > t.capacity) {
-				*t.overflow = 1;
-				return;
 			}
 		}
+		if (seen == hash)
+			break;
+		if (++i == t.capacity)
+			i = 0;
+		if (++probes > TABLE_MAX_PROBES) {
+			*t.overflow = 1;
+			return false;
+		}
+		seen = __ldcg(&t.slots[i].key);
 	}
 	// results unused -> RED.ADD.F64, fire and forget
 	atomicAdd(&s->re, mag.re);
 	atomicAdd(&s->im, mag.im);
+	return created;
+}
+
+__device__ __forceinline__ bool table_insert_zero_hash(const table_view &t, cplx mag, uint64_t rep) {
+	table_slot *s = t.slots + t.capacity;
+	const bool created = atomicCAS(&s->rep, 0ull, (unsigned long long)rep) == 0;
+	atomicAdd(&s->re, mag.re);
+	atomicAdd(&s->im, mag.im);
+	return created;
+}
+
+__device__ __forceinline__ bool table_insert(const table_view &t, uint64_t hash, cplx mag, uint64_t rep) {
+	if (hash == 0)
+		return table_insert_zero_hash(t, mag, rep);
+	const uint64_t home = table_home(hash, t.capacity);
+	return table_insert_from(t, hash, mag, rep, home, __ldcg(&t.slots[home].key));
+}
+
+// Up to N inserts by one thread (entries [0, count) are valid).  The table is far larger than any
+// cache, so an insert is one or more DRAM round trips: every ROUND issues the key loads of all
+// pending entries first (N independent requests in flight), then resolves them -- match: add the
+// magnitude; empty: try to claim the slot; other key: move to the next slot and stay pending.
+// The number of round trips is the LONGEST probe sequence of the batch, not the sum.
+// mag_of(i) is only called when entry i is resolved (keeps the magnitudes out of registers).
+template <int N, class MagOf, class RepOf>
+__device__ __forceinline__ uint32_t table_insert_batch(const table_view &t, int count, const uint64_t (&hash)[N], MagOf mag_of, RepOf rep_of) {
+	uint64_t slot[N];
+	uint32_t pending = 0, created = 0;
+#pragma unroll
+	for (int i = 0; i < N; ++i)
+		if (i < count) {
+			if (hash[i] == 0) {
+				created += table_insert_zero_hash(t, mag_of(i), rep_of(i));
+			} else {
+				slot[i] = table_home(hash[i], t.capacity);
+				pending |= 1u << i;
+			}
+		}
+	for (uint32_t round = 0; pending; ++round) {
+		unsigned long long seen[N];
+#pragma unroll
+		for (int i = 0; i < N; ++i)
+			if (pending & (1u << i))
+				seen[i] = __ldcg(&t.slots[slot[i]].key);
+#pragma unroll
+		for (int i = 0; i < N; ++i)
+			if (pending & (1u << i)) {
+				table_slot *s = t.slots + slot[i];
+				if (seen[i] == 0) {
+					seen[i] = atomicCAS(&s->key, 0ull, (unsigned long long)hash[i]);
+					if (seen[i] == 0) { // this child created the slot: it is the representative
+						s->rep = rep_of(i);
+						++created;
+						seen[i] = hash[i];
+					}
+				}
+				if (seen[i] == hash[i]) {
+					const cplx mag = mag_of(i);
+					atomicAdd(&s->re, mag.re); // results unused -> RED.ADD.F64, fire and forget
+					atomicAdd(&s->im, mag.im);
+					pending &= ~(1u << i);
+				} else if (++slot[i] == t.capacity) {
+					slot[i] = 0;
+				}
+			}
+		if (round > TABLE_MAX_PROBES) {
+			*t.overflow = 1;
+			break;
+		}
+	}
+	return created;
 }
 
 __device__ __forceinline__ bool slot_occupied(const table_slot &s, bool is_zero_slot) { return is_zero_slot ? s.rep != 0 : s.key != 0; }

@@ -31,6 +31,17 @@ def test_golden_vectors(gpu, port, name, suffix):
     assert golden_util.replay(name, gpu(suffix), port) > 0
 
 
+@pytest.mark.parametrize("name", [n for n in golden_util.fixtures() if n.startswith("qcgd")])
+def test_golden_vectors_with_parent_ordering(gpu, port, name):
+    """the locality ordering of the parents (an engine knob) must not change any result"""
+    import quids_b200 as qb
+    qb.config.locality_sort = 2
+    try:
+        assert golden_util.replay(name, gpu(""), port) > 0
+    finally:
+        qb.config.locality_sort = 0
+
+
 @pytest.mark.parametrize("align", [0, 4, 8, 16])
 def test_golden_vectors_other_alignments(gpu, port, align):
     for name in ("qc_example", "qcgd_example_seed1", "qcgd_truncate_children"):
@@ -67,6 +78,35 @@ def test_qcgd_random_graphs_vs_oracle(gpu, port, rule_id, suffix):
         assert eng.apply_modifier(want, orc.MOD_STEP).objects() == state.objects()
         if state.n > 60000:
             break
+
+
+@pytest.mark.parametrize("rule_id", [orc.RULE_ERASE_CREATE, orc.RULE_COIN])
+def test_qcgd_parent_ordering_and_groups_vs_oracle(gpu, port, rule_id):
+    """12-node graphs (parents of up to 4096 children = several warp groups), parents ordered by
+    locality key, with truncation of parents and children"""
+    import quids_b200 as qb
+    params = [0.37, 0.21, -0.4]
+    state = port.qcgd_random_state(12, 300, 21)
+    rng = np.random.default_rng(2)
+    mags = rng.normal(size=(300, 2))
+    state = orc.Packed(state.sizes, mags / np.sqrt((mags ** 2).sum()), state.data)
+    qb.config.locality_sort = 2
+    try:
+        want, nc, nu = port.simulate(state, rule_id, params, tolerance=1e-18)
+        got, gc, gu = gpu().simulate(state, rule_id, params, tol=1e-18)
+        assert (gc, gu) == (nc, nu)
+        orc.assert_same_state(got, port.hash_objects(got, rule_id), want, port.hash_objects(want, rule_id), True, what="ordered parents")
+        k = 250  # fewer than the parents: pre-truncation, then ordering of the kept parents
+        want, wc, wu = port.simulate(state, rule_id, params, k, 1e-18)
+        got, gc, gu = gpu().simulate(state, rule_id, params, k, 1e-18)
+        assert (gc, gu) == (wc, wu)
+        order = np.sort(np.argsort(-(np.abs(state.cmags) ** 2), kind="stable")[:k])
+        objs = state.objects()
+        sub = orc.Packed.from_objects([objs[j] for j in order], state.cmags[order])
+        full, _, _ = port.simulate(sub, rule_id, params, tolerance=1e-18)
+        orc.assert_same_truncated(got, port.hash_objects(got, rule_id), want, port.hash_objects(want, rule_id), full, port.hash_objects(full, rule_id), k, True)
+    finally:
+        qb.config.locality_sort = 0
 
 
 def test_qcgd_wide_graphs_vs_oracle(gpu, port):
