@@ -101,24 +101,36 @@ def algorithmic_bytes(n_p, s_p, n_c, n_u, n_s, s_s):
     return n_p * (s_p + 16) + 48 * n_c + 40 * n_u + n_s * (s_p + s_s + 16)
 
 
-def cpu_reference_rate(sample_parents, seed, repeats=1):
-    """children/s of the reference's own CPU implementation (oracle/_ref, else the port) on a bounded sample"""
+def cpu_checker():
+    """the reference's own CPU implementation (oracle/_ref) if it was built, else the port"""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import orc
     if orc.have_reference():
-        o = orc.Oracle(orc.REF_SO)
-    else:
-        if not os.path.exists(orc.PORT_SO):
-            orc.build()
-        o = orc.Oracle(orc.PORT_SO)
+        return orc, orc.Oracle(orc.REF_SO)
+    if not os.path.exists(orc.PORT_SO):
+        orc.build()
+    return orc, orc.Oracle(orc.PORT_SO)
+
+
+def cpu_reference_rate(sample_parents, seed, steps=1, warmup=0):
+    """children/s of the CPU implementation on a bounded sample: (rate, oracle, N_c, mean seconds per step).
+    The state is loaded once (the reference's append() re-initialises an index array on every call,
+    quids.hpp:279-306, so building a state is quadratic) and only quids::simulate is timed."""
+    orc, o = cpu_checker()
     sizes, mags, data = make_parents(sample_parents, seed)
-    st = orc.Packed(sizes, mags, data)
-    best = None
-    for _ in range(repeats):
-        _, nc, nu = o.simulate(st, orc.RULE_ERASE_CREATE, [THETA, 0, 0], sample_parents, TOLERANCE)
-        rate = nc / o.last_seconds
-        best = rate if best is None else max(best, rate)
-    return best, o, nc, o.last_seconds
+    a, b = orc.LoadedState(o, orc.Packed(sizes, mags, data)), orc.LoadedState(o)
+    times, nc = [], 0
+    for i in range(warmup + steps):
+        nc, nu, secs = a.simulate_into(b, orc.RULE_ERASE_CREATE, [THETA, 0, 0], sample_parents, TOLERANCE)
+        if i >= warmup:
+            times.append(secs)
+    a.close()
+    b.close()
+    mean = sum(times) / len(times)
+    return nc / mean, o, nc, mean
+
+
+CPU_SAMPLE_PARENTS = 1000000  # 1.3e8 children: a few seconds of CPU work per step, ~11 GB of host memory
 
 
 def run_reference(args):
@@ -126,27 +138,14 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # calibrate on a small sample, then size each step to a few seconds
-    rate, o, _, _ = cpu_reference_rate(20000, seed=0)
-    budget_s = 150.0 / max(1, args.steps + args.warmup)
-    parents = int(min(1e6, max(2e4, rate * min(8.0, budget_s) / 129.7)))
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import orc
-    sizes, mags, data = make_parents(parents, 0)
-    st = orc.Packed(sizes, mags, data)
-    times, nc = [], 0
-    for i in range(args.warmup + args.steps):
-        _, nc, nu = o.simulate(st, orc.RULE_ERASE_CREATE, [THETA, 0, 0], parents, TOLERANCE)
-        if i >= args.warmup:
-            times.append(o.last_seconds)
-    ms = 1e3 * sum(times) / len(times)
-    value = nc / (ms / 1e3)
+    parents = CPU_SAMPLE_PARENTS
+    rate, o, nc, secs = cpu_reference_rate(parents, 0, steps=args.steps, warmup=args.warmup)
     sample = f"{parents} random 12-node parents ({nc} children) per step, erase_create(pi/4), max_num_object={parents}"
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args.gpus),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": o.num_threads, "kind": o.kind, "sample": sample},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": o.num_threads, "kind": o.kind, "sample": sample},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
@@ -295,11 +294,10 @@ def run_ours(args):
     # ---- CPU baseline beside it (bounded sample, rank 0, N = 1 only) ----------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu:
-        rate, o, _, _ = cpu_reference_rate(20000, seed=0)
-        sample_parents = int(min(1e6, max(2e4, rate * 12.0 / 129.7)))
-        rate, o, nc_cpu, secs = cpu_reference_rate(sample_parents, seed=0)
+        rate, o, nc_cpu, secs = cpu_reference_rate(CPU_SAMPLE_PARENTS, seed=0, steps=3, warmup=1)
         cpu = {"value": rate, "unit": UNIT, "cores": o.num_threads, "kind": o.kind,
-               "sample": f"{sample_parents} parents of the same generator ({nc_cpu} children, {secs:.1f} s), erase_create(pi/4), max_num_object={sample_parents}"}
+               "sample": f"{CPU_SAMPLE_PARENTS} parents of the same generator ({nc_cpu} children, {secs:.2f} s per step, 3 steps after 1 warm-up), "
+                         f"erase_create(pi/4), max_num_object={CPU_SAMPLE_PARENTS}"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",

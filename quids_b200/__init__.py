@@ -319,6 +319,9 @@ class Iteration:
         if n:
             if (padded == s64).all():
                 objects[:] = data[:int(src_begin[n])]
+            elif (sizes == sizes[0]).all():
+                # same size everywhere: pad the rows of a matrix
+                objects.reshape(n, int(padded[0]))[:, :int(sizes[0])] = data[:int(src_begin[n])].reshape(n, int(sizes[0]))
             else:
                 # scatter every byte to its padded position
                 owner = np.repeat(np.arange(n), sizes)
@@ -351,6 +354,8 @@ class Iteration:
         total = int(size.sum(dtype=np.uint64))
         if total == int(begin[n]):
             return size, mag, objects[:total].copy()
+        if (size == size[0]).all() and int(begin[n]) % n == 0:
+            return size, mag, objects.reshape(n, int(begin[n]) // n)[:, :int(size[0])].reshape(-1).copy()
         owner = np.repeat(np.arange(n), size)
         dst_begin = np.zeros(n + 1, np.uint64)
         np.cumsum(size.astype(np.uint64), out=dst_begin[1:])

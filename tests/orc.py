@@ -182,6 +182,32 @@ class Oracle:
             self._free(b)
 
 
+class LoadedState:
+    """a state kept inside the checker between calls (the reference's append() is quadratic: load once)"""
+
+    def __init__(self, oracle: Oracle, p: Packed = None):
+        self.o = oracle
+        self.h = oracle._new()
+        if p is not None:
+            oracle._load(self.h, p)
+
+    def close(self):
+        if self.h is not None:
+            self.o._free(self.h)
+            self.h = None
+
+    def store(self) -> Packed:
+        return self.o._store(self.h)
+
+    def simulate_into(self, out: "LoadedState", rule_id, params=(), max_num_object=NO_TRUNCATION, tolerance=1e-30):
+        """returns (N_c, N_u, seconds inside simulate)"""
+        pr = self.o._params(params)
+        counters = np.zeros(2, np.uint64)
+        rc = self.o.lib.orc_simulate(self.h, rule_id, pr.ctypes.data, out.h, max_num_object, tolerance, counters.ctypes.data)
+        assert rc == 0, rc
+        return int(counters[0]), int(counters[1]), self.o.lib.orc_last_simulate_seconds()
+
+
 def have_reference():
     return os.path.exists(REF_SO)
 
