@@ -35,7 +35,7 @@ typedef enum qb_status {
 	QB_ERR_CUDA = -1,        /* a CUDA runtime call failed (includes "no device") */
 	QB_ERR_ARG = -2,         /* invalid argument */
 	QB_ERR_UNKNOWN_RULE = -3,
-	QB_ERR_UNSUPPORTED = -4, /* e.g. max_num_object == 0 (auto memory budget, quids.hpp:459-485): SURVEY 8(f) */
+	QB_ERR_UNSUPPORTED = -4, /* e.g. probabilistic truncation (quids::simple_truncation = false): SURVEY 8(f) */
 	QB_ERR_CAPACITY = -5,    /* an internal limit was exceeded (child index >= 2^40, object >= 16 MiB, table full) */
 	QB_ERR_COMM = -6         /* NCCL failure on the distributed path */
 } qb_status;
@@ -46,6 +46,10 @@ typedef struct qb_sym qb_sym;   /* quids::symbolic_iteration (quids.hpp:338-429)
 typedef struct qb_comm qb_comm; /* stands where MPI_Comm stands in quids_mpi.hpp   */
 
 #define QB_NO_TRUNCATION UINT64_MAX /* max_num_object = -1 in the reference (quids.hpp:445) */
+/* max_num_object = 0 is the reference's "automatic" budget (quids.hpp:459-485,510-536: truncate to what fits in free RAM).
+ * Here: keep everything if the workspace fits in the GPU memory left after the safety margin, otherwise FAIL with
+ * QB_ERR_CAPACITY and a message naming the size needed -- never a silent truncation.  The binary search for the largest
+ * fitting max_num_object is SURVEY 8(f) item 2 (next). */
 
 /* the mutable namespace globals of the reference that influence one call (quids.hpp:60-75) */
 typedef struct qb_options {
@@ -54,6 +58,7 @@ typedef struct qb_options {
 	int32_t simple_truncation; /* quids::simple_truncation; only 1 is supported */
 	double table_load;         /* engine knob: max load factor of the interference table, 0 = default */
 	int32_t profile;           /* 1: record CUDA events at the phase boundaries (qb_sym_phase_ms)     */
+	float safety_margin;       /* quids::safety_margin (quids.hpp:64): fraction of GPU memory the automatic budget leaves free */
 	int32_t locality_sort;     /* engine knob: order parents by the rule's locality key; 0 off (default), 1 when there are >= 2^17 parents, 2 always */
 } qb_options;
 

@@ -47,7 +47,7 @@ def build(verbose=False):
 
 class qb_options(C.Structure):
     _fields_ = [("tolerance", C.c_double), ("align_byte_length", C.c_uint32), ("simple_truncation", C.c_int32),
-                ("table_load", C.c_double), ("profile", C.c_int32), ("locality_sort", C.c_int32)]
+                ("table_load", C.c_double), ("profile", C.c_int32), ("safety_margin", C.c_float), ("locality_sort", C.c_int32)]
 
 
 STEP_CB = C.CFUNCTYPE(None, C.c_char_p, C.c_void_p)
@@ -133,6 +133,7 @@ class _Globals:
     tolerance = 1e-30          # quids::tolerance
     align_byte_length = 8      # quids::align_byte_length
     simple_truncation = True   # quids::simple_truncation (the only supported mode)
+    safety_margin = 0.2        # quids::safety_margin
     table_load = 0.0           # engine knob (0 = default)
     profile = False
     locality_sort = 0          # engine knob: 0 off, 1 auto, 2 always
@@ -144,6 +145,7 @@ class _Globals:
         o.align_byte_length = self.align_byte_length
         o.simple_truncation = 1 if self.simple_truncation else 0
         o.table_load = self.table_load
+        o.safety_margin = self.safety_margin
         o.profile = 1 if self.profile else 0
         o.locality_sort = self.locality_sort
         return o

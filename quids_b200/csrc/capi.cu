@@ -317,8 +317,9 @@ void simulate(qb_iter *it, int rule_id, const rule_ops *ops, const void *rule, q
 	qb_ctx *ctx = it->ctx;
 	QB_REQUIRE(next->ctx == ctx && sym->ctx == ctx, QB_ERR_ARG, "iteration, next iteration and symbolic iteration belong to different contexts");
 	QB_REQUIRE(next != it, QB_ERR_ARG, "next_iteration must be a different object from iteration");
-	QB_REQUIRE(max_num_object != 0, QB_ERR_UNSUPPORTED,
-	           "max_num_object = 0 (automatic memory budget, quids.hpp:459-485) is not supported: pass an explicit maximum or QB_NO_TRUNCATION");
+	const bool automatic = max_num_object == 0; // quids.hpp:459-485: keep what fits; here: everything, or fail loudly (see quids_b200.h)
+	if (automatic)
+		max_num_object = QB_NO_TRUNCATION;
 	ctx->use();
 	cudaStream_t stream = ctx->stream;
 	stepper step{ctx, cb, user};
@@ -431,6 +432,17 @@ void simulate(qb_iter *it, int rule_id, const rule_ops *ops, const void *rule, q
 		auto hint = sym->unique_ratio.find(rule_id);
 		if (hint != sym->unique_ratio.end())
 			capacity = std::min<uint64_t>(full_capacity, std::max<uint64_t>(1024, (uint64_t)((hint->second * (double)n_children * 1.3 + 1024) / 0.5)));
+	}
+	if (automatic) {
+		size_t free_bytes = 0, total_bytes = 0;
+		QB_CUDA(cudaMemGetInfo(&free_bytes, &total_bytes));
+		const double budget = (double)(free_bytes + sym->device_bytes()) - (double)opt.safety_margin * (double)total_bytes;
+		// interference table + compacted (key, slot) lists + a next state about the size of this one
+		const double need = (double)(capacity + 1) * sizeof(table_slot) + 12.0 * (double)std::min<uint64_t>(n_children, capacity + 1) + 2.0 * (double)it->n_bytes;
+		QB_REQUIRE(need <= budget, QB_ERR_CAPACITY,
+		           "max_num_object = 0 (automatic budget): " + std::to_string(n_children) + " children need about " + std::to_string((uint64_t)(need / 1e6)) +
+		               " MB of workspace, " + std::to_string((uint64_t)(std::max(0.0, budget) / 1e6)) +
+		               " MB are available after the safety margin; pass an explicit max_num_object");
 	}
 	L.child_begin = it->child_begin.as<uint64_t>();
 	L.group_begin = group_begin;
@@ -592,6 +604,7 @@ void qb_options_default(qb_options *opt) {
 	opt->table_load = 0;
 	opt->profile = 0;
 	opt->locality_sort = 0;
+	opt->safety_margin = 0.2f; // SAFETY_MARGIN, quids.hpp:33-35
 }
 
 const char *qb_last_error(void) { return g_last_error.c_str(); }

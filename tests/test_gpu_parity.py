@@ -245,8 +245,20 @@ def test_unsupported_requests_fail_loudly(gpu):
     import quids_b200 as qb
     it, nxt, sym = qb.Iteration(), qb.Iteration(), qb.SymbolicIteration()
     it.append(bytes([0, 1, 0]), 1.0)
-    with pytest.raises(qb.QuidsError):
-        qb.simulate(it, qb.Rule("hadamard", 1), nxt, sym, 0)  # auto memory budget: SURVEY 8(f), not silently ignored
+    qb.simulate(it, qb.Rule("hadamard", 1), nxt, sym, 0)  # automatic budget: everything is kept when it fits ...
+    assert nxt.num_object == 2
+    qb.config.safety_margin = 1.0  # ... and the call fails, instead of truncating silently, when it does not
+    try:
+        with pytest.raises(qb.QuidsError, match="automatic budget"):
+            qb.simulate(it, qb.Rule("hadamard", 1), nxt, sym, 0)
+    finally:
+        qb.config.safety_margin = 0.2
+    qb.config.simple_truncation = False
+    try:
+        with pytest.raises(qb.QuidsError, match="probabilistic"):
+            qb.simulate(it, qb.Rule("hadamard", 1), nxt, sym)
+    finally:
+        qb.config.simple_truncation = True
     with pytest.raises(qb.QuidsError):
         qb.simulate(it, qb.Rule("hadamard", 1), it, sym)
     with pytest.raises(qb.QuidsError):
