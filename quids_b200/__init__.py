@@ -443,3 +443,63 @@ def simulate(iteration: Iteration, rule, next_iteration: Iteration = None, symbo
     p, k = _params(rule.params)
     _check(lib().qb_simulate(iteration.handle, rule.id, p, k, next_iteration.handle, symbolic_iteration.handle, max_num_object,
                              C.byref(opt), cb, None))
+
+
+# -------------------------------------------------------------------------------------------------
+# distributed path: quids::mpi (quids_mpi.hpp) -- one process per GPU, NCCL inside the library
+# -------------------------------------------------------------------------------------------------
+class Communicator:
+    """stands where MPI_Comm stands in quids::mpi::simulate (quids_mpi.hpp:423)"""
+
+    def __init__(self, ctx, world_size, rank, unique_id: bytes):
+        assert len(unique_id) == 128
+        self.ctx, self.world_size, self.rank = ctx, world_size, rank
+        self.handle = C.c_void_p()
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        _check(lib().qb_comm_create(ctx.handle, world_size, rank, buf, C.byref(self.handle)))
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        _check(lib().qb_comm_unique_id(buf))
+        return bytes(buf)
+
+    @classmethod
+    def from_torch(cls, ctx, dist):
+        """bootstrap from an initialised torch.distributed process group (any backend): rank 0
+        creates the NCCL id, everybody receives it"""
+        rank, world = dist.get_rank(), dist.get_world_size()
+        box = [cls.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        return cls(ctx, world, rank, box[0])
+
+    def close(self):
+        if self.handle:
+            lib().qb_comm_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def allreduce_u64(self, values, op_max=False):
+        arr = np.ascontiguousarray(values, np.uint64).copy()
+        _check(lib().qb_comm_allreduce_u64(self.handle, arr.ctypes.data, arr.shape[0], 1 if op_max else 0))
+        return arr
+
+    def allreduce_f64(self, values):
+        arr = np.ascontiguousarray(values, np.float64).copy()
+        _check(lib().qb_comm_allreduce_f64(self.handle, arr.ctypes.data, arr.shape[0]))
+        return arr
+
+
+def mpi_simulate(iteration: Iteration, rule: Rule, next_iteration: Iteration, symbolic_iteration: SymbolicIteration, communicator: Communicator,
+                 max_num_object=NO_TRUNCATION, mid_step_function=None):
+    """quids::mpi::simulate (quids_mpi.hpp:423): every rank passes its own share of the state; the
+    truncation keeps the max_num_object most probable objects over ALL ranks.  Returns this rank's
+    node_total_proba (quids_mpi.hpp:67,892); next_iteration.total_proba is the global sum."""
+    iteration._flush()
+    next_iteration._pending = []
+    opt = config.options()
+    cb = STEP_CB(lambda label, user: mid_step_function(label.decode())) if mid_step_function else C.cast(None, STEP_CB)
+    p, k = _params(rule.params)
+    node = C.c_double()
+    _check(lib().qb_simulate_dist(iteration.handle, rule.id, p, k, next_iteration.handle, symbolic_iteration.handle, communicator.handle,
+                                  max_num_object, C.byref(opt), cb, None, C.byref(node)))
+    return node.value

@@ -58,6 +58,7 @@ enum { // u64 words of the small device scratch
 	DS_OVERFLOW = 2,
 	DS_TOTAL = 3,
 	DS_USED = 4,
+	DS_SELECT_GT = 5, // and 6
 	DS_WORDS = 8
 };
 
@@ -66,6 +67,7 @@ struct qb_ctx {
 	cudaStream_t stream = nullptr;
 	int sm_count = 0;
 	uint64_t launches = 0;
+	uint64_t select_k = 0; // rank requested from the last select_threshold
 	uint64_t *h_small = nullptr; // pinned mirror of d_small
 	dev_buf d_small;
 	dev_buf scan_ws;
@@ -118,11 +120,7 @@ struct qb_sym {
 	}
 };
 
-struct qb_comm {
-	qb_ctx *ctx;
-	int world = 1, rank = 0;
-	void *nccl = nullptr;
-};
+#include "dist.inc.cuh"
 
 // ---- helpers --------------------------------------------------------------------------------------------
 namespace {
@@ -185,37 +183,74 @@ void exclusive_scan(qb_ctx *ctx, F f, uint64_t *out, uint64_t n) {
 	QB_CUDA(cudaGetLastError());
 }
 
-// k-th largest key: leaves threshold / count_gt / need in ctx->select (device)
+// k-th largest key over this GPU's keys -- or, with a communicator, over the keys of ALL ranks: every
+// digit histogram is all-reduced before the digit is picked, so all ranks walk to the same threshold.
+// Leaves threshold / count_gt / need (global values) in ctx->select (device).
 template <class KeyFn>
-void radix_select(qb_ctx *ctx, KeyFn key_of, uint64_t n, uint64_t k) {
+void select_threshold(qb_ctx *ctx, comm_ops *comm, KeyFn key_of, uint64_t n, uint64_t k) {
 	ctx->select.ensure(sizeof(select_state), ctx->stream);
 	select_state init;
 	memset(&init, 0, sizeof init);
 	init.k = k;
 	QB_CUDA(cudaMemcpyAsync(ctx->select.ptr, &init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
 	ctx->sync(); // `init` lives on this stack frame
+	ctx->select_k = k;
 	const int grid = grid_for(n, 256, ctx->grid_cap());
 	int shift = 64;
 	while (shift > 0) {
 		const int bits = shift >= SELECT_MAX_BITS ? SELECT_MAX_BITS : shift;
 		shift -= bits;
-		select_histogram_kernel<<<grid, 256, 0, ctx->stream>>>(key_of, n, ctx->select.as<select_state>(), shift, bits);
+		if (n > 0) {
+			select_histogram_kernel<<<grid, 256, 0, ctx->stream>>>(key_of, n, ctx->select.as<select_state>(), shift, bits);
+			++ctx->launches;
+		}
+		if (comm)
+			comm->allreduce_u64_device(ctx->select.as<select_state>()->hist, SELECT_BINS);
 		select_pick_kernel<<<1, SCAN_THREADS, 0, ctx->stream>>>(ctx->select.as<select_state>(), shift, bits);
-		ctx->launches += 2;
-	}
-	QB_CUDA(cudaGetLastError());
-}
-
-template <class KeyFn, class OutFn>
-void select_compact(qb_ctx *ctx, KeyFn key_of, uint64_t n, OutFn out) {
-	const uint64_t tiles = div_up<uint64_t>(n, COMPACT_TILE);
-	for (int pass = 0; pass < 2; ++pass) {
-		scan_state st = ctx->scan(tiles);
-		select_compact_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, ctx->stream>>>(key_of, n, ctx->select.as<select_state>(), pass, out, st);
 		++ctx->launches;
 	}
 	QB_CUDA(cudaGetLastError());
 }
+
+// keeps the selected elements of THIS GPU (out(rank, index)) and returns how many.  Ties at the
+// threshold are arbitrary in the reference; here the first ones in storage order win, and across
+// ranks the lower ranks are served first.
+template <class KeyFn, class OutFn>
+uint64_t select_keep(qb_ctx *ctx, comm_ops *comm, KeyFn key_of, uint64_t n, OutFn out) {
+	uint64_t kept = ctx->select_k;
+	if (comm) {
+		unsigned long long *gt_eq = reinterpret_cast<unsigned long long *>(ctx->small(DS_SELECT_GT));
+		QB_CUDA(cudaMemsetAsync(gt_eq, 0, 2 * sizeof(uint64_t), ctx->stream));
+		if (n > 0) {
+			select_count_kernel<<<grid_for(n, 256, ctx->grid_cap()), 256, 0, ctx->stream>>>(key_of, n, ctx->select.as<select_state>(), gt_eq);
+			++ctx->launches;
+		}
+		uint64_t mine[3]; // gt, eq of this rank; the global `need`
+		QB_CUDA(cudaMemcpyAsync(mine, gt_eq, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+		QB_CUDA(cudaMemcpyAsync(&mine[2], &ctx->select.as<select_state>()->k, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+		ctx->sync();
+		std::vector<uint64_t> all = comm->allgather_u64(mine, 2);
+		uint64_t before = 0; // ties taken by lower ranks
+		for (int r = 0; r < comm->rank(); ++r)
+			before += all[2 * r + 1];
+		const uint64_t need = mine[2] > before ? std::min<uint64_t>(mine[2] - before, mine[1]) : 0;
+		select_patch_kernel<<<1, 1, 0, ctx->stream>>>(ctx->select.as<select_state>(), need, mine[0]);
+		++ctx->launches;
+		kept = mine[0] + need;
+	}
+	if (n > 0) {
+		const uint64_t tiles = div_up<uint64_t>(n, COMPACT_TILE);
+		for (int pass = 0; pass < 2; ++pass) {
+			scan_state st = ctx->scan(tiles);
+			select_compact_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, ctx->stream>>>(key_of, n, ctx->select.as<select_state>(), pass, out, st);
+			++ctx->launches;
+		}
+	}
+	QB_CUDA(cudaGetLastError());
+	return kept;
+}
+
+uint64_t global_sum(comm_ops *comm, uint64_t v) { return comm ? comm->sum_u64(v) : v; }
 
 struct key_from_mag {
 	const cplx *mag;
@@ -310,122 +345,116 @@ void resolve_options(const qb_options *in, qb_options &opt) {
 }
 
 // ======================================================================================================
-// one rule iteration on one GPU
+// one rule iteration
 // ======================================================================================================
-void simulate(qb_iter *it, int rule_id, const rule_ops *ops, const void *rule, qb_iter *next, qb_sym *sym, uint64_t max_num_object, const qb_options &opt,
-              qb_step_cb cb, void *user) {
+// stages 1-6 of an iteration on THIS GPU: child counts, parent pre-truncation, index ranges, children ->
+// interference table, compaction of the table into (norm key, slot) lists
+struct local_table {
+	uint64_t n_parents = 0;
+	const uint64_t *kept = nullptr;
+	uint64_t n_children = 0;
+	uint64_t n_unique = 0; // entries kept by the compaction
+	table_view table{};
+	int empty_from = -1; // >= 0: nothing to do from label `empty_from` on (no parents / no children)
+};
+
+local_table build_local_table(qb_iter *it, int rule_id, const rule_ops *ops, const void *rule, qb_sym *sym, uint64_t max_num_object, bool automatic,
+                              const qb_options &opt, double compaction_tolerance, phase_timer &timer, const stepper &step, engine_launch &L, comm_ops *comm) {
 	qb_ctx *ctx = it->ctx;
-	QB_REQUIRE(next->ctx == ctx && sym->ctx == ctx, QB_ERR_ARG, "iteration, next iteration and symbolic iteration belong to different contexts");
-	QB_REQUIRE(next != it, QB_ERR_ARG, "next_iteration must be a different object from iteration");
-	const bool automatic = max_num_object == 0; // quids.hpp:459-485: keep what fits; here: everything, or fail loudly (see quids_b200.h)
-	if (automatic)
-		max_num_object = QB_NO_TRUNCATION;
-	ctx->use();
 	cudaStream_t stream = ctx->stream;
-	stepper step{ctx, cb, user};
-	phase_timer timer(sym, opt.profile != 0);
-
-	engine_launch L;
-	memset(&L, 0, sizeof L);
-	L.stream = stream;
-	L.sm_count = ctx->sm_count;
-	L.launch_counter = &ctx->launches;
-	L.it = it->view();
-
-	auto finish_empty = [&](int from) { // the label sequences of the reference's early outs (quids.hpp:650-651,729-731,908-909,989-990)
-		static const char *labels[] = {"prepare_index", "symbolic_iteration", "compute_collisions - prepare", "compute_collisions - insert",
-		                               "compute_collisions - finalize", "truncate - prepare", "truncate", "prepare_final", "final", "normalize", "end"};
-		for (int i = from; i < 11; ++i)
-			step(labels[i]);
-		next->n = 0;
-		next->n_bytes = 0;
-		next->total_proba = 0;
-		next->begin.ensure(sizeof(uint64_t), stream);
-		QB_CUDA(cudaMemsetAsync(next->begin.ptr, 0, sizeof(uint64_t), stream));
-		ctx->sync();
-		timer.collect();
-	};
+	local_table R;
 
 	// ---- 1. number of children per parent (quids.hpp:548-569) --------------------------------------
 	step("num_child");
 	sym->n_children = sym->n_unique = 0;
-	if (it->n == 0) {
+	const uint64_t n_global = global_sum(comm, it->n);
+	if (n_global == 0) {
 		step("truncate_symbolic - prepare");
 		step("truncate_symbolic");
-		finish_empty(0);
-		return;
+		R.empty_from = 0;
+		return R;
 	}
-	timer.begin(QB_PHASE_NUM_CHILD);
-	it->num_childs.ensure(sizeof(uint32_t) * it->n, stream);
 	QB_CUDA(cudaMemsetAsync(ctx->d_small.ptr, 0, DS_WORDS * sizeof(uint64_t), stream));
-	L.num_childs = it->num_childs.as<uint32_t>();
-	if (ops->warp_groups) {
-		it->num_groups.ensure(sizeof(uint32_t) * it->n, stream);
-		L.num_groups = it->num_groups.as<uint32_t>();
+	bool order_parents = false;
+	if (it->n > 0) {
+		timer.begin(QB_PHASE_NUM_CHILD);
+		it->num_childs.ensure(sizeof(uint32_t) * it->n, stream);
+		L.num_childs = it->num_childs.as<uint32_t>();
+		if (ops->warp_groups) {
+			it->num_groups.ensure(sizeof(uint32_t) * it->n, stream);
+			L.num_groups = it->num_groups.as<uint32_t>();
+		}
+		// ordering the parents only pays when the table cannot stay in L2 anyway
+		order_parents = ops->has_locality_key && opt.locality_sort != 0 && it->n >= (opt.locality_sort > 1 ? 2u : 1u << 17);
+		if (order_parents) {
+			it->locality.ensure(sizeof(uint32_t) * it->n, stream);
+			L.locality = it->locality.as<uint32_t>();
+		}
+		L.max_child_size = reinterpret_cast<unsigned int *>(ctx->small(DS_MAX_CHILD_SIZE));
+		ops->launch_num_child(rule, L);
+		timer.end(QB_PHASE_NUM_CHILD);
 	}
-	// ordering the parents only pays when the table cannot stay in L2 anyway
-	const bool order_parents = ops->has_locality_key && opt.locality_sort != 0 && it->n >= (opt.locality_sort > 1 ? 2u : 1u << 17);
-	if (order_parents) {
-		it->locality.ensure(sizeof(uint32_t) * it->n, stream);
-		L.locality = it->locality.as<uint32_t>();
-	}
-	L.max_child_size = reinterpret_cast<unsigned int *>(ctx->small(DS_MAX_CHILD_SIZE));
-	ops->launch_num_child(rule, L);
-	timer.end(QB_PHASE_NUM_CHILD);
 
-	// ---- 2. parent pre-truncation: the max_num_object most probable parents (quids.hpp:613-642) ------
+	// ---- 2. parent pre-truncation: the max_num_object most probable parents (quids.hpp:613-642);
+	//         over ALL ranks on the distributed path, so that the result equals the single-GPU one ---------
 	step("truncate_symbolic - prepare");
 	step("truncate_symbolic");
-	uint64_t n_parents = it->n;
-	const uint64_t *kept = nullptr;
-	if (max_num_object < it->n) {
+	R.n_parents = it->n;
+	if (max_num_object < n_global) {
 		timer.begin(QB_PHASE_PRE_TRUNCATE);
-		n_parents = max_num_object;
-		sym->kept.ensure(sizeof(uint64_t) * n_parents, stream);
+		sym->kept.ensure(sizeof(uint64_t) * std::max<uint64_t>(1, std::min<uint64_t>(it->n, max_num_object)), stream);
 		key_from_mag keys{it->mag.as<cplx>()};
-		radix_select(ctx, keys, it->n, n_parents);
-		select_compact(ctx, keys, it->n, out_index{sym->kept.as<uint64_t>()});
-		kept = sym->kept.as<uint64_t>();
+		select_threshold(ctx, comm, keys, it->n, max_num_object);
+		R.n_parents = select_keep(ctx, comm, keys, it->n, out_index{sym->kept.as<uint64_t>()});
+		R.kept = sym->kept.as<uint64_t>();
 		timer.end(QB_PHASE_PRE_TRUNCATE);
 	}
-
-	if (order_parents) {
+	if (order_parents && R.n_parents > 0) {
 		timer.begin(QB_PHASE_PRE_TRUNCATE);
-		kept = sort_parents_by_locality(ctx, sym, it->locality.as<uint32_t>(), kept, n_parents);
+		R.kept = sort_parents_by_locality(ctx, sym, it->locality.as<uint32_t>(), R.kept, R.n_parents);
 		timer.end(QB_PHASE_PRE_TRUNCATE);
 	}
 
 	// ---- 3. child index ranges (quids.hpp:666-671: a serial loop in the reference) --------------------
 	step("prepare_index");
-	timer.begin(QB_PHASE_NUM_CHILD);
-	it->child_begin.ensure(sizeof(uint64_t) * (n_parents + 1), stream);
-	exclusive_scan(ctx, counts_through{it->num_childs.as<uint32_t>(), kept}, it->child_begin.as<uint64_t>(), n_parents);
-	const uint64_t *group_begin = it->child_begin.as<uint64_t>();
-	if (ops->warp_groups) { // children are produced in groups that share work: a second index space
-		it->group_begin.ensure(sizeof(uint64_t) * (n_parents + 1), stream);
-		exclusive_scan(ctx, counts_through{it->num_groups.as<uint32_t>(), kept}, it->group_begin.as<uint64_t>(), n_parents);
-		group_begin = it->group_begin.as<uint64_t>();
+	uint64_t n_groups = 0;
+	uint32_t max_child_size = 0;
+	const uint64_t *group_begin = nullptr;
+	if (R.n_parents > 0) {
+		timer.begin(QB_PHASE_NUM_CHILD);
+		it->child_begin.ensure(sizeof(uint64_t) * (R.n_parents + 1), stream);
+		exclusive_scan(ctx, counts_through{it->num_childs.as<uint32_t>(), R.kept}, it->child_begin.as<uint64_t>(), R.n_parents);
+		group_begin = it->child_begin.as<uint64_t>();
+		if (ops->warp_groups) { // children are produced in groups that share work: a second index space
+			it->group_begin.ensure(sizeof(uint64_t) * (R.n_parents + 1), stream);
+			exclusive_scan(ctx, counts_through{it->num_groups.as<uint32_t>(), R.kept}, it->group_begin.as<uint64_t>(), R.n_parents);
+			group_begin = it->group_begin.as<uint64_t>();
+		}
+		QB_CUDA(cudaMemcpyAsync(&ctx->h_small[DS_COUNT], it->child_begin.as<uint64_t>() + R.n_parents, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+		QB_CUDA(cudaMemcpyAsync(&ctx->h_small[DS_USED], group_begin + R.n_parents, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+		QB_CUDA(cudaMemcpyAsync(&ctx->h_small[DS_MAX_CHILD_SIZE], ctx->small(DS_MAX_CHILD_SIZE), sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+		timer.end(QB_PHASE_NUM_CHILD);
+		ctx->sync();
+		R.n_children = ctx->h_small[DS_COUNT];
+		n_groups = ctx->h_small[DS_USED];
+		max_child_size = (uint32_t)ctx->h_small[DS_MAX_CHILD_SIZE];
 	}
-	QB_CUDA(cudaMemcpyAsync(&ctx->h_small[DS_COUNT], it->child_begin.as<uint64_t>() + n_parents, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
-	QB_CUDA(cudaMemcpyAsync(&ctx->h_small[DS_USED], group_begin + n_parents, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
-	QB_CUDA(cudaMemcpyAsync(&ctx->h_small[DS_MAX_CHILD_SIZE], ctx->small(DS_MAX_CHILD_SIZE), sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
-	timer.end(QB_PHASE_NUM_CHILD);
-	ctx->sync();
-	const uint64_t n_children = ctx->h_small[DS_COUNT];
-	const uint64_t n_groups = ctx->h_small[DS_USED];
-	const uint32_t max_child_size = (uint32_t)ctx->h_small[DS_MAX_CHILD_SIZE];
-	sym->n_children = n_children;
-	if (n_children == 0) {
-		finish_empty(1);
-		return;
+	sym->n_children = R.n_children;
+	if (global_sum(comm, R.n_children) == 0) {
+		R.empty_from = 1;
+		return R;
 	}
-	QB_REQUIRE(n_children <= REP_MAX_INDEX, QB_ERR_CAPACITY, "more than 2^40 children in one iteration");
+	QB_REQUIRE(R.n_children <= REP_MAX_INDEX, QB_ERR_CAPACITY, "more than 2^40 children in one iteration");
 	QB_REQUIRE(max_child_size <= REP_MAX_SIZE, QB_ERR_CAPACITY, "child objects of 16 MiB or more are not supported");
+	step("symbolic_iteration");
+	if (R.n_children == 0) // this rank has nothing to contribute (distributed path only)
+		return R;
 
 	// ---- 4-6. interference: table sized from the last call of this rule, full size as fallback -------------
 	// Capacity: enough for every child to be unique at the configured load (safe), unless the previous
 	// call of the same rule showed how many slots are really created: then 2.6x that prediction.  An
 	// insert that probes too long raises `overflow` and the whole step is redone at full size.
+	const uint64_t n_children = R.n_children;
 	const uint64_t full_capacity = std::max<uint64_t>(1024, (uint64_t)std::ceil((double)n_children / opt.table_load));
 	uint64_t capacity = full_capacity;
 	{
@@ -446,8 +475,8 @@ void simulate(qb_iter *it, int rule_id, const rule_ops *ops, const void *rule, q
 	}
 	L.child_begin = it->child_begin.as<uint64_t>();
 	L.group_begin = group_begin;
-	L.kept = kept;
-	L.n_parents = n_parents;
+	L.kept = R.kept;
+	L.n_parents = R.n_parents;
 	L.n_children = n_children;
 	L.n_groups = n_groups;
 	sym->chunk_parent.ensure(sizeof(uint64_t) * (ops->symbolic_chunks(n_groups) + 2), stream);
@@ -459,9 +488,6 @@ void simulate(qb_iter *it, int rule_id, const rule_ops *ops, const void *rule, q
 		sym->scratch.ensure((size_t)ops->symbolic_grid(ctx->sm_count) * SYMBOLIC_THREADS * L.scratch_stride, stream);
 		L.scratch = sym->scratch.as<uint8_t>();
 	}
-	table_view table;
-	uint64_t n_unique = 0;
-	step("symbolic_iteration");
 	for (sym->table_attempts = 1;; ++sym->table_attempts) {
 		QB_REQUIRE(capacity + 1 <= 0xffffffffull, QB_ERR_CAPACITY, "interference table would need more than 2^32 slots");
 		timer.begin(QB_PHASE_TABLE_CLEAR);
@@ -469,13 +495,13 @@ void simulate(qb_iter *it, int rule_id, const rule_ops *ops, const void *rule, q
 		sym->table.ensure(table_bytes, stream);
 		QB_CUDA(cudaMemsetAsync(sym->table.ptr, 0, table_bytes, stream));
 		QB_CUDA(cudaMemsetAsync(ctx->small(DS_COUNT), 0, 4 * sizeof(uint64_t), stream)); // count, overflow, total, used
-		table = table_view{sym->table.as<table_slot>(), capacity, reinterpret_cast<unsigned int *>(ctx->small(DS_OVERFLOW)),
-		                   reinterpret_cast<unsigned long long *>(ctx->small(DS_USED))};
+		R.table = table_view{sym->table.as<table_slot>(), capacity, reinterpret_cast<unsigned int *>(ctx->small(DS_OVERFLOW)),
+		                     reinterpret_cast<unsigned long long *>(ctx->small(DS_USED))};
 		timer.end(QB_PHASE_TABLE_CLEAR);
 
 		// children -> (hash, magnitude) -> table (quids.hpp:705-719 fused with :785-809)
 		timer.begin(QB_PHASE_SYMBOLIC);
-		L.table = table;
+		L.table = R.table;
 		ops->launch_symbolic(rule, L);
 		QB_CUDA(cudaGetLastError());
 		timer.end(QB_PHASE_SYMBOLIC);
@@ -487,7 +513,7 @@ void simulate(qb_iter *it, int rule_id, const rule_ops *ops, const void *rule, q
 		sym->uslot.ensure(sizeof(uint32_t) * bound, stream);
 		const uint64_t tiles = div_up<uint64_t>(capacity + 1, COMPACT_TILE);
 		scan_state st = ctx->scan(tiles);
-		table_compact_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, stream>>>(table, opt.tolerance, sym->ukey.as<uint64_t>(), sym->uslot.as<uint32_t>(),
+		table_compact_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, stream>>>(R.table, compaction_tolerance, sym->ukey.as<uint64_t>(), sym->uslot.as<uint32_t>(),
 		                                                                    reinterpret_cast<unsigned long long *>(ctx->small(DS_COUNT)), st);
 		++ctx->launches;
 		QB_CUDA(cudaGetLastError());
@@ -498,10 +524,65 @@ void simulate(qb_iter *it, int rule_id, const rule_ops *ops, const void *rule, q
 		QB_REQUIRE(capacity < full_capacity, QB_ERR_CAPACITY, "interference table overflow at full size");
 		capacity = full_capacity; // the prediction was too small: redo at the safe size
 	}
-	n_unique = ctx->h_small[DS_COUNT];
-	sym->n_unique = n_unique;
+	R.n_unique = ctx->h_small[DS_COUNT];
 	sym->table_capacity = capacity;
 	sym->unique_ratio[rule_id] = (double)ctx->h_small[DS_USED] / (double)n_children;
+	return R;
+}
+
+// stages 8-9 on THIS GPU: sizes, offsets, populate_child_simple, normalisation.  The survivors are
+// given either as slots of the local table, or (distributed path) as (representative, magnitude) records.
+struct survivor_source {
+	table_view table{};
+	const uint32_t *slot = nullptr;
+	const survivor_record *records = nullptr;
+};
+
+void finalize_and_normalize(qb_iter *it, const rule_ops *ops, const void *rule, qb_iter *next, qb_sym *sym, const qb_options &opt, const local_table &R,
+                            const survivor_source &src, uint64_t n_survivors, phase_timer &timer, const stepper &step, engine_launch &L, comm_ops *comm,
+                            double *node_total_proba);
+
+void finish_empty(qb_ctx *ctx, qb_iter *next, const stepper &step, phase_timer &timer, int from) {
+	// the label sequences of the reference's early outs (quids.hpp:650-651,729-731,908-909,989-990)
+	static const char *labels[] = {"prepare_index", "symbolic_iteration", "compute_collisions - prepare", "compute_collisions - insert",
+	                               "compute_collisions - finalize", "truncate - prepare", "truncate", "prepare_final", "final", "normalize", "end"};
+	for (int i = from; i < 11; ++i)
+		step(labels[i]);
+	next->n = 0;
+	next->n_bytes = 0;
+	next->total_proba = 0;
+	next->begin.ensure(sizeof(uint64_t), ctx->stream);
+	QB_CUDA(cudaMemsetAsync(next->begin.ptr, 0, sizeof(uint64_t), ctx->stream));
+	ctx->sync();
+	timer.collect();
+}
+
+void simulate(qb_iter *it, int rule_id, const rule_ops *ops, const void *rule, qb_iter *next, qb_sym *sym, uint64_t max_num_object, const qb_options &opt,
+              qb_step_cb cb, void *user) {
+	qb_ctx *ctx = it->ctx;
+	QB_REQUIRE(next->ctx == ctx && sym->ctx == ctx, QB_ERR_ARG, "iteration, next iteration and symbolic iteration belong to different contexts");
+	QB_REQUIRE(next != it, QB_ERR_ARG, "next_iteration must be a different object from iteration");
+	const bool automatic = max_num_object == 0; // quids.hpp:459-485: keep what fits; here: everything, or fail loudly (see quids_b200.h)
+	if (automatic)
+		max_num_object = QB_NO_TRUNCATION;
+	ctx->use();
+	cudaStream_t stream = ctx->stream;
+	stepper step{ctx, cb, user};
+	phase_timer timer(sym, opt.profile != 0);
+
+	engine_launch L;
+	memset(&L, 0, sizeof L);
+	L.stream = stream;
+	L.sm_count = ctx->sm_count;
+	L.launch_counter = &ctx->launches;
+	L.it = it->view();
+
+	local_table R = build_local_table(it, rule_id, ops, rule, sym, max_num_object, automatic, opt, opt.tolerance, timer, step, L, nullptr);
+	if (R.empty_from >= 0) {
+		finish_empty(ctx, next, step, timer, R.empty_from);
+		return;
+	}
+	sym->n_unique = R.n_unique;
 	step("compute_collisions - prepare");
 	step("compute_collisions - insert");
 	step("compute_collisions - finalize");
@@ -509,84 +590,258 @@ void simulate(qb_iter *it, int rule_id, const rule_ops *ops, const void *rule, q
 	// ---- 7. child truncation: the max_num_object most probable (quids.hpp:866-900) ---------------------
 	step("truncate - prepare");
 	step("truncate");
-	uint64_t n_survivors = n_unique;
-	const uint32_t *survivor_slot = sym->uslot.as<uint32_t>();
-	if (max_num_object < n_unique) {
+	uint64_t n_survivors = R.n_unique;
+	survivor_source src;
+	src.table = R.table;
+	src.slot = sym->uslot.as<uint32_t>();
+	if (max_num_object < R.n_unique) {
 		timer.begin(QB_PHASE_TRUNCATE);
-		n_survivors = max_num_object;
-		sym->sslot.ensure(sizeof(uint32_t) * n_survivors, stream);
+		sym->sslot.ensure(sizeof(uint32_t) * max_num_object, stream);
 		key_from_array keys{sym->ukey.as<uint64_t>()};
-		radix_select(ctx, keys, n_unique, n_survivors);
-		select_compact(ctx, keys, n_unique, out_gather_u32{sym->sslot.as<uint32_t>(), sym->uslot.as<uint32_t>()});
-		survivor_slot = sym->sslot.as<uint32_t>();
+		select_threshold(ctx, nullptr, keys, R.n_unique, max_num_object);
+		n_survivors = select_keep(ctx, nullptr, keys, R.n_unique, out_gather_u32{sym->sslot.as<uint32_t>(), sym->uslot.as<uint32_t>()});
+		src.slot = sym->sslot.as<uint32_t>();
 		timer.end(QB_PHASE_TRUNCATE);
 	}
 	if (n_survivors == 0) {
-		finish_empty(7);
+		finish_empty(ctx, next, step, timer, 7);
 		return;
 	}
+	finalize_and_normalize(it, ops, rule, next, sym, opt, R, src, n_survivors, timer, step, L, nullptr, nullptr);
+}
+
+void finalize_and_normalize(qb_iter *it, const rule_ops *ops, const void *rule, qb_iter *next, qb_sym *sym, const qb_options &opt, const local_table &R,
+                            const survivor_source &src, uint64_t n_survivors, phase_timer &timer, const stepper &step, engine_launch &L, comm_ops *comm,
+                            double *node_total_proba) {
+	qb_ctx *ctx = it->ctx;
+	cudaStream_t stream = ctx->stream;
 
 	// ---- 8. finalisation (quids.hpp:905-968) ------------------------------------------------------------
 	step("prepare_final");
 	timer.begin(QB_PHASE_FINALIZE);
 	next->n = n_survivors;
-	next->size.ensure(sizeof(uint32_t) * n_survivors, stream);
-	next->mag.ensure(sizeof(cplx) * n_survivors, stream);
+	next->n_bytes = 0;
+	double local_total = 0;
 	next->begin.ensure(sizeof(uint64_t) * (n_survivors + 1), stream);
-	sym->padded.ensure(sizeof(uint32_t) * n_survivors, stream);
-	sym->survivor_parent.ensure(sizeof(uint64_t) * n_survivors, stream);
-	sym->survivor_child.ensure(sizeof(uint32_t) * n_survivors, stream);
-	ctx->partials.ensure(sizeof(double) * (size_t)ctx->grid_cap(), stream);
-	const int meta_grid = grid_for(n_survivors, SCAN_THREADS, ctx->grid_cap());
-	{
-		finalize_args a;
-		a.table = table;
-		a.survivor_slot = survivor_slot;
-		a.n_survivors = n_survivors;
-		a.child_begin = it->child_begin.as<uint64_t>();
-		a.kept = kept;
-		a.n_parents = n_parents;
-		a.align = opt.align_byte_length;
-		a.next_size = next->size.as<uint32_t>();
-		a.next_padded = sym->padded.as<uint32_t>();
-		a.next_mag = next->mag.as<cplx>();
-		a.survivor_parent = sym->survivor_parent.as<uint64_t>();
-		a.survivor_child = sym->survivor_child.as<uint32_t>();
-		a.partial_norm = ctx->partials.as<double>();
-		finalize_meta_kernel<<<meta_grid, SCAN_THREADS, 0, stream>>>(a);
+	if (n_survivors > 0) {
+		next->size.ensure(sizeof(uint32_t) * n_survivors, stream);
+		next->mag.ensure(sizeof(cplx) * n_survivors, stream);
+		sym->padded.ensure(sizeof(uint32_t) * n_survivors, stream);
+		sym->survivor_parent.ensure(sizeof(uint64_t) * n_survivors, stream);
+		sym->survivor_child.ensure(sizeof(uint32_t) * n_survivors, stream);
+		ctx->partials.ensure(sizeof(double) * (size_t)ctx->grid_cap(), stream);
+		const int meta_grid = grid_for(n_survivors, SCAN_THREADS, ctx->grid_cap());
+		if (src.records) {
+			finalize_record_args a;
+			a.records = src.records;
+			a.n_survivors = n_survivors;
+			a.child_begin = it->child_begin.as<uint64_t>();
+			a.kept = R.kept;
+			a.n_parents = R.n_parents;
+			a.align = opt.align_byte_length;
+			a.next_size = next->size.as<uint32_t>();
+			a.next_padded = sym->padded.as<uint32_t>();
+			a.next_mag = next->mag.as<cplx>();
+			a.survivor_parent = sym->survivor_parent.as<uint64_t>();
+			a.survivor_child = sym->survivor_child.as<uint32_t>();
+			a.partial_norm = ctx->partials.as<double>();
+			finalize_meta_records_kernel<<<meta_grid, SCAN_THREADS, 0, stream>>>(a);
+		} else {
+			finalize_args a;
+			a.table = src.table;
+			a.survivor_slot = src.slot;
+			a.n_survivors = n_survivors;
+			a.child_begin = it->child_begin.as<uint64_t>();
+			a.kept = R.kept;
+			a.n_parents = R.n_parents;
+			a.align = opt.align_byte_length;
+			a.next_size = next->size.as<uint32_t>();
+			a.next_padded = sym->padded.as<uint32_t>();
+			a.next_mag = next->mag.as<cplx>();
+			a.survivor_parent = sym->survivor_parent.as<uint64_t>();
+			a.survivor_child = sym->survivor_child.as<uint32_t>();
+			a.partial_norm = ctx->partials.as<double>();
+			finalize_meta_kernel<<<meta_grid, SCAN_THREADS, 0, stream>>>(a);
+		}
 		norm_total_kernel<<<1, SCAN_THREADS, 0, stream>>>(ctx->partials.as<double>(), meta_grid, reinterpret_cast<double *>(ctx->small(DS_TOTAL)));
 		ctx->launches += 2;
+		exclusive_scan(ctx, widen_u32{sym->padded.as<uint32_t>()}, next->begin.as<uint64_t>(), n_survivors);
+		QB_CUDA(cudaMemcpyAsync(&ctx->h_small[DS_COUNT], next->begin.as<uint64_t>() + n_survivors, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+		QB_CUDA(cudaMemcpyAsync(&ctx->h_small[DS_TOTAL], ctx->small(DS_TOTAL), sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+		ctx->sync();
+		next->n_bytes = ctx->h_small[DS_COUNT];
+		memcpy(&local_total, &ctx->h_small[DS_TOTAL], sizeof local_total);
+		next->objects.ensure(next->n_bytes + 16, stream);
+	} else {
+		QB_CUDA(cudaMemsetAsync(next->begin.ptr, 0, sizeof(uint64_t), stream));
 	}
-	exclusive_scan(ctx, widen_u32{sym->padded.as<uint32_t>()}, next->begin.as<uint64_t>(), n_survivors);
-	QB_CUDA(cudaMemcpyAsync(&ctx->h_small[DS_COUNT], next->begin.as<uint64_t>() + n_survivors, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
-	QB_CUDA(cudaMemcpyAsync(&ctx->h_small[DS_TOTAL], ctx->small(DS_TOTAL), sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
-	ctx->sync();
-	next->n_bytes = ctx->h_small[DS_COUNT];
-	double total;
-	memcpy(&total, &ctx->h_small[DS_TOTAL], sizeof total);
-	next->objects.ensure(next->n_bytes + 16, stream);
 
 	step("final");
-	L.n_survivors = n_survivors;
-	L.survivor_parent = sym->survivor_parent.as<uint64_t>();
-	L.survivor_child = sym->survivor_child.as<uint32_t>();
-	L.next_objects = next->objects.as<uint8_t>();
-	L.next_begin = next->begin.as<uint64_t>();
-	L.next_size = next->size.as<uint32_t>();
-	ops->launch_populate(rule, L);
-	QB_CUDA(cudaGetLastError());
+	if (n_survivors > 0) {
+		L.n_survivors = n_survivors;
+		L.survivor_parent = sym->survivor_parent.as<uint64_t>();
+		L.survivor_child = sym->survivor_child.as<uint32_t>();
+		L.next_objects = next->objects.as<uint8_t>();
+		L.next_begin = next->begin.as<uint64_t>();
+		L.next_size = next->size.as<uint32_t>();
+		ops->launch_populate(rule, L);
+		QB_CUDA(cudaGetLastError());
+	}
 	timer.end(QB_PHASE_FINALIZE);
 
-	// ---- 9. normalisation (quids.hpp:985-1017); total_proba keeps the pre-normalisation sum -------------
+	// ---- 9. normalisation (quids.hpp:985-1017, quids_mpi.hpp:870-895); total_proba keeps the pre-normalisation sum
 	step("normalize");
 	timer.begin(QB_PHASE_NORMALIZE);
+	const double total = comm ? comm->sum_f64(local_total) : local_total;
 	next->total_proba = total;
+	if (node_total_proba)
+		*node_total_proba = total > 0 ? local_total / total : 0; // quids_mpi.hpp:892
 	scale_state(ctx, next->mag.as<cplx>(), n_survivors, total);
 	timer.end(QB_PHASE_NORMALIZE);
 	ctx->sync();
 	QB_CUDA(cudaGetLastError());
 	timer.collect();
 	step("end");
+}
+
+// ======================================================================================================
+// one rule iteration over the GPUs of a communicator (see dist.inc.cuh for the protocol)
+// ======================================================================================================
+void simulate_dist(qb_iter *it, int rule_id, const rule_ops *ops, const void *rule, qb_iter *next, qb_sym *sym, qb_comm *cm, uint64_t max_num_object,
+                   const qb_options &opt, qb_step_cb cb, void *user, double *node_total_proba) {
+	qb_ctx *ctx = it->ctx;
+	QB_REQUIRE(next->ctx == ctx && sym->ctx == ctx && cm->ctx == ctx, QB_ERR_ARG, "handles belong to different contexts");
+	QB_REQUIRE(next != it, QB_ERR_ARG, "next_iteration must be a different object from iteration");
+	QB_REQUIRE(max_num_object != 0, QB_ERR_UNSUPPORTED, "the distributed path needs an explicit max_num_object (or QB_NO_TRUNCATION)");
+	ctx->use();
+	cudaStream_t stream = ctx->stream;
+	stepper step{ctx, cb, user};
+	phase_timer timer(sym, opt.profile != 0);
+	comm_ops comm{cm};
+	const uint32_t world = (uint32_t)cm->world;
+
+	engine_launch L;
+	memset(&L, 0, sizeof L);
+	L.stream = stream;
+	L.sm_count = ctx->sm_count;
+	L.launch_counter = &ctx->launches;
+	L.it = it->view();
+
+	// 1. local children, merged locally; the tolerance applies to GLOBAL sums only: keep every occupied slot
+	local_table R = build_local_table(it, rule_id, ops, rule, sym, max_num_object, false, opt, -1.0, timer, step, L, &comm);
+	if (R.empty_from >= 0) {
+		finish_empty(ctx, next, step, timer, R.empty_from);
+		if (node_total_proba) *node_total_proba = 0;
+		return;
+	}
+	step("compute_collisions - prepare");
+
+	// 2. partition the locally unique children by owner
+	const uint64_t n_local = R.n_unique;
+	cm->cursors.ensure(sizeof(uint64_t) * 2 * (world + 1), stream);
+	unsigned long long *counts = cm->cursors.as<unsigned long long>(), *cursor = counts + world + 1;
+	QB_CUDA(cudaMemsetAsync(counts, 0, sizeof(uint64_t) * 2 * (world + 1), stream));
+	std::vector<uint64_t> send_counts(world, 0);
+	const int grid_local = grid_for(n_local, 256, ctx->grid_cap());
+	if (n_local > 0) {
+		owner_count_kernel<<<grid_local, 256, sizeof(unsigned int) * world, stream>>>(R.table, sym->uslot.as<uint32_t>(), n_local, world, counts);
+		++ctx->launches;
+		QB_CUDA(cudaMemcpyAsync(send_counts.data(), counts, sizeof(uint64_t) * world, cudaMemcpyDeviceToHost, stream));
+		ctx->sync();
+		std::vector<uint64_t> offsets(world, 0);
+		for (uint32_t r = 1; r < world; ++r)
+			offsets[r] = offsets[r - 1] + send_counts[r - 1];
+		QB_CUDA(cudaMemcpyAsync(cursor, offsets.data(), sizeof(uint64_t) * world, cudaMemcpyHostToDevice, stream));
+		cm->send.ensure(sizeof(exchange_record) * n_local, stream);
+		owner_scatter_kernel<<<grid_local, 256, 0, stream>>>(R.table, sym->uslot.as<uint32_t>(), n_local, world, cursor, cm->send.as<exchange_record>());
+		++ctx->launches;
+		ctx->sync(); // `offsets` lives on this stack frame
+	}
+
+	// 3. all-to-allv of the records
+	step("compute_collisions - com");
+	uint64_t n_recv = 0;
+	std::vector<uint64_t> recv_counts = comm.alltoallv(cm->send.ptr, send_counts, cm->recv, sizeof(exchange_record), n_recv);
+	std::vector<uint64_t> recv_begin(world + 1, 0);
+	for (uint32_t r = 0; r < world; ++r)
+		recv_begin[r + 1] = recv_begin[r] + recv_counts[r];
+
+	// 4. owner: merge what arrived, apply the tolerance
+	step("compute_collisions - insert");
+	table_view owner{};
+	uint64_t n_owner_unique = 0;
+	if (n_recv > 0) {
+		const uint64_t capacity = std::max<uint64_t>(1024, (uint64_t)std::ceil((double)n_recv / 0.5));
+		QB_REQUIRE(capacity + 1 <= 0xffffffffull, QB_ERR_CAPACITY, "owner table would need more than 2^32 slots");
+		cm->owner_table.ensure((capacity + 1) * sizeof(table_slot), stream);
+		QB_CUDA(cudaMemsetAsync(cm->owner_table.ptr, 0, (capacity + 1) * sizeof(table_slot), stream));
+		QB_CUDA(cudaMemsetAsync(ctx->small(DS_COUNT), 0, 4 * sizeof(uint64_t), stream));
+		owner = table_view{cm->owner_table.as<table_slot>(), capacity, reinterpret_cast<unsigned int *>(ctx->small(DS_OVERFLOW)),
+		                   reinterpret_cast<unsigned long long *>(ctx->small(DS_USED))};
+		record_insert_kernel<<<grid_for(n_recv, 256, ctx->grid_cap()), 256, 0, stream>>>(owner, cm->recv.as<exchange_record>(), n_recv);
+		++ctx->launches;
+		cm->okey.ensure(sizeof(uint64_t) * n_recv, stream);
+		cm->oslot.ensure(sizeof(uint32_t) * n_recv, stream);
+		const uint64_t tiles = div_up<uint64_t>(capacity + 1, COMPACT_TILE);
+		scan_state st = ctx->scan(tiles);
+		table_compact_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, stream>>>(owner, opt.tolerance, cm->okey.as<uint64_t>(), cm->oslot.as<uint32_t>(),
+		                                                                    reinterpret_cast<unsigned long long *>(ctx->small(DS_COUNT)), st);
+		++ctx->launches;
+		QB_CUDA(cudaGetLastError());
+		ctx->fetch_small();
+		QB_REQUIRE(ctx->h_small[DS_OVERFLOW] == 0, QB_ERR_CAPACITY, "owner table overflow");
+		n_owner_unique = ctx->h_small[DS_COUNT];
+	}
+	step("compute_collisions - finalize");
+	const uint64_t n_unique_global = comm.sum_u64(n_owner_unique);
+	sym->n_unique = n_owner_unique; // this rank's share; qb_comm_allreduce_u64 gives the total (get_total_num_object_after_interferences)
+
+	// 5. truncation: the max_num_object most probable over ALL ranks
+	step("truncate - prepare");
+	step("truncate");
+	uint64_t n_owner_survivors = n_owner_unique;
+	const uint32_t *owner_survivor_slot = cm->oslot.as<uint32_t>();
+	if (max_num_object < n_unique_global) {
+		timer.begin(QB_PHASE_TRUNCATE);
+		sym->sslot.ensure(sizeof(uint32_t) * std::max<uint64_t>(1, std::min<uint64_t>(n_owner_unique, max_num_object)), stream);
+		key_from_array keys{cm->okey.as<uint64_t>()};
+		select_threshold(ctx, &comm, keys, n_owner_unique, max_num_object);
+		n_owner_survivors = select_keep(ctx, &comm, keys, n_owner_unique, out_gather_u32{sym->sslot.as<uint32_t>(), cm->oslot.as<uint32_t>()});
+		owner_survivor_slot = sym->sslot.as<uint32_t>();
+		timer.end(QB_PHASE_TRUNCATE);
+	}
+
+	// 6. survivors go back to the rank of their representative
+	QB_CUDA(cudaMemsetAsync(counts, 0, sizeof(uint64_t) * 2 * (world + 1), stream));
+	std::vector<uint64_t> back_counts(world, 0);
+	if (n_owner_survivors > 0) {
+		// recv_begin on the device: reuse the tail of the cursor buffer after the counts are read
+		dev_buf begin_dev;
+		begin_dev.ensure(sizeof(uint64_t) * (world + 1), stream);
+		QB_CUDA(cudaMemcpyAsync(begin_dev.ptr, recv_begin.data(), sizeof(uint64_t) * (world + 1), cudaMemcpyHostToDevice, stream));
+		const int grid_back = grid_for(n_owner_survivors, 256, ctx->grid_cap());
+		return_count_kernel<<<grid_back, 256, 0, stream>>>(owner, owner_survivor_slot, n_owner_survivors, begin_dev.as<uint64_t>(), world, counts);
+		++ctx->launches;
+		QB_CUDA(cudaMemcpyAsync(back_counts.data(), counts, sizeof(uint64_t) * world, cudaMemcpyDeviceToHost, stream));
+		ctx->sync();
+		std::vector<uint64_t> offsets(world, 0);
+		for (uint32_t r = 1; r < world; ++r)
+			offsets[r] = offsets[r - 1] + back_counts[r - 1];
+		QB_CUDA(cudaMemcpyAsync(cursor, offsets.data(), sizeof(uint64_t) * world, cudaMemcpyHostToDevice, stream));
+		cm->ret_send.ensure(sizeof(survivor_record) * n_owner_survivors, stream);
+		return_scatter_kernel<<<grid_back, 256, 0, stream>>>(owner, owner_survivor_slot, n_owner_survivors, begin_dev.as<uint64_t>(), world,
+		                                                     cm->recv.as<exchange_record>(), cursor, cm->ret_send.as<survivor_record>());
+		++ctx->launches;
+		ctx->sync();
+	}
+	step("compute_collisions - com");
+	uint64_t n_survivors = 0;
+	comm.alltoallv(cm->ret_send.ptr, back_counts, cm->ret_recv, sizeof(survivor_record), n_survivors);
+
+	// 7. every rank rebuilds the survivors whose representative it generated, then global normalisation
+	survivor_source src;
+	src.records = cm->ret_recv.as<survivor_record>();
+	finalize_and_normalize(it, ops, rule, next, sym, opt, R, src, n_survivors, timer, step, L, &comm, node_total_proba);
 }
 
 } // namespace
@@ -906,5 +1161,86 @@ int qb_hash_objects(const qb_iter *it, int rule_id, const double *params, uint32
 	});
 }
 
-// ---- distributed path: see dist.cu ---------------------------------------------------------------------
+// ---- distributed path (dist.inc.cuh) -------------------------------------------------------------------
+int qb_comm_unique_id(uint8_t id[128]) {
+	return guarded([&] {
+		QB_REQUIRE(id, QB_ERR_ARG, "null id");
+		QB_REQUIRE(nccl().ok, QB_ERR_COMM, "NCCL is not usable: " + nccl().why);
+		static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+		ncclUniqueId uid;
+		QB_NCCL(nccl().GetUniqueId(&uid));
+		memcpy(id, &uid, 128);
+	});
+}
+
+int qb_comm_create(qb_ctx *ctx, int world_size, int rank, const uint8_t id[128], qb_comm **out) {
+	return guarded([&] {
+		QB_REQUIRE(ctx && id && out && world_size >= 1 && rank >= 0 && rank < world_size, QB_ERR_ARG, "qb_comm_create: bad argument");
+		QB_REQUIRE(nccl().ok, QB_ERR_COMM, "NCCL is not usable: " + nccl().why);
+		ctx->use();
+		ncclUniqueId uid;
+		memcpy(&uid, id, 128);
+		qb_comm *c = new qb_comm();
+		c->ctx = ctx;
+		c->world = world_size;
+		c->rank = rank;
+		QB_NCCL(nccl().CommInitRank(&c->nccl, world_size, uid, rank));
+		*out = c;
+	});
+}
+
+int qb_comm_destroy(qb_comm *comm) {
+	return guarded([&] {
+		if (!comm) return;
+		comm->ctx->use();
+		comm->ctx->sync();
+		if (comm->nccl) nccl().CommDestroy(comm->nccl);
+		delete comm;
+	});
+}
+
+int qb_simulate_dist(qb_iter *it, int rule_id, const double *params, uint32_t num_params, qb_iter *next, qb_sym *sym, qb_comm *comm,
+                     uint64_t max_num_object, const qb_options *opt_in, qb_step_cb cb, void *user, double *node_total_proba) {
+	return guarded([&] {
+		QB_REQUIRE(it && next && sym && comm, QB_ERR_ARG, "qb_simulate_dist: null handle");
+		const rule_ops *ops = find_rule(rule_id);
+		QB_REQUIRE(ops, QB_ERR_UNKNOWN_RULE, "unknown rule id");
+		alignas(16) unsigned char storage[RULE_STORAGE_BYTES];
+		int rc = ops->make(params, num_params, storage);
+		QB_REQUIRE(rc == QB_OK, rc, std::string("bad parameters for rule ") + ops->name);
+		qb_options opt;
+		resolve_options(opt_in, opt);
+		if (comm->world == 1) { // quids_mpi.hpp:439-440
+			simulate(it, rule_id, ops, storage, next, sym, max_num_object, opt, cb, user);
+			if (node_total_proba) *node_total_proba = 1;
+			return;
+		}
+		simulate_dist(it, rule_id, ops, storage, next, sym, comm, max_num_object, opt, cb, user, node_total_proba);
+	});
+}
+
+int qb_comm_allreduce_u64(qb_comm *comm, uint64_t *values, uint32_t n, int op_max) {
+	return guarded([&] {
+		QB_REQUIRE(comm && values, QB_ERR_ARG, "null argument");
+		comm->ctx->use();
+		comm_ops ops{comm};
+		std::vector<uint64_t> all = ops.allgather_u64(values, n);
+		for (uint32_t i = 0; i < n; ++i) {
+			uint64_t acc = 0;
+			for (int r = 0; r < comm->world; ++r)
+				acc = op_max ? std::max(acc, all[(size_t)r * n + i]) : acc + all[(size_t)r * n + i];
+			values[i] = acc;
+		}
+	});
+}
+
+int qb_comm_allreduce_f64(qb_comm *comm, double *values, uint32_t n) {
+	return guarded([&] {
+		QB_REQUIRE(comm && values, QB_ERR_ARG, "null argument");
+		comm->ctx->use();
+		comm_ops ops{comm};
+		for (uint32_t i = 0; i < n; ++i)
+			values[i] = ops.sum_f64(values[i]);
+	});
+}
 }

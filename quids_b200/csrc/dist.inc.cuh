@@ -1,0 +1,223 @@
+// dist.inc.cuh -- the distributed path: quids::mpi::simulate (quids_mpi.hpp:423-598) over NCCL.
+// Textually included by capi.cu (it needs the handle structs and the pipeline stages defined there).
+//
+// The reference ships EVERY child's (hash, magnitude) to the rank that owns the hash
+// (MPI_Alltoallv x2, quids_mpi.hpp:741-743), merges there, and ships a magnitude back per child
+// (:842).  Here every GPU first merges its own children in its local interference table (the very
+// kernel of the single-GPU path), so only the locally unique (hash, magnitude, representative)
+// records cross NVLink -- for the workloads of BASELINE.json that is 1-10 % of the children -- and
+// only the SURVIVORS come back.  Steps (one process per GPU):
+//   1. local table                       build_local_table(), tolerance not applied yet
+//   2. owner(hash) = mulhi(mix64(hash), world); records partitioned by owner on the device
+//   3. counts: ncclAllGather;  records: grouped ncclSend/ncclRecv  (all-to-allv)
+//   4. owner: second interference table over the received records, tolerance, global N_u
+//   5. truncation: radix select with ncclAllReduce of every digit histogram = the GLOBAL top-k
+//      (the reference keeps max_num_object / local_size per rank, quids_mpi.hpp:537,590, which is
+//      not the single-node result; north_star asks for the latter)
+//   6. survivors go back to the rank of their representative (grouped send/recv), which rebuilds
+//      them next to their parents (finalisation of the single-GPU path)
+//   7. normalisation with the all-reduced total (quids_mpi.hpp:870-895)
+// NCCL is loaded with dlopen the first time a communicator is created: libquids_b200.so itself has
+// no NCCL dependency, and inside a PyTorch process the already-loaded libnccl.so.2 is reused.
+#pragma once
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+struct nccl_api {
+	ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+	ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+	ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*GroupStart)() = nullptr;
+	ncclResult_t (*GroupEnd)() = nullptr;
+	const char *(*GetErrorString)(ncclResult_t) = nullptr;
+	bool ok = false;
+	std::string why;
+};
+
+static nccl_api &nccl() {
+	static nccl_api api = [] {
+		nccl_api a;
+		void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+		if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+		if (!h) {
+			a.why = std::string("cannot load libnccl.so.2: ") + dlerror();
+			return a;
+		}
+		auto sym = [&](const char *name) {
+			void *p = dlsym(h, name);
+			if (!p) a.why += std::string(" missing ") + name;
+			return p;
+		};
+		a.GetUniqueId = (decltype(a.GetUniqueId))sym("ncclGetUniqueId");
+		a.CommInitRank = (decltype(a.CommInitRank))sym("ncclCommInitRank");
+		a.CommDestroy = (decltype(a.CommDestroy))sym("ncclCommDestroy");
+		a.AllReduce = (decltype(a.AllReduce))sym("ncclAllReduce");
+		a.AllGather = (decltype(a.AllGather))sym("ncclAllGather");
+		a.Send = (decltype(a.Send))sym("ncclSend");
+		a.Recv = (decltype(a.Recv))sym("ncclRecv");
+		a.GroupStart = (decltype(a.GroupStart))sym("ncclGroupStart");
+		a.GroupEnd = (decltype(a.GroupEnd))sym("ncclGroupEnd");
+		a.GetErrorString = (decltype(a.GetErrorString))sym("ncclGetErrorString");
+		a.ok = a.why.empty();
+		return a;
+	}();
+	return api;
+}
+
+#define QB_NCCL(call)                                                                                                              \
+	do {                                                                                                                           \
+		ncclResult_t qb_nccl_ = (call);                                                                                            \
+		if (qb_nccl_ != ncclSuccess)                                                                                               \
+			throw ::qb::error(QB_ERR_COMM, std::string(#call) + ": " + nccl().GetErrorString(qb_nccl_) + " (" + __FILE__ + ":" + \
+			                                   std::to_string(__LINE__) + ")");                                                   \
+	} while (0)
+
+struct qb_comm {
+	qb_ctx *ctx = nullptr;
+	int world = 1, rank = 0;
+	ncclComm_t nccl = nullptr;
+	dev_buf scratch; // small device staging for host-value collectives
+	dev_buf send, recv, owner_table, okey, oslot, ret_send, ret_recv, cursors;
+};
+
+namespace {
+
+struct comm_ops {
+	qb_comm *c;
+	qb_ctx *ctx() const { return c->ctx; }
+	int world() const { return c->world; }
+	int rank() const { return c->rank; }
+
+	void allreduce_u64_device(void *ptr, size_t n, bool max = false) {
+		QB_NCCL(nccl().AllReduce(ptr, ptr, n, ncclUint64, max ? ncclMax : ncclSum, c->nccl, c->ctx->stream));
+	}
+	std::vector<uint64_t> allgather_u64(const uint64_t *values, size_t n) { // n values per rank -> world * n
+		c->scratch.ensure(sizeof(uint64_t) * n * (c->world + 1), c->ctx->stream);
+		uint64_t *mine = c->scratch.as<uint64_t>(), *all = mine + n;
+		QB_CUDA(cudaMemcpyAsync(mine, values, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, c->ctx->stream));
+		QB_NCCL(nccl().AllGather(mine, all, n, ncclUint64, c->nccl, c->ctx->stream));
+		std::vector<uint64_t> out(n * c->world);
+		QB_CUDA(cudaMemcpyAsync(out.data(), all, sizeof(uint64_t) * out.size(), cudaMemcpyDeviceToHost, c->ctx->stream));
+		c->ctx->sync();
+		return out;
+	}
+	uint64_t sum_u64(uint64_t v) {
+		uint64_t total = 0;
+		for (uint64_t x : allgather_u64(&v, 1))
+			total += x;
+		return total;
+	}
+	double sum_f64(double v) { // summed in rank order on every rank: the same bits everywhere
+		uint64_t bits;
+		memcpy(&bits, &v, 8);
+		double total = 0;
+		for (uint64_t x : allgather_u64(&bits, 1)) {
+			double d;
+			memcpy(&d, &x, 8);
+			total += d;
+		}
+		return total;
+	}
+	// all-to-allv of fixed-size records: send_counts[r] records go to rank r (contiguous, rank order)
+	std::vector<uint64_t> alltoallv(const void *send, const std::vector<uint64_t> &send_counts, dev_buf &recv, size_t record_bytes, uint64_t &n_recv) {
+		std::vector<uint64_t> matrix = allgather_u64(send_counts.data(), c->world); // matrix[src * world + dst]
+		std::vector<uint64_t> recv_counts(c->world);
+		n_recv = 0;
+		for (int src = 0; src < c->world; ++src) {
+			recv_counts[src] = matrix[(size_t)src * c->world + c->rank];
+			n_recv += recv_counts[src];
+		}
+		recv.ensure(record_bytes * std::max<uint64_t>(1, n_recv), c->ctx->stream);
+		QB_NCCL(nccl().GroupStart());
+		uint64_t send_off = 0, recv_off = 0;
+		for (int r = 0; r < c->world; ++r) {
+			if (send_counts[r])
+				QB_NCCL(nccl().Send((const char *)send + send_off * record_bytes, send_counts[r] * record_bytes, ncclUint8, r, c->nccl, c->ctx->stream));
+			if (recv_counts[r])
+				QB_NCCL(nccl().Recv(recv.as<char>() + recv_off * record_bytes, recv_counts[r] * record_bytes, ncclUint8, r, c->nccl, c->ctx->stream));
+			send_off += send_counts[r];
+			recv_off += recv_counts[r];
+		}
+		QB_NCCL(nccl().GroupEnd());
+		return recv_counts;
+	}
+};
+
+// ---- records that cross NVLink ---------------------------------------------------------------------------
+struct __align__(32) exchange_record { // a locally unique child, on its way to the owner of its hash
+	unsigned long long hash;
+	double re, im;
+	unsigned long long rep; // representative in the symbolic order of the SENDING rank
+};
+
+__device__ __forceinline__ uint32_t owner_of(uint64_t hash, uint32_t world) { return (uint32_t)__umul64hi(mix64(hash ^ 0x9e3779b97f4a7c15ull), (uint64_t)world); }
+
+// counts[owner] over the locally unique children
+__global__ void __launch_bounds__(256) owner_count_kernel(table_view t, const uint32_t *uslot, uint64_t n, uint32_t world, unsigned long long *counts) {
+	extern __shared__ unsigned int s_counts[];
+	for (uint32_t i = threadIdx.x; i < world; i += blockDim.x)
+		s_counts[i] = 0;
+	__syncthreads();
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+		atomicAdd(&s_counts[owner_of(t.slots[uslot[i]].key, world)], 1u);
+	__syncthreads();
+	for (uint32_t i = threadIdx.x; i < world; i += blockDim.x)
+		if (s_counts[i])
+			atomicAdd(&counts[i], (unsigned long long)s_counts[i]);
+}
+
+// records grouped by owner: cursor[owner] starts at the owner's offset
+__global__ void __launch_bounds__(256) owner_scatter_kernel(table_view t, const uint32_t *uslot, uint64_t n, uint32_t world, unsigned long long *cursor,
+                                                            exchange_record *out) {
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+		const table_slot s = t.slots[uslot[i]];
+		const unsigned long long at = atomicAdd(&cursor[owner_of(s.key, world)], 1ull);
+		out[at] = exchange_record{s.key, s.re, s.im, s.rep};
+	}
+}
+
+// owner side: merge the received records; the representative of a slot is the POSITION of the record
+// that created it (its sender and its original representative are looked up there later)
+__global__ void __launch_bounds__(256) record_insert_kernel(table_view t, const exchange_record *records, uint64_t n) {
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	unsigned int created = 0;
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+		const exchange_record r = records[i];
+		created += table_insert(t, r.hash, cplx{r.re, r.im}, rep_pack(i, 0));
+	}
+	created = (unsigned int)warp_sum((uint64_t)created);
+	if (lane_id() == 0 && created)
+		atomicAdd(t.used, (unsigned long long)created);
+}
+
+// survivors (owner slots) -> which rank their representative came from; counts per rank
+__global__ void __launch_bounds__(256) return_count_kernel(table_view t, const uint32_t *slot, uint64_t n, const uint64_t *recv_begin, uint32_t world,
+                                                           unsigned long long *counts) {
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+		const uint64_t position = rep_index(t.slots[slot[i]].rep);
+		const uint32_t src = (uint32_t)upper_bound_u64(recv_begin, world + 1, position) - 1;
+		atomicAdd(&counts[src], 1ull);
+	}
+}
+
+__global__ void __launch_bounds__(256) return_scatter_kernel(table_view t, const uint32_t *slot, uint64_t n, const uint64_t *recv_begin, uint32_t world,
+                                                             const exchange_record *received, unsigned long long *cursor, survivor_record *out) {
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+		const table_slot s = t.slots[slot[i]];
+		const uint64_t position = rep_index(s.rep);
+		const uint32_t src = (uint32_t)upper_bound_u64(recv_begin, world + 1, position) - 1;
+		const unsigned long long at = atomicAdd(&cursor[src], 1ull);
+		out[at] = survivor_record{received[position].rep, s.re, s.im};
+	}
+}
+
+} // namespace

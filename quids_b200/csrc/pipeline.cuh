@@ -143,6 +143,80 @@ __global__ void __launch_bounds__(SCAN_THREADS) finalize_meta_kernel(finalize_ar
 	}
 }
 
+// distributed path: a survivor as it comes back from the rank that owns its hash
+struct __align__(8) survivor_record {
+	unsigned long long rep; // (child index + 1) << 24 | size, in the symbolic order of the receiving rank
+	double re, im;          // merged magnitude
+};
+
+struct finalize_record_args {
+	const survivor_record *records;
+	uint64_t n_survivors;
+	const uint64_t *child_begin;
+	const uint64_t *kept;
+	uint64_t n_parents;
+	uint32_t align;
+	uint32_t *next_size;
+	uint32_t *next_padded;
+	cplx *next_mag;
+	uint64_t *survivor_parent;
+	uint32_t *survivor_child;
+	double *partial_norm;
+};
+
+__global__ void __launch_bounds__(SCAN_THREADS) finalize_meta_records_kernel(finalize_record_args a) {
+	__shared__ double s_part[SCAN_WARPS];
+	double local = 0;
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < a.n_survivors; s += stride) {
+		const survivor_record r = a.records[s];
+		const cplx mag{r.re, r.im};
+		const uint64_t index = rep_index(r.rep);
+		const uint32_t size = rep_size(r.rep);
+		const uint64_t p = upper_bound_u64(a.child_begin, a.n_parents + 1, index) - 1;
+		a.survivor_parent[s] = a.kept ? a.kept[p] : p;
+		a.survivor_child[s] = (uint32_t)(index - a.child_begin[p]);
+		a.next_size[s] = size;
+		a.next_padded[s] = padded_size(size, a.align);
+		a.next_mag[s] = mag;
+		local += cnorm(mag);
+	}
+	local = warp_sum(local);
+	if (lane_id() == 0)
+		s_part[threadIdx.x >> 5] = local;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		double sum = 0;
+		for (int w = 0; w < SCAN_WARPS; ++w)
+			sum += s_part[w];
+		a.partial_norm[blockIdx.x] = sum;
+	}
+}
+
+// number of keys above / equal to the threshold of a finished select (distributed tie sharing)
+template <class KeyFn>
+__global__ void __launch_bounds__(256) select_count_kernel(KeyFn key_of, uint64_t n, const select_state *sel, unsigned long long *gt_eq) {
+	const uint64_t threshold = sel->prefix;
+	unsigned long long gt = 0, eq = 0;
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+		const uint64_t key = key_of(i);
+		gt += key > threshold;
+		eq += key == threshold;
+	}
+	gt = warp_sum((uint64_t)gt);
+	eq = warp_sum((uint64_t)eq);
+	if (lane_id() == 0) {
+		if (gt) atomicAdd(&gt_eq[0], gt);
+		if (eq) atomicAdd(&gt_eq[1], eq);
+	}
+}
+
+__global__ void select_patch_kernel(select_state *sel, uint64_t need, uint64_t count_gt) {
+	sel->k = need;
+	sel->count_gt = count_gt;
+}
+
 // sum |mag|^2 of a state (normalize() on its own, quids.hpp:1004-1006)
 __global__ void __launch_bounds__(SCAN_THREADS) norm_partial_kernel(const cplx *mag, uint64_t n, double *partial) {
 	__shared__ double s_part[SCAN_WARPS];
