@@ -1,0 +1,91 @@
+"""world_size-2 gloo test of the distributed protocol (CPU, no GPU): tests/dist_model.py mirrors the
+host-side logic of qb_simulate_dist; its union over the ranks must equal the single-process checker
+on the gathered state, truncation ties included."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import dist_model  # noqa: E402
+import orc  # noqa: E402
+
+
+def test_owner_function_is_balanced_and_total():
+    rng = np.random.default_rng(0)
+    hashes = rng.integers(0, 2**63, size=20000, dtype=np.int64).astype(np.uint64)
+    for world in (2, 3, 8):
+        owners = np.array([dist_model.owner_of(int(h), world) for h in hashes])
+        assert owners.min() == 0 and owners.max() == world - 1
+        counts = np.bincount(owners, minlength=world)
+        assert counts.max() < 1.1 * len(hashes) / world
+
+
+def test_tie_sharing_serves_lower_ranks_first():
+    assert [dist_model.share_ties(5, [2, 2, 4], r) for r in range(3)] == [2, 2, 1]
+    assert [dist_model.share_ties(0, [2, 2, 4], r) for r in range(3)] == [0, 0, 0]
+    assert sum(dist_model.share_ties(7, [3, 0, 9, 1], r) for r in range(4)) == 7
+
+
+def _worker(rank, world, port_number, results):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port_number))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    port = orc.Oracle(orc.PORT_SO)
+    rng = np.random.default_rng(7)
+    base = port.qcgd_random_state(7, 120, 4)
+    mags = rng.normal(size=(120, 2))
+    distinct = orc.Packed(base.sizes, mags / np.sqrt((mags ** 2).sum()), base.data)
+    tied = port.qcgd_random_state(6, 90, 9)
+    failures = []
+    cases = [(distinct, orc.RULE_ERASE_CREATE, orc.NO_TRUNCATION), (distinct, orc.RULE_SPLIT_MERGE, orc.NO_TRUNCATION), (distinct, orc.RULE_COIN, 300),
+             (distinct, orc.RULE_ERASE_CREATE, 50), (tied, orc.RULE_ERASE_CREATE, 211)]
+    for state, rid, k in cases:
+        params, tol = [0.37, 0.21, -0.4], 1e-18
+        objs = state.objects()
+        idx = [i for i in range(state.n) if i % world == rank]
+        mine = orc.Packed.from_objects([objs[i] for i in idx], state.cmags[idx])
+        nxt, nc, nu = dist_model.model_simulate(port, mine, None, rid, params, k, tol)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (nxt.sizes, nxt.mags, nxt.data, nxt.total_proba))
+        if rank == 0:
+            got = orc.Packed(np.concatenate([g[0] for g in gathered]), np.concatenate([g[1] for g in gathered]), np.concatenate([g[2] for g in gathered]),
+                             gathered[0][3])
+            want, wc, wu = port.simulate(state, rid, params, k, tol)
+            try:
+                assert (nc, nu) == (wc, wu), ((nc, nu), (wc, wu))
+                hg, hw = port.hash_objects(got, rid), port.hash_objects(want, rid)
+                if k >= wu:
+                    orc.assert_same_state(got, hg, want, hw, True, what=f"rule {rid} k {k}")
+                else:
+                    src = state
+                    if k < state.n:
+                        order = np.sort(np.argsort(-(np.abs(state.cmags) ** 2), kind="stable")[:k])
+                        src = orc.Packed.from_objects([objs[j] for j in order], state.cmags[order])
+                    full, _, _ = port.simulate(src, rid, params, orc.NO_TRUNCATION, tol)
+                    if state is tied:  # everything is tied: only the count and membership are defined
+                        assert got.n == k and set(hg.tolist()) <= set(port.hash_objects(full, rid).tolist())
+                    else:
+                        orc.assert_same_truncated(got, hg, want, hw, full, port.hash_objects(full, rid), k, True, what=f"rule {rid} k {k}")
+            except AssertionError as e:  # report through the queue: an exception here would hang the other rank
+                failures.append(f"rule {rid} k {k}: {e}")
+    if rank == 0:
+        results.put(failures)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_protocol_matches_single_process(port):
+    ctx = mp.get_context("spawn")
+    results = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, 29533, results)) for r in range(2)]
+    for p in procs:
+        p.start()
+    failures = results.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+    assert not failures, failures
+    assert all(p.exitcode == 0 for p in procs)
