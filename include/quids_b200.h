@@ -59,7 +59,8 @@ typedef struct qb_options {
 	double table_load;         /* engine knob: max load factor of the interference table, 0 = default */
 	int32_t profile;           /* 1: record CUDA events at the phase boundaries (qb_sym_phase_ms)     */
 	float safety_margin;       /* quids::safety_margin (quids.hpp:64): fraction of GPU memory the automatic budget leaves free */
-	int32_t locality_sort;     /* engine knob: order parents by the rule's locality key; 0 off (default), 1 when there are >= 2^17 parents, 2 always */
+	int32_t locality_sort;     /* engine knob: process the child groups in the order of the rule's group key so that equal
+	                              objects are merged on chip before the table; 0 off, 1 when there are >= 2^16 groups (default), 2 always */
 } qb_options;
 
 void qb_options_default(qb_options *opt);
@@ -111,7 +112,7 @@ int qb_sym_counts(const qb_sym *sym, uint64_t *num_object, uint64_t *num_object_
 /* per-phase device times of the last qb_simulate (needs options.profile = 1) */
 enum {
 	QB_PHASE_NUM_CHILD = 0, /* get_num_child kernel + scan           quids.hpp:548-569        */
-	QB_PHASE_PRE_TRUNCATE,  /* parent top-k (+ locality ordering)    quids.hpp:613-642        */
+	QB_PHASE_PRE_TRUNCATE,  /* parent top-k (+ ordering of groups)   quids.hpp:613-642        */
 	QB_PHASE_TABLE_CLEAR,   /* interference table reset                                       */
 	QB_PHASE_SYMBOLIC,      /* children -> (hash, mag) -> table      quids.hpp:647-721,785-809 */
 	QB_PHASE_COMPACT,       /* tolerance filter + compaction         quids.hpp:819-823        */

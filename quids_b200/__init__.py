@@ -136,7 +136,7 @@ class _Globals:
     safety_margin = 0.2        # quids::safety_margin
     table_load = 0.0           # engine knob (0 = default)
     profile = False
-    locality_sort = 0          # engine knob: 0 off, 1 auto, 2 always
+    locality_sort = 1          # engine knob: 0 off, 1 auto, 2 always
 
     def options(self):
         o = qb_options()

@@ -99,7 +99,7 @@ struct qb_iter {
 	qb_ctx *ctx;
 	uint64_t n = 0, n_bytes = 0;
 	double total_proba = 1; // quids.hpp:154
-	dev_buf objects, begin, size, mag, num_childs, child_begin, num_groups, group_begin, locality;
+	dev_buf objects, begin, size, mag, num_childs, child_begin, num_groups, group_begin;
 
 	iter_view view() const { return iter_view{objects.as<uint8_t>(), begin.as<uint64_t>(), size.as<uint32_t>(), mag.as<cplx>(), n}; }
 };
@@ -279,28 +279,15 @@ struct widen_u32 {
 	__device__ uint64_t operator()(uint64_t j) const { return v[j]; }
 };
 
-// keys[j] = locality[kept ? kept[j] : j], vals[j] = that object id
-__global__ void __launch_bounds__(256) sort_init_kernel(const uint32_t *locality, const uint64_t *kept, uint64_t n, uint32_t *keys, uint64_t *vals) {
-	const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (j < n) {
-		const uint64_t oid = kept ? kept[j] : j;
-		keys[j] = locality[oid];
-		vals[j] = oid;
-	}
-}
-
-// orders the kept parents by locality key; returns the sorted object ids (device)
-const uint64_t *sort_parents_by_locality(qb_ctx *ctx, qb_sym *sym, const uint32_t *locality, const uint64_t *kept, uint64_t n) {
+// stable radix sort of n (u32 key, u64 value) pairs that sit in the first halves of sym->sort_keys /
+// sort_vals (each sized for 2 n); returns the sorted values (device)
+const uint64_t *sort_items(qb_ctx *ctx, qb_sym *sym, uint64_t n) {
 	cudaStream_t stream = ctx->stream;
 	const uint64_t tiles = div_up<uint64_t>(n, SORT_TILE);
-	sym->sort_keys.ensure(2 * sizeof(uint32_t) * n, stream);
-	sym->sort_vals.ensure(2 * sizeof(uint64_t) * n, stream);
 	sym->sort_hist.ensure(sizeof(uint32_t) * SORT_BINS * tiles, stream);
 	sym->sort_base.ensure(sizeof(uint64_t) * (SORT_BINS * tiles + 1), stream);
 	uint32_t *keys[2] = {sym->sort_keys.as<uint32_t>(), sym->sort_keys.as<uint32_t>() + n};
 	uint64_t *vals[2] = {sym->sort_vals.as<uint64_t>(), sym->sort_vals.as<uint64_t>() + n};
-	sort_init_kernel<<<(unsigned)div_up<uint64_t>(n, 256), 256, 0, stream>>>(locality, kept, n, keys[0], vals[0]);
-	++ctx->launches;
 	int src = 0;
 	for (int shift = 0; shift < 32; shift += 8, src ^= 1) {
 		radix_histogram_kernel<<<(unsigned)tiles, SORT_THREADS, 0, stream>>>(keys[src], n, shift, sym->sort_hist.as<uint32_t>(), tiles);
@@ -375,7 +362,6 @@ local_table build_local_table(qb_iter *it, int rule_id, const rule_ops *ops, con
 		return R;
 	}
 	QB_CUDA(cudaMemsetAsync(ctx->d_small.ptr, 0, DS_WORDS * sizeof(uint64_t), stream));
-	bool order_parents = false;
 	if (it->n > 0) {
 		timer.begin(QB_PHASE_NUM_CHILD);
 		it->num_childs.ensure(sizeof(uint32_t) * it->n, stream);
@@ -383,12 +369,6 @@ local_table build_local_table(qb_iter *it, int rule_id, const rule_ops *ops, con
 		if (ops->warp_groups) {
 			it->num_groups.ensure(sizeof(uint32_t) * it->n, stream);
 			L.num_groups = it->num_groups.as<uint32_t>();
-		}
-		// ordering the parents only pays when the table cannot stay in L2 anyway
-		order_parents = ops->has_locality_key && opt.locality_sort != 0 && it->n >= (opt.locality_sort > 1 ? 2u : 1u << 17);
-		if (order_parents) {
-			it->locality.ensure(sizeof(uint32_t) * it->n, stream);
-			L.locality = it->locality.as<uint32_t>();
 		}
 		L.max_child_size = reinterpret_cast<unsigned int *>(ctx->small(DS_MAX_CHILD_SIZE));
 		ops->launch_num_child(rule, L);
@@ -409,12 +389,6 @@ local_table build_local_table(qb_iter *it, int rule_id, const rule_ops *ops, con
 		R.kept = sym->kept.as<uint64_t>();
 		timer.end(QB_PHASE_PRE_TRUNCATE);
 	}
-	if (order_parents && R.n_parents > 0) {
-		timer.begin(QB_PHASE_PRE_TRUNCATE);
-		R.kept = sort_parents_by_locality(ctx, sym, it->locality.as<uint32_t>(), R.kept, R.n_parents);
-		timer.end(QB_PHASE_PRE_TRUNCATE);
-	}
-
 	// ---- 3. child index ranges (quids.hpp:666-671: a serial loop in the reference) --------------------
 	step("prepare_index");
 	uint64_t n_groups = 0;
@@ -488,6 +462,20 @@ local_table build_local_table(qb_iter *it, int rule_id, const rule_ops *ops, con
 		sym->scratch.ensure((size_t)ops->symbolic_grid(ctx->sm_count) * SYMBOLIC_THREADS * L.scratch_stride, stream);
 		L.scratch = sym->scratch.as<uint8_t>();
 	}
+	// sorted order: all groups that produce the same objects become consecutive work items, so that the
+	// rule can merge them in shared memory before the table sees them (rule_api.cuh, has_group_key)
+	const bool sorted_order = ops->has_group_key && opt.locality_sort != 0 && (opt.locality_sort > 1 || n_groups >= (1u << 16)) &&
+	                          R.n_parents < (1ull << (64 - ITEM_GROUP_BITS));
+	if (sorted_order) {
+		timer.begin(QB_PHASE_PRE_TRUNCATE);
+		sym->sort_keys.ensure(2 * sizeof(uint32_t) * n_groups, stream);
+		sym->sort_vals.ensure(2 * sizeof(uint64_t) * n_groups, stream);
+		L.item_keys = sym->sort_keys.as<uint32_t>();
+		L.item_vals = sym->sort_vals.as<uint64_t>();
+		ops->launch_group_items(rule, L);
+		L.items = sort_items(ctx, sym, n_groups);
+		timer.end(QB_PHASE_PRE_TRUNCATE);
+	}
 	for (sym->table_attempts = 1;; ++sym->table_attempts) {
 		QB_REQUIRE(capacity + 1 <= 0xffffffffull, QB_ERR_CAPACITY, "interference table would need more than 2^32 slots");
 		timer.begin(QB_PHASE_TABLE_CLEAR);
@@ -502,7 +490,10 @@ local_table build_local_table(qb_iter *it, int rule_id, const rule_ops *ops, con
 		// children -> (hash, magnitude) -> table (quids.hpp:705-719 fused with :785-809)
 		timer.begin(QB_PHASE_SYMBOLIC);
 		L.table = R.table;
-		ops->launch_symbolic(rule, L);
+		if (sorted_order)
+			ops->launch_symbolic_items(rule, L);
+		else
+			ops->launch_symbolic(rule, L);
 		QB_CUDA(cudaGetLastError());
 		timer.end(QB_PHASE_SYMBOLIC);
 
@@ -858,7 +849,7 @@ void qb_options_default(qb_options *opt) {
 	opt->simple_truncation = 1;
 	opt->table_load = 0;
 	opt->profile = 0;
-	opt->locality_sort = 0;
+	opt->locality_sort = 1;
 	opt->safety_margin = 0.2f; // SAFETY_MARGIN, quids.hpp:33-35
 }
 

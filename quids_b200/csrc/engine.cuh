@@ -26,7 +26,6 @@ struct engine_launch {
 	// num_child
 	uint32_t *num_childs;
 	uint32_t *num_groups; // only for rules with warp_groups
-	uint32_t *locality;   // only for rules with has_locality_key
 	unsigned int *max_child_size;
 
 	// symbolic
@@ -34,6 +33,9 @@ struct engine_launch {
 	const uint64_t *kept;        // object ids of the kept parents, or nullptr = all parents in order
 	const uint64_t *group_begin; // same over the group counts (== child_begin for rules without groups)
 	const uint64_t *chunk_parent; // parent holding the first group of every chunk of the symbolic kernel (+ one sentinel)
+	uint32_t *item_keys;          // sorted order: key and (parent position << 24 | group) of every group
+	uint64_t *item_vals;
+	const uint64_t *items;        // item_vals after the sort
 	uint64_t n_parents;
 	uint64_t n_children;
 	uint64_t n_groups;
@@ -66,7 +68,7 @@ inline int resident_grid(const void *kernel, int threads, int sm_count) {
 
 template <class Rule>
 __global__ void __launch_bounds__(ENGINE_THREADS) num_child_kernel(const Rule rule, iter_view it, uint32_t *num_childs, uint32_t *num_groups,
-                                                                 uint32_t *locality, unsigned int *max_child_size) {
+                                                                 unsigned int *max_child_size) {
 	__shared__ unsigned int s_max;
 	if (threadIdx.x == 0)
 		s_max = 0;
@@ -81,8 +83,6 @@ __global__ void __launch_bounds__(ENGINE_THREADS) num_child_kernel(const Rule ru
 		num_childs[i] = count;
 		if (Rule::warp_groups)
 			num_groups[i] = rule.get_num_group(parent, size, count);
-		if (Rule::has_locality_key && locality)
-			locality[i] = rule.locality_key(parent, size);
 		local_max = max(local_max, bound);
 	}
 	atomicMax(&s_max, local_max);
@@ -99,6 +99,12 @@ struct table_emitter {
 	__device__ table_emitter(const table_view &t, uint64_t first) : table(t), first_child(first) {}
 	__device__ void operator()(uint32_t child_id, uint64_t hash, uint32_t size, cplx mag) {
 		created += table_insert(table, hash, mag, rep_pack(first_child + child_id, size));
+	}
+	__device__ uint64_t rep(uint32_t child_id, uint32_t size) const { return rep_pack(first_child + child_id, size); }
+	// objects whose representative is already known (a rule flushing what it accumulated)
+	template <int N, class MagOf, class RepOf>
+	__device__ void batch_raw(int count, const uint64_t (&hash)[N], MagOf mag_of, RepOf rep_of) {
+		created += table_insert_batch<N>(table, count, hash, mag_of, rep_of);
 	}
 	// batch<N>(count, hash[N], size, child_id_of(i), mag_of(i)): up to N children of the same size at once
 	template <int N, class ChildOf, class MagOf>
@@ -183,7 +189,7 @@ __global__ void __launch_bounds__(SYMBOLIC_THREADS, 5) symbolic_kernel(const Rul
 					while (s.group_begin[j + 1] <= c)
 						++j;
 					table_emitter emit(L.table, s.child_begin[j]);
-					rule.symbolic_warp(L.it.objects + s.object[j], s.size[j], s.ctx[j], (uint32_t)(c - s.group_begin[j]), s.group_ctx[c - lo],
+					rule.template symbolic_warp<false>(L.it.objects + s.object[j], s.size[j], s.ctx[j], (uint32_t)(c - s.group_begin[j]), s.group_ctx[c - lo],
 					                   s_workspace[threadIdx.x >> 5], emit);
 					created += emit.created;
 				}
@@ -202,6 +208,86 @@ __global__ void __launch_bounds__(SYMBOLIC_THREADS, 5) symbolic_kernel(const Rul
 		}
 	}
 	// slots created -> one global atomic per warp (sizes the next call's table)
+	created = (uint32_t)warp_sum((uint64_t)created);
+	if (lane == 0 && created)
+		atomicAdd(L.table.used, (unsigned long long)created);
+}
+
+// ---- sorted order: work items = (parent, group), ordered by the rule's group key -------------------------
+constexpr int ITEM_GROUP_BITS = 24;
+constexpr int ITEM_CHUNK = 128; // items one warp takes at a time
+
+// one thread per kept parent writes the keys and values of its groups
+template <class Rule>
+__global__ void __launch_bounds__(ENGINE_THREADS) group_items_kernel(const Rule rule, const engine_launch L) {
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < L.n_parents; p += stride) {
+		const uint64_t first = L.group_begin[p];
+		const uint32_t count = (uint32_t)(L.group_begin[p + 1] - first);
+		if (count == 0)
+			continue;
+		const uint64_t oid = L.kept ? L.kept[p] : p;
+		rule.group_keys(L.it.objects + L.it.begin[oid], L.it.size[oid], count, L.item_keys + first);
+		for (uint32_t g = 0; g < count; ++g)
+			L.item_vals[first + g] = (p << ITEM_GROUP_BITS) | g;
+	}
+}
+
+// every warp takes ITEM_CHUNK consecutive items of the sorted order; one lane per item prepares its
+// parent's context and the group's root, then all lanes produce one group after the other with
+// ACCUMULATE = true; what the rule still holds at the end of the chunk is flushed
+template <class Rule>
+__global__ void __launch_bounds__(SYMBOLIC_THREADS, 5) symbolic_items_kernel(const Rule rule, const engine_launch L) {
+	typedef typename Rule::ctx_t ctx_t;
+	struct warp_slice {
+		ctx_t ctx[32];
+		typename Rule::group_ctx_t group_ctx[32];
+		uint64_t child_begin[32];
+		uint64_t object[32];
+		uint32_t size[32];
+		uint32_t group[32];
+	};
+	__shared__ warp_slice s_slices[ENGINE_WARPS];
+	__shared__ typename Rule::workspace_t s_workspace[ENGINE_WARPS];
+	warp_slice &s = s_slices[threadIdx.x >> 5];
+	typename Rule::workspace_t &ws = s_workspace[threadIdx.x >> 5];
+	const unsigned lane = lane_id();
+	uint32_t created = 0;
+	rule.init_warp(ws);
+	__syncwarp();
+
+	const uint64_t num_chunks = div_up<uint64_t>(L.n_groups, ITEM_CHUNK);
+	const uint64_t warp_stride = (uint64_t)gridDim.x * ENGINE_WARPS;
+	for (uint64_t chunk = (uint64_t)blockIdx.x * ENGINE_WARPS + (threadIdx.x >> 5); chunk < num_chunks; chunk += warp_stride) {
+		const uint64_t c0 = chunk * ITEM_CHUNK, c1 = min(c0 + (uint64_t)ITEM_CHUNK, L.n_groups);
+		for (uint64_t b = c0; b < c1; b += 32) {
+			const uint32_t count = (uint32_t)min((uint64_t)32, c1 - b);
+			if (lane < count) {
+				const uint64_t item = L.items[b + lane];
+				const uint64_t p = item >> ITEM_GROUP_BITS;
+				const uint32_t group = (uint32_t)(item & ((1u << ITEM_GROUP_BITS) - 1));
+				const uint64_t oid = L.kept ? L.kept[p] : p;
+				const uint64_t off = L.it.begin[oid];
+				const uint32_t sz = L.it.size[oid];
+				s.child_begin[lane] = L.child_begin[p];
+				s.object[lane] = off;
+				s.size[lane] = sz;
+				s.group[lane] = group;
+				rule.prepare(L.it.objects + off, sz, s.ctx[lane]);
+				rule.prepare_group(s.ctx[lane], group, L.it.mag[oid], s.group_ctx[lane]);
+			}
+			__syncwarp();
+			for (uint32_t i = 0; i < count; ++i) {
+				table_emitter emit(L.table, s.child_begin[i]);
+				rule.template symbolic_warp<true>(L.it.objects + s.object[i], s.size[i], s.ctx[i], s.group[i], s.group_ctx[i], ws, emit);
+				created += emit.created;
+			}
+			__syncwarp();
+		}
+		table_emitter emit(L.table, 0);
+		rule.flush_warp(ws, emit);
+		created += emit.created;
+	}
 	created = (uint32_t)warp_sum((uint64_t)created);
 	if (lane == 0 && created)
 		atomicAdd(L.table.used, (unsigned long long)created);
@@ -265,7 +351,7 @@ struct rule_glue {
 
 	static void num_child(const void *rule, const engine_launch &L) {
 		int grid = grid_for(L.it.n, ENGINE_THREADS, resident_grid((const void *)num_child_kernel<Rule>, ENGINE_THREADS, L.sm_count));
-		num_child_kernel<Rule><<<grid, ENGINE_THREADS, 0, L.stream>>>(*static_cast<const Rule *>(rule), L.it, L.num_childs, L.num_groups, L.locality, L.max_child_size);
+		num_child_kernel<Rule><<<grid, ENGINE_THREADS, 0, L.stream>>>(*static_cast<const Rule *>(rule), L.it, L.num_childs, L.num_groups, L.max_child_size);
 		++*L.launch_counter;
 	}
 	static uint64_t symbolic_chunks(uint64_t n_groups) { return div_up<uint64_t>(n_groups, Rule::warp_groups ? 32 : SYMBOLIC_CHUNK); }
@@ -279,6 +365,21 @@ struct rule_glue {
 		int grid = grid_for(warps * 32, SYMBOLIC_THREADS, symbolic_grid(L.sm_count));
 		symbolic_kernel<Rule><<<grid, SYMBOLIC_THREADS, 0, L.stream>>>(*static_cast<const Rule *>(rule), L);
 		++*L.launch_counter;
+	}
+	static void group_items(const void *rule, const engine_launch &L) {
+		if constexpr (Rule::has_group_key) {
+			int grid = grid_for(L.n_parents, ENGINE_THREADS, resident_grid((const void *)group_items_kernel<Rule>, ENGINE_THREADS, L.sm_count));
+			group_items_kernel<Rule><<<grid, ENGINE_THREADS, 0, L.stream>>>(*static_cast<const Rule *>(rule), L);
+			++*L.launch_counter;
+		}
+	}
+	static void symbolic_items(const void *rule, const engine_launch &L) {
+		if constexpr (Rule::has_group_key) {
+			const uint64_t warps = div_up<uint64_t>(L.n_groups, ITEM_CHUNK);
+			int grid = grid_for(warps * 32, SYMBOLIC_THREADS, resident_grid((const void *)symbolic_items_kernel<Rule>, SYMBOLIC_THREADS, L.sm_count));
+			symbolic_items_kernel<Rule><<<grid, SYMBOLIC_THREADS, 0, L.stream>>>(*static_cast<const Rule *>(rule), L);
+			++*L.launch_counter;
+		}
 	}
 	static void populate(const void *rule, const engine_launch &L) {
 		int grid = grid_for(L.n_survivors, ENGINE_THREADS, resident_grid((const void *)populate_kernel<Rule>, ENGINE_THREADS, L.sm_count));
@@ -300,7 +401,9 @@ struct rule_glue {
 		o.launch_hash = hash;
 		o.needs_scratch = Rule::needs_scratch;
 		o.warp_groups = Rule::warp_groups;
-		o.has_locality_key = Rule::has_locality_key;
+		o.has_group_key = Rule::has_group_key;
+		o.launch_group_items = group_items;
+		o.launch_symbolic_items = symbolic_items;
 		o.symbolic_grid = symbolic_grid;
 		o.symbolic_chunks = symbolic_chunks;
 		return o;

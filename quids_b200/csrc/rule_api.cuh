@@ -96,7 +96,7 @@ struct rule_base {
 	//     workspace_t                                  per-warp shared memory it needs
 	//     get_num_group(parent, parent_size, num_child) -> number of groups
 	//     group_ctx_t, prepare_group(ctx, group, parent_mag, group_ctx&)   one lane per group
-	//     symbolic_warp(parent, parent_size, ctx, group, group_ctx, workspace&, emit)
+	//     symbolic_warp<ACCUMULATE>(parent, parent_size, ctx, group, group_ctx, workspace&, emit)
 	// symbolic_warp is called by all 32 lanes of a warp with identical arguments; every child of the
 	// group must be emitted exactly once, by any lane: emit(child_id, hash, size, mag) or
 	// emit.batch<N>(count, hash[N], size, child_id_of(i), mag_of(i)).
@@ -110,12 +110,21 @@ struct rule_base {
 
 	__device__ uint32_t get_num_group(const uint8_t *, uint32_t, uint32_t num_child) const { return num_child; }
 
-	// optional: a 32-bit key such that parents producing the same children have equal keys.  The
-	// engine then generates children in key order, so that all contributions to one object reach
-	// the interference table close together in time (L2 hits instead of DRAM round trips).  Purely a
-	// performance hint: any key gives correct results.
-	static constexpr bool has_locality_key = false;
-	__device__ uint32_t locality_key(const uint8_t *, uint32_t) const { return 0; }
+	// optional, for rules with warp_groups: ORDERING of the groups.  group_keys() gives every group of a
+	// parent a 32-bit key such that groups producing the SAME set of objects (from different parents)
+	// have equal keys.  The engine then sorts all (parent, group) work items by key and hands them to
+	// the warps in that order with symbolic_warp<true>: the rule may keep the magnitudes of a run of
+	// equal-target groups in its per-warp workspace and emit each object once per run (flush_warp)
+	// instead of once per child -- the global interference table then sees ~N_u inserts, not N_c.
+	// Purely a performance device: any keys give correct results.
+	//     init_warp(workspace&)                       once per warp, before the first group
+	//     symbolic_warp<ACCUMULATE>(...)              ACCUMULATE = true only in sorted order
+	//     flush_warp(workspace&, emit)                emit whatever the workspace still holds
+	static constexpr bool has_group_key = false;
+	__device__ void group_keys(const uint8_t *, uint32_t, uint32_t, uint32_t *) const {}
+	__device__ void init_warp(workspace_t &) const {}
+	template <class Emit>
+	__device__ void flush_warp(workspace_t &, Emit &) const {}
 };
 
 // ---- modifiers: f(begin, end, mag&) in place (quids.hpp:86,973-980) as a device functor
@@ -144,7 +153,9 @@ struct rule_ops {
 	void (*launch_hash)(const void *rule, const engine_launch &L);
 	bool needs_scratch;
 	bool warp_groups;
-	bool has_locality_key;
+	bool has_group_key;
+	void (*launch_group_items)(const void *rule, const engine_launch &L);
+	void (*launch_symbolic_items)(const void *rule, const engine_launch &L);
 	int (*symbolic_grid)(int sm_count); // CTAs the symbolic kernel is launched with at most (sizes the scratch)
 	uint64_t (*symbolic_chunks)(uint64_t n_groups); // work chunks of the symbolic kernel (sizes chunk_parent)
 };

@@ -114,28 +114,38 @@ struct amplitudes {
 // coin: eligible = left != right.  Size unchanged, names untouched.  In both rules the amplitude is
 // conjugated exactly when the left particle is present.
 // ===================================================================================================
-constexpr int FLIP_LEVELS = 8;               // tree levels one warp expands in shared memory
+constexpr int FLIP_LEVELS = 7;               // tree levels one warp expands in shared memory
 constexpr int FLIP_BLOCK = 1 << FLIP_LEVELS; // children per group (at most)
 
 struct flip_ctx {
 	uint64_t left, right; // particle masks (only when n <= 64)
 	uint64_t names_hash;  // fold of the first-atom hashes: the same for every child
 	uint32_t n;
+	uint32_t prefix_bits;         // left-particle bits of the first k - levels eligible nodes (the ones the group index decides)
 	uint8_t eligible;             // number of eligible nodes k: the parent has 2^k children
 	uint8_t levels;               // min(k, FLIP_LEVELS): tree levels of one group
+	uint8_t tree_bits;            // left-particle bits of the tree nodes (bit l = level l)
 	uint8_t pos[FLIP_LEVELS + 1]; // node index of the last `levels` eligible nodes, then n
 };
 
-// per-warp tree states: after level l, state i (i < 2^l) = fold of hash_graph's left/right hashes and
-// the magnitude product over every node before the next tree node, for the choice bits i
 struct flip_root { // state before the first tree level of one group
 	uint64_t hl, hr;
 	cplx mag;
 };
 
+// per-warp shared memory.  Tree states: after level l, state i (i < 2^l) = fold of hash_graph's left /
+// right hashes and the magnitude product over every node before the next tree node, for choice bits i.
+// Accumulators: the objects of the current run of equal-target groups, indexed by the TARGET's particle
+// bits on the tree nodes (leaf index xor the parent's own bits), so that every member of a family adds
+// into the same slots.
 struct flip_workspace {
 	uint64_t hl[FLIP_BLOCK], hr[FLIP_BLOCK];
 	double re[FLIP_BLOCK], im[FLIP_BLOCK];
+	double acc_re[FLIP_BLOCK], acc_im[FLIP_BLOCK];
+	uint64_t acc_hash[FLIP_BLOCK], acc_rep[FLIP_BLOCK];
+	// what the accumulators hold: family (eligible nodes, particles elsewhere, names) and target of the group
+	uint64_t run_eligible, run_fixed, run_names;
+	uint32_t run_n, run_target, run_leaves, run_valid;
 };
 
 template <bool WANT_EQUAL>
@@ -182,24 +192,7 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 	typedef flip_root group_ctx_t;
 	static constexpr bool needs_scratch = false;
 	static constexpr bool warp_groups = true;
-	static constexpr bool has_locality_key = true;
-
-	// Two parents produce the same children exactly when they have the same eligible nodes, the same
-	// particles on the other nodes and the same names: each of them reaches all 2^k settings of the
-	// eligible nodes.  The key folds the first two (names are left out: grouping a few unrelated
-	// parents together costs nothing).
-	__device__ uint32_t locality_key(const uint8_t *parent, uint32_t) const {
-		graph g(parent);
-		uint64_t key = g.n;
-		for (uint32_t i = 0; i < g.n; ++i) {
-			const bool l = g.left(i), r = g.right(i);
-			const uint64_t code = ((l == r) == WANT_EQUAL) ? 2 : (l ? 1 : 0);
-			key = key * 3 + code;
-			if ((i & 31) == 31)
-				key = mix64(key);
-		}
-		return (uint32_t)(mix64(key) >> 32);
-	}
+	static constexpr bool has_group_key = true;
 
 	// The 2^k children of a parent are the leaves of a binary tree over its k eligible nodes, and
 	// hash_graph folds the nodes in index order: two children share the fold (and the magnitude
@@ -208,12 +201,46 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 	// k - levels eligible nodes (the low bits of child_id); the tree over the last `levels` ones is
 	// expanded level by level in shared memory, one lane per tree node.  ~2 fold steps per child
 	// instead of n, and all lanes run the same control flow because they share the parent.
+	//
+	// FAMILIES.  A child keeps its parent's eligible nodes, its particles on the other nodes and its
+	// names, so two parents that agree on those produce the SAME 2^k objects.  A group's objects are
+	// those whose particles on the first k - levels eligible nodes equal  target = group xor the
+	// parent's own bits there.  group_keys() hashes (family, target); in sorted order the warp meets
+	// all groups with the same objects in a row, adds their magnitudes in shared memory (only the
+	// magnitude tree is expanded after the first group: the hashes are known), and sends each object
+	// to the global interference table once per run.
 	// Graphs wider than the 64-bit masks: groups of 32 children, one per lane, walking the bytes.
 	__device__ uint32_t get_num_group(const uint8_t *parent, uint32_t, uint32_t num_child) const {
 		const uint32_t n = *reinterpret_cast<const uint16_t *>(parent);
 		if (n > 64)
 			return (num_child + 31) / 32;
 		return num_child > (uint32_t)FLIP_BLOCK ? num_child >> FLIP_LEVELS : 1;
+	}
+
+	__device__ void group_keys(const uint8_t *parent, uint32_t, uint32_t num_groups, uint32_t *keys) const {
+		graph g(parent);
+		uint64_t family = g.n;
+		uint32_t eligible = 0, prefix_bits = 0;
+		for (uint32_t i = 0; i < g.n; ++i) { // pass 1: the family, and k
+			const bool l = g.left(i), r = g.right(i);
+			const bool is_eligible = (l == r) == WANT_EQUAL;
+			eligible += is_eligible;
+			family = family * 3 + (is_eligible ? 2 : (l ? 1 : 0));
+			if ((i & 31) == 31)
+				family = mix64(family);
+		}
+		family = mix64(family);
+		if (g.n <= 64) { // the parent's own bits on the nodes the group index decides
+			const uint32_t prefix = eligible > (uint32_t)FLIP_LEVELS ? eligible - FLIP_LEVELS : 0;
+			uint32_t seen = 0;
+			for (uint32_t i = 0; i < g.n && seen < prefix; ++i)
+				if ((g.left(i) == g.right(i)) == WANT_EQUAL) {
+					prefix_bits |= (uint32_t)g.left(i) << seen;
+					++seen;
+				}
+		}
+		for (uint32_t group = 0; group < num_groups; ++group)
+			keys[group] = (uint32_t)(mix64(family + 0x9e3779b97f4a7c15ull * ((group ^ prefix_bits) + 1)) >> 32);
 	}
 
 	__device__ void prepare(const uint8_t *parent, uint32_t, flip_ctx &ctx) const {
@@ -236,16 +263,24 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 		ctx.eligible = (uint8_t)eligible;
 		const uint32_t levels = min(eligible, (uint32_t)FLIP_LEVELS);
 		ctx.levels = (uint8_t)levels;
+		uint32_t prefix_bits = 0, tree_bits = 0;
 		if (g.n <= 64) {
 			uint32_t seen = 0;
 			for (uint32_t i = 0; i < g.n; ++i)
 				if ((((l ^ r) >> i) & 1) != (uint64_t)WANT_EQUAL) {
-					if (seen + levels >= eligible)
+					const uint32_t bit = (uint32_t)((l >> i) & 1);
+					if (seen + levels >= eligible) {
 						ctx.pos[seen + levels - eligible] = (uint8_t)i;
+						tree_bits |= bit << (seen + levels - eligible);
+					} else {
+						prefix_bits |= bit << seen;
+					}
 					++seen;
 				}
 			ctx.pos[levels] = (uint8_t)g.n;
 		}
+		ctx.prefix_bits = prefix_bits;
+		ctx.tree_bits = (uint8_t)tree_bits;
 	}
 
 	// one child on its own (also the symbolic hook of the one-child-per-lane path)
@@ -296,7 +331,38 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 		root.mag = mag;
 	}
 
+	__device__ void init_warp(flip_workspace &ws) const {
+		if (lane_id() == 0)
+			ws.run_valid = 0;
+	}
+
+	// the objects of the current run go to the global table, four per lane at a time
 	template <class Emit>
+	__device__ void flush_warp(flip_workspace &ws, Emit &emit) const {
+		__syncwarp();
+		if (ws.run_valid) {
+			const uint32_t leaves = ws.run_leaves;
+			for (uint32_t base = lane_id(); base < leaves; base += 128) {
+				uint64_t hash[4];
+				int count = 0;
+#pragma unroll
+				for (int q = 0; q < 4; ++q)
+					if (base + q * 32 < leaves) {
+						hash[q] = ws.acc_hash[base + q * 32];
+						count = q + 1;
+					}
+				emit.template batch_raw<4>(
+				    count, hash, [&ws, base](int q) { return cplx{ws.acc_re[base + q * 32], ws.acc_im[base + q * 32]}; },
+				    [&ws, base](int q) { return ws.acc_rep[base + q * 32]; });
+			}
+		}
+		__syncwarp();
+		if (lane_id() == 0)
+			ws.run_valid = 0;
+		__syncwarp();
+	}
+
+	template <bool ACCUMULATE, class Emit>
 	__device__ void symbolic_warp(const uint8_t *parent, uint32_t parent_size, const flip_ctx &ctx, uint32_t group, const flip_root &root,
 	                              flip_workspace &ws, Emit &emit) const {
 		const uint32_t lane = lane_id();
@@ -312,6 +378,57 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 		}
 		const uint64_t left = ctx.left, right = ctx.right;
 		const uint32_t levels = ctx.levels;
+		const uint32_t leaves = 1u << levels;
+		const uint32_t tree_bits = ctx.tree_bits;
+
+		if (ACCUMULATE) {
+			const uint64_t all = ctx.n == 64 ? ~0ull : ((1ull << ctx.n) - 1);
+			const uint64_t eligible = (WANT_EQUAL ? ~(left ^ right) : (left ^ right)) & all;
+			const uint64_t fixed = left & ~eligible & all;
+			const uint32_t target = group ^ ctx.prefix_bits;
+			const bool same = ws.run_valid && ws.run_eligible == eligible && ws.run_fixed == fixed && ws.run_names == ctx.names_hash &&
+			                  ws.run_n == ctx.n && ws.run_target == target;
+			if (same) {
+				// the objects of this group are already in the accumulators: only their magnitudes are needed
+				if (lane == 0) {
+					ws.re[0] = root.mag.re;
+					ws.im[0] = root.mag.im;
+				}
+				__syncwarp();
+				for (uint32_t l = 0; l < levels; ++l) {
+					const bool pl = (left >> ctx.pos[l]) & 1;
+					const cplx stay = this->amp.get(false, pl), go = this->amp.get(true, pl);
+					const uint32_t width = 1u << l;
+					for (uint32_t i = lane; i < width; i += 32) {
+						const cplx m{ws.re[i], ws.im[i]};
+						const cplx m0 = cmul(m, stay), m1 = cmul(m, go);
+						ws.re[i] = m0.re;
+						ws.im[i] = m0.im;
+						ws.re[i + width] = m1.re;
+						ws.im[i + width] = m1.im;
+					}
+					__syncwarp();
+				}
+				for (uint32_t leaf = lane; leaf < leaves; leaf += 32) {
+					const uint32_t slot = leaf ^ tree_bits;
+					ws.acc_re[slot] += ws.re[leaf];
+					ws.acc_im[slot] += ws.im[leaf];
+				}
+				__syncwarp();
+				return;
+			}
+			flush_warp(ws, emit); // a new run starts: send the previous one to the table
+			if (lane == 0) {
+				ws.run_eligible = eligible;
+				ws.run_fixed = fixed;
+				ws.run_names = ctx.names_hash;
+				ws.run_n = ctx.n;
+				ws.run_target = target;
+				ws.run_leaves = leaves;
+				ws.run_valid = 1;
+			}
+		}
+
 		if (lane == 0) {
 			ws.hl[0] = root.hl;
 			ws.hr[0] = root.hr;
@@ -357,11 +474,22 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 			__syncwarp();
 		}
 
-		// leaves: finish the hash and insert, four per lane at a time (four table loads in flight);
-		// magnitudes stay in shared memory until their entry is resolved
-		const uint32_t leaves = 1u << levels;
 		const uint32_t shift = ctx.eligible - levels; // child_id = group | leaf << shift
 		const uint64_t names_hash = ctx.names_hash;
+		if (ACCUMULATE) {
+			// first group of a run: its objects (hash, representative) and magnitudes open the accumulators
+			for (uint32_t leaf = lane; leaf < leaves; leaf += 32) {
+				const uint32_t slot = leaf ^ tree_bits;
+				ws.acc_hash[slot] = hash_combine(hash_combine(names_hash, ws.hl[leaf]), ws.hr[leaf]);
+				ws.acc_rep[slot] = emit.rep(group | (leaf << shift), parent_size);
+				ws.acc_re[slot] = ws.re[leaf];
+				ws.acc_im[slot] = ws.im[leaf];
+			}
+			__syncwarp();
+			return;
+		}
+		// unsorted order: finish the hash and insert, four per lane at a time (four table loads in
+		// flight); magnitudes stay in shared memory until their entry is resolved
 		for (uint32_t base = lane; base < leaves; base += 128) {
 			uint64_t hash[4];
 			int count = 0;

@@ -39,7 +39,7 @@ def test_golden_vectors_with_parent_ordering(gpu, port, name):
     try:
         assert golden_util.replay(name, gpu(""), port) > 0
     finally:
-        qb.config.locality_sort = 0
+        qb.config.locality_sort = 1
 
 
 @pytest.mark.parametrize("align", [0, 4, 8, 16])
@@ -106,7 +106,7 @@ def test_qcgd_parent_ordering_and_groups_vs_oracle(gpu, port, rule_id):
         full, _, _ = port.simulate(sub, rule_id, params, tolerance=1e-18)
         orc.assert_same_truncated(got, port.hash_objects(got, rule_id), want, port.hash_objects(want, rule_id), full, port.hash_objects(full, rule_id), k, True)
     finally:
-        qb.config.locality_sort = 0
+        qb.config.locality_sort = 1
 
 
 def test_qcgd_wide_graphs_vs_oracle(gpu, port):
