@@ -107,7 +107,7 @@ struct qb_iter {
 struct qb_sym {
 	qb_ctx *ctx;
 	uint64_t n_children = 0, n_unique = 0; // quids.hpp:344-346
-	dev_buf table, ukey, uslot, sslot, kept, scratch, survivor_parent, survivor_child, padded, chunk_parent, sort_keys, sort_vals, sort_hist, sort_base;
+	dev_buf table, ukey, uslot, sslot, kept, scratch, survivor_parent, survivor_child, padded, chunk_parent, sort_keys, sort_vals, sort_hist, sort_base, parent_ctx;
 	cudaEvent_t ev[2 * QB_PHASE_COUNT] = {};
 	bool ev_used[QB_PHASE_COUNT] = {};
 	float phase_ms[QB_PHASE_COUNT] = {};
@@ -116,7 +116,7 @@ struct qb_sym {
 	int table_attempts = 0;
 
 	uint64_t device_bytes() const {
-		return table.cap + ukey.cap + uslot.cap + sslot.cap + kept.cap + scratch.cap + survivor_parent.cap + survivor_child.cap + padded.cap + chunk_parent.cap + sort_keys.cap + sort_vals.cap + sort_hist.cap + sort_base.cap;
+		return table.cap + ukey.cap + uslot.cap + sslot.cap + kept.cap + scratch.cap + survivor_parent.cap + survivor_child.cap + padded.cap + chunk_parent.cap + sort_keys.cap + sort_vals.cap + sort_hist.cap + sort_base.cap + parent_ctx.cap;
 	}
 };
 
@@ -470,6 +470,8 @@ local_table build_local_table(qb_iter *it, int rule_id, const rule_ops *ops, con
 		timer.begin(QB_PHASE_PRE_TRUNCATE);
 		sym->sort_keys.ensure(2 * sizeof(uint32_t) * n_groups, stream);
 		sym->sort_vals.ensure(2 * sizeof(uint64_t) * n_groups, stream);
+		sym->parent_ctx.ensure(ops->ctx_bytes * R.n_parents, stream);
+		L.parent_ctx = sym->parent_ctx.ptr;
 		L.item_keys = sym->sort_keys.as<uint32_t>();
 		L.item_vals = sym->sort_vals.as<uint64_t>();
 		ops->launch_group_items(rule, L);

@@ -36,6 +36,7 @@ struct engine_launch {
 	uint32_t *item_keys;          // sorted order: key and (parent position << 24 | group) of every group
 	uint64_t *item_vals;
 	const uint64_t *items;        // item_vals after the sort
+	void *parent_ctx;             // sorted order: Rule::ctx_t of every kept parent, prepared once
 	uint64_t n_parents;
 	uint64_t n_children;
 	uint64_t n_groups;
@@ -227,6 +228,9 @@ __global__ void __launch_bounds__(ENGINE_THREADS) group_items_kernel(const Rule 
 		if (count == 0)
 			continue;
 		const uint64_t oid = L.kept ? L.kept[p] : p;
+		// the parent's context is prepared here once (this thread already walks the object) instead of once
+		// per work item in the symbolic kernel, where 32 lanes would each chase a different object
+		rule.prepare(L.it.objects + L.it.begin[oid], L.it.size[oid], static_cast<typename Rule::ctx_t *>(L.parent_ctx)[p]);
 		rule.group_keys(L.it.objects + L.it.begin[oid], L.it.size[oid], count, L.item_keys + first);
 		for (uint32_t g = 0; g < count; ++g)
 			L.item_vals[first + g] = (p << ITEM_GROUP_BITS) | g;
@@ -273,7 +277,7 @@ __global__ void __launch_bounds__(SYMBOLIC_THREADS, 5) symbolic_items_kernel(con
 				s.object[lane] = off;
 				s.size[lane] = sz;
 				s.group[lane] = group;
-				rule.prepare(L.it.objects + off, sz, s.ctx[lane]);
+				s.ctx[lane] = static_cast<const typename Rule::ctx_t *>(L.parent_ctx)[p];
 				rule.prepare_group(s.ctx[lane], group, L.it.mag[oid], s.group_ctx[lane]);
 			}
 			__syncwarp();
@@ -304,17 +308,80 @@ static __global__ void __launch_bounds__(ENGINE_THREADS) chunk_parent_kernel(con
 		chunk_parent[c] = n_parents - 1;
 }
 
-// v1 finalisation: one thread rebuilds one surviving child in place (populate_child_simple) and
-// zeroes its alignment padding
+// finalisation (quids.hpp:958-967): every surviving child is rebuilt in place from its parent.
+// Rules with edit_child: a warp takes 32 survivors at a time -- one lane per survivor fetches its
+// metadata (coalesced), the warp copies the 32 parents with 8-byte words, four copies in flight, then
+// one lane per survivor applies the rule's edits and zeroes the alignment padding.
+// Other rules: one thread per child runs populate_child_simple.
 template <class Rule>
 __global__ void __launch_bounds__(ENGINE_THREADS) populate_kernel(const Rule rule, const engine_launch L) {
-	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-	for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < L.n_survivors; s += stride) {
-		const uint64_t oid = L.survivor_parent[s];
-		uint8_t *child = L.next_objects + L.next_begin[s];
-		rule.populate_child_simple(L.it.objects + L.it.begin[oid], L.it.size[oid], child, L.survivor_child[s]);
-		for (uint64_t b = L.next_begin[s] + L.next_size[s]; b < L.next_begin[s + 1]; ++b)
-			L.next_objects[b] = 0;
+	if constexpr (Rule::has_edit_child) {
+		const unsigned lane = lane_id();
+		const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+		const uint64_t batches = div_up<uint64_t>(L.n_survivors, 32);
+		for (uint64_t batch = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; batch < batches; batch += warps) {
+			const uint64_t mine = batch * 32 + lane;
+			const bool valid = mine < L.n_survivors;
+			const uint8_t *parent = nullptr;
+			uint8_t *child = nullptr;
+			uint32_t size = 0, child_id = 0, padded = 0;
+			if (valid) {
+				const uint64_t oid = L.survivor_parent[mine];
+				const uint64_t begin = L.next_begin[mine];
+				parent = L.it.objects + L.it.begin[oid];
+				child = L.next_objects + begin;
+				size = L.it.size[oid];
+				child_id = L.survivor_child[mine];
+				padded = (uint32_t)(L.next_begin[mine + 1] - begin);
+			}
+			const unsigned count = __popc(__ballot_sync(0xffffffffu, valid));
+			for (unsigned j = 0; j < count; j += 4) {
+				// four parents at a time: all their loads are issued before the first store
+				uint2 word[4];
+				const uint8_t *src[4];
+				uint8_t *dst[4];
+				uint32_t bytes[4];
+				bool fast[4];
+#pragma unroll
+				for (int q = 0; q < 4; ++q) {
+					const unsigned from = min(j + q, count - 1);
+					src[q] = reinterpret_cast<const uint8_t *>(__shfl_sync(0xffffffffu, reinterpret_cast<uintptr_t>(parent), from));
+					dst[q] = reinterpret_cast<uint8_t *>(__shfl_sync(0xffffffffu, reinterpret_cast<uintptr_t>(child), from));
+					bytes[q] = j + q < count ? __shfl_sync(0xffffffffu, size, from) : 0;
+					fast[q] = ((reinterpret_cast<uintptr_t>(src[q]) | reinterpret_cast<uintptr_t>(dst[q])) & 7) == 0 && bytes[q] <= 256;
+					if (fast[q] && lane < bytes[q] / 8)
+						word[q] = reinterpret_cast<const uint2 *>(src[q])[lane];
+				}
+#pragma unroll
+				for (int q = 0; q < 4; ++q) {
+					if (fast[q]) { // 8-byte words, then the (size % 8) trailing bytes
+						if (lane < bytes[q] / 8)
+							reinterpret_cast<uint2 *>(dst[q])[lane] = word[q];
+						const uint32_t tail = bytes[q] & ~7u;
+						if (tail + lane < bytes[q])
+							dst[q][tail + lane] = src[q][tail + lane];
+					} else { // any size, any alignment
+						for (uint32_t b = lane; b < bytes[q]; b += 32)
+							dst[q][b] = src[q][b];
+					}
+				}
+			}
+			__syncwarp();
+			if (valid) {
+				rule.edit_child(parent, size, child, child_id);
+				for (uint32_t b = size; b < padded; ++b)
+					child[b] = 0;
+			}
+		}
+	} else {
+		const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+		for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < L.n_survivors; s += stride) {
+			const uint64_t oid = L.survivor_parent[s];
+			uint8_t *child = L.next_objects + L.next_begin[s];
+			rule.populate_child_simple(L.it.objects + L.it.begin[oid], L.it.size[oid], child, L.survivor_child[s]);
+			for (uint64_t b = L.next_begin[s] + L.next_size[s]; b < L.next_begin[s + 1]; ++b)
+				L.next_objects[b] = 0;
+		}
 	}
 }
 
@@ -402,6 +469,7 @@ struct rule_glue {
 		o.needs_scratch = Rule::needs_scratch;
 		o.warp_groups = Rule::warp_groups;
 		o.has_group_key = Rule::has_group_key;
+		o.ctx_bytes = sizeof(typename Rule::ctx_t);
 		o.launch_group_items = group_items;
 		o.launch_symbolic_items = symbolic_items;
 		o.symbolic_grid = symbolic_grid;

@@ -120,6 +120,13 @@ struct rule_base {
 	//     init_warp(workspace&)                       once per warp, before the first group
 	//     symbolic_warp<ACCUMULATE>(...)              ACCUMULATE = true only in sorted order
 	//     flush_warp(workspace&, emit)                emit whatever the workspace still holds
+	// optional, for rules whose children have the parent's size and differ from it in a few bytes:
+	//     edit_child(parent, parent_size, child, child_id)   child already holds a copy of the parent
+	// The finalisation then copies parents to children itself, a warp at a time with coalesced wide
+	// loads and several copies in flight, and calls edit_child from one lane per child.
+	static constexpr bool has_edit_child = false;
+	__device__ void edit_child(const uint8_t *, uint32_t, uint8_t *, uint32_t) const {}
+
 	static constexpr bool has_group_key = false;
 	__device__ void group_keys(const uint8_t *, uint32_t, uint32_t, uint32_t *) const {}
 	__device__ void init_warp(workspace_t &) const {}
@@ -154,6 +161,7 @@ struct rule_ops {
 	bool needs_scratch;
 	bool warp_groups;
 	bool has_group_key;
+	size_t ctx_bytes;
 	void (*launch_group_items)(const void *rule, const engine_launch &L);
 	void (*launch_symbolic_items)(const void *rule, const engine_launch &L);
 	int (*symbolic_grid)(int sm_count); // CTAs the symbolic kernel is launched with at most (sizes the scratch)

@@ -33,6 +33,9 @@ struct hadamard : rule_base<hadamard> {
 // nothing is written in the symbolic phase
 struct hadamard_fused : hadamard {
 	static constexpr bool needs_scratch = false;
+	static constexpr bool has_edit_child = true;
+
+	__device__ void edit_child(const uint8_t *, uint32_t, uint8_t *child, uint32_t child_id) const { child[bit] ^= (uint8_t)!child_id; }
 
 	__device__ uint64_t symbolic(const uint8_t *parent, uint32_t parent_size, const no_ctx &, uint32_t child_id, uint8_t *, uint32_t &size,
 	                             cplx &mag) const {

@@ -139,10 +139,9 @@ struct flip_root { // state before the first tree level of one group
 // bits on the tree nodes (leaf index xor the parent's own bits), so that every member of a family adds
 // into the same slots.
 struct flip_workspace {
-	uint64_t hl[FLIP_BLOCK], hr[FLIP_BLOCK];
+	uint64_t hl[FLIP_BLOCK], hr[FLIP_BLOCK]; // tree states; once a run is open: hash and representative of its objects
 	double re[FLIP_BLOCK], im[FLIP_BLOCK];
 	double acc_re[FLIP_BLOCK], acc_im[FLIP_BLOCK];
-	uint64_t acc_hash[FLIP_BLOCK], acc_rep[FLIP_BLOCK];
 	// what the accumulators hold: family (eligible nodes, particles elsewhere, names) and target of the group
 	uint64_t run_eligible, run_fixed, run_names;
 	uint32_t run_n, run_target, run_leaves, run_valid;
@@ -193,6 +192,22 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 	static constexpr bool needs_scratch = false;
 	static constexpr bool warp_groups = true;
 	static constexpr bool has_group_key = true;
+	static constexpr bool has_edit_child = true;
+
+	// a child is its parent with some eligible nodes toggled
+	__device__ void edit_child(const uint8_t *parent, uint32_t, uint8_t *child, uint32_t child_id) const {
+		graph g(parent);
+		for (uint32_t i = 0; i < g.n; ++i) {
+			const bool l = g.left(i), r = g.right(i);
+			if ((l == r) != WANT_EQUAL)
+				continue;
+			if (child_id & 1) {
+				child[2 + i] = !l;
+				child[2 + g.n + i] = !r;
+			}
+			child_id >>= 1;
+		}
+	}
 
 	// The 2^k children of a parent are the leaves of a binary tree over its k eligible nodes, and
 	// hash_graph folds the nodes in index order: two children share the fold (and the magnitude
@@ -338,7 +353,7 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 
 	// the objects of the current run go to the global table, four per lane at a time
 	template <class Emit>
-	__device__ void flush_warp(flip_workspace &ws, Emit &emit) const {
+	__device__ __noinline__ void flush_warp(flip_workspace &ws, Emit &emit) const {
 		__syncwarp();
 		if (ws.run_valid) {
 			const uint32_t leaves = ws.run_leaves;
@@ -348,12 +363,12 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 #pragma unroll
 				for (int q = 0; q < 4; ++q)
 					if (base + q * 32 < leaves) {
-						hash[q] = ws.acc_hash[base + q * 32];
+						hash[q] = ws.hl[base + q * 32];
 						count = q + 1;
 					}
 				emit.template batch_raw<4>(
 				    count, hash, [&ws, base](int q) { return cplx{ws.acc_re[base + q * 32], ws.acc_im[base + q * 32]}; },
-				    [&ws, base](int q) { return ws.acc_rep[base + q * 32]; });
+				    [&ws, base](int q) { return ws.hr[base + q * 32]; });
 			}
 		}
 		__syncwarp();
@@ -362,73 +377,11 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 		__syncwarp();
 	}
 
-	template <bool ACCUMULATE, class Emit>
-	__device__ void symbolic_warp(const uint8_t *parent, uint32_t parent_size, const flip_ctx &ctx, uint32_t group, const flip_root &root,
-	                              flip_workspace &ws, Emit &emit) const {
+	// full expansion of one group: tree states (hash folds and magnitudes) of all its leaves in ws
+	__device__ __forceinline__ void expand_full(const flip_ctx &ctx, const flip_root &root, flip_workspace &ws) const {
 		const uint32_t lane = lane_id();
-		if (ctx.n > 64) { // wide graph: 32 children per group, one per lane
-			const uint32_t child_id = group * 32 + lane;
-			if (ctx.eligible < 32 && child_id < (1u << ctx.eligible)) {
-				uint32_t size;
-				cplx mag = root.mag;
-				const uint64_t hash = symbolic(parent, parent_size, ctx, child_id, nullptr, size, mag);
-				emit(child_id, hash, size, mag);
-			}
-			return;
-		}
 		const uint64_t left = ctx.left, right = ctx.right;
 		const uint32_t levels = ctx.levels;
-		const uint32_t leaves = 1u << levels;
-		const uint32_t tree_bits = ctx.tree_bits;
-
-		if (ACCUMULATE) {
-			const uint64_t all = ctx.n == 64 ? ~0ull : ((1ull << ctx.n) - 1);
-			const uint64_t eligible = (WANT_EQUAL ? ~(left ^ right) : (left ^ right)) & all;
-			const uint64_t fixed = left & ~eligible & all;
-			const uint32_t target = group ^ ctx.prefix_bits;
-			const bool same = ws.run_valid && ws.run_eligible == eligible && ws.run_fixed == fixed && ws.run_names == ctx.names_hash &&
-			                  ws.run_n == ctx.n && ws.run_target == target;
-			if (same) {
-				// the objects of this group are already in the accumulators: only their magnitudes are needed
-				if (lane == 0) {
-					ws.re[0] = root.mag.re;
-					ws.im[0] = root.mag.im;
-				}
-				__syncwarp();
-				for (uint32_t l = 0; l < levels; ++l) {
-					const bool pl = (left >> ctx.pos[l]) & 1;
-					const cplx stay = this->amp.get(false, pl), go = this->amp.get(true, pl);
-					const uint32_t width = 1u << l;
-					for (uint32_t i = lane; i < width; i += 32) {
-						const cplx m{ws.re[i], ws.im[i]};
-						const cplx m0 = cmul(m, stay), m1 = cmul(m, go);
-						ws.re[i] = m0.re;
-						ws.im[i] = m0.im;
-						ws.re[i + width] = m1.re;
-						ws.im[i + width] = m1.im;
-					}
-					__syncwarp();
-				}
-				for (uint32_t leaf = lane; leaf < leaves; leaf += 32) {
-					const uint32_t slot = leaf ^ tree_bits;
-					ws.acc_re[slot] += ws.re[leaf];
-					ws.acc_im[slot] += ws.im[leaf];
-				}
-				__syncwarp();
-				return;
-			}
-			flush_warp(ws, emit); // a new run starts: send the previous one to the table
-			if (lane == 0) {
-				ws.run_eligible = eligible;
-				ws.run_fixed = fixed;
-				ws.run_names = ctx.names_hash;
-				ws.run_n = ctx.n;
-				ws.run_target = target;
-				ws.run_leaves = leaves;
-				ws.run_valid = 1;
-			}
-		}
-
 		if (lane == 0) {
 			ws.hl[0] = root.hl;
 			ws.hr[0] = root.hr;
@@ -436,7 +389,6 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 			ws.im[0] = root.mag.im;
 		}
 		__syncwarp();
-
 		// level l: tree node pos[l] with both choices, then the non-eligible nodes up to the next tree
 		// node.  State i keeps choice 0 in place; choice 1 becomes state i + 2^l (bit l of the leaf index).
 		for (uint32_t l = 0; l < levels; ++l) {
@@ -473,23 +425,117 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 			}
 			__syncwarp();
 		}
+	}
 
+	// a new run starts (rare next to the groups that continue one): the previous run goes to the table,
+	// this group is expanded in full and opens the accumulators.  Kept out of line so that the hot path
+	// of symbolic_warp<true> stays small.
+	template <class Emit>
+	__device__ __noinline__ void open_run(uint32_t parent_size, const flip_ctx &ctx, uint32_t group, const flip_root &root, flip_workspace &ws,
+	                                      Emit &emit, uint64_t eligible, uint64_t fixed, uint32_t target) const {
+		const uint32_t lane = lane_id();
+		const uint32_t levels = ctx.levels, leaves = 1u << levels, tree_bits = ctx.tree_bits;
+		flush_warp(ws, emit);
+		if (lane == 0) {
+			ws.run_eligible = eligible;
+			ws.run_fixed = fixed;
+			ws.run_names = ctx.names_hash;
+			ws.run_n = ctx.n;
+			ws.run_target = target;
+			ws.run_leaves = leaves;
+			ws.run_valid = 1;
+		}
+		expand_full(ctx, root, ws);
+		// hash and representative take the place of the tree states (another slot of the same arrays:
+		// read everything first, then write)
 		const uint32_t shift = ctx.eligible - levels; // child_id = group | leaf << shift
 		const uint64_t names_hash = ctx.names_hash;
-		if (ACCUMULATE) {
-			// first group of a run: its objects (hash, representative) and magnitudes open the accumulators
-			for (uint32_t leaf = lane; leaf < leaves; leaf += 32) {
+		uint64_t hash[FLIP_BLOCK / 32];
+#pragma unroll
+		for (int q = 0; q < FLIP_BLOCK / 32; ++q) {
+			const uint32_t leaf = lane + q * 32;
+			if (leaf < leaves)
+				hash[q] = hash_combine(hash_combine(names_hash, ws.hl[leaf]), ws.hr[leaf]);
+		}
+		__syncwarp();
+#pragma unroll
+		for (int q = 0; q < FLIP_BLOCK / 32; ++q) {
+			const uint32_t leaf = lane + q * 32;
+			if (leaf < leaves) {
 				const uint32_t slot = leaf ^ tree_bits;
-				ws.acc_hash[slot] = hash_combine(hash_combine(names_hash, ws.hl[leaf]), ws.hr[leaf]);
-				ws.acc_rep[slot] = emit.rep(group | (leaf << shift), parent_size);
+				ws.hl[slot] = hash[q];
+				ws.hr[slot] = emit.rep(group | (leaf << shift), parent_size);
 				ws.acc_re[slot] = ws.re[leaf];
 				ws.acc_im[slot] = ws.im[leaf];
+			}
+		}
+		__syncwarp();
+	}
+
+	template <bool ACCUMULATE, class Emit>
+	__device__ void symbolic_warp(const uint8_t *parent, uint32_t parent_size, const flip_ctx &ctx, uint32_t group, const flip_root &root,
+	                              flip_workspace &ws, Emit &emit) const {
+		const uint32_t lane = lane_id();
+		if (ctx.n > 64) { // wide graph: 32 children per group, one per lane
+			const uint32_t child_id = group * 32 + lane;
+			if (ctx.eligible < 32 && child_id < (1u << ctx.eligible)) {
+				uint32_t size;
+				cplx mag = root.mag;
+				const uint64_t hash = symbolic(parent, parent_size, ctx, child_id, nullptr, size, mag);
+				emit(child_id, hash, size, mag);
+			}
+			return;
+		}
+		const uint32_t levels = ctx.levels;
+		const uint32_t leaves = 1u << levels;
+
+		if (ACCUMULATE) {
+			const uint64_t left = ctx.left, right = ctx.right;
+			const uint64_t all = ctx.n == 64 ? ~0ull : ((1ull << ctx.n) - 1);
+			const uint64_t eligible = (WANT_EQUAL ? ~(left ^ right) : (left ^ right)) & all;
+			const uint64_t fixed = left & ~eligible & all;
+			const uint32_t target = group ^ ctx.prefix_bits;
+			const bool same = ws.run_valid && ws.run_eligible == eligible && ws.run_fixed == fixed && ws.run_names == ctx.names_hash &&
+			                  ws.run_n == ctx.n && ws.run_target == target;
+			if (!same) {
+				open_run(parent_size, ctx, group, root, ws, emit, eligible, fixed, target);
+				return;
+			}
+			// the objects of this group are already in the accumulators: only their magnitudes are needed
+			if (lane == 0) {
+				ws.re[0] = root.mag.re;
+				ws.im[0] = root.mag.im;
+			}
+			__syncwarp();
+			for (uint32_t l = 0; l < levels; ++l) {
+				const bool pl = (left >> ctx.pos[l]) & 1;
+				const cplx stay = this->amp.get(false, pl), go = this->amp.get(true, pl);
+				const uint32_t width = 1u << l;
+				for (uint32_t i = lane; i < width; i += 32) {
+					const cplx m{ws.re[i], ws.im[i]};
+					const cplx m0 = cmul(m, stay), m1 = cmul(m, go);
+					ws.re[i] = m0.re;
+					ws.im[i] = m0.im;
+					ws.re[i + width] = m1.re;
+					ws.im[i + width] = m1.im;
+				}
+				__syncwarp();
+			}
+			const uint32_t tree_bits = ctx.tree_bits;
+			for (uint32_t leaf = lane; leaf < leaves; leaf += 32) {
+				const uint32_t slot = leaf ^ tree_bits;
+				ws.acc_re[slot] += ws.re[leaf];
+				ws.acc_im[slot] += ws.im[leaf];
 			}
 			__syncwarp();
 			return;
 		}
-		// unsorted order: finish the hash and insert, four per lane at a time (four table loads in
-		// flight); magnitudes stay in shared memory until their entry is resolved
+
+		// unsorted order: expand, finish the hash and insert, four per lane at a time (four table loads
+		// in flight); magnitudes stay in shared memory until their entry is resolved
+		expand_full(ctx, root, ws);
+		const uint32_t shift = ctx.eligible - levels; // child_id = group | leaf << shift
+		const uint64_t names_hash = ctx.names_hash;
 		for (uint32_t base = lane; base < leaves; base += 128) {
 			uint64_t hash[4];
 			int count = 0;
