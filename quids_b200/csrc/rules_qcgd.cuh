@@ -353,7 +353,7 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 
 	// the objects of the current run go to the global table, four per lane at a time
 	template <class Emit>
-	__device__ __noinline__ void flush_warp(flip_workspace &ws, Emit &emit) const {
+	__device__ void flush_warp(flip_workspace &ws, Emit &emit) const {
 		__syncwarp();
 		if (ws.run_valid) {
 			const uint32_t leaves = ws.run_leaves;
@@ -431,7 +431,7 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 	// this group is expanded in full and opens the accumulators.  Kept out of line so that the hot path
 	// of symbolic_warp<true> stays small.
 	template <class Emit>
-	__device__ __noinline__ void open_run(uint32_t parent_size, const flip_ctx &ctx, uint32_t group, const flip_root &root, flip_workspace &ws,
+	__device__ void open_run(uint32_t parent_size, const flip_ctx &ctx, uint32_t group, const flip_root &root, flip_workspace &ws,
 	                                      Emit &emit, uint64_t eligible, uint64_t fixed, uint32_t target) const {
 		const uint32_t lane = lane_id();
 		const uint32_t levels = ctx.levels, leaves = 1u << levels, tree_bits = ctx.tree_bits;
@@ -501,31 +501,25 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 				open_run(parent_size, ctx, group, root, ws, emit, eligible, fixed, target);
 				return;
 			}
-			// the objects of this group are already in the accumulators: only their magnitudes are needed
-			if (lane == 0) {
-				ws.re[0] = root.mag.re;
-				ws.im[0] = root.mag.im;
-			}
-			__syncwarp();
-			for (uint32_t l = 0; l < levels; ++l) {
-				const bool pl = (left >> ctx.pos[l]) & 1;
-				const cplx stay = this->amp.get(false, pl), go = this->amp.get(true, pl);
-				const uint32_t width = 1u << l;
-				for (uint32_t i = lane; i < width; i += 32) {
-					const cplx m{ws.re[i], ws.im[i]};
-					const cplx m0 = cmul(m, stay), m1 = cmul(m, go);
-					ws.re[i] = m0.re;
-					ws.im[i] = m0.im;
-					ws.re[i + width] = m1.re;
-					ws.im[i + width] = m1.im;
-				}
-				__syncwarp();
-			}
+			// the objects of this group are already in the accumulators: only their magnitudes are needed.
+			// Leaf = lane + 32 q; its magnitude is the root times one amplitude per tree level, multiplied
+			// in node order like the reference does -- computed in registers, no tree in shared memory:
+			// the five low levels are decided by the lane, the (at most two) high ones by q.
 			const uint32_t tree_bits = ctx.tree_bits;
-			for (uint32_t leaf = lane; leaf < leaves; leaf += 32) {
-				const uint32_t slot = leaf ^ tree_bits;
-				ws.acc_re[slot] += ws.re[leaf];
-				ws.acc_im[slot] += ws.im[leaf];
+			const uint32_t low = levels < 5 ? levels : 5;
+			cplx m = root.mag;
+			for (uint32_t l = 0; l < low; ++l)
+				m = cmul(m, this->amp.get((lane >> l) & 1, (tree_bits >> l) & 1));
+			if (lane < leaves) {
+				const uint32_t reps = leaves >> low; // 1, 2 or 4 leaves per lane
+				for (uint32_t q = 0; q < reps; ++q) {
+					cplx mq = m;
+					for (uint32_t l = 5; l < levels; ++l)
+						mq = cmul(mq, this->amp.get((q >> (l - 5)) & 1, (tree_bits >> l) & 1));
+					const uint32_t slot = (lane + 32 * q) ^ tree_bits;
+					ws.acc_re[slot] += mq.re;
+					ws.acc_im[slot] += mq.im;
+				}
 			}
 			__syncwarp();
 			return;
