@@ -144,6 +144,10 @@ __global__ void __launch_bounds__(SYMBOLIC_THREADS, 5) symbolic_kernel(const Rul
 
 	uint8_t *scratch = Rule::needs_scratch ? L.scratch + ((size_t)blockIdx.x * SYMBOLIC_THREADS + threadIdx.x) * L.scratch_stride : nullptr;
 	uint32_t created = 0;
+	if constexpr (Rule::warp_groups) {
+		rule.init_warp(s_workspace[threadIdx.x >> 5]);
+		__syncwarp();
+	}
 
 	const uint64_t num_chunks = div_up<uint64_t>(L.n_groups, CHUNK);
 	const uint64_t warp_stride = (uint64_t)gridDim.x * ENGINE_WARPS;

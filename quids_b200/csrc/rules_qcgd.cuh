@@ -145,6 +145,7 @@ struct flip_workspace {
 	// what the accumulators hold: family (eligible nodes, particles elsewhere, names) and target of the group
 	uint64_t run_eligible, run_fixed, run_names;
 	uint32_t run_n, run_target, run_leaves, run_valid;
+	cplx amp[4]; // the rule's four amplitudes, index = taken * 2 + conjugated: one 16-byte shared load per factor
 };
 
 template <bool WANT_EQUAL>
@@ -349,6 +350,8 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 	__device__ void init_warp(flip_workspace &ws) const {
 		if (lane_id() == 0)
 			ws.run_valid = 0;
+		if (lane_id() < 4)
+			ws.amp[lane_id()] = this->amp.f[lane_id()];
 	}
 
 	// the objects of the current run go to the global table, four per lane at a time
@@ -509,13 +512,13 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 			const uint32_t low = levels < 5 ? levels : 5;
 			cplx m = root.mag;
 			for (uint32_t l = 0; l < low; ++l)
-				m = cmul(m, this->amp.get((lane >> l) & 1, (tree_bits >> l) & 1));
+				m = cmul(m, ws.amp[((lane >> l) & 1) * 2 + ((tree_bits >> l) & 1)]);
 			if (lane < leaves) {
 				const uint32_t reps = leaves >> low; // 1, 2 or 4 leaves per lane
 				for (uint32_t q = 0; q < reps; ++q) {
 					cplx mq = m;
 					for (uint32_t l = 5; l < levels; ++l)
-						mq = cmul(mq, this->amp.get((q >> (l - 5)) & 1, (tree_bits >> l) & 1));
+						mq = cmul(mq, ws.amp[((q >> (l - 5)) & 1) * 2 + ((tree_bits >> l) & 1)]);
 					const uint32_t slot = (lane + 32 * q) ^ tree_bits;
 					ws.acc_re[slot] += mq.re;
 					ws.acc_im[slot] += mq.im;
