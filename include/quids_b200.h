@@ -119,6 +119,8 @@ enum {
 	QB_PHASE_TRUNCATE,      /* child top-k                           quids.hpp:866-900        */
 	QB_PHASE_FINALIZE,      /* sizes, scan, populate_child_simple    quids.hpp:905-968        */
 	QB_PHASE_NORMALIZE,     /* quids.hpp:985-1017                                             */
+	QB_PHASE_EXCHANGE,      /* distributed: all-to-allv of records and survivors   quids_mpi.hpp:741-743,842 */
+	QB_PHASE_OWNER,         /* distributed: owner-side merge, tolerance, return lists   quids_mpi.hpp:762-830 */
 	QB_PHASE_COUNT
 };
 int qb_sym_phase_ms(const qb_sym *sym, float *ms /* [QB_PHASE_COUNT] */);

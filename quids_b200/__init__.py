@@ -27,7 +27,7 @@ CSRC = os.path.join(_HERE, "csrc")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "quids_b200.h")
 
 NO_TRUNCATION = 2**64 - 1
-PHASES = ("num_child", "pre_truncate", "table_clear", "symbolic", "compact", "truncate", "finalize", "normalize")
+PHASES = ("num_child", "pre_truncate", "table_clear", "symbolic", "compact", "truncate", "finalize", "normalize", "exchange", "owner")
 
 
 class QuidsError(RuntimeError):

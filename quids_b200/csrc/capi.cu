@@ -1,5 +1,6 @@
 // capi.cu -- implementation of the C ABI of include/quids_b200.h: contexts, states in HBM, and the
 // orchestration of one rule iteration (the GPU counterpart of quids::simulate, quids.hpp:448-543).
+#include <chrono>
 #include <cmath>
 #include <complex>
 #include <map>
@@ -712,6 +713,15 @@ void simulate_dist(qb_iter *it, int rule_id, const rule_ops *ops, const void *ru
 	phase_timer timer(sym, opt.profile != 0);
 	comm_ops comm{cm};
 	const uint32_t world = (uint32_t)cm->world;
+	const bool trace = getenv("QB_DIST_TRACE") != nullptr; // developer aid: wall-clock of every distributed sub-step (drains the stream)
+	auto t_last = std::chrono::steady_clock::now();
+	auto mark = [&](const char *what) {
+		if (!trace) return;
+		ctx->sync();
+		auto now = std::chrono::steady_clock::now();
+		fprintf(stderr, "[qb dist rank %d] %-28s %8.3f ms\n", cm->rank, what, std::chrono::duration<double, std::milli>(now - t_last).count());
+		t_last = now;
+	};
 
 	engine_launch L;
 	memset(&L, 0, sizeof L);
@@ -727,9 +737,11 @@ void simulate_dist(qb_iter *it, int rule_id, const rule_ops *ops, const void *ru
 		if (node_total_proba) *node_total_proba = 0;
 		return;
 	}
+	mark("local table");
 	step("compute_collisions - prepare");
 
 	// 2. partition the locally unique children by owner
+	timer.begin(QB_PHASE_OWNER);
 	const uint64_t n_local = R.n_unique;
 	cm->cursors.ensure(sizeof(uint64_t) * 2 * (world + 1), stream);
 	unsigned long long *counts = cm->cursors.as<unsigned long long>(), *cursor = counts + world + 1;
@@ -746,21 +758,27 @@ void simulate_dist(qb_iter *it, int rule_id, const rule_ops *ops, const void *ru
 			offsets[r] = offsets[r - 1] + send_counts[r - 1];
 		QB_CUDA(cudaMemcpyAsync(cursor, offsets.data(), sizeof(uint64_t) * world, cudaMemcpyHostToDevice, stream));
 		cm->send.ensure(sizeof(exchange_record) * n_local, stream);
-		owner_scatter_kernel<<<grid_local, 256, 0, stream>>>(R.table, sym->uslot.as<uint32_t>(), n_local, world, cursor, cm->send.as<exchange_record>());
+		owner_scatter_kernel<<<grid_for(div_up<uint64_t>(n_local, SCATTER_TILE) * 256, 256, ctx->grid_cap()), 256, 2 * sizeof(unsigned long long) * world, stream>>>(R.table, sym->uslot.as<uint32_t>(), n_local, world, cursor, cm->send.as<exchange_record>());
 		++ctx->launches;
 		ctx->sync(); // `offsets` lives on this stack frame
 	}
 
+	mark("partition by owner");
 	// 3. all-to-allv of the records
+	timer.end(QB_PHASE_OWNER);
 	step("compute_collisions - com");
+	timer.begin(QB_PHASE_EXCHANGE);
 	uint64_t n_recv = 0;
 	std::vector<uint64_t> recv_counts = comm.alltoallv(cm->send.ptr, send_counts, cm->recv, sizeof(exchange_record), n_recv);
+	timer.end(QB_PHASE_EXCHANGE);
 	std::vector<uint64_t> recv_begin(world + 1, 0);
 	for (uint32_t r = 0; r < world; ++r)
 		recv_begin[r + 1] = recv_begin[r] + recv_counts[r];
 
+	mark("exchange records");
 	// 4. owner: merge what arrived, apply the tolerance
 	step("compute_collisions - insert");
+	timer.begin(QB_PHASE_OWNER);
 	table_view owner{};
 	uint64_t n_owner_unique = 0;
 	if (n_recv > 0) {
@@ -785,10 +803,12 @@ void simulate_dist(qb_iter *it, int rule_id, const rule_ops *ops, const void *ru
 		QB_REQUIRE(ctx->h_small[DS_OVERFLOW] == 0, QB_ERR_CAPACITY, "owner table overflow");
 		n_owner_unique = ctx->h_small[DS_COUNT];
 	}
+	timer.end(QB_PHASE_OWNER);
 	step("compute_collisions - finalize");
 	const uint64_t n_unique_global = comm.sum_u64(n_owner_unique);
 	sym->n_unique = n_owner_unique; // this rank's share; qb_comm_allreduce_u64 gives the total (get_total_num_object_after_interferences)
 
+	mark("owner merge + compact");
 	// 5. truncation: the max_num_object most probable over ALL ranks
 	step("truncate - prepare");
 	step("truncate");
@@ -804,7 +824,9 @@ void simulate_dist(qb_iter *it, int rule_id, const rule_ops *ops, const void *ru
 		timer.end(QB_PHASE_TRUNCATE);
 	}
 
+	mark("global select");
 	// 6. survivors go back to the rank of their representative
+	timer.begin(QB_PHASE_OWNER);
 	QB_CUDA(cudaMemsetAsync(counts, 0, sizeof(uint64_t) * 2 * (world + 1), stream));
 	std::vector<uint64_t> back_counts(world, 0);
 	if (n_owner_survivors > 0) {
@@ -813,7 +835,7 @@ void simulate_dist(qb_iter *it, int rule_id, const rule_ops *ops, const void *ru
 		begin_dev.ensure(sizeof(uint64_t) * (world + 1), stream);
 		QB_CUDA(cudaMemcpyAsync(begin_dev.ptr, recv_begin.data(), sizeof(uint64_t) * (world + 1), cudaMemcpyHostToDevice, stream));
 		const int grid_back = grid_for(n_owner_survivors, 256, ctx->grid_cap());
-		return_count_kernel<<<grid_back, 256, 0, stream>>>(owner, owner_survivor_slot, n_owner_survivors, begin_dev.as<uint64_t>(), world, counts);
+		return_count_kernel<<<grid_back, 256, sizeof(unsigned int) * world, stream>>>(owner, owner_survivor_slot, n_owner_survivors, begin_dev.as<uint64_t>(), world, counts);
 		++ctx->launches;
 		QB_CUDA(cudaMemcpyAsync(back_counts.data(), counts, sizeof(uint64_t) * world, cudaMemcpyDeviceToHost, stream));
 		ctx->sync();
@@ -822,19 +844,24 @@ void simulate_dist(qb_iter *it, int rule_id, const rule_ops *ops, const void *ru
 			offsets[r] = offsets[r - 1] + back_counts[r - 1];
 		QB_CUDA(cudaMemcpyAsync(cursor, offsets.data(), sizeof(uint64_t) * world, cudaMemcpyHostToDevice, stream));
 		cm->ret_send.ensure(sizeof(survivor_record) * n_owner_survivors, stream);
-		return_scatter_kernel<<<grid_back, 256, 0, stream>>>(owner, owner_survivor_slot, n_owner_survivors, begin_dev.as<uint64_t>(), world,
+		return_scatter_kernel<<<grid_for(div_up<uint64_t>(n_owner_survivors, SCATTER_TILE) * 256, 256, ctx->grid_cap()), 256, 2 * sizeof(unsigned long long) * world, stream>>>(owner, owner_survivor_slot, n_owner_survivors, begin_dev.as<uint64_t>(), world,
 		                                                     cm->recv.as<exchange_record>(), cursor, cm->ret_send.as<survivor_record>());
 		++ctx->launches;
 		ctx->sync();
 	}
+	timer.end(QB_PHASE_OWNER);
 	step("compute_collisions - com");
+	timer.begin(QB_PHASE_EXCHANGE);
 	uint64_t n_survivors = 0;
 	comm.alltoallv(cm->ret_send.ptr, back_counts, cm->ret_recv, sizeof(survivor_record), n_survivors);
+	timer.end(QB_PHASE_EXCHANGE);
 
+	mark("return survivors");
 	// 7. every rank rebuilds the survivors whose representative it generated, then global normalisation
 	survivor_source src;
 	src.records = cm->ret_recv.as<survivor_record>();
 	finalize_and_normalize(it, ops, rule, next, sym, opt, R, src, n_survivors, timer, step, L, &comm, node_total_proba);
+	mark("finalize + normalize");
 }
 
 } // namespace

@@ -157,7 +157,8 @@ struct __align__(32) exchange_record { // a locally unique child, on its way to 
 
 __device__ __forceinline__ uint32_t owner_of(uint64_t hash, uint32_t world) { return (uint32_t)__umul64hi(mix64(hash ^ 0x9e3779b97f4a7c15ull), (uint64_t)world); }
 
-// counts[owner] over the locally unique children
+// counts[owner] over the locally unique children (shared-memory histogram per CTA: a global atomic per
+// element on `world` addresses would serialise in L2)
 __global__ void __launch_bounds__(256) owner_count_kernel(table_view t, const uint32_t *uslot, uint64_t n, uint32_t world, unsigned long long *counts) {
 	extern __shared__ unsigned int s_counts[];
 	for (uint32_t i = threadIdx.x; i < world; i += blockDim.x)
@@ -172,25 +173,80 @@ __global__ void __launch_bounds__(256) owner_count_kernel(table_view t, const ui
 			atomicAdd(&counts[i], (unsigned long long)s_counts[i]);
 }
 
-// records grouped by owner: cursor[owner] starts at the owner's offset
+constexpr int SCATTER_TILE = 2048; // elements one CTA places per round: `world` global atomics per tile
+
+// records grouped by owner: cursor[owner] starts at the owner's offset.  Per tile: histogram in shared
+// memory, one global atomicAdd per owner reserves the tile's range, ranks inside the tile come from
+// shared-memory atomics.
 __global__ void __launch_bounds__(256) owner_scatter_kernel(table_view t, const uint32_t *uslot, uint64_t n, uint32_t world, unsigned long long *cursor,
                                                             exchange_record *out) {
-	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-		const table_slot s = t.slots[uslot[i]];
-		const unsigned long long at = atomicAdd(&cursor[owner_of(s.key, world)], 1ull);
-		out[at] = exchange_record{s.key, s.re, s.im, s.rep};
+	extern __shared__ unsigned long long s_base[]; // [world] tile base, then [world] running rank (as u64 for alignment)
+	unsigned long long *s_rank = s_base + world;
+	for (uint64_t tile = (uint64_t)blockIdx.x * SCATTER_TILE; tile < n; tile += (uint64_t)gridDim.x * SCATTER_TILE) {
+		for (uint32_t i = threadIdx.x; i < 2 * world; i += blockDim.x)
+			s_base[i] = 0;
+		__syncthreads();
+		const uint64_t end = min(tile + (uint64_t)SCATTER_TILE, n);
+		for (uint64_t i = tile + threadIdx.x; i < end; i += blockDim.x)
+			atomicAdd(&s_base[owner_of(t.slots[uslot[i]].key, world)], 1ull);
+		__syncthreads();
+		for (uint32_t o = threadIdx.x; o < world; o += blockDim.x)
+			s_base[o] = s_base[o] ? atomicAdd(&cursor[o], s_base[o]) : 0;
+		__syncthreads();
+		for (uint64_t i = tile + threadIdx.x; i < end; i += blockDim.x) {
+			const table_slot s = t.slots[uslot[i]];
+			const uint32_t o = owner_of(s.key, world);
+			const unsigned long long at = s_base[o] + atomicAdd(&s_rank[o], 1ull);
+			out[at] = exchange_record{s.key, s.re, s.im, s.rep};
+		}
+		__syncthreads();
 	}
 }
 
-// owner side: merge the received records; the representative of a slot is the POSITION of the record
-// that created it (its sender and its original representative are looked up there later)
+// owner side: the representative of a slot is the POSITION of one of the records merged into it (its
+// sender and its original representative are looked up there later).  Which one: the record with the
+// largest pseudo-random byte (atomicMax), NOT the one that created the slot -- the receive buffer is in
+// rank order, so "first come" would hand most survivors, hence most of the finalisation, to rank 0.
+__device__ __forceinline__ uint64_t owner_rep_pack(uint64_t position, uint64_t hash) { return ((mix64(position ^ hash) >> 56) << 56) | (position + 1); }
+__device__ __forceinline__ uint64_t owner_rep_position(uint64_t rep) { return (rep & ((1ull << 56) - 1)) - 1; }
+
 __global__ void __launch_bounds__(256) record_insert_kernel(table_view t, const exchange_record *records, uint64_t n) {
 	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
 	unsigned int created = 0;
 	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
 		const exchange_record r = records[i];
-		created += table_insert(t, r.hash, cplx{r.re, r.im}, rep_pack(i, 0));
+		table_slot *s;
+		if (r.hash == 0) {
+			s = t.slots + t.capacity;
+		} else {
+			uint64_t at = table_home(r.hash, t.capacity);
+			uint32_t probes = 0;
+			while (true) {
+				s = t.slots + at;
+				unsigned long long seen = __ldcg(&s->key);
+				if (seen == 0) {
+					seen = atomicCAS(&s->key, 0ull, (unsigned long long)r.hash);
+					if (seen == 0) {
+						++created;
+						break;
+					}
+				}
+				if (seen == r.hash)
+					break;
+				if (++at == t.capacity)
+					at = 0;
+				if (++probes > TABLE_MAX_PROBES) {
+					*t.overflow = 1;
+					s = nullptr;
+					break;
+				}
+			}
+		}
+		if (s) {
+			atomicAdd(&s->re, r.re);
+			atomicAdd(&s->im, r.im);
+			atomicMax(&s->rep, (unsigned long long)owner_rep_pack(i, r.hash));
+		}
 	}
 	created = (unsigned int)warp_sum((uint64_t)created);
 	if (lane_id() == 0 && created)
@@ -200,23 +256,46 @@ __global__ void __launch_bounds__(256) record_insert_kernel(table_view t, const 
 // survivors (owner slots) -> which rank their representative came from; counts per rank
 __global__ void __launch_bounds__(256) return_count_kernel(table_view t, const uint32_t *slot, uint64_t n, const uint64_t *recv_begin, uint32_t world,
                                                            unsigned long long *counts) {
+	extern __shared__ unsigned int s_counts[];
+	for (uint32_t i = threadIdx.x; i < world; i += blockDim.x)
+		s_counts[i] = 0;
+	__syncthreads();
 	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
 	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-		const uint64_t position = rep_index(t.slots[slot[i]].rep);
-		const uint32_t src = (uint32_t)upper_bound_u64(recv_begin, world + 1, position) - 1;
-		atomicAdd(&counts[src], 1ull);
+		const uint64_t position = owner_rep_position(t.slots[slot[i]].rep);
+		atomicAdd(&s_counts[(uint32_t)upper_bound_u64(recv_begin, world + 1, position) - 1], 1u);
 	}
+	__syncthreads();
+	for (uint32_t i = threadIdx.x; i < world; i += blockDim.x)
+		if (s_counts[i])
+			atomicAdd(&counts[i], (unsigned long long)s_counts[i]);
 }
 
 __global__ void __launch_bounds__(256) return_scatter_kernel(table_view t, const uint32_t *slot, uint64_t n, const uint64_t *recv_begin, uint32_t world,
                                                              const exchange_record *received, unsigned long long *cursor, survivor_record *out) {
-	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-		const table_slot s = t.slots[slot[i]];
-		const uint64_t position = rep_index(s.rep);
-		const uint32_t src = (uint32_t)upper_bound_u64(recv_begin, world + 1, position) - 1;
-		const unsigned long long at = atomicAdd(&cursor[src], 1ull);
-		out[at] = survivor_record{received[position].rep, s.re, s.im};
+	extern __shared__ unsigned long long s_base[];
+	unsigned long long *s_rank = s_base + world;
+	for (uint64_t tile = (uint64_t)blockIdx.x * SCATTER_TILE; tile < n; tile += (uint64_t)gridDim.x * SCATTER_TILE) {
+		for (uint32_t i = threadIdx.x; i < 2 * world; i += blockDim.x)
+			s_base[i] = 0;
+		__syncthreads();
+		const uint64_t end = min(tile + (uint64_t)SCATTER_TILE, n);
+		for (uint64_t i = tile + threadIdx.x; i < end; i += blockDim.x) {
+			const uint64_t position = owner_rep_position(t.slots[slot[i]].rep);
+			atomicAdd(&s_base[(uint32_t)upper_bound_u64(recv_begin, world + 1, position) - 1], 1ull);
+		}
+		__syncthreads();
+		for (uint32_t o = threadIdx.x; o < world; o += blockDim.x)
+			s_base[o] = s_base[o] ? atomicAdd(&cursor[o], s_base[o]) : 0;
+		__syncthreads();
+		for (uint64_t i = tile + threadIdx.x; i < end; i += blockDim.x) {
+			const table_slot s = t.slots[slot[i]];
+			const uint64_t position = owner_rep_position(s.rep);
+			const uint32_t src = (uint32_t)upper_bound_u64(recv_begin, world + 1, position) - 1;
+			const unsigned long long at = s_base[src] + atomicAdd(&s_rank[src], 1ull);
+			out[at] = survivor_record{received[position].rep, s.re, s.im};
+		}
+		__syncthreads();
 	}
 }
 
