@@ -63,7 +63,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -284,7 +284,7 @@ def run_ours(args):
         if tj.get("parents") == parents and tj.get("kernel") == "symbolic_kernel":
             traffic = tj.get("dram_bytes_per_launch")
     total_bytes = algorithmic_bytes(parents, s_p, n_c, n_u, n_s, s_p)
-    roofline = {"bound": "hbm", "kernel": "symbolic_kernel<erase_create> (child generation fused with interference-table insert)",
+    roofline = {"bound": "hbm", "kernel": "symbolic_items_kernel<erase_create> (child generation in sorted order, on-chip family accumulation, interference-table insert)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": sym_bytes, "kernel_ms": sym_ms, "kernel_share_of_step": sym_ms / ms_per_step,
                 "dominant_phase": dominant, "phase_ms": phase_ms,

@@ -280,6 +280,17 @@ struct widen_u32 {
 	__device__ uint64_t operator()(uint64_t j) const { return v[j]; }
 };
 
+// number of positions where the sorted key changes (= runs - 1)
+__global__ void __launch_bounds__(256) key_changes_kernel(const uint32_t *keys, uint64_t n, unsigned long long *count) {
+	unsigned long long local = 0;
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x + 1; i < n; i += stride)
+		local += keys[i] != keys[i - 1];
+	local = warp_sum((uint64_t)local);
+	if (lane_id() == 0 && local)
+		atomicAdd(count, local);
+}
+
 // stable radix sort of n (u32 key, u64 value) pairs that sit in the first halves of sym->sort_keys /
 // sort_vals (each sized for 2 n); returns the sorted values (device)
 const uint64_t *sort_items(qb_ctx *ctx, qb_sym *sym, uint64_t n) {
@@ -477,6 +488,17 @@ local_table build_local_table(qb_iter *it, int rule_id, const rule_ops *ops, con
 		L.item_vals = sym->sort_vals.as<uint64_t>();
 		ops->launch_group_items(rule, L);
 		L.items = sort_items(ctx, sym, n_groups);
+		if (capacity == full_capacity) {
+			// no history yet: in sorted order the table receives at most one group's worth of objects per run
+			// of equal keys (plus one split per chunk of work items), usually far fewer than one per child
+			QB_CUDA(cudaMemsetAsync(ctx->small(DS_COUNT), 0, sizeof(uint64_t), stream));
+			key_changes_kernel<<<grid_for(n_groups, 256, ctx->grid_cap()), 256, 0, stream>>>(sym->sort_keys.as<uint32_t>(), n_groups,
+			                                                                              reinterpret_cast<unsigned long long *>(ctx->small(DS_COUNT)));
+			++ctx->launches;
+			ctx->fetch_small();
+			const double flushes = 1.25 * (double)(ctx->h_small[DS_COUNT] + 1 + div_up<uint64_t>(n_groups, ITEM_CHUNK)) + 4096;
+			capacity = std::min<uint64_t>(full_capacity, std::max<uint64_t>(1024, (uint64_t)(flushes * ops->group_capacity / opt.table_load)));
+		}
 		timer.end(QB_PHASE_PRE_TRUNCATE);
 	}
 	for (sym->table_attempts = 1;; ++sym->table_attempts) {

@@ -474,6 +474,7 @@ struct rule_glue {
 		o.warp_groups = Rule::warp_groups;
 		o.has_group_key = Rule::has_group_key;
 		o.ctx_bytes = sizeof(typename Rule::ctx_t);
+		o.group_capacity = Rule::group_capacity;
 		o.launch_group_items = group_items;
 		o.launch_symbolic_items = symbolic_items;
 		o.symbolic_grid = symbolic_grid;

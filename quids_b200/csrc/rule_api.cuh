@@ -128,6 +128,7 @@ struct rule_base {
 	__device__ void edit_child(const uint8_t *, uint32_t, uint8_t *, uint32_t) const {}
 
 	static constexpr bool has_group_key = false;
+	static constexpr uint32_t group_capacity = 1; // most children one group can hold (bounds what a run can send to the table)
 	__device__ void group_keys(const uint8_t *, uint32_t, uint32_t, uint32_t *) const {}
 	__device__ void init_warp(workspace_t &) const {}
 	template <class Emit>
@@ -161,6 +162,7 @@ struct rule_ops {
 	bool needs_scratch;
 	bool warp_groups;
 	bool has_group_key;
+	uint32_t group_capacity;
 	size_t ctx_bytes;
 	void (*launch_group_items)(const void *rule, const engine_launch &L);
 	void (*launch_symbolic_items)(const void *rule, const engine_launch &L);

@@ -193,6 +193,7 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 	static constexpr bool needs_scratch = false;
 	static constexpr bool warp_groups = true;
 	static constexpr bool has_group_key = true;
+	static constexpr uint32_t group_capacity = FLIP_BLOCK;
 	static constexpr bool has_edit_child = true;
 
 	// a child is its parent with some eligible nodes toggled

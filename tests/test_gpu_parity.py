@@ -341,3 +341,41 @@ def test_probability_is_conserved_without_truncation(gpu, port):
         assert len(np.unique(h)) == b.num_object == sym.num_object_after_interferences
         a, b = b, a
     qb.config.tolerance = 1e-30
+
+
+def test_sorted_and_unsorted_order_agree_at_scale(gpu):
+    """2e6 random 12-node parents (2.6e8 children): the sorted order with on-chip family accumulation
+    and the plain order (every child goes to the table) must produce the same objects, the same
+    hashes and magnitudes within 1e-12; erase_create is unitary, so without truncation the
+    probability of the (duplicate-free) input is conserved."""
+    import quids_b200 as qb
+    from quids_b200 import qcgd
+    n = 2_000_000
+    sizes, data = qcgd.random_graphs(12, n, seed=3)
+    # drop duplicate parents: the state must be a proper superposition for unitarity to show
+    rows = np.unique(data.reshape(n, -1), axis=0)
+    n = rows.shape[0]
+    rng = np.random.default_rng(0)
+    mags = rng.normal(size=(n, 2))
+    mags /= np.sqrt((mags ** 2).sum())
+    qb.config.tolerance = 1e-30
+    qb.config.align_byte_length = 8
+    rule = qb.Rule("erase_create", 0.7, 0.3, -0.2)
+    results = []
+    for mode in (0, 2):
+        qb.config.locality_sort = mode
+        a, b, sym = qb.Iteration(), qb.Iteration(), qb.SymbolicIteration()
+        a.upload_packed(np.full(n, rows.shape[1], np.uint32), mags, rows.reshape(-1))
+        qb.simulate(a, rule, b, sym)
+        h = b.hashes(rule)
+        _, m, _ = b.download_packed()
+        order = np.argsort(h)
+        results.append((h[order], m[order], b.total_proba, sym.num_object, sym.num_object_after_interferences))
+    qb.config.locality_sort = 1
+    (h0, m0, p0, c0, u0), (h1, m1, p1, c1, u1) = results
+    assert (c0, u0) == (c1, u1) and c0 > 2e8
+    assert len(np.unique(h0)) == len(h0) and np.array_equal(h0, h1)
+    scale = np.maximum(np.abs(m0).max(axis=1), 1e-300)
+    assert (np.abs(m0 - m1).max(axis=1) <= 1e-12 * np.maximum(scale, np.abs(m0).max() * 1e-6)).all()
+    assert abs(p0 - 1) < 1e-10 and abs(p1 - 1) < 1e-10
+    qb.config.tolerance = 1e-30
