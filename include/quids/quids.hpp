@@ -14,7 +14,8 @@
 //     factories cnot/Xgate/Ygate/Zgate and qcgd::step / reversed_step keep their names.  A host
 //     lambda is NOT accepted: there is no CPU fallback.
 //   * simple_truncation defaults to true (the probabilistic mode is not reproducible even in the
-//     reference); setting it to false makes simulate throw.
+//     reference).  false selects the probabilistic truncation of the reference
+//     (keep the smallest u / |mag|^2) with a counter-based generator seeded by quids::truncation_seed.
 //   * states live in HBM; append/get_object/average_value work on a host mirror that is synchronised
 //     lazily (uploaded before a simulate, downloaded on the first read after one).
 //
@@ -64,6 +65,7 @@ namespace quids {
 	inline float equalize_factor = EQUALIZE_FACTOR;           // kept for source compatibility (host-memory heuristic of the reference)
 	inline int load_balancing_bucket_per_thread = LOAD_BALANCING_BUCKET_PER_THREAD; // no effect: no CPU bucket partition here
 	inline bool simple_truncation = true;
+	inline unsigned truncation_seed = 0; // probabilistic truncation only (no counterpart in the reference, which seeds from rand())
 
 	namespace utils { // utils/vector.hpp:29-33, kept so that drivers assigning them still compile
 		inline float upsize_policy = 1.1f;
@@ -110,6 +112,7 @@ namespace quids {
 			o.align_byte_length = align_byte_length;
 			o.simple_truncation = simple_truncation ? 1 : 0;
 			o.safety_margin = safety_margin;
+			o.seed = truncation_seed;
 			return o;
 		}
 		inline void forward_step(const char *label, void *user) { (*static_cast<debug_t *>(user))(label); }

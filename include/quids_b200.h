@@ -35,7 +35,7 @@ typedef enum qb_status {
 	QB_ERR_CUDA = -1,        /* a CUDA runtime call failed (includes "no device") */
 	QB_ERR_ARG = -2,         /* invalid argument */
 	QB_ERR_UNKNOWN_RULE = -3,
-	QB_ERR_UNSUPPORTED = -4, /* e.g. probabilistic truncation (quids::simple_truncation = false): SURVEY 8(f) */
+	QB_ERR_UNSUPPORTED = -4, /* the request is outside what this build implements */
 	QB_ERR_CAPACITY = -5,    /* an internal limit was exceeded (child index >= 2^40, object >= 16 MiB, table full) */
 	QB_ERR_COMM = -6         /* NCCL failure on the distributed path */
 } qb_status;
@@ -55,10 +55,12 @@ typedef struct qb_comm qb_comm; /* stands where MPI_Comm stands in quids_mpi.hpp
 typedef struct qb_options {
 	double tolerance;          /* quids::tolerance, strict > on re^2+im^2 (quids.hpp:62,821)        */
 	uint32_t align_byte_length; /* quids::align_byte_length (quids.hpp:60,93-102)                    */
-	int32_t simple_truncation; /* quids::simple_truncation; only 1 is supported */
+	int32_t simple_truncation; /* quids::simple_truncation (quids.hpp:69-75): 1 = keep the most probable; 0 = probabilistic: keep the
+	                              smallest u / |mag|^2, u uniform in (0,1) (quids.hpp:594-608,829-845), drawn from `seed` */
 	double table_load;         /* engine knob: max load factor of the interference table, 0 = default */
 	int32_t profile;           /* 1: record CUDA events at the phase boundaries (qb_sym_phase_ms)     */
 	float safety_margin;       /* quids::safety_margin (quids.hpp:64): fraction of GPU memory the automatic budget leaves free */
+	uint32_t seed;             /* probabilistic truncation: seed of the counter-based generator (the reference seeds from rand()) */
 	int32_t locality_sort;     /* engine knob: process the child groups in the order of the rule's group key so that equal
 	                              objects are merged on chip before the table; 0 off, 1 when there are >= 2^16 groups (default), 2 always */
 } qb_options;

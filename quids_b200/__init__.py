@@ -47,7 +47,7 @@ def build(verbose=False):
 
 class qb_options(C.Structure):
     _fields_ = [("tolerance", C.c_double), ("align_byte_length", C.c_uint32), ("simple_truncation", C.c_int32),
-                ("table_load", C.c_double), ("profile", C.c_int32), ("safety_margin", C.c_float), ("locality_sort", C.c_int32)]
+                ("table_load", C.c_double), ("profile", C.c_int32), ("safety_margin", C.c_float), ("seed", C.c_uint32), ("locality_sort", C.c_int32)]
 
 
 STEP_CB = C.CFUNCTYPE(None, C.c_char_p, C.c_void_p)
@@ -132,7 +132,8 @@ def _check(rc):
 class _Globals:
     tolerance = 1e-30          # quids::tolerance
     align_byte_length = 8      # quids::align_byte_length
-    simple_truncation = True   # quids::simple_truncation (the only supported mode)
+    simple_truncation = True   # quids::simple_truncation; False = probabilistic truncation (the reference's default)
+    seed = 0                   # seed of the probabilistic truncation
     safety_margin = 0.2        # quids::safety_margin
     table_load = 0.0           # engine knob (0 = default)
     profile = False
@@ -146,6 +147,7 @@ class _Globals:
         o.simple_truncation = 1 if self.simple_truncation else 0
         o.table_load = self.table_load
         o.safety_margin = self.safety_margin
+        o.seed = self.seed
         o.profile = 1 if self.profile else 0
         o.locality_sort = self.locality_sort
         return o

@@ -257,6 +257,30 @@ struct key_from_mag {
 	const cplx *mag;
 	__device__ uint64_t operator()(uint64_t i) const { return key_of_norm(cnorm(mag[i])); }
 };
+// probabilistic truncation (quids.hpp:594-608, 829-845): the reference keeps the objects with the SMALLEST
+// random_selector = rng() / |mag|^2, rng uniform in [0, 1).  Here u comes from a counter-based generator
+// (splitmix64 of seed and element index: reproducible for a given seed), and the selector's bit pattern is
+// inverted so that the same "k largest keys" select applies.
+__device__ __forceinline__ uint64_t random_selector_key(double norm, uint64_t index, uint32_t seed) {
+	uint64_t x = (index + 1) * 0x9e3779b97f4a7c15ull + ((uint64_t)seed << 32 | seed);
+	x = mix64(x);
+	const double u = ((double)(x >> 11) + 0.5) * (1.0 / 9007199254740992.0); // (0, 1)
+	return ~(uint64_t)__double_as_longlong(u / norm);
+}
+struct key_from_mag_random {
+	const cplx *mag;
+	uint32_t seed;
+	__device__ uint64_t operator()(uint64_t i) const { return random_selector_key(cnorm(mag[i]), i, seed); }
+};
+// the compacted keys of the unique children are |mag|^2 bit patterns: replace them by selector keys.  The counter of
+// the generator is the object's HASH (not its table slot, which depends on insertion order and table capacity), so a
+// seed picks the same objects on every run and on any number of GPUs.
+__global__ void __launch_bounds__(256) randomize_keys_kernel(uint64_t *keys, table_view t, const uint32_t *slot, uint64_t n, uint32_t seed) {
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+		keys[i] = random_selector_key(__longlong_as_double((long long)keys[i]), t.slots[slot[i]].key, seed ^ 0x5bd1e995u);
+}
+
 struct key_from_array {
 	const uint64_t *key;
 	__device__ uint64_t operator()(uint64_t i) const { return key[i]; }
@@ -339,8 +363,6 @@ void resolve_options(const qb_options *in, qb_options &opt) {
 		opt = *in;
 	if (!(opt.table_load > 0 && opt.table_load <= 0.95))
 		opt.table_load = 0.75;
-	QB_REQUIRE(opt.simple_truncation != 0, QB_ERR_UNSUPPORTED,
-	           "probabilistic truncation (quids::simple_truncation = false) is not supported: set simple_truncation (SURVEY 8f)");
 }
 
 // ======================================================================================================
@@ -395,9 +417,15 @@ local_table build_local_table(qb_iter *it, int rule_id, const rule_ops *ops, con
 	if (max_num_object < n_global) {
 		timer.begin(QB_PHASE_PRE_TRUNCATE);
 		sym->kept.ensure(sizeof(uint64_t) * std::max<uint64_t>(1, std::min<uint64_t>(it->n, max_num_object)), stream);
-		key_from_mag keys{it->mag.as<cplx>()};
-		select_threshold(ctx, comm, keys, it->n, max_num_object);
-		R.n_parents = select_keep(ctx, comm, keys, it->n, out_index{sym->kept.as<uint64_t>()});
+		if (opt.simple_truncation) {
+			key_from_mag keys{it->mag.as<cplx>()};
+			select_threshold(ctx, comm, keys, it->n, max_num_object);
+			R.n_parents = select_keep(ctx, comm, keys, it->n, out_index{sym->kept.as<uint64_t>()});
+		} else {
+			key_from_mag_random keys{it->mag.as<cplx>(), opt.seed + (comm ? 0x9e3779b9u * (uint32_t)comm->rank() : 0u)};
+			select_threshold(ctx, comm, keys, it->n, max_num_object);
+			R.n_parents = select_keep(ctx, comm, keys, it->n, out_index{sym->kept.as<uint64_t>()});
+		}
 		R.kept = sym->kept.as<uint64_t>();
 		timer.end(QB_PHASE_PRE_TRUNCATE);
 	}
@@ -613,6 +641,11 @@ void simulate(qb_iter *it, int rule_id, const rule_ops *ops, const void *rule, q
 	if (max_num_object < R.n_unique) {
 		timer.begin(QB_PHASE_TRUNCATE);
 		sym->sslot.ensure(sizeof(uint32_t) * max_num_object, stream);
+		if (!opt.simple_truncation) {
+			randomize_keys_kernel<<<grid_for(R.n_unique, 256, ctx->grid_cap()), 256, 0, stream>>>(sym->ukey.as<uint64_t>(), R.table, sym->uslot.as<uint32_t>(),
+			                                                                                    R.n_unique, opt.seed);
+			++ctx->launches;
+		}
 		key_from_array keys{sym->ukey.as<uint64_t>()};
 		select_threshold(ctx, nullptr, keys, R.n_unique, max_num_object);
 		n_survivors = select_keep(ctx, nullptr, keys, R.n_unique, out_gather_u32{sym->sslot.as<uint32_t>(), sym->uslot.as<uint32_t>()});
@@ -839,6 +872,11 @@ void simulate_dist(qb_iter *it, int rule_id, const rule_ops *ops, const void *ru
 	if (max_num_object < n_unique_global) {
 		timer.begin(QB_PHASE_TRUNCATE);
 		sym->sslot.ensure(sizeof(uint32_t) * std::max<uint64_t>(1, std::min<uint64_t>(n_owner_unique, max_num_object)), stream);
+		if (!opt.simple_truncation && n_owner_unique > 0) {
+			randomize_keys_kernel<<<grid_for(n_owner_unique, 256, ctx->grid_cap()), 256, 0, stream>>>(cm->okey.as<uint64_t>(), owner, cm->oslot.as<uint32_t>(),
+			                                                                                         n_owner_unique, opt.seed);
+			++ctx->launches;
+		}
 		key_from_array keys{cm->okey.as<uint64_t>()};
 		select_threshold(ctx, &comm, keys, n_owner_unique, max_num_object);
 		n_owner_survivors = select_keep(ctx, &comm, keys, n_owner_unique, out_gather_u32{sym->sslot.as<uint32_t>(), cm->oslot.as<uint32_t>()});

@@ -253,12 +253,6 @@ def test_unsupported_requests_fail_loudly(gpu):
             qb.simulate(it, qb.Rule("hadamard", 1), nxt, sym, 0)
     finally:
         qb.config.safety_margin = 0.2
-    qb.config.simple_truncation = False
-    try:
-        with pytest.raises(qb.QuidsError, match="probabilistic"):
-            qb.simulate(it, qb.Rule("hadamard", 1), nxt, sym)
-    finally:
-        qb.config.simple_truncation = True
     with pytest.raises(qb.QuidsError):
         qb.simulate(it, qb.Rule("hadamard", 1), it, sym)
     with pytest.raises(qb.QuidsError):
@@ -379,3 +373,50 @@ def test_sorted_and_unsorted_order_agree_at_scale(gpu):
     assert (np.abs(m0 - m1).max(axis=1) <= 1e-12 * np.maximum(scale, np.abs(m0).max() * 1e-6)).all()
     assert abs(p0 - 1) < 1e-10 and abs(p1 - 1) < 1e-10
     qb.config.tolerance = 1e-30
+
+
+def test_probabilistic_truncation(gpu, port):
+    """the reference's default truncation (quids.hpp:594-608, 829-845): keep the k smallest u / |mag|^2.
+    Not reproducible in the reference (seeded from rand()), so the checks are structural and statistical:
+    exactly k objects, all of them genuine children with the right magnitudes, reproducible for a seed,
+    different for another seed, and objects are kept more often the more probable they are."""
+    import quids_b200 as qb
+    base = port.qcgd_random_state(7, 200, 31, 1.0)
+    rng = np.random.default_rng(9)
+    mags = rng.normal(size=(200, 2)) * np.exp(rng.normal(size=(200, 1)))
+    st = orc.Packed(base.sizes, mags / np.sqrt((mags ** 2).sum()), base.data)
+    rid, params, k = orc.RULE_ERASE_CREATE, [0.6, 0.1, 0.2], 400
+    full, nc, nu = port.simulate(st, rid, params, tolerance=1e-18)
+    kf = orc.keyed(full, port.hash_objects(full, rid), True)
+    fscale = math.sqrt(full.total_proba)
+    assert nu > 3 * k
+    eng = gpu()
+    qb.config.simple_truncation = False
+    try:
+        kept_count = {h: 0 for h in kf}
+        first = None
+        seeds = range(24)
+        for seed in seeds:
+            qb.config.seed = seed
+            got, gc, gu = eng.simulate(st, rid, params, k, 1e-18)
+            assert (gc, gu, got.n) == (nc, nu, k)
+            kg = orc.keyed(got, port.hash_objects(got, rid), True)
+            scale = math.sqrt(got.total_proba)
+            for h, (o, m) in kg.items():
+                assert h in kf and kf[h][0] == o
+                assert abs(m * scale - kf[h][1] * fscale) <= 1e-12 * abs(m * scale)
+                kept_count[h] += 1
+            if seed == 0:
+                first = set(kg)
+                again, _, _ = eng.simulate(st, rid, params, k, 1e-18)
+                assert set(orc.keyed(again, port.hash_objects(again, rid), True)) == first  # same seed, same choice
+            elif seed == 1:
+                assert set(kg) != first
+        probs = np.array([abs(kf[h][1]) ** 2 for h in kf])
+        freq = np.array([kept_count[h] / len(seeds) for h in kf])
+        order = np.argsort(probs)
+        low, high = freq[order[:len(order) // 4]].mean(), freq[order[-len(order) // 4:]].mean()
+        assert high > low + 0.3, (low, high)
+    finally:
+        qb.config.simple_truncation = True
+        qb.config.seed = 0
