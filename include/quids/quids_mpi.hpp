@@ -10,9 +10,9 @@
 // Differences from the reference, on purpose:
 //   * truncation keeps the max_num_object most probable objects over ALL ranks (the single-node result);
 //     the reference keeps max_num_object / local_size per rank (quids_mpi.hpp:537,590).
-//   * object migration and load balancing (send_objects / receive_objects / equalize / distribute_objects /
-//     gather_objects, quids_mpi.hpp:124-231,903-1077) are not provided yet: every
-//     rank builds or loads its own share of the state.
+//   * object migration (send_objects / receive_objects / equalize / distribute_objects / gather_objects,
+//     quids_mpi.hpp:124-231,903-1077) moves the tail of a state HBM -> NVLink -> HBM in one NCCL group; the
+//     node arguments are ranks of the communicator, which comes LAST-but-one as in the reference.
 #pragma once
 
 #include <chrono>
@@ -26,6 +26,7 @@ namespace quids::mpi {
 	// knobs of the reference's load balancer (quids_mpi.hpp:46-56), kept so that drivers assigning them compile
 	inline size_t min_equalize_size = 100;
 	inline float equalize_inbalance = 0.1f;
+	inline float min_equalize_step = 0.2f;
 	inline bool equalize_children = true;
 
 	/// the job's communicator: stands where MPI_Comm stands in the reference
@@ -97,14 +98,57 @@ namespace quids::mpi {
 		mpi_iteration(char *object_begin_, char *object_end_) : quids::iteration(object_begin_, object_end_) {}
 
 		size_t get_total_num_object(communicator const &comm) const { return comm.sum(num_object); }          // quids_mpi.hpp:77-87
+		/// children counted by the last rule iteration over this state, summed over the ranks (quids_mpi.hpp:92-96)
+		size_t get_total_num_symbolic_object(communicator const &comm) const {
+			uint64_t n = 0;
+			quids::detail::check(qb_iter_num_symbolic_object(handle_, &n));
+			return comm.sum((size_t)n);
+		}
 		PROBA_TYPE average_value(const quids::observable_t observable) const { return quids::iteration::average_value(observable); }
 		/// global average of an observable (quids_mpi.hpp:101-116): local averages weighted by the local share, summed
 		PROBA_TYPE average_value(const quids::observable_t observable, communicator const &comm) const {
 			return comm.sum(quids::iteration::average_value(observable));
 		}
 
+		/// send the last num_object_sent objects to rank `node`, which must call receive_objects (quids_mpi.hpp:124-172)
+		void send_objects(size_t num_object_sent, int node, communicator const &comm, bool /*send_num_child*/ = false) {
+			to_device();
+			quids::detail::check(qb_iter_send_objects(handle_, comm.handle(), num_object_sent, node, nullptr));
+			after_migration();
+		}
+		/// receive at the tail what rank `node` sends (quids_mpi.hpp:180-231); max_mem = -1: whatever fits the GPU
+		void receive_objects(int node, communicator const &comm, bool /*receive_num_child*/ = false, size_t max_mem = -1) {
+			to_device();
+			quids::detail::check(qb_iter_receive_objects(handle_, comm.handle(), node, (uint64_t)max_mem, nullptr));
+			after_migration();
+		}
+		/// one pairing round: the i-th fullest rank gives half of the difference to the i-th emptiest (quids_mpi.hpp:903-960)
+		void equalize(communicator const &comm) {
+			to_device();
+			quids::detail::check(qb_iter_equalize(handle_, comm.handle(), 0, nullptr, 0, 1, 0, -1.f, 0.f, nullptr));
+			after_migration();
+		}
+		/// spread the objects of rank node_id evenly over all ranks (quids_mpi.hpp:1031-1051)
+		void distribute_objects(communicator const &comm, int node_id = 0) {
+			to_device();
+			quids::detail::check(qb_iter_distribute_objects(handle_, comm.handle(), node_id));
+			after_migration();
+		}
+		/// bring every object to rank node_id (quids_mpi.hpp:1056-1077)
+		void gather_objects(communicator const &comm, int node_id = 0) {
+			to_device();
+			quids::detail::check(qb_iter_gather_objects(handle_, comm.handle(), node_id));
+			after_migration();
+			node_total_proba = comm.rank == node_id; // quids_mpi.hpp:1076
+		}
+
 	private:
 		friend void simulate(mpi_it_t &, quids::rule_t const *, mpi_it_t &, mpi_sy_it_t &, communicator &, size_t, quids::debug_t);
+		void after_migration() { // counts changed on the device; total_proba is a property of the whole wave function and stays
+			const PROBA_TYPE proba = total_proba;
+			after_device_write();
+			total_proba = proba;
+		}
 	};
 
 	class mpi_symbolic_iteration : public quids::symbolic_iteration {
@@ -122,12 +166,17 @@ namespace quids::mpi {
 	                     size_t max_num_object = 0, quids::debug_t mid_step_function = [](const char *) {}) {
 		iteration.to_device();
 		qb_options opt = quids::detail::options();
+		opt.equalize = equalize_children ? 2 : 1; // quids_mpi.hpp:442-500
+		opt.equalize_inbalance = equalize_inbalance;
+		opt.min_equalize_step = min_equalize_step;
+		opt.min_equalize_size = min_equalize_size;
 		const uint64_t k = (max_num_object == 0 || max_num_object == std::numeric_limits<size_t>::max()) ? QB_NO_TRUNCATION : (uint64_t)max_num_object;
 		double node = 1;
 		quids::detail::check(qb_simulate_dist(iteration.handle_, rule->id(), rule->params().data(), (uint32_t)rule->params().size(), next_iteration.handle_,
 		                                      symbolic_iteration.handle_, comm.handle(), k, &opt, mid_step_function ? quids::detail::forward_step : nullptr,
 		                                      &mid_step_function, &node));
 		symbolic_iteration.refresh();
+		iteration.after_migration(); // the load balancer may have moved parents
 		next_iteration.after_device_write();
 		next_iteration.node_total_proba = node;
 	}

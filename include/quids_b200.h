@@ -63,6 +63,11 @@ typedef struct qb_options {
 	uint32_t seed;             /* probabilistic truncation: seed of the counter-based generator (the reference seeds from rand()) */
 	int32_t locality_sort;     /* engine knob: process the child groups in the order of the rule's group key so that equal
 	                              objects are merged on chip before the table; 0 off, 1 when there are >= 2^16 groups (default), 2 always */
+	/* load balancing at the head of quids::mpi::simulate (quids_mpi.hpp:442-500); only qb_simulate_dist reads these */
+	int32_t equalize;            /* 0 off (default of the C ABI), 1 by objects (quids::mpi::equalize_children = false), 2 by children */
+	float equalize_inbalance;    /* quids::mpi::equalize_inbalance (quids_mpi.hpp:48): stop below this (max - avg) / max      */
+	float min_equalize_step;     /* quids::mpi::min_equalize_step (:50): stop when a round improves the gap by less than this */
+	uint64_t min_equalize_size;  /* quids::mpi::min_equalize_size (:46): do nothing when every rank holds fewer objects        */
 } qb_options;
 
 void qb_options_default(qb_options *opt);
@@ -161,6 +166,29 @@ int qb_comm_destroy(qb_comm *comm);
 int qb_simulate_dist(qb_iter *it, int rule_id, const double *params, uint32_t num_params, qb_iter *next,
                      qb_sym *sym, qb_comm *comm, uint64_t max_num_object, const qb_options *opt,
                      qb_step_cb cb, void *user, double *node_total_proba);
+
+/* ---- object migration (quids_mpi.hpp:124-231, 903-1077): the tail of a state moves HBM -> NVLink -> HBM ------------
+ * send_objects / receive_objects are called on the two ranks of a pair (not collective), like MPI_Send / MPI_Recv:
+ * the sender pops the objects it sent (without normalising, quids_mpi.hpp:170).  *moved = objects really moved
+ * (0 when the receiver had no room, quids_mpi.hpp:136-138,196-198). */
+int qb_iter_send_objects(qb_iter *it, qb_comm *comm, uint64_t num_object_sent, int node, uint64_t *moved);
+/* max_mem: most bytes (52 per object + object bytes) this rank accepts, UINT64_MAX = whatever fits the GPU */
+int qb_iter_receive_objects(qb_iter *it, qb_comm *comm, int node, uint64_t max_mem, uint64_t *moved);
+/* mpi_iteration::distribute_objects (quids_mpi.hpp:1031-1051) / gather_objects (:1056-1077); collective */
+int qb_iter_distribute_objects(qb_iter *it, qb_comm *comm, int node_id);
+int qb_iter_gather_objects(qb_iter *it, qb_comm *comm, int node_id);
+/* number of children the local objects have under a rule = get_num_symbolic_object after compute_num_child
+ * (quids.hpp:548-569); not collective */
+/* children counted by the last rule iteration (or qb_iter_count_children) over this state: get_num_symbolic_object, quids.hpp:322-324 */
+int qb_iter_num_symbolic_object(const qb_iter *it, uint64_t *num_symbolic_object);
+int qb_iter_count_children(qb_iter *it, int rule_id, const double *params, uint32_t num_params, uint64_t *num_children);
+/* pairing rounds of mpi_iteration::equalize (rule_id = 0, quids_mpi.hpp:903-960) or equalize_symbolic (rule_id >= 1,
+ * ranks weighed by the children of that rule, :965-1026); collective.  max_rounds = 1 and inbalance = 0 is one
+ * unconditional round (the public equalize()); the loop of quids::mpi::simulate (:442-500) passes
+ * ceil(log2(world)) and the quids::mpi thresholds.  *rounds = pairing rounds run. */
+int qb_iter_equalize(qb_iter *it, qb_comm *comm, int rule_id, const double *params, uint32_t num_params, int max_rounds,
+                     uint64_t min_equalize_size, float equalize_inbalance, float min_equalize_step, int *rounds);
+
 /* get_total_num_object / get_total_num_symbolic_object style all-reduced counters (quids_mpi.hpp:77-99,322-339) */
 int qb_comm_allreduce_u64(qb_comm *comm, uint64_t *values, uint32_t n, int op_max);
 int qb_comm_allreduce_f64(qb_comm *comm, double *values, uint32_t n);

@@ -47,7 +47,8 @@ def build(verbose=False):
 
 class qb_options(C.Structure):
     _fields_ = [("tolerance", C.c_double), ("align_byte_length", C.c_uint32), ("simple_truncation", C.c_int32),
-                ("table_load", C.c_double), ("profile", C.c_int32), ("safety_margin", C.c_float), ("seed", C.c_uint32), ("locality_sort", C.c_int32)]
+                ("table_load", C.c_double), ("profile", C.c_int32), ("safety_margin", C.c_float), ("seed", C.c_uint32), ("locality_sort", C.c_int32),
+                ("equalize", C.c_int32), ("equalize_inbalance", C.c_float), ("min_equalize_step", C.c_float), ("min_equalize_size", C.c_uint64)]
 
 
 STEP_CB = C.CFUNCTYPE(None, C.c_char_p, C.c_void_p)
@@ -100,6 +101,13 @@ def lib():
         "qb_comm_create": (i32, [vp, i32, i32, vp, P(vp)]),
         "qb_comm_destroy": (i32, [vp]),
         "qb_simulate_dist": (i32, [vp, i32, P(dbl), u32, vp, vp, vp, u64, P(qb_options), STEP_CB, vp, P(dbl)]),
+        "qb_iter_send_objects": (i32, [vp, vp, u64, i32, P(u64)]),
+        "qb_iter_receive_objects": (i32, [vp, vp, i32, u64, P(u64)]),
+        "qb_iter_distribute_objects": (i32, [vp, vp, i32]),
+        "qb_iter_gather_objects": (i32, [vp, vp, i32]),
+        "qb_iter_num_symbolic_object": (i32, [vp, P(u64)]),
+        "qb_iter_count_children": (i32, [vp, i32, P(dbl), u32, P(u64)]),
+        "qb_iter_equalize": (i32, [vp, vp, i32, P(dbl), u32, i32, u64, C.c_float, C.c_float, P(i32)]),
         "qb_comm_allreduce_u64": (i32, [vp, vp, u32, i32]),
         "qb_comm_allreduce_f64": (i32, [vp, vp, u32]),
     }
@@ -137,6 +145,10 @@ class _Globals:
     safety_margin = 0.2        # quids::safety_margin
     table_load = 0.0           # engine knob (0 = default)
     profile = False
+    equalize = 0               # distributed path: 0 off, 1 by objects, 2 by children (quids::mpi::equalize_children)
+    equalize_inbalance = 0.1   # quids::mpi::equalize_inbalance
+    min_equalize_step = 0.2    # quids::mpi::min_equalize_step
+    min_equalize_size = 100    # quids::mpi::min_equalize_size
     locality_sort = 1          # engine knob: 0 off, 1 auto, 2 always
 
     def options(self):
@@ -150,6 +162,10 @@ class _Globals:
         o.seed = self.seed
         o.profile = 1 if self.profile else 0
         o.locality_sort = self.locality_sort
+        o.equalize = self.equalize
+        o.equalize_inbalance = self.equalize_inbalance
+        o.min_equalize_step = self.min_equalize_step
+        o.min_equalize_size = self.min_equalize_size
         return o
 
 
@@ -379,6 +395,45 @@ class Iteration:
     def normalize(self):
         self._flush()
         _check(lib().qb_iter_normalize(self.handle))
+
+    # -- object migration over NCCL (quids_mpi.hpp:124-231, 903-1077) ----------------------------
+    def send_objects(self, num_object_sent, node, communicator):
+        """send the last objects to rank `node` (which calls receive_objects) and pop them; returns how many moved"""
+        self._flush()
+        moved = C.c_uint64()
+        _check(lib().qb_iter_send_objects(self.handle, communicator.handle, num_object_sent, node, C.byref(moved)))
+        return moved.value
+
+    def receive_objects(self, node, communicator, max_mem=NO_TRUNCATION):
+        self._flush()
+        moved = C.c_uint64()
+        _check(lib().qb_iter_receive_objects(self.handle, communicator.handle, node, max_mem, C.byref(moved)))
+        return moved.value
+
+    def distribute_objects(self, communicator, node_id=0):
+        self._flush()
+        _check(lib().qb_iter_distribute_objects(self.handle, communicator.handle, node_id))
+
+    def gather_objects(self, communicator, node_id=0):
+        self._flush()
+        _check(lib().qb_iter_gather_objects(self.handle, communicator.handle, node_id))
+
+    def equalize(self, communicator, rule: "Rule" = None, max_rounds=1, min_equalize_size=0, equalize_inbalance=-1.0, min_equalize_step=0.0):
+        """pairing rounds of equalize (rule None: by objects) or equalize_symbolic (by the children of `rule`); returns the rounds run"""
+        self._flush()
+        rounds = C.c_int()
+        p, k = _params(rule.params) if rule else (None, 0)
+        _check(lib().qb_iter_equalize(self.handle, communicator.handle, rule.id if rule else 0, p, k, max_rounds, min_equalize_size,
+                                      equalize_inbalance, min_equalize_step, C.byref(rounds)))
+        return rounds.value
+
+    def count_children(self, rule: "Rule"):
+        """children the local objects have under `rule` (compute_num_child, quids.hpp:548-569)"""
+        self._flush()
+        n = C.c_uint64()
+        p, k = _params(rule.params)
+        _check(lib().qb_iter_count_children(self.handle, rule.id, p, k, C.byref(n)))
+        return n.value
 
     def hashes(self, rule: Rule):
         """rule->hasher over every object"""

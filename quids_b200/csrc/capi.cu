@@ -100,6 +100,7 @@ struct qb_iter {
 	qb_ctx *ctx;
 	uint64_t n = 0, n_bytes = 0;
 	double total_proba = 1; // quids.hpp:154
+	uint64_t n_symbolic = 0; // children counted by the last compute_num_child over this state (get_num_symbolic_object, quids.hpp:322-324)
 	dev_buf objects, begin, size, mag, num_childs, child_begin, num_groups, group_begin;
 
 	iter_view view() const { return iter_view{objects.as<uint8_t>(), begin.as<uint64_t>(), size.as<uint32_t>(), mag.as<cplx>(), n}; }
@@ -454,6 +455,7 @@ local_table build_local_table(qb_iter *it, int rule_id, const rule_ops *ops, con
 		max_child_size = (uint32_t)ctx->h_small[DS_MAX_CHILD_SIZE];
 	}
 	sym->n_children = R.n_children;
+	it->n_symbolic = R.n_children;
 	if (global_sum(comm, R.n_children) == 0) {
 		R.empty_from = 1;
 		return R;
@@ -753,6 +755,8 @@ void finalize_and_normalize(qb_iter *it, const rule_ops *ops, const void *rule, 
 	step("end");
 }
 
+#include "migrate.inc.cuh"
+
 // ======================================================================================================
 // one rule iteration over the GPUs of a communicator (see dist.inc.cuh for the protocol)
 // ======================================================================================================
@@ -777,6 +781,15 @@ void simulate_dist(qb_iter *it, int rule_id, const rule_ops *ops, const void *ru
 		fprintf(stderr, "[qb dist rank %d] %-28s %8.3f ms\n", cm->rank, what, std::chrono::duration<double, std::milli>(now - t_last).count());
 		t_last = now;
 	};
+
+	// 0. load balancing (quids_mpi.hpp:442-500): pairs of ranks level their objects or their children
+	if (opt.equalize) {
+		step(opt.equalize == 2 ? "equalize_child" : "equalize_object");
+		int max_rounds = 0;
+		while ((1u << max_rounds) < world) ++max_rounds; // utils::log_2_upper_bound(size), quids_mpi.hpp:432
+		equalize_loop(it, cm, ops, rule, opt.equalize == 2, opt.min_equalize_size, opt.equalize_inbalance, opt.min_equalize_step, max_rounds);
+		mark("equalize");
+	}
 
 	engine_launch L;
 	memset(&L, 0, sizeof L);
@@ -940,6 +953,10 @@ void qb_options_default(qb_options *opt) {
 	opt->profile = 0;
 	opt->locality_sort = 1;
 	opt->safety_margin = 0.2f; // SAFETY_MARGIN, quids.hpp:33-35
+	opt->equalize = 0;
+	opt->equalize_inbalance = 0.1f; // EQUALIZE_INBALANCE, quids_mpi.hpp:28-30
+	opt->min_equalize_step = 0.2f;  // MIN_INBALANCE_STEP, quids_mpi.hpp:31-33
+	opt->min_equalize_size = 100;   // MIN_EQUALIZE_SIZE, quids_mpi.hpp:13-15
 }
 
 const char *qb_last_error(void) { return g_last_error.c_str(); }
@@ -1296,6 +1313,94 @@ int qb_simulate_dist(qb_iter *it, int rule_id, const double *params, uint32_t nu
 			return;
 		}
 		simulate_dist(it, rule_id, ops, storage, next, sym, comm, max_num_object, opt, cb, user, node_total_proba);
+	});
+}
+
+int qb_iter_send_objects(qb_iter *it, qb_comm *comm, uint64_t num_object_sent, int node, uint64_t *moved) {
+	return guarded([&] {
+		QB_REQUIRE(it && comm && it->ctx == comm->ctx, QB_ERR_ARG, "qb_iter_send_objects: bad handle");
+		it->ctx->use();
+		const uint64_t n = send_objects(it, comm, num_object_sent, node);
+		if (moved) *moved = n;
+	});
+}
+
+int qb_iter_receive_objects(qb_iter *it, qb_comm *comm, int node, uint64_t max_mem, uint64_t *moved) {
+	return guarded([&] {
+		QB_REQUIRE(it && comm && it->ctx == comm->ctx, QB_ERR_ARG, "qb_iter_receive_objects: bad handle");
+		it->ctx->use();
+		const uint64_t n = receive_objects(it, comm, node, max_mem);
+		if (moved) *moved = n;
+	});
+}
+
+int qb_iter_distribute_objects(qb_iter *it, qb_comm *comm, int node_id) {
+	return guarded([&] {
+		QB_REQUIRE(it && comm && it->ctx == comm->ctx, QB_ERR_ARG, "qb_iter_distribute_objects: bad handle");
+		QB_REQUIRE(node_id >= 0 && node_id < comm->world, QB_ERR_ARG, "qb_iter_distribute_objects: bad node id");
+		it->ctx->use();
+		if (comm->rank == node_id) {
+			const uint64_t initial = it->n;
+			for (int node = 1; node < comm->world; ++node) {
+				const int node_to_send = node <= node_id ? node - 1 : node; // skip this node, quids_mpi.hpp:1040
+				const uint64_t share = (uint64_t)(((unsigned __int128)initial * (node + 1)) / comm->world - ((unsigned __int128)initial * node) / comm->world);
+				send_objects(it, comm, share, node_to_send);
+			}
+		} else {
+			receive_objects(it, comm, node_id, ~0ull);
+		}
+	});
+}
+
+int qb_iter_gather_objects(qb_iter *it, qb_comm *comm, int node_id) {
+	return guarded([&] {
+		QB_REQUIRE(it && comm && it->ctx == comm->ctx, QB_ERR_ARG, "qb_iter_gather_objects: bad handle");
+		QB_REQUIRE(node_id >= 0 && node_id < comm->world, QB_ERR_ARG, "qb_iter_gather_objects: bad node id");
+		it->ctx->use();
+		if (comm->rank == node_id) {
+			for (int node = 1; node < comm->world; ++node)
+				receive_objects(it, comm, node <= node_id ? node - 1 : node, ~0ull);
+		} else {
+			send_objects(it, comm, it->n, node_id);
+		}
+	});
+}
+
+int qb_iter_num_symbolic_object(const qb_iter *it, uint64_t *num_symbolic_object) {
+	return guarded([&] {
+		QB_REQUIRE(it && num_symbolic_object, QB_ERR_ARG, "qb_iter_num_symbolic_object: null argument");
+		*num_symbolic_object = it->n_symbolic;
+	});
+}
+
+int qb_iter_count_children(qb_iter *it, int rule_id, const double *params, uint32_t num_params, uint64_t *num_children) {
+	return guarded([&] {
+		QB_REQUIRE(it && num_children, QB_ERR_ARG, "qb_iter_count_children: null argument");
+		const rule_ops *ops = find_rule(rule_id);
+		QB_REQUIRE(ops, QB_ERR_UNKNOWN_RULE, "unknown rule id");
+		alignas(16) unsigned char storage[RULE_STORAGE_BYTES];
+		int rc = ops->make(params, num_params, storage);
+		QB_REQUIRE(rc == QB_OK, rc, std::string("bad parameters for rule ") + ops->name);
+		it->ctx->use();
+		*num_children = count_children(it, ops, storage);
+	});
+}
+
+int qb_iter_equalize(qb_iter *it, qb_comm *comm, int rule_id, const double *params, uint32_t num_params, int max_rounds, uint64_t min_equalize_size,
+                     float equalize_inbalance, float min_equalize_step, int *rounds) {
+	return guarded([&] {
+		QB_REQUIRE(it && comm && it->ctx == comm->ctx, QB_ERR_ARG, "qb_iter_equalize: bad handle");
+		const rule_ops *ops = nullptr;
+		alignas(16) unsigned char storage[RULE_STORAGE_BYTES];
+		if (rule_id != 0) {
+			ops = find_rule(rule_id);
+			QB_REQUIRE(ops, QB_ERR_UNKNOWN_RULE, "unknown rule id");
+			int rc = ops->make(params, num_params, storage);
+			QB_REQUIRE(rc == QB_OK, rc, std::string("bad parameters for rule ") + ops->name);
+		}
+		it->ctx->use();
+		const int r = comm->world > 1 ? equalize_loop(it, comm, ops, storage, ops != nullptr, min_equalize_size, equalize_inbalance, min_equalize_step, max_rounds) : 0;
+		if (rounds) *rounds = r;
 	});
 }
 

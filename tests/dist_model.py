@@ -121,3 +121,66 @@ def model_simulate(port: orc.Oracle, mine: orc.Packed, all_parent_norms_fn, rule
     counts = [None] * world
     dist.all_gather_object(counts, nc)
     return nxt, sum(counts), nu_global
+
+
+# ---- object migration (quids_b200/csrc/migrate.inc.cuh; quids_mpi.hpp:903-1077) ------------------------------------
+def make_equal_pairs(weights):
+    """utils/mpi_utils.hpp:9-24: the i-th heaviest rank is paired with the i-th lightest (ties: lower rank first)"""
+    ids = sorted(range(len(weights)), key=lambda r: (-weights[r], r))
+    pair = [0] * len(weights)
+    for i, r in enumerate(ids):
+        pair[r] = ids[len(ids) - 1 - i]
+    return pair
+
+
+def distribute_shares(n, world, root):
+    """objects every rank holds after distribute_objects(root) (quids_mpi.hpp:1031-1051)"""
+    out = [0] * world
+    for node in range(1, world):
+        out[node - 1 if node <= root else node] = (n * (node + 1)) // world - (n * node) // world
+    out[root] = n - sum(out)
+    return out
+
+
+def model_send_recv(objs, n_send, peer, sender):
+    """the tail of a python list travels to the peer (send_objects pops, receive_objects appends)"""
+    if sender:
+        tail = objs[len(objs) - n_send:]
+        dist.send_object_list([tail], dst=peer)
+        return objs[:len(objs) - n_send]
+    box = [None]
+    dist.recv_object_list(box, src=peer)
+    return objs + box[0]
+
+
+def model_equalize(objs, weight_of, max_rounds, min_size, inbalance_limit, min_step):
+    """equalize_loop of migrate.inc.cuh over python lists: returns (objects of this rank, rounds)"""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    rounds, previous_diff, avg0 = 0, 0.0, None
+    for i in range(max_rounds):
+        begins = np.concatenate([[0], np.cumsum([weight_of(o) if weight_of else 1 for o in objs])]).astype(np.int64)
+        mine = int(begins[-1])
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (mine, len(objs)))
+        weights = [g[0] for g in gathered]
+        if avg0 is None:
+            avg0 = sum(weights) / world
+        diff = max(weights) - avg0
+        inbalance = diff / max(weights) if max(weights) else 0.0
+        if max(g[1] for g in gathered) < min_size or inbalance < inbalance_limit or (i > 0 and diff > previous_diff * (1 - min_step)):
+            break
+        other = make_equal_pairs(weights)[rank]
+        if other != rank and mine != weights[other]:
+            if mine > weights[other]:
+                if weight_of is None:  # equalize: half of the difference (quids_mpi.hpp:954-955)
+                    n_send = (mine - weights[other]) // 2
+                else:  # equalize_symbolic: the objects holding the last half of the difference (quids_mpi.hpp:1013-1019)
+                    target = mine - (mine - weights[other]) // 2
+                    limit = max(int(np.searchsorted(begins[:len(objs)], target, side="left")) - 1, 0)  # std::lower_bound - 1
+                    n_send = len(objs) - limit
+                objs = model_send_recv(objs, n_send, other, True)
+            else:
+                objs = model_send_recv(objs, 0, other, False)
+        previous_diff = diff
+        rounds += 1
+    return objs, rounds

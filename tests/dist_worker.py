@@ -23,10 +23,127 @@ def share(p: orc.Packed, rank, world) -> orc.Packed:
     return orc.Packed.from_objects([objs[i] for i in idx], p.cmags[idx])
 
 
-def run_case(comm, port, state, rid, params, k, tol, qcgd, what):
+def skewed_share(p: orc.Packed, rank, world) -> orc.Packed:
+    """rank 0 holds 70 % of the objects, the others split the rest: work for the load balancer"""
+    objs = p.objects()
+    cut = (p.n * 7) // 10
+    idx = list(range(cut)) if rank == 0 else [i for i in range(cut, p.n) if (i - cut) % (world - 1) == rank - 1]
+    return orc.Packed.from_objects([objs[i] for i in idx], p.cmags[idx]) if idx else orc.Packed.from_objects([], [])
+
+
+def multiset(sizes, mags, data):
+    begin = np.concatenate([[0], np.cumsum(sizes.astype(np.int64))])
+    return sorted((data[begin[i]:begin[i + 1]].tobytes(), float(mags[i, 0]), float(mags[i, 1])) for i in range(len(sizes)))
+
+
+def gather_states(it):
+    world = dist.get_world_size()
+    got = [None] * world
+    dist.all_gather_object(got, it.download_packed())
+    return got
+
+
+def migration_cases(comm, port):
+    """send/receive, distribute, gather, equalize (quids_mpi.hpp:124-231, 903-1077): objects are moved, never changed"""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    qb.config.align_byte_length = 8
+    base = port.qcgd_random_state(6, 240, 11)
+    ragged, _, _ = port.simulate(base, orc.RULE_SPLIT_MERGE, [0.4, 0.1, 0.2], orc.NO_TRUNCATION, 1e-18)  # objects of many sizes
+    assert len(set(ragged.sizes.tolist())) > 3
+    want = multiset(ragged.sizes, ragged.mags, ragged.data)
+    root = world - 1
+
+    # distribute_objects from `root`: shares of quids_mpi.hpp:1042, taken from the tail in rank order
+    it = qb.Iteration()
+    if rank == root:
+        it.upload_packed(ragged.sizes, ragged.mags, ragged.data, total_proba=0.75)
+    it.distribute_objects(comm, root)
+    states = gather_states(it)
+    if rank == 0:
+        n = ragged.n
+        expect = {root: n - sum((n * (node + 1)) // world - (n * node) // world for node in range(1, world))}
+        for node in range(1, world):
+            expect[node - 1 if node <= root else node] = (n * (node + 1)) // world - (n * node) // world
+        assert [len(s[0]) for s in states] == [expect[r] for r in range(world)], ([len(s[0]) for s in states], expect)
+        merged = sorted(sum((multiset(*s) for s in states), []))
+        assert merged == want, "distribute_objects changed the objects"
+        print(f"ok distribute_objects: {[len(s[0]) for s in states]}", flush=True)
+    # the layout that arrived must be usable: one rule iteration on the distributed state equals the oracle's
+    nxt, sym = qb.Iteration(), qb.SymbolicIteration()
+    qb.config.tolerance = 1e-18
+    qb.mpi_simulate(it, qb.Rule("erase_create", 0.3, 0.1, 0.2), nxt, sym, comm, orc.NO_TRUNCATION)
+    outs = gather_states(nxt)
+    if rank == 0:
+        ref, _, _ = port.simulate(ragged, orc.RULE_ERASE_CREATE, [0.3, 0.1, 0.2], orc.NO_TRUNCATION, 1e-18)
+        got = orc.Packed(np.concatenate([g[0] for g in outs]), np.concatenate([g[1] for g in outs]), np.concatenate([g[2] for g in outs]), ref.total_proba)
+        orc.assert_same_state(got, port.hash_objects(got, orc.RULE_ERASE_CREATE), ref, port.hash_objects(ref, orc.RULE_ERASE_CREATE), True,
+                              what="rule iteration after distribute_objects")
+        print("ok rule iteration after distribute_objects", flush=True)
+
+    # gather_objects back to rank 0
+    it.gather_objects(comm, 0)
+    states = gather_states(it)
+    if rank == 0:
+        assert [len(s[0]) for s in states] == [ragged.n] + [0] * (world - 1)
+        assert multiset(*states[0]) == want, "gather_objects changed the objects"
+        print("ok gather_objects", flush=True)
+    at_rank0 = orc.Packed(*states[0])
+
+    # send_objects / receive_objects between rank 0 and rank 1; asking for more room than allowed moves nothing
+    if rank == 0:
+        assert it.send_objects(17, 1, comm) == 17
+        assert it.send_objects(5, 1, comm) == 0 and it.num_object == ragged.n - 17  # refused by the receiver
+        assert it.send_objects(0, 1, comm) == 0
+    elif rank == 1:
+        assert it.receive_objects(0, comm) == 17
+        assert it.receive_objects(0, comm, max_mem=16) == 0 and it.num_object == 17
+        assert it.receive_objects(0, comm) == 0
+    states = gather_states(it)
+    if rank == 0:
+        assert [len(s[0]) for s in states][:2] == [ragged.n - 17, 17]
+        assert multiset(*states[1]) == want_tail(at_rank0, 17), "send_objects must take the tail"
+        assert sorted(sum((multiset(*s) for s in states), [])) == want
+        print("ok send_objects / receive_objects", flush=True)
+
+    # equalize by objects: every round pairs the fullest rank with the emptiest
+    before = comm.allreduce_u64([it.num_object], op_max=True)[0]
+    rounds = it.equalize(comm, max_rounds=8, min_equalize_size=10, equalize_inbalance=0.05, min_equalize_step=0.0)
+    states = gather_states(it)
+    after = max(len(s[0]) for s in states)
+    if rank == 0:
+        assert rounds >= 1 and after < before, (rounds, before, after)
+        if world == 2:
+            assert after <= int(1.06 * ragged.n / world) + 1, (before, after)
+        assert sorted(sum((multiset(*s) for s in states), [])) == want, "equalize changed the objects"
+        print(f"ok equalize by objects: {rounds} rounds, max per rank {before} -> {after}", flush=True)
+
+    # equalize by children of a rule (equalize_symbolic): the children counts of a pair meet in the middle
+    it.gather_objects(comm, 0)
+    rule = qb.Rule("erase_create", 0.3, 0.1, 0.2)
+    c_before = comm.allreduce_u64([it.count_children(rule)], op_max=True)[0]
+    c_total = comm.allreduce_u64([it.count_children(rule)])[0]
+    rounds = it.equalize(comm, rule, max_rounds=8, min_equalize_size=10, equalize_inbalance=0.05, min_equalize_step=0.0)
+    c_after = comm.allreduce_u64([it.count_children(rule)], op_max=True)[0]
+    states = gather_states(it)
+    if rank == 0:
+        assert c_before == c_total and rounds >= 1 and c_after < c_before
+        if world == 2:
+            assert c_after <= 0.56 * c_total, (c_after, c_total)
+        assert sorted(sum((multiset(*s) for s in states), [])) == want
+        print(f"ok equalize by children: {rounds} rounds, max children per rank {c_before} -> {c_after} of {c_total}", flush=True)
+
+
+def want_tail(p: orc.Packed, n):
+    sizes, mags = p.sizes[-n:], p.mags[-n:]
+    begin = int(p.sizes[:-n].astype(np.int64).sum())
+    return multiset(sizes, mags, p.data[begin:])
+
+
+def run_case(comm, port, state, rid, params, k, tol, qcgd, what, share=share, equalize=0):
     rank, world = dist.get_rank(), dist.get_world_size()
     qb.config.tolerance = tol
     qb.config.align_byte_length = 8
+    qb.config.equalize = equalize
     mine = share(state, rank, world)
     it, nxt, sym = qb.Iteration(), qb.Iteration(), qb.SymbolicIteration()
     it.upload_packed(mine.sizes, mine.mags, mine.data)
@@ -77,6 +194,12 @@ def main():
     # equal magnitudes: the ties at the threshold must be shared out between the ranks, exactly k kept
     tied = port.qcgd_random_state(7, 300, 9)
     run_case(comm, port, tied, orc.RULE_ERASE_CREATE, [math.pi / 4, 0, 0], 777, 1e-18, True, "ties across ranks")
+    # load balancing at the head of mpi::simulate (quids_mpi.hpp:442-500): skewed shares, same result
+    for rid in orc.QCGD_RULES:
+        run_case(comm, port, state, rid, p, orc.NO_TRUNCATION, 1e-18, True, f"rule {rid} skewed shares, equalize by children", share=skewed_share, equalize=2)
+    run_case(comm, port, state, orc.RULE_ERASE_CREATE, p, 900, 1e-18, True, "skewed shares, equalize by objects, children truncated", share=skewed_share,
+             equalize=1)
+    migration_cases(comm, port)
     # one rank empty: fewer objects than ranks
     tiny = orc.Packed.from_objects([bytes([0, 1, 0, 1])], [1.0])
     run_case(comm, port, tiny, orc.RULE_HADAMARD, [2], orc.NO_TRUNCATION, 1e-30, False, "single object, other ranks empty")

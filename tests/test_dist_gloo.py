@@ -89,3 +89,46 @@ def test_two_rank_protocol_matches_single_process(port):
         p.join(timeout=60)
     assert not failures, failures
     assert all(p.exitcode == 0 for p in procs)
+
+
+def test_pairing_and_shares_of_the_migration_logic():
+    assert dist_model.make_equal_pairs([5, 9, 1, 7]) == [3, 2, 1, 0]
+    assert dist_model.make_equal_pairs([4, 4, 4]) == [2, 1, 0]  # the middle rank is alone
+    for n, world, root in ((10, 4, 0), (10, 4, 2), (7, 3, 2), (2, 8, 5), (1000003, 8, 1)):
+        shares = dist_model.distribute_shares(n, world, root)
+        assert sum(shares) == n and max(shares) - min(shares) <= 1, shares
+
+
+def _equalize_worker(rank, world, port_number, results):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port_number))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(3)
+    everything = [(i, int(w)) for i, w in enumerate(rng.integers(1, 200, size=400))]
+    objs = everything if rank == 0 else []
+    # by children (weights), then by objects (weight 1 each) from the same skewed start
+    by_children, r1 = dist_model.model_equalize(list(objs), lambda o: o[1], 4, 10, 0.05, 0.0)
+    by_objects, r2 = dist_model.model_equalize(list(objs), None, 4, 10, 0.05, 0.0)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (by_children, by_objects, r1, r2))
+    if rank == 0:
+        results.put(gathered)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_equalize_model():
+    ctx = mp.get_context("spawn")
+    results = ctx.Queue()
+    procs = [ctx.Process(target=_equalize_worker, args=(r, 2, 29534, results)) for r in range(2)]
+    for p in procs:
+        p.start()
+    gathered = results.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+    assert all(p.exitcode == 0 for p in procs)
+    children = [sum(w for _, w in g[0]) for g in gathered]
+    objects = [len(g[1]) for g in gathered]
+    assert sorted(o for g in gathered for o in g[0]) == sorted(o for g in gathered for o in g[1])  # nothing lost, nothing duplicated
+    assert len({o for g in gathered for o in g[0]}) == 400
+    assert gathered[0][2] >= 1 and abs(children[0] - children[1]) <= 200, children  # within one object's weight
+    assert gathered[0][3] >= 1 and abs(objects[0] - objects[1]) <= 1, objects
