@@ -296,7 +296,7 @@ namespace quids {
 
 	/// apply a dynamic to a wave function, quids.hpp:448-543.
 	/// max_num_object: maximum number of objects kept; -1 (SIZE_MAX) = no maximum; 0 = as many as fit in the
-	/// GPU memory left (fails rather than silently truncating if even the interference table does not fit).
+	/// GPU memory left after quids::safety_margin (parents first, then children, like quids.hpp:459-485,510-536).
 	void inline simulate(it_t &iteration, rule_t const *rule, it_t &next_iteration, sy_it_t &symbolic_iteration, size_t max_num_object = 0,
 	                     debug_t mid_step_function = [](const char *) {}) {
 		iteration.to_device();

@@ -47,9 +47,10 @@ typedef struct qb_comm qb_comm; /* stands where MPI_Comm stands in quids_mpi.hpp
 
 #define QB_NO_TRUNCATION UINT64_MAX /* max_num_object = -1 in the reference (quids.hpp:445) */
 /* max_num_object = 0 is the reference's "automatic" budget (quids.hpp:459-485,510-536: truncate to what fits in free RAM).
- * Here: keep everything if the workspace fits in the GPU memory left after the safety margin, otherwise FAIL with
- * QB_ERR_CAPACITY and a message naming the size needed -- never a silent truncation.  The binary search for the largest
- * fitting max_num_object is SURVEY 8(f) item 2 (next). */
+ * Here the budget is the GPU memory left after the safety margin (cudaMemGetInfo, or qb_options.memory_budget): the most
+ * probable parents whose symbolic workspace (interference table at its safe size, compacted lists, work items) fits are
+ * kept, then as many of the most probable children as the next state has room for.  QB_ERR_CAPACITY only when not even
+ * one parent's children fit.  The distributed path needs an explicit max_num_object. */
 
 /* the mutable namespace globals of the reference that influence one call (quids.hpp:60-75) */
 typedef struct qb_options {
@@ -63,6 +64,8 @@ typedef struct qb_options {
 	uint32_t seed;             /* probabilistic truncation: seed of the counter-based generator (the reference seeds from rand()) */
 	int32_t locality_sort;     /* engine knob: process the child groups in the order of the rule's group key so that equal
 	                              objects are merged on chip before the table; 0 off, 1 when there are >= 2^16 groups (default), 2 always */
+	uint64_t memory_budget;    /* engine knob: bytes the automatic budget (max_num_object = 0) may spend on the symbolic workspace and
+	                              on the next state; 0 = measured (cudaMemGetInfo minus safety_margin of the GPU) */
 	/* load balancing at the head of quids::mpi::simulate (quids_mpi.hpp:442-500); only qb_simulate_dist reads these */
 	int32_t equalize;            /* 0 off (default of the C ABI), 1 by objects (quids::mpi::equalize_children = false), 2 by children */
 	float equalize_inbalance;    /* quids::mpi::equalize_inbalance (quids_mpi.hpp:48): stop below this (max - avg) / max      */
@@ -104,6 +107,15 @@ int qb_iter_counts(const qb_iter *it, uint64_t *num_object, uint64_t *num_bytes,
 /* copies the state out (what get_object() reads, quids.hpp:242-258); any pointer may be NULL */
 int qb_iter_download(const qb_iter *it, uint8_t *objects, uint64_t *object_begin, uint32_t *object_size, double *magnitude);
 /* device pointers of the four arrays (for zero-copy consumers; valid until the next call that writes `it`) */
+/* The same two transfers on dedicated copy streams, overlapping the rule iterations of OTHER states (double buffering:
+ * upload the input of step i+1 and download the result of step i-1 while step i computes).  The host arrays must be
+ * page-locked (qb_host_alloc) and stay untouched until qb_iter_wait(it) returns; every later call that uses `it` orders
+ * itself after the transfers on the device, so only the HOST side ever needs qb_iter_wait.  Counters (qb_iter_counts)
+ * are valid as soon as qb_iter_upload_async returns. */
+int qb_iter_upload_async(qb_iter *it, uint64_t num_object, const uint8_t *objects, uint64_t num_bytes,
+                         const uint64_t *object_begin, const uint32_t *object_size, const double *magnitude, double total_proba);
+int qb_iter_download_async(const qb_iter *it, uint8_t *objects, uint64_t *object_begin, uint32_t *object_size, double *magnitude);
+int qb_iter_wait(const qb_iter *it);
 int qb_iter_device_ptrs(const qb_iter *it, void **objects, void **object_begin, void **object_size, void **magnitude);
 /* pop(n, normalize) quids.hpp:194-203 */
 int qb_iter_pop(qb_iter *it, uint64_t n, int normalize);

@@ -47,7 +47,7 @@ def build(verbose=False):
 
 class qb_options(C.Structure):
     _fields_ = [("tolerance", C.c_double), ("align_byte_length", C.c_uint32), ("simple_truncation", C.c_int32),
-                ("table_load", C.c_double), ("profile", C.c_int32), ("safety_margin", C.c_float), ("seed", C.c_uint32), ("locality_sort", C.c_int32),
+                ("table_load", C.c_double), ("profile", C.c_int32), ("safety_margin", C.c_float), ("seed", C.c_uint32), ("locality_sort", C.c_int32), ("memory_budget", C.c_uint64),
                 ("equalize", C.c_int32), ("equalize_inbalance", C.c_float), ("min_equalize_step", C.c_float), ("min_equalize_size", C.c_uint64)]
 
 
@@ -82,6 +82,9 @@ def lib():
         "qb_iter_create": (i32, [vp, P(vp)]),
         "qb_iter_destroy": (i32, [vp]),
         "qb_iter_upload": (i32, [vp, u64, vp, u64, vp, vp, vp, dbl]),
+        "qb_iter_upload_async": (i32, [vp, u64, vp, u64, vp, vp, vp, dbl]),
+        "qb_iter_download_async": (i32, [vp, vp, vp, vp, vp]),
+        "qb_iter_wait": (i32, [vp]),
         "qb_iter_counts": (i32, [vp, P(u64), P(u64), P(dbl)]),
         "qb_iter_download": (i32, [vp, vp, vp, vp, vp]),
         "qb_iter_device_ptrs": (i32, [vp, P(vp), P(vp), P(vp), P(vp)]),
@@ -145,6 +148,7 @@ class _Globals:
     safety_margin = 0.2        # quids::safety_margin
     table_load = 0.0           # engine knob (0 = default)
     profile = False
+    memory_budget = 0          # engine knob: bytes the automatic budget may spend (0 = measured on the GPU)
     equalize = 0               # distributed path: 0 off, 1 by objects, 2 by children (quids::mpi::equalize_children)
     equalize_inbalance = 0.1   # quids::mpi::equalize_inbalance
     min_equalize_step = 0.2    # quids::mpi::min_equalize_step
@@ -162,6 +166,7 @@ class _Globals:
         o.seed = self.seed
         o.profile = 1 if self.profile else 0
         o.locality_sort = self.locality_sort
+        o.memory_budget = self.memory_budget
         o.equalize = self.equalize
         o.equalize_inbalance = self.equalize_inbalance
         o.min_equalize_step = self.min_equalize_step

@@ -75,8 +75,22 @@ struct qb_ctx {
 	dev_buf partials;
 	dev_buf select;
 
+	cudaStream_t copy_in = nullptr, copy_out = nullptr; // host <-> device transfers that overlap the compute stream (qb_iter_*_async)
+	cudaEvent_t fence = nullptr;
+
 	void use() const { QB_CUDA(cudaSetDevice(device)); }
 	void sync() const { QB_CUDA(cudaStreamSynchronize(stream)); }
+	void copy_streams() {
+		if (copy_in) return;
+		QB_CUDA(cudaStreamCreateWithFlags(&copy_in, cudaStreamNonBlocking));
+		QB_CUDA(cudaStreamCreateWithFlags(&copy_out, cudaStreamNonBlocking));
+		QB_CUDA(cudaEventCreateWithFlags(&fence, cudaEventDisableTiming));
+	}
+	// `other` waits for everything enqueued on the compute stream so far
+	void order_after_compute(cudaStream_t other) {
+		QB_CUDA(cudaEventRecord(fence, stream));
+		QB_CUDA(cudaStreamWaitEvent(other, fence, 0));
+	}
 
 	// zeroed look-back workspace for a scan over `tiles` tiles
 	scan_state scan(uint64_t tiles) {
@@ -102,6 +116,21 @@ struct qb_iter {
 	double total_proba = 1; // quids.hpp:154
 	uint64_t n_symbolic = 0; // children counted by the last compute_num_child over this state (get_num_symbolic_object, quids.hpp:322-324)
 	dev_buf objects, begin, size, mag, num_childs, child_begin, num_groups, group_begin;
+	// transfers in flight on the copy streams (qb_iter_upload_async / qb_iter_download_async)
+	cudaEvent_t uploaded = nullptr, downloaded = nullptr;
+	mutable bool upload_pending = false, download_pending = false;
+
+	// the compute stream waits for the transfers of this state; called at the head of every entry point that touches it
+	void settle() const {
+		if (upload_pending) {
+			QB_CUDA(cudaStreamWaitEvent(ctx->stream, uploaded, 0));
+			upload_pending = false;
+		}
+		if (download_pending) {
+			QB_CUDA(cudaStreamWaitEvent(ctx->stream, downloaded, 0));
+			download_pending = false;
+		}
+	}
 
 	iter_view view() const { return iter_view{objects.as<uint8_t>(), begin.as<uint64_t>(), size.as<uint32_t>(), mag.as<cplx>(), n}; }
 };
@@ -146,6 +175,7 @@ struct phase_timer {
 		}
 		QB_CUDA(cudaEventRecord(sym->ev[2 * phase], sym->ctx->stream));
 	}
+	void restart(int phase) { started[phase] = false; }
 	void end(int phase) {
 		if (!on) return;
 		QB_CUDA(cudaEventRecord(sym->ev[2 * phase + 1], sym->ctx->stream));
@@ -370,11 +400,25 @@ void resolve_options(const qb_options *in, qb_options &opt) {
 // one rule iteration
 // ======================================================================================================
 // stages 1-6 of an iteration on THIS GPU: child counts, parent pre-truncation, index ranges, children ->
+// bytes the automatic budget (max_num_object = 0) may spend: what is free now + what `sym` (and `next`) already hold
+// and will reuse, minus the safety margin (quids.hpp:459-470 with cudaMemGetInfo in place of /proc/meminfo);
+// qb_options.memory_budget overrides the measurement (tests, or a share of a GPU)
+double automatic_budget(qb_ctx *ctx, const qb_sym *sym, const qb_iter *next, const qb_options &opt, double workspace = 0) {
+	if (opt.memory_budget > 0)
+		return (double)opt.memory_budget - (next ? workspace : 0.0);
+	size_t free_bytes = 0, total_bytes = 0;
+	QB_CUDA(cudaMemGetInfo(&free_bytes, &total_bytes));
+	double reusable = next ? (double)(next->objects.cap + next->begin.cap + next->size.cap + next->mag.cap) : (double)sym->device_bytes();
+	return (double)free_bytes + reusable - (double)opt.safety_margin * (double)total_bytes;
+}
+
 // interference table, compaction of the table into (norm key, slot) lists
 struct local_table {
 	uint64_t n_parents = 0;
 	const uint64_t *kept = nullptr;
 	uint64_t n_children = 0;
+	uint32_t max_child_size = 0;
+	double workspace = 0; // automatic budget: bytes the symbolic workspace of the kept parents was counted for
 	uint64_t n_unique = 0; // entries kept by the compaction
 	table_view table{};
 	int empty_from = -1; // >= 0: nothing to do from label `empty_from` on (no parents / no children)
@@ -410,6 +454,58 @@ local_table build_local_table(qb_iter *it, int rule_id, const rule_ops *ops, con
 		timer.end(QB_PHASE_NUM_CHILD);
 	}
 
+	// child index ranges of a set of kept parents (quids.hpp:666-671: a serial loop in the reference)
+	uint64_t n_groups = 0;
+	uint32_t max_child_size = 0;
+	const uint64_t *group_begin = nullptr;
+	auto index_children = [&](const uint64_t *kept, uint64_t n_parents) -> uint64_t {
+		it->child_begin.ensure(sizeof(uint64_t) * (n_parents + 1), stream);
+		exclusive_scan(ctx, counts_through{it->num_childs.as<uint32_t>(), kept}, it->child_begin.as<uint64_t>(), n_parents);
+		group_begin = it->child_begin.as<uint64_t>();
+		if (ops->warp_groups) { // children are produced in groups that share work: a second index space
+			it->group_begin.ensure(sizeof(uint64_t) * (n_parents + 1), stream);
+			exclusive_scan(ctx, counts_through{it->num_groups.as<uint32_t>(), kept}, it->group_begin.as<uint64_t>(), n_parents);
+			group_begin = it->group_begin.as<uint64_t>();
+		}
+		QB_CUDA(cudaMemcpyAsync(&ctx->h_small[DS_COUNT], it->child_begin.as<uint64_t>() + n_parents, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+		QB_CUDA(cudaMemcpyAsync(&ctx->h_small[DS_USED], group_begin + n_parents, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+		QB_CUDA(cudaMemcpyAsync(&ctx->h_small[DS_MAX_CHILD_SIZE], ctx->small(DS_MAX_CHILD_SIZE), sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+		ctx->sync();
+		n_groups = ctx->h_small[DS_USED];
+		max_child_size = (uint32_t)ctx->h_small[DS_MAX_CHILD_SIZE];
+		return ctx->h_small[DS_COUNT];
+	};
+
+	// ---- 2a. automatic budget (max_num_object = 0, quids.hpp:459-485): keep the most probable parents whose
+	//          symbolic workspace fits in the GPU memory left after the safety margin.  The reference bisects
+	//          over get_truncated_mem_size (:574-589); here the count shrinks by the ratio budget / need until it fits.
+	if (automatic && it->n > 0) {
+		const double budget = automatic_budget(ctx, sym, nullptr, opt);
+		uint64_t k = it->n;
+		const uint64_t *kept = nullptr;
+		double need = 0;
+		for (int round = 0; round < 64; ++round) {
+			const uint64_t children = index_children(kept, k);
+			// interference table at its safe size + the compacted (key, slot) lists + sorted work items and parent contexts
+			need = (std::ceil((double)children / opt.table_load) + 2) * sizeof(table_slot) + 12.0 * (double)children +
+			       (ops->has_group_key ? 24.0 * (double)n_groups + (double)ops->ctx_bytes * (double)k : 0.0) + 16.0 * (double)k;
+			if (need <= budget || k <= 1)
+				break;
+			k = std::max<uint64_t>(1, std::min<uint64_t>(k - 1, (uint64_t)((double)k * std::min(0.9, budget / need))));
+			sym->kept.ensure(sizeof(uint64_t) * k, stream);
+			key_from_mag keys{it->mag.as<cplx>()};
+			select_threshold(ctx, nullptr, keys, it->n, k);
+			k = select_keep(ctx, nullptr, keys, it->n, out_index{sym->kept.as<uint64_t>()});
+			kept = sym->kept.as<uint64_t>();
+		}
+		QB_REQUIRE(need <= budget, QB_ERR_CAPACITY,
+		           "max_num_object = 0 (automatic budget): the children of a single parent need about " + std::to_string((uint64_t)(need / 1e6)) +
+		               " MB of workspace, " + std::to_string((uint64_t)(std::max(0.0, budget) / 1e6)) + " MB are available after the safety margin");
+		if (k < it->n)
+			max_num_object = k;
+		R.workspace = need;
+	}
+
 	// ---- 2. parent pre-truncation: the max_num_object most probable parents (quids.hpp:613-642);
 	//         over ALL ranks on the distributed path, so that the result equals the single-GPU one ---------
 	step("truncate_symbolic - prepare");
@@ -430,30 +526,14 @@ local_table build_local_table(qb_iter *it, int rule_id, const rule_ops *ops, con
 		R.kept = sym->kept.as<uint64_t>();
 		timer.end(QB_PHASE_PRE_TRUNCATE);
 	}
-	// ---- 3. child index ranges (quids.hpp:666-671: a serial loop in the reference) --------------------
+	// ---- 3. child index ranges ---------------------------------------------------------------------------
 	step("prepare_index");
-	uint64_t n_groups = 0;
-	uint32_t max_child_size = 0;
-	const uint64_t *group_begin = nullptr;
 	if (R.n_parents > 0) {
 		timer.begin(QB_PHASE_NUM_CHILD);
-		it->child_begin.ensure(sizeof(uint64_t) * (R.n_parents + 1), stream);
-		exclusive_scan(ctx, counts_through{it->num_childs.as<uint32_t>(), R.kept}, it->child_begin.as<uint64_t>(), R.n_parents);
-		group_begin = it->child_begin.as<uint64_t>();
-		if (ops->warp_groups) { // children are produced in groups that share work: a second index space
-			it->group_begin.ensure(sizeof(uint64_t) * (R.n_parents + 1), stream);
-			exclusive_scan(ctx, counts_through{it->num_groups.as<uint32_t>(), R.kept}, it->group_begin.as<uint64_t>(), R.n_parents);
-			group_begin = it->group_begin.as<uint64_t>();
-		}
-		QB_CUDA(cudaMemcpyAsync(&ctx->h_small[DS_COUNT], it->child_begin.as<uint64_t>() + R.n_parents, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
-		QB_CUDA(cudaMemcpyAsync(&ctx->h_small[DS_USED], group_begin + R.n_parents, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
-		QB_CUDA(cudaMemcpyAsync(&ctx->h_small[DS_MAX_CHILD_SIZE], ctx->small(DS_MAX_CHILD_SIZE), sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+		R.n_children = index_children(R.kept, R.n_parents);
 		timer.end(QB_PHASE_NUM_CHILD);
-		ctx->sync();
-		R.n_children = ctx->h_small[DS_COUNT];
-		n_groups = ctx->h_small[DS_USED];
-		max_child_size = (uint32_t)ctx->h_small[DS_MAX_CHILD_SIZE];
 	}
+	R.max_child_size = max_child_size;
 	sym->n_children = R.n_children;
 	it->n_symbolic = R.n_children;
 	if (global_sum(comm, R.n_children) == 0) {
@@ -473,21 +553,12 @@ local_table build_local_table(qb_iter *it, int rule_id, const rule_ops *ops, con
 	const uint64_t n_children = R.n_children;
 	const uint64_t full_capacity = std::max<uint64_t>(1024, (uint64_t)std::ceil((double)n_children / opt.table_load));
 	uint64_t capacity = full_capacity;
+	bool have_history = false;
 	{
 		auto hint = sym->unique_ratio.find(rule_id);
-		if (hint != sym->unique_ratio.end())
+		have_history = hint != sym->unique_ratio.end();
+		if (have_history)
 			capacity = std::min<uint64_t>(full_capacity, std::max<uint64_t>(1024, (uint64_t)((hint->second * (double)n_children * 1.3 + 1024) / 0.5)));
-	}
-	if (automatic) {
-		size_t free_bytes = 0, total_bytes = 0;
-		QB_CUDA(cudaMemGetInfo(&free_bytes, &total_bytes));
-		const double budget = (double)(free_bytes + sym->device_bytes()) - (double)opt.safety_margin * (double)total_bytes;
-		// interference table + compacted (key, slot) lists + a next state about the size of this one
-		const double need = (double)(capacity + 1) * sizeof(table_slot) + 12.0 * (double)std::min<uint64_t>(n_children, capacity + 1) + 2.0 * (double)it->n_bytes;
-		QB_REQUIRE(need <= budget, QB_ERR_CAPACITY,
-		           "max_num_object = 0 (automatic budget): " + std::to_string(n_children) + " children need about " + std::to_string((uint64_t)(need / 1e6)) +
-		               " MB of workspace, " + std::to_string((uint64_t)(std::max(0.0, budget) / 1e6)) +
-		               " MB are available after the safety margin; pass an explicit max_num_object");
 	}
 	L.child_begin = it->child_begin.as<uint64_t>();
 	L.group_begin = group_begin;
@@ -518,9 +589,10 @@ local_table build_local_table(qb_iter *it, int rule_id, const rule_ops *ops, con
 		L.item_vals = sym->sort_vals.as<uint64_t>();
 		ops->launch_group_items(rule, L);
 		L.items = sort_items(ctx, sym, n_groups);
-		if (capacity == full_capacity) {
-			// no history yet: in sorted order the table receives at most one group's worth of objects per run
-			// of equal keys (plus one split per chunk of work items), usually far fewer than one per child
+		if (!have_history) {
+			// in sorted order the table typically receives one group's worth of objects per run of equal keys (plus one
+			// split per chunk of work items), far fewer than one per child: a prediction that needs no history.  It is
+			// not a bound (groups with equal keys may still hold different objects): an overflow falls back to the full size.
 			QB_CUDA(cudaMemsetAsync(ctx->small(DS_COUNT), 0, sizeof(uint64_t), stream));
 			key_changes_kernel<<<grid_for(n_groups, 256, ctx->grid_cap()), 256, 0, stream>>>(sym->sort_keys.as<uint32_t>(), n_groups,
 			                                                                              reinterpret_cast<unsigned long long *>(ctx->small(DS_COUNT)));
@@ -565,10 +637,17 @@ local_table build_local_table(qb_iter *it, int rule_id, const rule_ops *ops, con
 		QB_CUDA(cudaGetLastError());
 		timer.end(QB_PHASE_COMPACT);
 		ctx->fetch_small();
+		if (getenv("QB_TABLE_TRACE"))
+			fprintf(stderr, "[qb table] rule %s attempt %d: children %llu groups %llu capacity %llu (full %llu) sorted %d -> used %llu kept %llu overflow %llu\n", ops->name,
+			        sym->table_attempts, (unsigned long long)n_children, (unsigned long long)n_groups, (unsigned long long)capacity, (unsigned long long)full_capacity,
+			        (int)sorted_order, (unsigned long long)ctx->h_small[DS_USED], (unsigned long long)ctx->h_small[DS_COUNT], (unsigned long long)ctx->h_small[DS_OVERFLOW]);
 		if (ctx->h_small[DS_OVERFLOW] == 0)
 			break;
 		QB_REQUIRE(capacity < full_capacity, QB_ERR_CAPACITY, "interference table overflow at full size");
-		capacity = full_capacity; // the prediction was too small: redo at the safe size
+		// the prediction was too small (the kernels stop early once an insert gives up): redo at the always-safe full size
+		capacity = full_capacity;
+		for (int p : {QB_PHASE_TABLE_CLEAR, QB_PHASE_SYMBOLIC, QB_PHASE_COMPACT})
+			timer.restart(p); // report the attempt that counted
 	}
 	R.n_unique = ctx->h_small[DS_COUNT];
 	sym->table_capacity = capacity;
@@ -608,10 +687,12 @@ void simulate(qb_iter *it, int rule_id, const rule_ops *ops, const void *rule, q
 	qb_ctx *ctx = it->ctx;
 	QB_REQUIRE(next->ctx == ctx && sym->ctx == ctx, QB_ERR_ARG, "iteration, next iteration and symbolic iteration belong to different contexts");
 	QB_REQUIRE(next != it, QB_ERR_ARG, "next_iteration must be a different object from iteration");
-	const bool automatic = max_num_object == 0; // quids.hpp:459-485: keep what fits; here: everything, or fail loudly (see quids_b200.h)
+	const bool automatic = max_num_object == 0; // quids.hpp:459-485, 510-536: keep what fits in the memory left
 	if (automatic)
 		max_num_object = QB_NO_TRUNCATION;
 	ctx->use();
+	it->settle();
+	next->settle();
 	cudaStream_t stream = ctx->stream;
 	stepper step{ctx, cb, user};
 	phase_timer timer(sym, opt.profile != 0);
@@ -640,6 +721,15 @@ void simulate(qb_iter *it, int rule_id, const rule_ops *ops, const void *rule, q
 	survivor_source src;
 	src.table = R.table;
 	src.slot = sym->uslot.as<uint32_t>();
+	if (automatic) {
+		// quids.hpp:510-536: as many children as the next state can hold.  Per survivor: its bytes (bounded by the largest
+		// child, padded) + object_begin 8 + size 4 + magnitude 16 + the finalisation's parent 8, child id 4, padded size 4, slot 4
+		const double budget = automatic_budget(ctx, sym, next, opt, R.workspace);
+		const double per_object = (double)((R.max_child_size + 7u) & ~7u) + 48.0;
+		const uint64_t fit = budget > 0 ? (uint64_t)(budget / per_object) : 0;
+		QB_REQUIRE(fit >= 1, QB_ERR_CAPACITY, "max_num_object = 0 (automatic budget): no room left for a next state after the interference table");
+		max_num_object = fit;
+	}
 	if (max_num_object < R.n_unique) {
 		timer.begin(QB_PHASE_TRUNCATE);
 		sym->sslot.ensure(sizeof(uint32_t) * max_num_object, stream);
@@ -767,6 +857,8 @@ void simulate_dist(qb_iter *it, int rule_id, const rule_ops *ops, const void *ru
 	QB_REQUIRE(next != it, QB_ERR_ARG, "next_iteration must be a different object from iteration");
 	QB_REQUIRE(max_num_object != 0, QB_ERR_UNSUPPORTED, "the distributed path needs an explicit max_num_object (or QB_NO_TRUNCATION)");
 	ctx->use();
+	it->settle();
+	next->settle();
 	cudaStream_t stream = ctx->stream;
 	stepper step{ctx, cb, user};
 	phase_timer timer(sym, opt.profile != 0);
@@ -953,6 +1045,7 @@ void qb_options_default(qb_options *opt) {
 	opt->profile = 0;
 	opt->locality_sort = 1;
 	opt->safety_margin = 0.2f; // SAFETY_MARGIN, quids.hpp:33-35
+	opt->memory_budget = 0;
 	opt->equalize = 0;
 	opt->equalize_inbalance = 0.1f; // EQUALIZE_INBALANCE, quids_mpi.hpp:28-30
 	opt->min_equalize_step = 0.2f;  // MIN_INBALANCE_STEP, quids_mpi.hpp:31-33
@@ -1044,6 +1137,12 @@ int qb_iter_destroy(qb_iter *it) {
 	return guarded([&] {
 		if (!it) return;
 		it->ctx->use();
+		if (it->uploaded) {
+			cudaEventSynchronize(it->uploaded);
+			cudaEventSynchronize(it->downloaded);
+			cudaEventDestroy(it->uploaded);
+			cudaEventDestroy(it->downloaded);
+		}
 		it->ctx->sync();
 		delete it;
 	});
@@ -1057,6 +1156,7 @@ int qb_iter_upload(qb_iter *it, uint64_t n, const uint8_t *objects, uint64_t num
 		QB_REQUIRE(num_bytes == 0 || objects, QB_ERR_ARG, "qb_iter_upload: null objects");
 		qb_ctx *ctx = it->ctx;
 		ctx->use();
+		it->settle();
 		cudaStream_t s = ctx->stream;
 		it->objects.ensure(num_bytes + 16, s);
 		it->begin.ensure(sizeof(uint64_t) * (n + 1), s);
@@ -1077,6 +1177,81 @@ int qb_iter_upload(qb_iter *it, uint64_t n, const uint8_t *objects, uint64_t num
 	});
 }
 
+// ---- transfers that overlap the rule iterations: pinned host memory <-> HBM on dedicated copy streams --------------
+static void transfer_events(qb_iter *it) {
+	it->ctx->copy_streams();
+	if (!it->uploaded) {
+		QB_CUDA(cudaEventCreateWithFlags(&it->uploaded, cudaEventDisableTiming));
+		QB_CUDA(cudaEventCreateWithFlags(&it->downloaded, cudaEventDisableTiming));
+	}
+}
+
+int qb_iter_upload_async(qb_iter *it, uint64_t n, const uint8_t *objects, uint64_t num_bytes, const uint64_t *object_begin, const uint32_t *object_size,
+                         const double *magnitude, double total_proba) {
+	return guarded([&] {
+		QB_REQUIRE(it, QB_ERR_ARG, "null iteration");
+		QB_REQUIRE(n == 0 || (object_begin && object_size && magnitude), QB_ERR_ARG, "qb_iter_upload_async: null array");
+		QB_REQUIRE(num_bytes == 0 || objects, QB_ERR_ARG, "qb_iter_upload_async: null objects");
+		qb_ctx *ctx = it->ctx;
+		ctx->use();
+		transfer_events(it);
+		cudaStream_t s = ctx->copy_in;
+		// the old contents may still be in use: by kernels already enqueued, or by a download in flight
+		ctx->order_after_compute(s);
+		if (it->download_pending)
+			QB_CUDA(cudaStreamWaitEvent(s, it->downloaded, 0));
+		it->objects.ensure(num_bytes + 16, ctx->stream);
+		it->begin.ensure(sizeof(uint64_t) * (n + 1), ctx->stream);
+		it->size.ensure(sizeof(uint32_t) * (n ? n : 1), ctx->stream);
+		it->mag.ensure(sizeof(cplx) * (n ? n : 1), ctx->stream);
+		if (num_bytes) QB_CUDA(cudaMemcpyAsync(it->objects.ptr, objects, num_bytes, cudaMemcpyHostToDevice, s));
+		if (n) {
+			QB_CUDA(cudaMemcpyAsync(it->begin.ptr, object_begin, sizeof(uint64_t) * (n + 1), cudaMemcpyHostToDevice, s));
+			QB_CUDA(cudaMemcpyAsync(it->size.ptr, object_size, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, s));
+			QB_CUDA(cudaMemcpyAsync(it->mag.ptr, magnitude, sizeof(cplx) * n, cudaMemcpyHostToDevice, s));
+		} else {
+			QB_CUDA(cudaMemsetAsync(it->begin.ptr, 0, sizeof(uint64_t), s));
+		}
+		QB_CUDA(cudaEventRecord(it->uploaded, s));
+		it->upload_pending = true;
+		it->n = n;
+		it->n_bytes = num_bytes;
+		it->total_proba = total_proba;
+	});
+}
+
+int qb_iter_download_async(const qb_iter *cit, uint8_t *objects, uint64_t *object_begin, uint32_t *object_size, double *magnitude) {
+	return guarded([&] {
+		QB_REQUIRE(cit, QB_ERR_ARG, "null iteration");
+		qb_iter *it = const_cast<qb_iter *>(cit);
+		qb_ctx *ctx = it->ctx;
+		ctx->use();
+		transfer_events(it);
+		cudaStream_t s = ctx->copy_out;
+		ctx->order_after_compute(s); // the state as the calls made so far leave it
+		if (it->upload_pending)
+			QB_CUDA(cudaStreamWaitEvent(s, it->uploaded, 0));
+		if (objects && it->n_bytes) QB_CUDA(cudaMemcpyAsync(objects, it->objects.ptr, it->n_bytes, cudaMemcpyDeviceToHost, s));
+		if (object_begin) QB_CUDA(cudaMemcpyAsync(object_begin, it->begin.ptr, sizeof(uint64_t) * (it->n + 1), cudaMemcpyDeviceToHost, s));
+		if (object_size && it->n) QB_CUDA(cudaMemcpyAsync(object_size, it->size.ptr, sizeof(uint32_t) * it->n, cudaMemcpyDeviceToHost, s));
+		if (magnitude && it->n) QB_CUDA(cudaMemcpyAsync(magnitude, it->mag.ptr, sizeof(cplx) * it->n, cudaMemcpyDeviceToHost, s));
+		QB_CUDA(cudaEventRecord(it->downloaded, s));
+		it->download_pending = true;
+	});
+}
+
+int qb_iter_wait(const qb_iter *it) {
+	return guarded([&] {
+		QB_REQUIRE(it, QB_ERR_ARG, "null iteration");
+		it->ctx->use();
+		if (it->uploaded) {
+			QB_CUDA(cudaEventSynchronize(it->uploaded));
+			QB_CUDA(cudaEventSynchronize(it->downloaded));
+		}
+		it->upload_pending = it->download_pending = false;
+	});
+}
+
 int qb_iter_counts(const qb_iter *it, uint64_t *num_object, uint64_t *num_bytes, double *total_proba) {
 	return guarded([&] {
 		QB_REQUIRE(it, QB_ERR_ARG, "null iteration");
@@ -1091,6 +1266,7 @@ int qb_iter_download(const qb_iter *it, uint8_t *objects, uint64_t *object_begin
 		QB_REQUIRE(it, QB_ERR_ARG, "null iteration");
 		qb_ctx *ctx = it->ctx;
 		ctx->use();
+		it->settle();
 		cudaStream_t s = ctx->stream;
 		if (objects && it->n_bytes) QB_CUDA(cudaMemcpyAsync(objects, it->objects.ptr, it->n_bytes, cudaMemcpyDeviceToHost, s));
 		if (object_begin) QB_CUDA(cudaMemcpyAsync(object_begin, it->begin.ptr, sizeof(uint64_t) * (it->n + 1), cudaMemcpyDeviceToHost, s));
@@ -1115,6 +1291,7 @@ int qb_iter_normalize(qb_iter *it) {
 		QB_REQUIRE(it, QB_ERR_ARG, "null iteration");
 		qb_ctx *ctx = it->ctx;
 		ctx->use();
+		it->settle();
 		it->total_proba = 0; // quids.hpp:986
 		if (it->n == 0) return;
 		it->total_proba = reduce_norm_total(ctx, it->mag.as<cplx>(), it->n);
@@ -1130,6 +1307,7 @@ int qb_iter_pop(qb_iter *it, uint64_t n, int normalize) {
 		if (n < 1) return; // quids.hpp:195-196
 		qb_ctx *ctx = it->ctx;
 		ctx->use();
+		it->settle();
 		it->n -= n;
 		QB_CUDA(cudaMemcpyAsync(&ctx->h_small[DS_COUNT], it->begin.as<uint64_t>() + it->n, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
 		ctx->sync();
@@ -1208,6 +1386,7 @@ int qb_apply_modifier(qb_iter *it, int modifier_id, const double *params, uint32
 		QB_REQUIRE(rc == QB_OK, rc, std::string("bad parameters for modifier ") + ops->name);
 		qb_ctx *ctx = it->ctx;
 		ctx->use();
+		it->settle();
 		if (it->n == 0) return;
 		ops->launch(storage, it->view(), ctx->stream, ctx->sm_count);
 		++ctx->launches;
@@ -1242,6 +1421,7 @@ int qb_hash_objects(const qb_iter *it, int rule_id, const double *params, uint32
 		if (it->n == 0) return;
 		qb_ctx *ctx = it->ctx;
 		ctx->use();
+		it->settle();
 		dev_buf out;
 		out.ensure(sizeof(uint64_t) * it->n, ctx->stream);
 		engine_launch L;
@@ -1320,6 +1500,7 @@ int qb_iter_send_objects(qb_iter *it, qb_comm *comm, uint64_t num_object_sent, i
 	return guarded([&] {
 		QB_REQUIRE(it && comm && it->ctx == comm->ctx, QB_ERR_ARG, "qb_iter_send_objects: bad handle");
 		it->ctx->use();
+		it->settle();
 		const uint64_t n = send_objects(it, comm, num_object_sent, node);
 		if (moved) *moved = n;
 	});
@@ -1329,6 +1510,7 @@ int qb_iter_receive_objects(qb_iter *it, qb_comm *comm, int node, uint64_t max_m
 	return guarded([&] {
 		QB_REQUIRE(it && comm && it->ctx == comm->ctx, QB_ERR_ARG, "qb_iter_receive_objects: bad handle");
 		it->ctx->use();
+		it->settle();
 		const uint64_t n = receive_objects(it, comm, node, max_mem);
 		if (moved) *moved = n;
 	});
@@ -1339,6 +1521,7 @@ int qb_iter_distribute_objects(qb_iter *it, qb_comm *comm, int node_id) {
 		QB_REQUIRE(it && comm && it->ctx == comm->ctx, QB_ERR_ARG, "qb_iter_distribute_objects: bad handle");
 		QB_REQUIRE(node_id >= 0 && node_id < comm->world, QB_ERR_ARG, "qb_iter_distribute_objects: bad node id");
 		it->ctx->use();
+		it->settle();
 		if (comm->rank == node_id) {
 			const uint64_t initial = it->n;
 			for (int node = 1; node < comm->world; ++node) {
@@ -1357,6 +1540,7 @@ int qb_iter_gather_objects(qb_iter *it, qb_comm *comm, int node_id) {
 		QB_REQUIRE(it && comm && it->ctx == comm->ctx, QB_ERR_ARG, "qb_iter_gather_objects: bad handle");
 		QB_REQUIRE(node_id >= 0 && node_id < comm->world, QB_ERR_ARG, "qb_iter_gather_objects: bad node id");
 		it->ctx->use();
+		it->settle();
 		if (comm->rank == node_id) {
 			for (int node = 1; node < comm->world; ++node)
 				receive_objects(it, comm, node <= node_id ? node - 1 : node, ~0ull);
@@ -1382,6 +1566,7 @@ int qb_iter_count_children(qb_iter *it, int rule_id, const double *params, uint3
 		int rc = ops->make(params, num_params, storage);
 		QB_REQUIRE(rc == QB_OK, rc, std::string("bad parameters for rule ") + ops->name);
 		it->ctx->use();
+		it->settle();
 		*num_children = count_children(it, ops, storage);
 	});
 }
@@ -1399,6 +1584,7 @@ int qb_iter_equalize(qb_iter *it, qb_comm *comm, int rule_id, const double *para
 			QB_REQUIRE(rc == QB_OK, rc, std::string("bad parameters for rule ") + ops->name);
 		}
 		it->ctx->use();
+		it->settle();
 		const int r = comm->world > 1 ? equalize_loop(it, comm, ops, storage, ops != nullptr, min_equalize_size, equalize_inbalance, min_equalize_step, max_rounds) : 0;
 		if (rounds) *rounds = r;
 	});

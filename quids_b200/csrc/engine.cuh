@@ -152,6 +152,8 @@ __global__ void __launch_bounds__(SYMBOLIC_THREADS, 5) symbolic_kernel(const Rul
 	const uint64_t num_chunks = div_up<uint64_t>(L.n_groups, CHUNK);
 	const uint64_t warp_stride = (uint64_t)gridDim.x * ENGINE_WARPS;
 	for (uint64_t chunk = (uint64_t)blockIdx.x * ENGINE_WARPS + (threadIdx.x >> 5); chunk < num_chunks; chunk += warp_stride) {
+		if (table_overflowed(L.table)) // the table was sized too small: the host redoes the step, stop feeding it
+			break;
 		const uint64_t c0 = chunk * CHUNK;
 		const uint64_t c1 = min(c0 + (uint64_t)CHUNK, L.n_groups);
 		// parents of this chunk: from the one holding group c0 to the one holding group c1 - 1
@@ -267,6 +269,8 @@ __global__ void __launch_bounds__(SYMBOLIC_THREADS, 5) symbolic_items_kernel(con
 	const uint64_t num_chunks = div_up<uint64_t>(L.n_groups, ITEM_CHUNK);
 	const uint64_t warp_stride = (uint64_t)gridDim.x * ENGINE_WARPS;
 	for (uint64_t chunk = (uint64_t)blockIdx.x * ENGINE_WARPS + (threadIdx.x >> 5); chunk < num_chunks; chunk += warp_stride) {
+		if (table_overflowed(L.table))
+			break;
 		const uint64_t c0 = chunk * ITEM_CHUNK, c1 = min(c0 + (uint64_t)ITEM_CHUNK, L.n_groups);
 		for (uint64_t b = c0; b < c1; b += 32) {
 			const uint32_t count = (uint32_t)min((uint64_t)32, c1 - b);

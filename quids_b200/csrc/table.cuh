@@ -41,6 +41,11 @@ __device__ __forceinline__ uint64_t table_home(uint64_t hash, uint64_t capacity)
 
 constexpr uint32_t TABLE_MAX_PROBES = 4096; // longer probe sequences mean the table was sized too small: the host retries larger
 
+// warp-uniform: has any insert of this launch given up?  Checked at chunk boundaries and every 64 probes, so that a
+// table that turns out too small costs milliseconds, not one full-length probe sequence per child.
+__device__ __forceinline__ bool table_overflowed(const table_view &t) { return __shfl_sync(0xffffffffu, *(volatile unsigned int *)t.overflow, 0) != 0; }
+__device__ __forceinline__ bool table_overflowed_lane(const table_view &t) { return *(volatile unsigned int *)t.overflow != 0; }
+
 // the probe loop, entered with the key already observed in slot `i` (0 = the slot looked empty).
 // Returns true when this call created the slot (first child with that hash).
 __device__ __forceinline__ bool table_insert_from(const table_view &t, uint64_t hash, cplx mag, uint64_t rep, uint64_t i, unsigned long long seen) {
@@ -67,6 +72,8 @@ __device__ __forceinline__ bool table_insert_from(const table_view &t, uint64_t 
 			*t.overflow = 1;
 			return false;
 		}
+		if ((probes & 63) == 0 && table_overflowed_lane(t))
+			return false;
 		seen = __ldcg(&t.slots[i].key);
 	}
 	// results unused -> RED.ADD.F64, fire and forget
@@ -141,6 +148,8 @@ __device__ __forceinline__ uint32_t table_insert_batch(const table_view &t, int 
 			*t.overflow = 1;
 			break;
 		}
+		if ((round & 63) == 63 && table_overflowed_lane(t))
+			break;
 	}
 	return created;
 }

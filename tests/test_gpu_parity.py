@@ -247,7 +247,7 @@ def test_unsupported_requests_fail_loudly(gpu):
     it.append(bytes([0, 1, 0]), 1.0)
     qb.simulate(it, qb.Rule("hadamard", 1), nxt, sym, 0)  # automatic budget: everything is kept when it fits ...
     assert nxt.num_object == 2
-    qb.config.safety_margin = 1.0  # ... and the call fails, instead of truncating silently, when it does not
+    qb.config.safety_margin = 1.0  # ... and the call fails when not even one parent's children do
     try:
         with pytest.raises(qb.QuidsError, match="automatic budget"):
             qb.simulate(it, qb.Rule("hadamard", 1), nxt, sym, 0)
@@ -420,3 +420,86 @@ def test_probabilistic_truncation(gpu, port):
     finally:
         qb.config.simple_truncation = True
         qb.config.seed = 0
+
+
+def test_table_sized_from_misleading_history_is_redone(gpu, port):
+    """the interference table is sized from the previous call of the same rule; when the state changes nature (many
+    duplicates -> all distinct) the prediction is far too small: the kernels must stop early, the step is redone at the
+    safe size, and the result is the oracle's (both orders of processing the children)."""
+    import time
+    import quids_b200 as qb
+    one = port.qcgd_random_state(9, 1, 5)
+    same = orc.Packed.from_objects(one.objects() * 70000, [1 / math.sqrt(70000)] * 70000)  # >= 2^16 groups: sorted order
+    grown, _, _ = port.simulate(port.qcgd_random_state(9, 3000, 8), orc.RULE_SPLIT_MERGE, [0.4, 0.3, 0.2], orc.NO_TRUNCATION, 1e-18)
+    assert grown.n > 20000
+    rid, params = orc.RULE_ERASE_CREATE, [0.7, 0.2, 0.1]
+    for sort in (1, 2, 0):
+        qb.config.locality_sort = sort
+        try:
+            eng = gpu()
+            got, gc, gu = eng.simulate(same, rid, params, tol=1e-18)  # N_u / N_c tiny: the history says "small table"
+            assert gu <= 512 < gc // 1000
+            want, nc, nu = port.simulate(grown, rid, params, orc.NO_TRUNCATION, 1e-18)
+            t0 = time.perf_counter()
+            got, gc, gu = eng.simulate(grown, rid, params, tol=1e-18)
+            assert time.perf_counter() - t0 < 20, "a table that is too small must cost milliseconds, not a probe sequence per child"
+            assert (gc, gu) == (nc, nu)
+            orc.assert_same_state(got, port.hash_objects(got, rid), want, port.hash_objects(want, rid), True, what=f"redo after overflow, sort={sort}")
+        finally:
+            qb.config.locality_sort = 1
+
+
+def test_automatic_budget_keeps_what_fits(gpu, port):
+    """max_num_object = 0 (quids.hpp:459-485, 510-536): the most probable parents whose symbolic workspace fits the
+    budget, then the most probable children the next state has room for.  The budget is given (qb_options.memory_budget)
+    so that a small state exercises both truncations; the result must be the oracle's for the same two counts."""
+    import quids_b200 as qb
+    base = port.qcgd_random_state(8, 500, 21)
+    rng = np.random.default_rng(4)
+    mags = rng.normal(size=(500, 2)) * np.exp(rng.normal(size=(500, 1)))
+    st = orc.Packed(base.sizes, mags / np.sqrt((mags ** 2).sum()), base.data)
+    rid, params, tol = orc.RULE_ERASE_CREATE, [0.6, 0.1, 0.2], 1e-18
+    objs = st.objects()
+    order = np.argsort(-(np.abs(st.cmags) ** 2), kind="stable")
+    children = np.array([port.simulate(orc.Packed.from_objects([objs[i]], [1.0]), rid, params, orc.NO_TRUNCATION, tol)[1] for i in order])
+    cum = np.cumsum(children)
+    eng = gpu()
+    full, nc, nu = port.simulate(st, rid, params, orc.NO_TRUNCATION, tol)
+    got, gc, gu = eng.simulate(st, rid, params, 0, tol)  # measured budget: a B200 holds all of it
+    assert (gc, gu) == (nc, nu)
+    orc.assert_same_state(got, port.hash_objects(got, rid), full, port.hash_objects(full, rid), True, what="automatic budget, everything fits")
+    seen, refused = set(), 0
+    try:
+        for budget in [int(6e6 * 0.8 ** i) for i in range(22)]:  # 6 MB (everything fits) down to 55 KB
+            qb.config.memory_budget = budget
+            try:
+                got, gc, gu = eng.simulate(st, rid, params, 0, tol)
+            except qb.QuidsError as e:  # too small even for one parent, or no room left for a next state
+                assert "automatic budget" in str(e)
+                refused += 1
+                continue
+            assert 0 < got.n
+            k_p = int(np.searchsorted(cum, gc)) + 1  # parents kept: the children counted are those of the k_p most probable
+            assert k_p <= st.n and cum[k_p - 1] == gc, (k_p, gc)
+            kept = np.sort(order[:k_p])
+            src = orc.Packed.from_objects([objs[j] for j in kept], st.cmags[kept])
+            fullk, nck, nuk = port.simulate(src, rid, params, orc.NO_TRUNCATION, tol)
+            assert (gc, gu) == (nck, nuk)
+            hg = port.hash_objects(got, rid)
+            if got.n == nuk:
+                orc.assert_same_state(got, hg, fullk, port.hash_objects(fullk, rid), True, what=f"automatic budget {budget}")
+            else:
+                # children-only truncation of the oracle's untruncated result (an explicit max_num_object would cut the parents too)
+                raw = fullk.cmags * math.sqrt(fullk.total_proba)
+                top = np.sort(np.argsort(-(np.abs(raw) ** 2), kind="stable")[:got.n])
+                total = float((np.abs(raw[top]) ** 2).sum())
+                fobjs = fullk.objects()
+                want = orc.Packed.from_objects([fobjs[j] for j in top], raw[top] / math.sqrt(total))
+                want.total_proba = total
+                orc.assert_same_truncated(got, hg, want, port.hash_objects(want, rid), fullk, port.hash_objects(fullk, rid), got.n, True,
+                                          what=f"automatic budget {budget}")
+            seen.add((k_p < st.n, got.n < nuk))
+    finally:
+        qb.config.memory_budget = 0
+    assert (False, False) in seen and (False, True) in seen, seen  # everything fits; only the children are truncated
+    assert any(s[0] for s in seen), seen                           # parents are truncated
