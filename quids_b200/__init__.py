@@ -325,6 +325,30 @@ class Iteration:
         _check(lib().qb_iter_upload(self.handle, n, objects.ctypes.data, nbytes, object_begin.ctypes.data, object_size.ctypes.data,
                                     magnitude.ctypes.data, total_proba))
 
+    def upload_async(self, objects, object_begin, object_size, magnitude, total_proba=1.0):
+        """upload on the copy stream, overlapping rule iterations on other states; the arrays must be page-locked,
+        C-contiguous, of the exact dtypes, and stay untouched until wait() (qb_iter_upload_async)"""
+        n = object_size.shape[0]
+        assert objects.dtype == np.uint8 and object_begin.dtype == np.uint64 and object_size.dtype == np.uint32 and magnitude.dtype == np.float64
+        assert object_begin.shape[0] == n + 1 and magnitude.size == 2 * n
+        self._pending = []
+        self._async_refs = (objects, object_begin, object_size, magnitude)
+        _check(lib().qb_iter_upload_async(self.handle, n, objects.ctypes.data, int(object_begin[n]) if n else 0, object_begin.ctypes.data,
+                                          object_size.ctypes.data, magnitude.ctypes.data, total_proba))
+
+    def download_async(self, objects, object_begin, object_size, magnitude):
+        """download into page-locked arrays on the copy stream; valid after wait() (qb_iter_download_async)"""
+        n, nb, _ = self._counts_noflush()
+        assert objects.nbytes >= nb and object_begin.shape[0] >= n + 1 and object_size.shape[0] >= n and magnitude.size >= 2 * n
+        self._async_refs = (objects, object_begin, object_size, magnitude)
+        _check(lib().qb_iter_download_async(self.handle, objects.ctypes.data, object_begin.ctypes.data, object_size.ctypes.data, magnitude.ctypes.data))
+        return n, nb
+
+    def wait(self):
+        """block the host until the asynchronous transfers of this state are complete"""
+        _check(lib().qb_iter_wait(self.handle))
+        self._async_refs = None
+
     def upload_packed(self, sizes, mags, data, total_proba=1.0, align=None):
         """objects given back to back without padding: lay them out with align_byte_length"""
         sizes = np.ascontiguousarray(sizes, np.uint32)

@@ -503,3 +503,49 @@ def test_automatic_budget_keeps_what_fits(gpu, port):
         qb.config.memory_budget = 0
     assert (False, False) in seen and (False, True) in seen, seen  # everything fits; only the children are truncated
     assert any(s[0] for s in seen), seen                           # parents are truncated
+
+
+def test_async_transfers_double_buffered(gpu, port):
+    """qb_iter_upload_async / qb_iter_download_async / qb_iter_wait: the pipelined use of bench.py's e2e leg (upload of
+    step i+1 and download of step i-1 around the rule iteration of step i) gives the results of the synchronous calls"""
+    import quids_b200 as qb
+    qb.config.tolerance, qb.config.align_byte_length = 1e-18, 8
+    rule = qb.Rule("erase_create", 0.4, 0.1, 0.2)
+    states = [port.qcgd_random_state(7, 300 + 50 * i, 40 + i) for i in range(5)]
+    sym = qb.SymbolicIteration()
+    want = []
+    for st in states:
+        it, nxt = qb.Iteration(), qb.Iteration()
+        it.upload_packed(st.sizes, st.mags, st.data)
+        qb.simulate(it, rule, nxt, sym)
+        want.append(nxt.download())
+    hosts = []
+    for st in states:  # the reference's storage layout on the host, as a driver would hold it
+        it = qb.Iteration()
+        it.upload_packed(st.sizes, st.mags, st.data)
+        o, b, s, m = it.download()
+        hosts.append((o.copy(), b.copy(), s.copy(), m.reshape(-1).copy()))
+    ins, outs = [qb.Iteration(), qb.Iteration()], [qb.Iteration(), qb.Iteration()]
+    results = [None] * len(states)
+    bufs = [None, None]
+    ins[0].upload_async(*hosts[0])
+    for i in range(len(states)):
+        cur = i % 2
+        if i + 1 < len(states):
+            ins[1 - cur].upload_async(*hosts[i + 1])
+        if bufs[cur] is not None:  # the result of step i-2 must have left before its state is overwritten on the host side
+            outs[cur].wait()
+            results[i - 2] = [x.copy() for x in bufs[cur]]
+        qb.simulate(ins[cur], rule, outs[cur], sym)
+        n, nb = outs[cur].num_object, outs[cur].num_bytes
+        bufs[cur] = [np.zeros(nb, np.uint8), np.zeros(n + 1, np.uint64), np.zeros(n, np.uint32), np.zeros(2 * n, np.float64)]
+        outs[cur].download_async(*bufs[cur])
+    for i in (len(states) - 2, len(states) - 1):
+        outs[i % 2].wait()
+        results[i] = bufs[i % 2]
+    for got, (o, b, s, m) in zip(results, want):
+        assert np.array_equal(got[1], b) and np.array_equal(got[2], s)
+        # same kernels, same inputs: the objects arrive in the same order only if the table fills the same way; compare as sets
+        key = lambda oo, bb, ss, mm: sorted((oo[int(bb[j]):int(bb[j]) + int(ss[j])].tobytes(), round(float(mm[2 * j]), 12), round(float(mm[2 * j + 1]), 12))
+                                            for j in range(len(ss)))
+        assert key(got[0], got[1], got[2], got[3]) == key(o, b, s, m.reshape(-1))
