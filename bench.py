@@ -43,6 +43,11 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def qcgd_magnitude(n_parents):
+    from quids_b200 import qcgd
+    return qcgd.read_state_magnitude(n_parents)[0]
+
+
 def make_parents(n_parents, seed):
     from quids_b200 import qcgd
     sizes, data = qcgd.random_graphs(N_NODE, n_parents, seed=seed)
@@ -293,6 +298,45 @@ def run_ours(args):
         e2e_ms = float(t.item())
     e2e_value = n_c_total / (e2e_ms / 1e3)
 
+    # ---- the 1e8-object QCGD configuration on ONE GPU (north_star's target line; BASELINE.json configs[4] without the
+    # sharding): same generator, ten chunks of 1e7 parents appended in HBM, max_num_object = parents.  N = 1 only. ----
+    large = None
+    if world == 1 and args.large_parents > parents:
+        del ins, outs, out_host, pinned, host
+        big, big_next, chunk_state = qb.Iteration(ctx), qb.Iteration(ctx), qb.Iteration(ctx)
+        done = 0
+        while done < args.large_parents:
+            n_chunk = min(parents, args.large_parents - done)
+            cs, cm, cd = make_parents(n_chunk, seed=1000 + done // parents)
+            cm[:, 0] = qcgd_magnitude(args.large_parents)
+            chunk_state.upload_packed(cs, cm, cd)
+            big.append_state(chunk_state)
+            done += n_chunk
+        del chunk_state
+        for _ in range(2):
+            qb.simulate(big, rule, big_next, sym, args.large_parents)
+        barrier()
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record(stream)
+        large_steps = 3
+        large_phase = {}
+        for _ in range(large_steps):
+            qb.simulate(big, rule, big_next, sym, args.large_parents)
+            for name, ms in sym.phase_ms.items():
+                large_phase[name] = large_phase.get(name, 0.0) + ms / large_steps
+        l1.record(stream)
+        barrier()
+        large_ms = l0.elapsed_time(l1) / large_steps
+        lc, lu, ls = sym.num_object, sym.num_object_after_interferences, big_next.num_object
+        free_b, total_b = torch.cuda.mem_get_info()
+        lbytes = algorithmic_bytes(args.large_parents, 248, lc, lu, ls, 248)
+        peak_l, _ = measured_peak_gbs()
+        large = {"workload": f"the same rule and generator on {args.large_parents} parents on one GPU, max_num_object = parents", "value": lc / (large_ms / 1e3),
+                 "unit": UNIT, "ms_per_step": large_ms, "steps": large_steps, "counts": {"N_p": args.large_parents, "N_c": lc, "N_u": lu, "N_s": ls},
+                 "whole_iteration": {"algorithmic_bytes": lbytes, "achieved": lbytes / (large_ms / 1e3) / 1e9, "frac": lbytes / (large_ms / 1e3) / 1e9 / peak_l},
+                 "phase_ms": large_phase, "hbm_in_use_gb": (total_b - free_b) / 1e9}
+        del big, big_next
+
     if rank != 0:
         return
     # ---- roofline of the dominant kernel (symbolic_kernel: children -> (hash, magnitude) -> table) --------
@@ -334,6 +378,8 @@ def run_ours(args):
                     "how": "per step: qb_iter_upload_async of the input state from pinned host memory, qb_simulate, qb_iter_download_async of the result "
                            "state into pinned host memory; double-buffered on the library's copy streams, wall clock over all steps incl. the first upload and the last download"},
             "gpu_launches": int(launches)}
+    if large is not None:
+        line["large"] = large
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
@@ -347,6 +393,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--parents", type=int, default=10**7, help="parents per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--large-parents", type=int, default=10**8, help="N = 1 only: also time this many parents on the one GPU (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -31,6 +31,7 @@ typedef unsigned uint;
 #include <initializer_list>
 #include <limits>
 #include <stdexcept>
+#include <type_traits>
 #include <string>
 #include <vector>
 
@@ -56,7 +57,9 @@ typedef unsigned uint;
 #endif
 
 namespace quids {
-	static_assert(sizeof(PROBA_TYPE) == sizeof(double), "this build of the library carries the double instantiation only (PROBA_TYPE = double)");
+	// PROBA_TYPE = double (default) or float (quids.hpp:21-23).  With float the host mirror, the magnitudes crossing the C ABI
+	// and every value a driver sees are complex<float>; the state in HBM and the device arithmetic stay double.
+	static_assert(std::is_same<PROBA_TYPE, double>::value || std::is_same<PROBA_TYPE, float>::value, "PROBA_TYPE must be double or float");
 
 	// ---- the mutable namespace globals drivers assign (quids.hpp:60-75) -----------------------------
 	inline uint align_byte_length = ALIGNMENT_BYTE_LENGTH;
@@ -231,9 +234,14 @@ namespace quids {
 			if (device_valid_)
 				return;
 			static_assert(sizeof(size_t) == sizeof(uint64_t) && sizeof(uint) == sizeof(uint32_t), "LP64 expected");
-			detail::check(qb_iter_upload(handle_, num_object, reinterpret_cast<const uint8_t *>(objects.data()), object_begin[num_object],
-			                             reinterpret_cast<const uint64_t *>(object_begin.data()), object_size.data(),
-			                             reinterpret_cast<const double *>(magnitude.data()), total_proba));
+			if constexpr (std::is_same<PROBA_TYPE, float>::value)
+				detail::check(qb_iter_upload_f32(handle_, num_object, reinterpret_cast<const uint8_t *>(objects.data()), object_begin[num_object],
+				                                 reinterpret_cast<const uint64_t *>(object_begin.data()), object_size.data(),
+				                                 reinterpret_cast<const float *>(magnitude.data()), total_proba));
+			else
+				detail::check(qb_iter_upload(handle_, num_object, reinterpret_cast<const uint8_t *>(objects.data()), object_begin[num_object],
+				                             reinterpret_cast<const uint64_t *>(object_begin.data()), object_size.data(),
+				                             reinterpret_cast<const double *>(magnitude.data()), total_proba));
 			device_valid_ = true;
 		}
 		void to_host() const {
@@ -246,8 +254,12 @@ namespace quids {
 			object_begin.resize(n + 1);
 			object_size.resize(n);
 			magnitude.resize(n);
-			detail::check(qb_iter_download(handle_, reinterpret_cast<uint8_t *>(objects.data()), reinterpret_cast<uint64_t *>(object_begin.data()),
-			                               object_size.data(), reinterpret_cast<double *>(magnitude.data())));
+			if constexpr (std::is_same<PROBA_TYPE, float>::value)
+				detail::check(qb_iter_download_f32(handle_, reinterpret_cast<uint8_t *>(objects.data()), reinterpret_cast<uint64_t *>(object_begin.data()),
+				                                   object_size.data(), reinterpret_cast<float *>(magnitude.data())));
+			else
+				detail::check(qb_iter_download(handle_, reinterpret_cast<uint8_t *>(objects.data()), reinterpret_cast<uint64_t *>(object_begin.data()),
+				                               object_size.data(), reinterpret_cast<double *>(magnitude.data())));
 			if (n == 0)
 				object_begin[0] = 0;
 			host_valid_ = true;

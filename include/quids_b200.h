@@ -107,6 +107,12 @@ int qb_iter_counts(const qb_iter *it, uint64_t *num_object, uint64_t *num_bytes,
 /* copies the state out (what get_object() reads, quids.hpp:242-258); any pointer may be NULL */
 int qb_iter_download(const qb_iter *it, uint8_t *objects, uint64_t *object_begin, uint32_t *object_size, double *magnitude);
 /* device pointers of the four arrays (for zero-copy consumers; valid until the next call that writes `it`) */
+/* PROBA_TYPE = float (quids.hpp:21-23): the same two transfers with complex<float> magnitudes (2 x f32 per object).
+ * The state in HBM and the device arithmetic stay double, so a float build of a driver agrees with the reference's
+ * float build to the reference's own rounding (1e-5 relative). */
+int qb_iter_upload_f32(qb_iter *it, uint64_t num_object, const uint8_t *objects, uint64_t num_bytes,
+                       const uint64_t *object_begin, const uint32_t *object_size, const float *magnitude, double total_proba);
+int qb_iter_download_f32(const qb_iter *it, uint8_t *objects, uint64_t *object_begin, uint32_t *object_size, float *magnitude);
 /* The same two transfers on dedicated copy streams, overlapping the rule iterations of OTHER states (double buffering:
  * upload the input of step i+1 and download the result of step i-1 while step i computes).  The host arrays must be
  * page-locked (qb_host_alloc) and stay untouched until qb_iter_wait(it) returns; every later call that uses `it` orders
@@ -116,6 +122,9 @@ int qb_iter_upload_async(qb_iter *it, uint64_t num_object, const uint8_t *object
                          const uint64_t *object_begin, const uint32_t *object_size, const double *magnitude, double total_proba);
 int qb_iter_download_async(const qb_iter *it, uint8_t *objects, uint64_t *object_begin, uint32_t *object_size, double *magnitude);
 int qb_iter_wait(const qb_iter *it);
+/* iteration::append (quids.hpp:174-188) for a whole state at once, HBM to HBM: the objects of `other` are appended to
+ * `it` with their magnitudes (no normalisation; total_proba of `it` is kept) */
+int qb_iter_append_state(qb_iter *it, const qb_iter *other);
 int qb_iter_device_ptrs(const qb_iter *it, void **objects, void **object_begin, void **object_size, void **magnitude);
 /* pop(n, normalize) quids.hpp:194-203 */
 int qb_iter_pop(qb_iter *it, uint64_t n, int normalize);

@@ -82,9 +82,12 @@ def lib():
         "qb_iter_create": (i32, [vp, P(vp)]),
         "qb_iter_destroy": (i32, [vp]),
         "qb_iter_upload": (i32, [vp, u64, vp, u64, vp, vp, vp, dbl]),
+        "qb_iter_upload_f32": (i32, [vp, u64, vp, u64, vp, vp, vp, dbl]),
+        "qb_iter_download_f32": (i32, [vp, vp, vp, vp, vp]),
         "qb_iter_upload_async": (i32, [vp, u64, vp, u64, vp, vp, vp, dbl]),
         "qb_iter_download_async": (i32, [vp, vp, vp, vp, vp]),
         "qb_iter_wait": (i32, [vp]),
+        "qb_iter_append_state": (i32, [vp, vp]),
         "qb_iter_counts": (i32, [vp, P(u64), P(u64), P(dbl)]),
         "qb_iter_download": (i32, [vp, vp, vp, vp, vp]),
         "qb_iter_device_ptrs": (i32, [vp, P(vp), P(vp), P(vp), P(vp)]),
@@ -316,14 +319,15 @@ class Iteration:
         objects = np.ascontiguousarray(objects, np.uint8)
         object_begin = np.ascontiguousarray(object_begin, np.uint64)
         object_size = np.ascontiguousarray(object_size, np.uint32)
-        magnitude = np.ascontiguousarray(magnitude, np.float64).reshape(-1, 2)
+        f32 = np.asarray(magnitude).dtype == np.float32  # PROBA_TYPE = float at the boundary (qb_iter_upload_f32)
+        magnitude = np.ascontiguousarray(magnitude, np.float32 if f32 else np.float64).reshape(-1, 2)
         n = object_size.shape[0]
         assert object_begin.shape[0] == n + 1 and magnitude.shape[0] == n
         nbytes = int(object_begin[n]) if n else 0
         assert objects.shape[0] >= nbytes
         self._pending = []
-        _check(lib().qb_iter_upload(self.handle, n, objects.ctypes.data, nbytes, object_begin.ctypes.data, object_size.ctypes.data,
-                                    magnitude.ctypes.data, total_proba))
+        fn = lib().qb_iter_upload_f32 if f32 else lib().qb_iter_upload
+        _check(fn(self.handle, n, objects.ctypes.data, nbytes, object_begin.ctypes.data, object_size.ctypes.data, magnitude.ctypes.data, total_proba))
 
     def upload_async(self, objects, object_begin, object_size, magnitude, total_proba=1.0):
         """upload on the copy stream, overlapping rule iterations on other states; the arrays must be page-locked,
@@ -378,15 +382,17 @@ class Iteration:
                 objects[pos.astype(np.int64)] = data[:int(src_begin[n])]
         self.upload(objects, begin, sizes, mags, total_proba)
 
-    def download(self):
+    def download(self, dtype=np.float64):
+        """the reference's four arrays; dtype=np.float32 reads the magnitudes as complex<float> (qb_iter_download_f32)"""
         if self._pending:
             self._flush()
         n, nb, _ = self._counts_noflush()
         objects = np.zeros(nb, np.uint8)
         begin = np.zeros(n + 1, np.uint64)
         size = np.zeros(n, np.uint32)
-        mag = np.zeros((n, 2), np.float64)
-        _check(lib().qb_iter_download(self.handle, objects.ctypes.data, begin.ctypes.data, size.ctypes.data, mag.ctypes.data))
+        mag = np.zeros((n, 2), dtype)
+        fn = lib().qb_iter_download_f32 if np.dtype(dtype) == np.float32 else lib().qb_iter_download
+        _check(fn(self.handle, objects.ctypes.data, begin.ctypes.data, size.ctypes.data, mag.ctypes.data))
         return objects, begin, size, mag
 
     def _counts_noflush(self):
@@ -416,6 +422,12 @@ class Iteration:
         objects, begin, size, mag = self.download()
         b = int(begin[object_id])
         return objects[b:b + int(size[object_id])].tobytes(), complex(mag[object_id, 0], mag[object_id, 1])
+
+    def append_state(self, other: "Iteration"):
+        """append every object of `other` (HBM to HBM, no normalisation)"""
+        self._flush()
+        other._flush()
+        _check(lib().qb_iter_append_state(self.handle, other.handle))
 
     def pop(self, n=1, normalize=True):
         self._flush()

@@ -1177,6 +1177,78 @@ int qb_iter_upload(qb_iter *it, uint64_t n, const uint8_t *objects, uint64_t num
 	});
 }
 
+// ---- PROBA_TYPE = float at the boundary (quids.hpp:21-23): magnitudes cross the C ABI as complex<float>; the state in HBM
+// and all device arithmetic stay double (at least the reference's float accuracy: parity 1e-5) ---------------
+__global__ void __launch_bounds__(256) widen_mag_kernel(const float2 *in, cplx *out, uint64_t n) {
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+		const float2 v = in[i];
+		out[i] = cplx{(double)v.x, (double)v.y};
+	}
+}
+__global__ void __launch_bounds__(256) narrow_mag_kernel(const cplx *in, float2 *out, uint64_t n) {
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+		const cplx v = in[i];
+		out[i] = make_float2((float)v.re, (float)v.im);
+	}
+}
+
+int qb_iter_upload_f32(qb_iter *it, uint64_t n, const uint8_t *objects, uint64_t num_bytes, const uint64_t *object_begin, const uint32_t *object_size,
+                       const float *magnitude, double total_proba) {
+	return guarded([&] {
+		QB_REQUIRE(it, QB_ERR_ARG, "null iteration");
+		QB_REQUIRE(n == 0 || (object_begin && object_size && magnitude), QB_ERR_ARG, "qb_iter_upload_f32: null array");
+		QB_REQUIRE(num_bytes == 0 || objects, QB_ERR_ARG, "qb_iter_upload_f32: null objects");
+		qb_ctx *ctx = it->ctx;
+		ctx->use();
+		it->settle();
+		cudaStream_t s = ctx->stream;
+		it->objects.ensure(num_bytes + 16, s);
+		it->begin.ensure(sizeof(uint64_t) * (n + 1), s);
+		it->size.ensure(sizeof(uint32_t) * (n ? n : 1), s);
+		it->mag.ensure(sizeof(cplx) * (n ? n : 1), s);
+		if (num_bytes) QB_CUDA(cudaMemcpyAsync(it->objects.ptr, objects, num_bytes, cudaMemcpyHostToDevice, s));
+		if (n) {
+			dev_buf staging;
+			staging.ensure(sizeof(float2) * n, s);
+			QB_CUDA(cudaMemcpyAsync(it->begin.ptr, object_begin, sizeof(uint64_t) * (n + 1), cudaMemcpyHostToDevice, s));
+			QB_CUDA(cudaMemcpyAsync(it->size.ptr, object_size, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, s));
+			QB_CUDA(cudaMemcpyAsync(staging.ptr, magnitude, sizeof(float2) * n, cudaMemcpyHostToDevice, s));
+			widen_mag_kernel<<<grid_for(n, 256, ctx->grid_cap()), 256, 0, s>>>(staging.as<float2>(), it->mag.as<cplx>(), n);
+			++ctx->launches;
+			ctx->sync();
+		} else {
+			QB_CUDA(cudaMemsetAsync(it->begin.ptr, 0, sizeof(uint64_t), s));
+			ctx->sync();
+		}
+		it->n = n;
+		it->n_bytes = num_bytes;
+		it->total_proba = total_proba;
+	});
+}
+
+int qb_iter_download_f32(const qb_iter *it, uint8_t *objects, uint64_t *object_begin, uint32_t *object_size, float *magnitude) {
+	return guarded([&] {
+		QB_REQUIRE(it, QB_ERR_ARG, "null iteration");
+		qb_ctx *ctx = it->ctx;
+		ctx->use();
+		it->settle();
+		cudaStream_t s = ctx->stream;
+		if (objects && it->n_bytes) QB_CUDA(cudaMemcpyAsync(objects, it->objects.ptr, it->n_bytes, cudaMemcpyDeviceToHost, s));
+		if (object_begin) QB_CUDA(cudaMemcpyAsync(object_begin, it->begin.ptr, sizeof(uint64_t) * (it->n + 1), cudaMemcpyDeviceToHost, s));
+		if (object_size && it->n) QB_CUDA(cudaMemcpyAsync(object_size, it->size.ptr, sizeof(uint32_t) * it->n, cudaMemcpyDeviceToHost, s));
+		dev_buf staging;
+		if (magnitude && it->n) {
+			staging.ensure(sizeof(float2) * it->n, s);
+			narrow_mag_kernel<<<grid_for(it->n, 256, ctx->grid_cap()), 256, 0, s>>>(it->mag.as<cplx>(), staging.as<float2>(), it->n);
+			++ctx->launches;
+			QB_CUDA(cudaMemcpyAsync(magnitude, staging.ptr, sizeof(float2) * it->n, cudaMemcpyDeviceToHost, s));
+		}
+		ctx->sync();
+	});
+}
+
 // ---- transfers that overlap the rule iterations: pinned host memory <-> HBM on dedicated copy streams --------------
 static void transfer_events(qb_iter *it) {
 	it->ctx->copy_streams();
@@ -1283,6 +1355,34 @@ int qb_iter_device_ptrs(const qb_iter *it, void **objects, void **object_begin, 
 		if (object_begin) *object_begin = it->begin.ptr;
 		if (object_size) *object_size = it->size.ptr;
 		if (magnitude) *magnitude = it->mag.ptr;
+	});
+}
+
+int qb_iter_append_state(qb_iter *it, const qb_iter *other) {
+	return guarded([&] {
+		QB_REQUIRE(it && other && it != other && it->ctx == other->ctx, QB_ERR_ARG, "qb_iter_append_state: bad handle");
+		qb_ctx *ctx = it->ctx;
+		ctx->use();
+		it->settle();
+		other->settle();
+		const uint64_t n = other->n, bytes = other->n_bytes;
+		if (n == 0) return;
+		cudaStream_t s = ctx->stream;
+		it->objects.ensure(it->n_bytes + bytes + 16, s, true, it->n_bytes);
+		it->begin.ensure(sizeof(uint64_t) * (it->n + n + 1), s, true, sizeof(uint64_t) * (it->n + 1));
+		it->size.ensure(sizeof(uint32_t) * (it->n + n), s, true, sizeof(uint32_t) * it->n);
+		it->mag.ensure(sizeof(cplx) * (it->n + n), s, true, sizeof(cplx) * it->n);
+		QB_CUDA(cudaMemcpyAsync(it->objects.as<uint8_t>() + it->n_bytes, other->objects.ptr, bytes, cudaMemcpyDeviceToDevice, s));
+		QB_CUDA(cudaMemcpyAsync(it->begin.as<uint64_t>() + it->n + 1, other->begin.as<uint64_t>() + 1, sizeof(uint64_t) * n, cudaMemcpyDeviceToDevice, s));
+		QB_CUDA(cudaMemcpyAsync(it->size.as<uint32_t>() + it->n, other->size.ptr, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, s));
+		QB_CUDA(cudaMemcpyAsync(it->mag.as<cplx>() + it->n, other->mag.ptr, sizeof(cplx) * n, cudaMemcpyDeviceToDevice, s));
+		if (it->n_bytes) {
+			rebase_begin_kernel<<<grid_for(n, 256, ctx->grid_cap()), 256, 0, s>>>(it->begin.as<uint64_t>() + it->n + 1, n, 0, it->n_bytes);
+			++ctx->launches;
+		}
+		ctx->sync();
+		it->n += n;
+		it->n_bytes += bytes;
 	});
 }
 

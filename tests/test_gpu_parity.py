@@ -549,3 +549,33 @@ def test_async_transfers_double_buffered(gpu, port):
         key = lambda oo, bb, ss, mm: sorted((oo[int(bb[j]):int(bb[j]) + int(ss[j])].tobytes(), round(float(mm[2 * j]), 12), round(float(mm[2 * j + 1]), 12))
                                             for j in range(len(ss)))
         assert key(got[0], got[1], got[2], got[3]) == key(o, b, s, m.reshape(-1))
+
+
+def test_float_magnitudes_at_the_boundary(gpu, port):
+    """PROBA_TYPE = float (quids.hpp:21-23): complex<float> magnitudes cross the C ABI (qb_iter_upload_f32 /
+    qb_iter_download_f32); the result agrees with the double oracle within 1e-5 relative (north_star's float tolerance)"""
+    import quids_b200 as qb
+    qb.config.tolerance, qb.config.align_byte_length = 1e-18, 8
+    st = port.qcgd_random_state(8, 400, 13)
+    rng = np.random.default_rng(2)
+    mags = rng.normal(size=(400, 2))
+    mags = (mags / np.sqrt((mags ** 2).sum())).astype(np.float32)
+    st = orc.Packed(st.sizes, mags.astype(np.float64), st.data)  # the oracle sees exactly the float values, widened
+    rid, params = orc.RULE_ERASE_CREATE, [0.5, 0.2, 0.1]
+    want, nc, nu = port.simulate(st, rid, params, orc.NO_TRUNCATION, 1e-18)
+    it, nxt, sym = qb.Iteration(), qb.Iteration(), qb.SymbolicIteration()
+    begin = np.concatenate([[0], np.cumsum((st.sizes.astype(np.uint64) + 7) // 8 * 8)]).astype(np.uint64)
+    objects = np.zeros(int(begin[-1]), np.uint8)
+    for j, o in enumerate(st.objects()):
+        objects[int(begin[j]):int(begin[j]) + len(o)] = np.frombuffer(o, np.uint8)
+    it.upload(objects, begin, st.sizes, mags)  # float32 magnitudes select the f32 entry point
+    o64, b64, s64, m64 = it.download()
+    assert np.array_equal(m64, mags.astype(np.float64))  # widened exactly
+    qb.simulate(it, qb.Rule("erase_create", *params), nxt, sym)
+    assert (sym.num_object, sym.num_object_after_interferences) == (nc, nu)
+    o, b, s, m32 = nxt.download(np.float32)
+    _, _, _, m = nxt.download()
+    assert m32.dtype == np.float32 and np.array_equal(m32, m.astype(np.float32))  # narrowed with round-to-nearest
+    sizes, mags_out, data = nxt.download_packed()
+    got = orc.Packed(sizes, m32.astype(np.float64), data, nxt.total_proba)
+    orc.assert_same_state(got, port.hash_objects(got, rid), want, port.hash_objects(want, rid), True, rtol=1e-5, what="float boundary")
