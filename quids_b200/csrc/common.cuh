@@ -47,6 +47,7 @@ __device__ __forceinline__ cplx cmul(cplx a, cplx b) {
 	r.im = __dadd_rn(__dmul_rn(a.re, b.im), __dmul_rn(a.im, b.re));
 	return r;
 }
+__device__ __forceinline__ cplx cadd(cplx a, cplx b) { return cplx{__dadd_rn(a.re, b.re), __dadd_rn(a.im, b.im)}; }
 __device__ __forceinline__ cplx cscale(cplx a, double f) { return cplx{__dmul_rn(a.re, f), __dmul_rn(a.im, f)}; }
 __device__ __forceinline__ double cnorm(cplx a) { return __dadd_rn(__dmul_rn(a.re, a.re), __dmul_rn(a.im, a.im)); }
 

@@ -355,12 +355,39 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 			ws.amp[lane_id()] = this->amp.f[lane_id()];
 	}
 
+	// A run's accumulators hold, per pattern t of the parents' own particles on the tree nodes, the SUM of the roots of
+	// the groups with that pattern (a continuing group costs one addition).  The magnitude a group gives to object s is
+	// root * prod_l amp[taken_l][t_l] with taken_l = s_l xor t_l, so the objects' magnitudes are
+	//     acc[s] = sum_t R[t] * prod_l A[s_l xor t_l][t_l]
+	// -- a Kronecker product of one 2x2 matrix per tree level, applied in place level by level (64 butterflies each),
+	// instead of one product chain per child.  Same value as summing the children one by one up to rounding
+	// (the interference table adds them in no particular order either).
+	__device__ __forceinline__ void spread_run(flip_workspace &ws) const {
+		const uint32_t lane = lane_id();
+		const uint32_t leaves = ws.run_leaves;
+		const cplx a00 = ws.amp[0], a01 = ws.amp[1], a10 = ws.amp[2], a11 = ws.amp[3]; // index = taken * 2 + parent's bit
+		for (uint32_t bit = 1; bit < leaves; bit <<= 1) {
+			for (uint32_t b = lane; b < leaves / 2; b += 32) {
+				const uint32_t i0 = ((b & ~(bit - 1)) << 1) | (b & (bit - 1)), i1 = i0 | bit;
+				const cplx x0{ws.acc_re[i0], ws.acc_im[i0]}, x1{ws.acc_re[i1], ws.acc_im[i1]};
+				const cplx y0 = cadd(cmul(x0, a00), cmul(x1, a11)); // object bit 0: pattern 0 stays, pattern 1 goes
+				const cplx y1 = cadd(cmul(x0, a10), cmul(x1, a01)); // object bit 1: pattern 0 goes, pattern 1 stays
+				ws.acc_re[i0] = y0.re;
+				ws.acc_im[i0] = y0.im;
+				ws.acc_re[i1] = y1.re;
+				ws.acc_im[i1] = y1.im;
+			}
+			__syncwarp();
+		}
+	}
+
 	// the objects of the current run go to the global table, four per lane at a time
 	template <class Emit>
 	__device__ void flush_warp(flip_workspace &ws, Emit &emit) const {
 		__syncwarp();
 		if (ws.run_valid) {
 			const uint32_t leaves = ws.run_leaves;
+			spread_run(ws);
 			for (uint32_t base = lane_id(); base < leaves; base += 128) {
 				uint64_t hash[4];
 				int count = 0;
@@ -382,6 +409,7 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 	}
 
 	// full expansion of one group: tree states (hash folds and magnitudes) of all its leaves in ws
+	template <bool WITH_MAG = true>
 	__device__ __forceinline__ void expand_full(const flip_ctx &ctx, const flip_root &root, flip_workspace &ws) const {
 		const uint32_t lane = lane_id();
 		const uint64_t left = ctx.left, right = ctx.right;
@@ -417,15 +445,17 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 						hr1 = hash_combine_index(hr1, j);
 					}
 				}
-				const cplx m0 = cmul(m, stay), m1 = cmul(m, go);
 				ws.hl[i] = hl0;
 				ws.hr[i] = hr0;
-				ws.re[i] = m0.re;
-				ws.im[i] = m0.im;
 				ws.hl[i + width] = hl1;
 				ws.hr[i + width] = hr1;
-				ws.re[i + width] = m1.re;
-				ws.im[i + width] = m1.im;
+				if (WITH_MAG) {
+					const cplx m0 = cmul(m, stay), m1 = cmul(m, go);
+					ws.re[i] = m0.re;
+					ws.im[i] = m0.im;
+					ws.re[i + width] = m1.re;
+					ws.im[i + width] = m1.im;
+				}
 			}
 			__syncwarp();
 		}
@@ -449,7 +479,7 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 			ws.run_leaves = leaves;
 			ws.run_valid = 1;
 		}
-		expand_full(ctx, root, ws);
+		expand_full<false>(ctx, root, ws);
 		// hash and representative take the place of the tree states (another slot of the same arrays:
 		// read everything first, then write)
 		const uint32_t shift = ctx.eligible - levels; // child_id = group | leaf << shift
@@ -469,8 +499,8 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 				const uint32_t slot = leaf ^ tree_bits;
 				ws.hl[slot] = hash[q];
 				ws.hr[slot] = emit.rep(group | (leaf << shift), parent_size);
-				ws.acc_re[slot] = ws.re[leaf];
-				ws.acc_im[slot] = ws.im[leaf];
+				ws.acc_re[leaf] = leaf == tree_bits ? root.mag.re : 0.0;
+				ws.acc_im[leaf] = leaf == tree_bits ? root.mag.im : 0.0;
 			}
 		}
 		__syncwarp();
@@ -505,25 +535,10 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 				open_run(parent_size, ctx, group, root, ws, emit, eligible, fixed, target);
 				return;
 			}
-			// the objects of this group are already in the accumulators: only their magnitudes are needed.
-			// Leaf = lane + 32 q; its magnitude is the root times one amplitude per tree level, multiplied
-			// in node order like the reference does -- computed in registers, no tree in shared memory:
-			// the five low levels are decided by the lane, the (at most two) high ones by q.
-			const uint32_t tree_bits = ctx.tree_bits;
-			const uint32_t low = levels < 5 ? levels : 5;
-			cplx m = root.mag;
-			for (uint32_t l = 0; l < low; ++l)
-				m = cmul(m, ws.amp[((lane >> l) & 1) * 2 + ((tree_bits >> l) & 1)]);
-			if (lane < leaves) {
-				const uint32_t reps = leaves >> low; // 1, 2 or 4 leaves per lane
-				for (uint32_t q = 0; q < reps; ++q) {
-					cplx mq = m;
-					for (uint32_t l = 5; l < levels; ++l)
-						mq = cmul(mq, ws.amp[((q >> (l - 5)) & 1) * 2 + ((tree_bits >> l) & 1)]);
-					const uint32_t slot = (lane + 32 * q) ^ tree_bits;
-					ws.acc_re[slot] += mq.re;
-					ws.acc_im[slot] += mq.im;
-				}
+			// the objects of this group are already in the accumulators: its root joins the sum of its pattern
+			if (lane == 0) {
+				ws.acc_re[ctx.tree_bits] += root.mag.re;
+				ws.acc_im[ctx.tree_bits] += root.mag.im;
 			}
 			__syncwarp();
 			return;
