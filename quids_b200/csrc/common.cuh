@@ -100,6 +100,49 @@ __device__ __forceinline__ uint64_t upper_bound_u64(const uint64_t *a, uint64_t 
 	return lo;
 }
 
+// ---- staging of a byte range into shared memory with a 1-D bulk copy (cp.async.bulk, the TMA engine) ------------------
+// One warp owns a stage: lane 0 arms the mbarrier with the byte count and issues the copy, all lanes wait on the
+// barrier's phase.  Source and destination must be 16-byte aligned and the size a multiple of 16: the range is widened
+// to those bounds (the callers' buffers start 256-byte aligned and carry 16 bytes of slack at the end).
+constexpr uint32_t STAGE_BYTES = 8192; // 32 objects of up to 256 bytes
+
+struct __align__(16) warp_stage {
+	uint8_t bytes[STAGE_BYTES + 32];
+	unsigned long long mbar;
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void stage_init(warp_stage &st) {
+	if (lane_id() == 0) {
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&st.mbar)));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncwarp();
+}
+
+// copies [src, src + nbytes) (nbytes <= STAGE_BYTES) and returns the shared-memory address of src[0]; `phase` is the
+// caller's phase bit of this stage (starts at 0, flipped here)
+__device__ __forceinline__ const uint8_t *stage_range(warp_stage &st, const uint8_t *src, uint32_t nbytes, uint32_t &phase) {
+	const uint32_t lead = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15);
+	const uint32_t total = (lead + nbytes + 15u) & ~15u;
+	const uint32_t bar = smem_addr(&st.mbar);
+	// what the lanes read from the stage before must not be overtaken by the asynchronous writes of this copy
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+	__syncwarp();
+	if (lane_id() == 0) {
+		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
+		asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(st.bytes)), "l"(src - lead),
+		             "r"(total), "r"(bar)
+		             : "memory");
+	}
+	uint32_t done = 0;
+	while (!done)
+		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+	phase ^= 1;
+	return st.bytes + lead;
+}
+
 // ---- growable device buffer (stands for utils::fast_vector, utils/vector.hpp:36-160) -----------
 // Grows geometrically (upsize policy 1.1 like the reference), never shrinks implicitly; content is
 // NOT preserved by ensure() unless keep = true.

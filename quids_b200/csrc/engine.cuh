@@ -222,22 +222,48 @@ __global__ void __launch_bounds__(SYMBOLIC_THREADS, 5) symbolic_kernel(const Rul
 
 // ---- sorted order: work items = (parent, group), ordered by the rule's group key -------------------------
 constexpr int ITEM_GROUP_BITS = 24;
+constexpr int STAGED_THREADS = 128; // kernels whose warps stage their parents in shared memory: 4 stages of 8 KB per CTA
 constexpr int ITEM_CHUNK = 128; // items one warp takes at a time
 
-// one thread per kept parent writes the keys and values of its groups
+// one lane per kept parent writes the keys and values of its groups.  A warp takes 32 consecutive parents; when they
+// are consecutive in storage too (no parent truncation) and fit the stage, their bytes come to shared memory with one
+// bulk copy and the lanes walk their object there: 32 lanes chasing 32 different objects in global memory cost one
+// L1 wavefront per lane and load, the copy costs none.
 template <class Rule>
-__global__ void __launch_bounds__(ENGINE_THREADS) group_items_kernel(const Rule rule, const engine_launch L) {
-	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-	for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < L.n_parents; p += stride) {
+__global__ void __launch_bounds__(STAGED_THREADS) group_items_kernel(const Rule rule, const engine_launch L) {
+	__shared__ warp_stage s_stage[STAGED_THREADS / 32];
+	warp_stage &stage = s_stage[threadIdx.x >> 5];
+	stage_init(stage);
+	uint32_t phase = 0;
+	const unsigned lane = lane_id();
+	const uint64_t batches = div_up<uint64_t>(L.n_parents, 32);
+	const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+	for (uint64_t batch = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; batch < batches; batch += warps) {
+		const uint64_t p0 = batch * 32, p = p0 + lane;
+		const uint32_t in_batch = (uint32_t)min((uint64_t)32, L.n_parents - p0);
+		const bool valid = lane < in_batch;
+		const uint64_t oid = valid ? (L.kept ? L.kept[p] : p) : 0;
+		const uint64_t off = valid ? L.it.begin[oid] : 0;
+		const uint32_t size = valid ? L.it.size[oid] : 0;
+		const uint8_t *object = L.it.objects + off;
+		if (!L.kept) { // storage order: the batch is the byte range [begin of the first, end of the last]
+			const uint64_t lo = __shfl_sync(0xffffffffu, off, 0);
+			const uint64_t hi = __shfl_sync(0xffffffffu, off + size, in_batch - 1);
+			if (hi - lo <= STAGE_BYTES) {
+				const uint8_t *staged = stage_range(stage, L.it.objects + lo, (uint32_t)(hi - lo), phase);
+				object = staged + (off - lo);
+			}
+		}
+		if (!valid)
+			continue;
 		const uint64_t first = L.group_begin[p];
 		const uint32_t count = (uint32_t)(L.group_begin[p + 1] - first);
 		if (count == 0)
 			continue;
-		const uint64_t oid = L.kept ? L.kept[p] : p;
-		// the parent's context is prepared here once (this thread already walks the object) instead of once
+		// the parent's context is prepared here once (this lane already walks the object) instead of once
 		// per work item in the symbolic kernel, where 32 lanes would each chase a different object
-		rule.prepare(L.it.objects + L.it.begin[oid], L.it.size[oid], static_cast<typename Rule::ctx_t *>(L.parent_ctx)[p]);
-		rule.group_keys(L.it.objects + L.it.begin[oid], L.it.size[oid], count, L.item_keys + first);
+		rule.prepare(object, size, static_cast<typename Rule::ctx_t *>(L.parent_ctx)[p]);
+		rule.group_keys(object, size, count, L.item_keys + first);
 		for (uint32_t g = 0; g < count; ++g)
 			L.item_vals[first + g] = (p << ITEM_GROUP_BITS) | g;
 	}
@@ -289,10 +315,32 @@ __global__ void __launch_bounds__(SYMBOLIC_THREADS, 5) symbolic_items_kernel(con
 				rule.prepare_group(s.ctx[lane], group, L.it.mag[oid], s.group_ctx[lane]);
 			}
 			__syncwarp();
-			for (uint32_t i = 0; i < count; ++i) {
-				table_emitter emit(L.table, s.child_begin[i]);
-				rule.template symbolic_warp<true>(L.it.objects + s.object[i], s.size[i], s.ctx[i], s.group[i], s.group_ctx[i], ws, emit);
-				created += emit.created;
+			if constexpr (Rule::has_run_identity) {
+				// stretches of items with the same identity: the head goes through the warp-wide path (it opens a run or
+				// continues the one that is open), the others join it one per lane
+				typename Rule::run_id_t id{};
+				if (lane < count)
+					id = rule.run_identity(s.ctx[lane], s.group[lane]);
+				const typename Rule::run_id_t before = id.shuffle_up();
+				const bool follows = lane > 0 && lane < count && id == before;
+				unsigned heads = __ballot_sync(0xffffffffu, lane < count && !follows);
+				while (heads) {
+					const uint32_t h = __ffs(heads) - 1;
+					heads &= heads - 1;
+					const uint32_t e = heads ? __ffs(heads) - 1 : count;
+					table_emitter emit(L.table, s.child_begin[h]);
+					rule.template symbolic_warp<true>(L.it.objects + s.object[h], s.size[h], s.ctx[h], s.group[h], s.group_ctx[h], ws, emit);
+					created += emit.created;
+					if (lane > h && lane < e)
+						rule.continue_run(s.ctx[lane], s.group_ctx[lane], ws);
+					__syncwarp();
+				}
+			} else {
+				for (uint32_t i = 0; i < count; ++i) {
+					table_emitter emit(L.table, s.child_begin[i]);
+					rule.template symbolic_warp<true>(L.it.objects + s.object[i], s.size[i], s.ctx[i], s.group[i], s.group_ctx[i], ws, emit);
+					created += emit.created;
+				}
 			}
 			__syncwarp();
 		}
@@ -443,8 +491,8 @@ struct rule_glue {
 	}
 	static void group_items(const void *rule, const engine_launch &L) {
 		if constexpr (Rule::has_group_key) {
-			int grid = grid_for(L.n_parents, ENGINE_THREADS, resident_grid((const void *)group_items_kernel<Rule>, ENGINE_THREADS, L.sm_count));
-			group_items_kernel<Rule><<<grid, ENGINE_THREADS, 0, L.stream>>>(*static_cast<const Rule *>(rule), L);
+			int grid = grid_for(L.n_parents, STAGED_THREADS, resident_grid((const void *)group_items_kernel<Rule>, STAGED_THREADS, L.sm_count));
+			group_items_kernel<Rule><<<grid, STAGED_THREADS, 0, L.stream>>>(*static_cast<const Rule *>(rule), L);
 			++*L.launch_counter;
 		}
 	}

@@ -127,6 +127,13 @@ struct rule_base {
 	static constexpr bool has_edit_child = false;
 	__device__ void edit_child(const uint8_t *, uint32_t, uint8_t *, uint32_t) const {}
 
+	// optional, with has_group_key: items that CONTINUE the run of the item before them are handed to the rule
+	// one per lane instead of one per warp-wide call:
+	//     run_id_t run_identity(ctx, group)            equal identities = same objects; compared with ==
+	//     continue_run(ctx, group_ctx, workspace&)     this lane's group joins the open run (shared-memory atomics)
+	// The head of every stretch of equal identities still goes through symbolic_warp<true>.
+	static constexpr bool has_run_identity = false;
+
 	static constexpr bool has_group_key = false;
 	static constexpr uint32_t group_capacity = 1; // most children one group can hold (bounds what a run can send to the table)
 	__device__ void group_keys(const uint8_t *, uint32_t, uint32_t, uint32_t *) const {}

@@ -195,6 +195,42 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 	static constexpr bool has_group_key = true;
 	static constexpr uint32_t group_capacity = FLIP_BLOCK;
 	static constexpr bool has_edit_child = true;
+	static constexpr bool has_run_identity = true;
+
+	// what makes two groups produce the same objects: family (eligible nodes, particles elsewhere, names, size) and target
+	struct run_id_t {
+		uint64_t eligible, fixed, names;
+		uint32_t n, target;
+		__device__ bool operator==(const run_id_t &o) const {
+			return eligible == o.eligible && fixed == o.fixed && names == o.names && n == o.n && target == o.target;
+		}
+		__device__ run_id_t shuffle_up() const {
+			run_id_t r;
+			r.eligible = __shfl_up_sync(0xffffffffu, eligible, 1);
+			r.fixed = __shfl_up_sync(0xffffffffu, fixed, 1);
+			r.names = __shfl_up_sync(0xffffffffu, names, 1);
+			r.n = __shfl_up_sync(0xffffffffu, n, 1);
+			r.target = __shfl_up_sync(0xffffffffu, target, 1);
+			return r;
+		}
+	};
+	__device__ run_id_t run_identity(const flip_ctx &ctx, uint32_t group) const {
+		run_id_t id;
+		const uint64_t all = ctx.n >= 64 ? ~0ull : ((1ull << ctx.n) - 1);
+		id.eligible = (WANT_EQUAL ? ~(ctx.left ^ ctx.right) : (ctx.left ^ ctx.right)) & all;
+		id.fixed = ctx.left & ~id.eligible & all;
+		id.names = ctx.names_hash;
+		id.n = ctx.n;
+		id.target = group ^ ctx.prefix_bits;
+		if (ctx.n > 64) // wide graphs have no runs: make every item its own stretch
+			id.target = group, id.eligible = ~0ull, id.fixed = (uint64_t)lane_id();
+		return id;
+	}
+	// this lane's group has the identity of the run that is open: its root joins the sum of its parent pattern
+	__device__ void continue_run(const flip_ctx &ctx, const flip_root &root, flip_workspace &ws) const {
+		atomicAdd(&ws.acc_re[ctx.tree_bits], root.mag.re);
+		atomicAdd(&ws.acc_im[ctx.tree_bits], root.mag.im);
+	}
 
 	// a child is its parent with some eligible nodes toggled
 	__device__ void edit_child(const uint8_t *parent, uint32_t, uint8_t *child, uint32_t child_id) const {
