@@ -222,7 +222,9 @@ __global__ void __launch_bounds__(SYMBOLIC_THREADS, 5) symbolic_kernel(const Rul
 
 // ---- sorted order: work items = (parent, group), ordered by the rule's group key -------------------------
 constexpr int ITEM_GROUP_BITS = 24;
+constexpr int POPULATE_COPIES = 4;  // parent copies one warp keeps in flight in the finalisation
 constexpr int STAGED_THREADS = 128; // kernels whose warps stage their parents in shared memory: 4 stages of 8 KB per CTA
+constexpr int ITEMS_BLOCKS_PER_SM = 5; // occupancy target of the sorted-order kernel (latency bound: ncu shows 29 % issue utilisation at 5)
 constexpr int ITEM_CHUNK = 128; // items one warp takes at a time
 
 // one lane per kept parent writes the keys and values of its groups.  A warp takes 32 consecutive parents; when they
@@ -273,7 +275,7 @@ __global__ void __launch_bounds__(STAGED_THREADS) group_items_kernel(const Rule 
 // parent's context and the group's root, then all lanes produce one group after the other with
 // ACCUMULATE = true; what the rule still holds at the end of the chunk is flushed
 template <class Rule>
-__global__ void __launch_bounds__(SYMBOLIC_THREADS, 5) symbolic_items_kernel(const Rule rule, const engine_launch L) {
+__global__ void __launch_bounds__(SYMBOLIC_THREADS, ITEMS_BLOCKS_PER_SM) symbolic_items_kernel(const Rule rule, const engine_launch L) {
 	typedef typename Rule::ctx_t ctx_t;
 	struct warp_slice {
 		ctx_t ctx[32];
@@ -284,9 +286,9 @@ __global__ void __launch_bounds__(SYMBOLIC_THREADS, 5) symbolic_items_kernel(con
 		uint32_t group[32];
 	};
 	__shared__ warp_slice s_slices[ENGINE_WARPS];
-	__shared__ typename Rule::workspace_t s_workspace[ENGINE_WARPS];
+	__shared__ typename Rule::items_workspace_t s_workspace[ENGINE_WARPS];
 	warp_slice &s = s_slices[threadIdx.x >> 5];
-	typename Rule::workspace_t &ws = s_workspace[threadIdx.x >> 5];
+	typename Rule::items_workspace_t &ws = s_workspace[threadIdx.x >> 5];
 	const unsigned lane = lane_id();
 	uint32_t created = 0;
 	rule.init_warp(ws);
@@ -391,15 +393,45 @@ __global__ void __launch_bounds__(ENGINE_THREADS) populate_kernel(const Rule rul
 				padded = (uint32_t)(L.next_begin[mine + 1] - begin);
 			}
 			const unsigned count = __popc(__ballot_sync(0xffffffffu, valid));
-			for (unsigned j = 0; j < count; j += 4) {
-				// four parents at a time: all their loads are issued before the first store
-				uint2 word[4];
-				const uint8_t *src[4];
-				uint8_t *dst[4];
-				uint32_t bytes[4];
-				bool fast[4];
+			// small objects of one size (a qubit register: 24 bytes): one object would keep 3 of the 32 lanes busy, so the
+			// words of the whole batch are spread over the lanes instead -- word k of the batch = word k % w of object k / w
+			const uint32_t size0 = __shfl_sync(0xffffffffu, size, 0);
+			const bool regular = !valid || (size == size0 && padded == size0 && ((reinterpret_cast<uintptr_t>(parent) | reinterpret_cast<uintptr_t>(child)) & 7) == 0);
+			if (size0 > 0 && size0 <= 128 && (size0 & 7) == 0 && __all_sync(0xffffffffu, regular)) {
+				const uint32_t w = size0 / 8, total = count * w;
+				const uint32_t inv = (65536u + w - 1) / w; // k / w for k < 512
+				uint2 *out = reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(__shfl_sync(0xffffffffu, reinterpret_cast<uintptr_t>(child), 0)));
+				for (uint32_t k0 = 0; k0 < total; k0 += 32 * POPULATE_COPIES) {
+					uint2 word[POPULATE_COPIES];
 #pragma unroll
-				for (int q = 0; q < 4; ++q) {
+					for (int q = 0; q < POPULATE_COPIES; ++q) {
+						const uint32_t k = k0 + q * 32 + lane;
+						const uint32_t obj = min((k * inv) >> 16, count - 1);
+						const uint2 *from = reinterpret_cast<const uint2 *>(__shfl_sync(0xffffffffu, reinterpret_cast<uintptr_t>(parent), obj));
+						if (k < total)
+							word[q] = from[k - obj * w];
+					}
+#pragma unroll
+					for (int q = 0; q < POPULATE_COPIES; ++q) {
+						const uint32_t k = k0 + q * 32 + lane;
+						if (k < total)
+							out[k] = word[q];
+					}
+				}
+				__syncwarp();
+				if (valid)
+					rule.edit_child(parent, size, child, child_id);
+				continue;
+			}
+			for (unsigned j = 0; j < count; j += POPULATE_COPIES) {
+				// several parents at a time: all their loads are issued before the first store
+				uint2 word[POPULATE_COPIES];
+				const uint8_t *src[POPULATE_COPIES];
+				uint8_t *dst[POPULATE_COPIES];
+				uint32_t bytes[POPULATE_COPIES];
+				bool fast[POPULATE_COPIES];
+#pragma unroll
+				for (int q = 0; q < POPULATE_COPIES; ++q) {
 					const unsigned from = min(j + q, count - 1);
 					src[q] = reinterpret_cast<const uint8_t *>(__shfl_sync(0xffffffffu, reinterpret_cast<uintptr_t>(parent), from));
 					dst[q] = reinterpret_cast<uint8_t *>(__shfl_sync(0xffffffffu, reinterpret_cast<uintptr_t>(child), from));
@@ -409,7 +441,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS) populate_kernel(const Rule rul
 						word[q] = reinterpret_cast<const uint2 *>(src[q])[lane];
 				}
 #pragma unroll
-				for (int q = 0; q < 4; ++q) {
+				for (int q = 0; q < POPULATE_COPIES; ++q) {
 					if (fast[q]) { // 8-byte words, then the (size % 8) trailing bytes
 						if (lane < bytes[q] / 8)
 							reinterpret_cast<uint2 *>(dst[q])[lane] = word[q];

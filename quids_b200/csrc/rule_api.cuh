@@ -102,6 +102,7 @@ struct rule_base {
 	// emit.batch<N>(count, hash[N], size, child_id_of(i), mag_of(i)).
 	static constexpr bool warp_groups = false;
 	struct workspace_t {};
+	typedef workspace_t items_workspace_t; // the sorted order may need less (or other) per-warp memory than the unsorted one
 	// per-group precomputation done by ONE lane per group, 32 groups at a time (whatever is the same
 	// for all children of the group and would otherwise be recomputed identically by all 32 lanes)
 	struct group_ctx_t {};

@@ -138,9 +138,10 @@ struct flip_root { // state before the first tree level of one group
 // Accumulators: the objects of the current run of equal-target groups, indexed by the TARGET's particle
 // bits on the tree nodes (leaf index xor the parent's own bits), so that every member of a family adds
 // into the same slots.
-struct flip_workspace {
+template <bool WITH_MAG_TREE>
+struct flip_workspace_t {
 	uint64_t hl[FLIP_BLOCK], hr[FLIP_BLOCK]; // tree states; once a run is open: hash and representative of its objects
-	double re[FLIP_BLOCK], im[FLIP_BLOCK];
+	double re[WITH_MAG_TREE ? FLIP_BLOCK : 1], im[WITH_MAG_TREE ? FLIP_BLOCK : 1]; // magnitude tree (unsorted order only)
 	double acc_re[FLIP_BLOCK], acc_im[FLIP_BLOCK];
 	// what the accumulators hold: family (eligible nodes, particles elsewhere, names) and target of the group
 	uint64_t run_eligible, run_fixed, run_names;
@@ -188,7 +189,8 @@ struct flip_rule : rule_base<flip_rule<WANT_EQUAL>> {
 template <bool WANT_EQUAL>
 struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 	typedef flip_ctx ctx_t;
-	typedef flip_workspace workspace_t;
+	typedef flip_workspace_t<true> workspace_t;        // unsorted order: hash and magnitude trees
+	typedef flip_workspace_t<false> items_workspace_t; // sorted order: hash tree and accumulators
 	typedef flip_root group_ctx_t;
 	static constexpr bool needs_scratch = false;
 	static constexpr bool warp_groups = true;
@@ -227,7 +229,8 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 		return id;
 	}
 	// this lane's group has the identity of the run that is open: its root joins the sum of its parent pattern
-	__device__ void continue_run(const flip_ctx &ctx, const flip_root &root, flip_workspace &ws) const {
+	template <class WS>
+	__device__ void continue_run(const flip_ctx &ctx, const flip_root &root, WS &ws) const {
 		atomicAdd(&ws.acc_re[ctx.tree_bits], root.mag.re);
 		atomicAdd(&ws.acc_im[ctx.tree_bits], root.mag.im);
 	}
@@ -384,7 +387,8 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 		root.mag = mag;
 	}
 
-	__device__ void init_warp(flip_workspace &ws) const {
+	template <class WS>
+	__device__ void init_warp(WS &ws) const {
 		if (lane_id() == 0)
 			ws.run_valid = 0;
 		if (lane_id() < 4)
@@ -398,7 +402,8 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 	// -- a Kronecker product of one 2x2 matrix per tree level, applied in place level by level (64 butterflies each),
 	// instead of one product chain per child.  Same value as summing the children one by one up to rounding
 	// (the interference table adds them in no particular order either).
-	__device__ __forceinline__ void spread_run(flip_workspace &ws) const {
+	template <class WS>
+	__device__ __forceinline__ void spread_run(WS &ws) const {
 		const uint32_t lane = lane_id();
 		const uint32_t leaves = ws.run_leaves;
 		const cplx a00 = ws.amp[0], a01 = ws.amp[1], a10 = ws.amp[2], a11 = ws.amp[3]; // index = taken * 2 + parent's bit
@@ -406,6 +411,7 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 			for (uint32_t b = lane; b < leaves / 2; b += 32) {
 				const uint32_t i0 = ((b & ~(bit - 1)) << 1) | (b & (bit - 1)), i1 = i0 | bit;
 				const cplx x0{ws.acc_re[i0], ws.acc_im[i0]}, x1{ws.acc_re[i1], ws.acc_im[i1]};
+				// products rounded like the reference's, then added: two contributions that cancel exactly there cancel exactly here
 				const cplx y0 = cadd(cmul(x0, a00), cmul(x1, a11)); // object bit 0: pattern 0 stays, pattern 1 goes
 				const cplx y1 = cadd(cmul(x0, a10), cmul(x1, a01)); // object bit 1: pattern 0 goes, pattern 1 stays
 				ws.acc_re[i0] = y0.re;
@@ -418,8 +424,8 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 	}
 
 	// the objects of the current run go to the global table, four per lane at a time
-	template <class Emit>
-	__device__ void flush_warp(flip_workspace &ws, Emit &emit) const {
+	template <class WS, class Emit>
+	__device__ void flush_warp(WS &ws, Emit &emit) const {
 		__syncwarp();
 		if (ws.run_valid) {
 			const uint32_t leaves = ws.run_leaves;
@@ -445,16 +451,18 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 	}
 
 	// full expansion of one group: tree states (hash folds and magnitudes) of all its leaves in ws
-	template <bool WITH_MAG = true>
-	__device__ __forceinline__ void expand_full(const flip_ctx &ctx, const flip_root &root, flip_workspace &ws) const {
+	template <bool WITH_MAG = true, class WS>
+	__device__ __forceinline__ void expand_full(const flip_ctx &ctx, const flip_root &root, WS &ws) const {
 		const uint32_t lane = lane_id();
 		const uint64_t left = ctx.left, right = ctx.right;
 		const uint32_t levels = ctx.levels;
 		if (lane == 0) {
 			ws.hl[0] = root.hl;
 			ws.hr[0] = root.hr;
-			ws.re[0] = root.mag.re;
-			ws.im[0] = root.mag.im;
+			if (WITH_MAG) {
+				ws.re[0] = root.mag.re;
+				ws.im[0] = root.mag.im;
+			}
 		}
 		__syncwarp();
 		// level l: tree node pos[l] with both choices, then the non-eligible nodes up to the next tree
@@ -466,7 +474,7 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 			const uint32_t width = 1u << l;
 			for (uint32_t i = lane; i < width; i += 32) {
 				uint64_t hl0 = ws.hl[i], hr0 = ws.hr[i];
-				const cplx m{ws.re[i], ws.im[i]};
+				const cplx m = WITH_MAG ? cplx{ws.re[i], ws.im[i]} : cplx{0, 0};
 				uint64_t hl1 = hl0, hr1 = hr0;
 				// choice 0 keeps the parent's particles, choice 1 toggles both
 				if (pl) hl0 = hash_combine_index(hl0, e); else hl1 = hash_combine_index(hl1, e);
@@ -500,8 +508,8 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 	// a new run starts (rare next to the groups that continue one): the previous run goes to the table,
 	// this group is expanded in full and opens the accumulators.  Kept out of line so that the hot path
 	// of symbolic_warp<true> stays small.
-	template <class Emit>
-	__device__ void open_run(uint32_t parent_size, const flip_ctx &ctx, uint32_t group, const flip_root &root, flip_workspace &ws,
+	template <class WS, class Emit>
+	__device__ void open_run(uint32_t parent_size, const flip_ctx &ctx, uint32_t group, const flip_root &root, WS &ws,
 	                                      Emit &emit, uint64_t eligible, uint64_t fixed, uint32_t target) const {
 		const uint32_t lane = lane_id();
 		const uint32_t levels = ctx.levels, leaves = 1u << levels, tree_bits = ctx.tree_bits;
@@ -542,9 +550,9 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 		__syncwarp();
 	}
 
-	template <bool ACCUMULATE, class Emit>
+	template <bool ACCUMULATE, class WS, class Emit>
 	__device__ void symbolic_warp(const uint8_t *parent, uint32_t parent_size, const flip_ctx &ctx, uint32_t group, const flip_root &root,
-	                              flip_workspace &ws, Emit &emit) const {
+	                              WS &ws, Emit &emit) const {
 		const uint32_t lane = lane_id();
 		if (ctx.n > 64) { // wide graph: 32 children per group, one per lane
 			const uint32_t child_id = group * 32 + lane;
