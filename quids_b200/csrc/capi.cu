@@ -60,7 +60,9 @@ enum { // u64 words of the small device scratch
 	DS_TOTAL = 3,
 	DS_USED = 4,
 	DS_SELECT_GT = 5, // and 6
-	DS_WORDS = 8
+	DS_CURSOR = 7,    // region mode: slots handed out
+	DS_REGIONS = 8,   // region mode: regions created
+	DS_WORDS = 10
 };
 
 struct qb_ctx {
@@ -138,16 +140,17 @@ struct qb_iter {
 struct qb_sym {
 	qb_ctx *ctx;
 	uint64_t n_children = 0, n_unique = 0; // quids.hpp:344-346
-	dev_buf table, ukey, uslot, sslot, kept, scratch, survivor_parent, survivor_child, padded, chunk_parent, sort_keys, sort_vals, sort_hist, sort_base, parent_ctx;
+	dev_buf table, directory, ukey, uslot, sslot, kept, scratch, survivor_parent, survivor_child, padded, chunk_parent, sort_keys, sort_vals, sort_hist, sort_base, parent_ctx;
 	cudaEvent_t ev[2 * QB_PHASE_COUNT] = {};
 	bool ev_used[QB_PHASE_COUNT] = {};
 	float phase_ms[QB_PHASE_COUNT] = {};
 	std::map<int, double> unique_ratio; // per rule id: slots created / children of the last call (sizes the next table)
+	std::map<int, std::pair<double, double>> region_ratio; // region mode: (slots handed out, regions created) / children of the last call
 	uint64_t table_capacity = 0;        // of the last call
 	int table_attempts = 0;
 
 	uint64_t device_bytes() const {
-		return table.cap + ukey.cap + uslot.cap + sslot.cap + kept.cap + scratch.cap + survivor_parent.cap + survivor_child.cap + padded.cap + chunk_parent.cap + sort_keys.cap + sort_vals.cap + sort_hist.cap + sort_base.cap + parent_ctx.cap;
+		return table.cap + directory.cap + ukey.cap + uslot.cap + sslot.cap + kept.cap + scratch.cap + survivor_parent.cap + survivor_child.cap + padded.cap + chunk_parent.cap + sort_keys.cap + sort_vals.cap + sort_hist.cap + sort_base.cap + parent_ctx.cap;
 	}
 };
 
@@ -551,9 +554,9 @@ local_table build_local_table(qb_iter *it, int rule_id, const rule_ops *ops, con
 	// call of the same rule showed how many slots are really created: then 2.6x that prediction.  An
 	// insert that probes too long raises `overflow` and the whole step is redone at full size.
 	const uint64_t n_children = R.n_children;
-	const uint64_t full_capacity = std::max<uint64_t>(1024, (uint64_t)std::ceil((double)n_children / opt.table_load));
-	uint64_t capacity = full_capacity;
-	bool have_history = false;
+	uint64_t full_capacity = std::max<uint64_t>(1024, (uint64_t)std::ceil((double)n_children / opt.table_load));
+	uint64_t capacity = full_capacity, directory = 0, full_directory = 0;
+	bool have_history = false, region_mode = false;
 	{
 		auto hint = sym->unique_ratio.find(rule_id);
 		have_history = hint != sym->unique_ratio.end();
@@ -589,6 +592,22 @@ local_table build_local_table(qb_iter *it, int rule_id, const rule_ops *ops, con
 		L.item_vals = sym->sort_vals.as<uint64_t>();
 		ops->launch_group_items(rule, L);
 		L.items = sort_items(ctx, sym, n_groups);
+		// region mode (table.cuh): the rule sends every run to a region of consecutive slots found through a directory
+		// hashed by the run's identity.  Slots: one per child is always enough and needs no load factor.
+		region_mode = ops->region_size_limit > 0 && max_child_size < ops->region_size_limit;
+		if (region_mode) {
+			full_capacity = std::max<uint64_t>(1024, n_children);
+			full_directory = 2 * n_groups + 1024;
+			auto hint = sym->region_ratio.find(rule_id);
+			have_history = hint != sym->region_ratio.end();
+			if (have_history) {
+				capacity = std::min<uint64_t>(full_capacity, (uint64_t)(hint->second.first * (double)n_children * 1.3) + 4096);
+				directory = std::min<uint64_t>(full_directory, (uint64_t)(hint->second.second * (double)n_children * 2.6) + 1024);
+			} else {
+				capacity = full_capacity;
+				directory = full_directory;
+			}
+		}
 		if (!have_history) {
 			// in sorted order the table typically receives one group's worth of objects per run of equal keys (plus one
 			// split per chunk of work items), far fewer than one per child: a prediction that needs no history.  It is
@@ -599,7 +618,12 @@ local_table build_local_table(qb_iter *it, int rule_id, const rule_ops *ops, con
 			++ctx->launches;
 			ctx->fetch_small();
 			const double flushes = 1.25 * (double)(ctx->h_small[DS_COUNT] + 1 + div_up<uint64_t>(n_groups, ITEM_CHUNK)) + 4096;
-			capacity = std::min<uint64_t>(full_capacity, std::max<uint64_t>(1024, (uint64_t)(flushes * ops->group_capacity / opt.table_load)));
+			if (region_mode) {
+				capacity = std::min<uint64_t>(full_capacity, std::max<uint64_t>(1024, (uint64_t)(flushes * ops->group_capacity)));
+				directory = std::min<uint64_t>(full_directory, (uint64_t)(2 * flushes));
+			} else {
+				capacity = std::min<uint64_t>(full_capacity, std::max<uint64_t>(1024, (uint64_t)(flushes * ops->group_capacity / opt.table_load)));
+			}
 		}
 		timer.end(QB_PHASE_PRE_TRUNCATE);
 	}
@@ -612,6 +636,15 @@ local_table build_local_table(qb_iter *it, int rule_id, const rule_ops *ops, con
 		QB_CUDA(cudaMemsetAsync(ctx->small(DS_COUNT), 0, 4 * sizeof(uint64_t), stream)); // count, overflow, total, used
 		R.table = table_view{sym->table.as<table_slot>(), capacity, reinterpret_cast<unsigned int *>(ctx->small(DS_OVERFLOW)),
 		                     reinterpret_cast<unsigned long long *>(ctx->small(DS_USED))};
+		if (region_mode) {
+			sym->directory.ensure(directory * sizeof(region_entry), stream);
+			QB_CUDA(cudaMemsetAsync(sym->directory.ptr, 0, directory * sizeof(region_entry), stream));
+			QB_CUDA(cudaMemsetAsync(ctx->small(DS_CURSOR), 0, 2 * sizeof(uint64_t), stream)); // cursor, regions
+			R.table.dir = sym->directory.as<region_entry>();
+			R.table.dir_capacity = directory;
+			R.table.cursor = reinterpret_cast<unsigned long long *>(ctx->small(DS_CURSOR));
+			R.table.regions = reinterpret_cast<unsigned long long *>(ctx->small(DS_REGIONS));
+		}
 		timer.end(QB_PHASE_TABLE_CLEAR);
 
 		// children -> (hash, magnitude) -> table (quids.hpp:705-719 fused with :785-809)
@@ -626,32 +659,44 @@ local_table build_local_table(qb_iter *it, int rule_id, const rule_ops *ops, con
 
 		// unique children above the tolerance (quids.hpp:819-823)
 		timer.begin(QB_PHASE_COMPACT);
-		const uint64_t bound = std::min<uint64_t>(n_children, capacity + 1);
+		uint64_t scan_slots = capacity; // hashed table: every slot may be occupied; regions: only the slots handed out
+		if (region_mode) {
+			ctx->fetch_small();
+			scan_slots = std::min<uint64_t>(capacity, ctx->h_small[DS_CURSOR]);
+		}
+		const uint64_t bound = std::min<uint64_t>(n_children, scan_slots + 1);
 		sym->ukey.ensure(sizeof(uint64_t) * bound, stream);
 		sym->uslot.ensure(sizeof(uint32_t) * bound, stream);
-		const uint64_t tiles = div_up<uint64_t>(capacity + 1, COMPACT_TILE);
+		const uint64_t tiles = div_up<uint64_t>(scan_slots + 1, COMPACT_TILE);
 		scan_state st = ctx->scan(tiles);
-		table_compact_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, stream>>>(R.table, compaction_tolerance, sym->ukey.as<uint64_t>(), sym->uslot.as<uint32_t>(),
+		table_view scanned = R.table;
+		scanned.capacity = scan_slots; // slot `scan_slots` was never handed out: empty unless it is the hashed table's slot for hash 0
+		table_compact_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, stream>>>(scanned, compaction_tolerance, sym->ukey.as<uint64_t>(), sym->uslot.as<uint32_t>(),
 		                                                                    reinterpret_cast<unsigned long long *>(ctx->small(DS_COUNT)), st);
 		++ctx->launches;
 		QB_CUDA(cudaGetLastError());
 		timer.end(QB_PHASE_COMPACT);
 		ctx->fetch_small();
 		if (getenv("QB_TABLE_TRACE"))
-			fprintf(stderr, "[qb table] rule %s attempt %d: children %llu groups %llu capacity %llu (full %llu) sorted %d -> used %llu kept %llu overflow %llu\n", ops->name,
-			        sym->table_attempts, (unsigned long long)n_children, (unsigned long long)n_groups, (unsigned long long)capacity, (unsigned long long)full_capacity,
-			        (int)sorted_order, (unsigned long long)ctx->h_small[DS_USED], (unsigned long long)ctx->h_small[DS_COUNT], (unsigned long long)ctx->h_small[DS_OVERFLOW]);
+			fprintf(stderr, "[qb table] rule %s attempt %d: children %llu groups %llu capacity %llu (full %llu) sorted %d regions %d (directory %llu, created %llu, slots %llu) -> used %llu kept %llu overflow %llu\n",
+			        ops->name, sym->table_attempts, (unsigned long long)n_children, (unsigned long long)n_groups, (unsigned long long)capacity, (unsigned long long)full_capacity,
+			        (int)sorted_order, (int)region_mode, (unsigned long long)directory, (unsigned long long)ctx->h_small[DS_REGIONS], (unsigned long long)ctx->h_small[DS_CURSOR],
+			        (unsigned long long)ctx->h_small[DS_USED], (unsigned long long)ctx->h_small[DS_COUNT], (unsigned long long)ctx->h_small[DS_OVERFLOW]);
 		if (ctx->h_small[DS_OVERFLOW] == 0)
 			break;
-		QB_REQUIRE(capacity < full_capacity, QB_ERR_CAPACITY, "interference table overflow at full size");
+		QB_REQUIRE(capacity < full_capacity || directory < full_directory, QB_ERR_CAPACITY, "interference table overflow at full size");
 		// the prediction was too small (the kernels stop early once an insert gives up): redo at the always-safe full size
 		capacity = full_capacity;
+		directory = full_directory;
 		for (int p : {QB_PHASE_TABLE_CLEAR, QB_PHASE_SYMBOLIC, QB_PHASE_COMPACT})
 			timer.restart(p); // report the attempt that counted
 	}
 	R.n_unique = ctx->h_small[DS_COUNT];
 	sym->table_capacity = capacity;
-	sym->unique_ratio[rule_id] = (double)ctx->h_small[DS_USED] / (double)n_children;
+	if (region_mode)
+		sym->region_ratio[rule_id] = std::make_pair((double)ctx->h_small[DS_CURSOR] / (double)n_children, (double)ctx->h_small[DS_REGIONS] / (double)n_children);
+	else
+		sym->unique_ratio[rule_id] = (double)ctx->h_small[DS_USED] / (double)n_children;
 	return R;
 }
 

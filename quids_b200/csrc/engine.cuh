@@ -557,6 +557,7 @@ struct rule_glue {
 		o.needs_scratch = Rule::needs_scratch;
 		o.warp_groups = Rule::warp_groups;
 		o.has_group_key = Rule::has_group_key;
+		o.region_size_limit = Rule::region_size_limit;
 		o.ctx_bytes = sizeof(typename Rule::ctx_t);
 		o.group_capacity = Rule::group_capacity;
 		o.launch_group_items = group_items;

@@ -33,7 +33,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) table_compact_kernel(table_view 
 		if (i < n) {
 			const ulonglong2 lo = reinterpret_cast<const ulonglong2 *>(t.slots + i)[0]; // key, re
 			const ulonglong2 hi = reinterpret_cast<const ulonglong2 *>(t.slots + i)[1]; // im, rep
-			const bool occupied = i == t.capacity ? hi.y != 0 : lo.x != 0;
+			// a slot is occupied once it has a representative (set by whoever created it; never 0): true for hashed slots,
+			// for the dedicated slot of the hash 0, and for region slots (whose object may hash to 0)
+			const bool occupied = hi.y != 0;
 			const double norm = cnorm(cplx{__longlong_as_double((long long)lo.y), __longlong_as_double((long long)hi.x)});
 			keep[j] = occupied && norm > tolerance;
 			key[j] = key_of_norm(norm);

@@ -134,6 +134,9 @@ struct rule_base {
 	//     continue_run(ctx, group_ctx, workspace&)     this lane's group joins the open run (shared-memory atomics)
 	// The head of every stretch of equal identities still goes through symbolic_warp<true>.
 	static constexpr bool has_run_identity = false;
+	// optional, with has_run_identity: the rule can send a run to a REGION of the table (table.cuh: region_acquire) when
+	// every object of the state is smaller than this many bytes (0 = the rule does not use regions)
+	static constexpr uint32_t region_size_limit = 0;
 
 	static constexpr bool has_group_key = false;
 	static constexpr uint32_t group_capacity = 1; // most children one group can hold (bounds what a run can send to the table)
@@ -170,6 +173,7 @@ struct rule_ops {
 	bool needs_scratch;
 	bool warp_groups;
 	bool has_group_key;
+	uint32_t region_size_limit;
 	uint32_t group_capacity;
 	size_t ctx_bytes;
 	void (*launch_group_items)(const void *rule, const engine_launch &L);

@@ -147,6 +147,12 @@ struct flip_workspace_t {
 	uint64_t run_eligible, run_fixed, run_names;
 	uint32_t run_n, run_target, run_leaves, run_valid;
 	cplx amp[4]; // the rule's four amplitudes, index = taken * 2 + conjugated: one 16-byte shared load per factor
+	// region mode: the group that opened the run, kept so that the run can still write the objects' hashes and
+	// representatives if it turns out to be the one that creates their region
+	flip_ctx open_ctx;
+	flip_root open_root;
+	uint64_t open_first_child;
+	uint32_t open_group, open_size;
 };
 
 template <bool WANT_EQUAL>
@@ -198,6 +204,9 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 	static constexpr uint32_t group_capacity = FLIP_BLOCK;
 	static constexpr bool has_edit_child = true;
 	static constexpr bool has_run_identity = true;
+	// sorted order with table regions needs every parent to go through the mask-based path (n <= 64 nodes); an object
+	// of fewer bytes than the smallest 65-node graph (4 + 4 n + 16 per name atom) cannot have more nodes
+	static constexpr uint32_t region_size_limit = 4 + 20 * 65;
 
 	// what makes two groups produce the same objects: family (eligible nodes, particles elsewhere, names, size) and target
 	struct run_id_t {
@@ -427,7 +436,42 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 	template <class WS, class Emit>
 	__device__ void flush_warp(WS &ws, Emit &emit) const {
 		__syncwarp();
-		if (ws.run_valid) {
+		if (ws.run_valid && emit.table.dir) {
+			// region mode: one directory probe for the whole run, then the run's magnitudes land on consecutive slots
+			const uint32_t lane = lane_id(), leaves = ws.run_leaves;
+			spread_run(ws);
+			unsigned long long base = 0;
+			int made = 0;
+			if (lane == 0) {
+				const uint64_t key = mix64(ws.run_eligible ^ mix64(ws.run_fixed + 0x9e3779b97f4a7c15ull * (ws.run_target + 1ull)) ^
+				                           mix64(ws.run_names ^ (0xc2b2ae3d27d4eb4full * ws.run_n)));
+				bool created;
+				base = region_acquire(emit.table, key, leaves, created);
+				made = created;
+			}
+			base = __shfl_sync(0xffffffffu, base, 0);
+			made = __shfl_sync(0xffffffffu, made, 0);
+			if (base != ~0ull) {
+				table_slot *slots = emit.table.slots + base;
+				if (made) { // first run of these objects anywhere: their hashes (tree of the opening group) and representatives
+					expand_full<false>(ws.open_ctx, ws.open_root, ws);
+					const uint32_t levels = ws.open_ctx.levels, tree_bits = ws.open_ctx.tree_bits;
+					const uint32_t shift = ws.open_ctx.eligible - levels; // child_id = group | leaf << shift
+					const uint64_t names_hash = ws.open_ctx.names_hash;
+					for (uint32_t leaf = lane; leaf < leaves; leaf += 32) {
+						table_slot *s = slots + (leaf ^ tree_bits);
+						s->key = hash_combine(hash_combine(names_hash, ws.hl[leaf]), ws.hr[leaf]);
+						s->rep = rep_pack(ws.open_first_child + (ws.open_group | (leaf << shift)), ws.open_size);
+					}
+					if (lane == 0)
+						emit.created += leaves;
+				}
+				for (uint32_t i = lane; i < leaves; i += 32) {
+					atomicAdd(&slots[i].re, ws.acc_re[i]); // results unused -> RED.ADD.F64 on consecutive sectors
+					atomicAdd(&slots[i].im, ws.acc_im[i]);
+				}
+			}
+		} else if (ws.run_valid) {
 			const uint32_t leaves = ws.run_leaves;
 			spread_run(ws);
 			for (uint32_t base = lane_id(); base < leaves; base += 128) {
@@ -522,6 +566,21 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 			ws.run_target = target;
 			ws.run_leaves = leaves;
 			ws.run_valid = 1;
+		}
+		if (emit.table.dir) { // region mode: hashes and representatives are only needed if this run creates the region (flush_warp)
+			if (lane == 0) {
+				ws.open_ctx = ctx;
+				ws.open_root = root;
+				ws.open_first_child = emit.first_child;
+				ws.open_group = group;
+				ws.open_size = parent_size;
+			}
+			for (uint32_t leaf = lane; leaf < leaves; leaf += 32) {
+				ws.acc_re[leaf] = leaf == tree_bits ? root.mag.re : 0.0;
+				ws.acc_im[leaf] = leaf == tree_bits ? root.mag.im : 0.0;
+			}
+			__syncwarp();
+			return;
 		}
 		expand_full<false>(ctx, root, ws);
 		// hash and representative take the place of the tree states (another slot of the same arrays:

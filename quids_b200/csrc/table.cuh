@@ -30,11 +30,29 @@ __host__ __device__ __forceinline__ uint64_t rep_pack(uint64_t child_index, uint
 __host__ __device__ __forceinline__ uint64_t rep_index(uint64_t rep) { return (rep >> REP_SIZE_BITS) - 1; }
 __host__ __device__ __forceinline__ uint32_t rep_size(uint64_t rep) { return (uint32_t)(rep & REP_MAX_SIZE); }
 
+// REGIONS (sorted order of rules whose groups are dense blocks of the object space, e.g. erase_create / coin: a child
+// is its parent with any subset of the eligible nodes toggled, so the objects of one group are ALL 2^levels settings of
+// the group's tree nodes).  Instead of one hashed slot per object, a DIRECTORY hashed by the group's identity gives the
+// group a region of 2^levels CONSECUTIVE slots (allocated from a cursor), object s of the group at slot base + s:
+// one probe per run of groups instead of one per object, and the magnitudes of a run reach the table as consecutive
+// 32-byte sectors (one 4 KB burst) instead of 128 random ones.  The slots keep the same layout (key = the object's
+// hash, written by the run that created the region), so compaction, selection, finalisation and the distributed
+// exchange read them as before.
+struct __align__(16) region_entry {
+	unsigned long long key;  // identity of the group's objects (0 = free)
+	unsigned long long base; // first slot + 1 (0 = the creator has not published it yet)
+};
+
 struct table_view {
 	table_slot *slots;     // capacity + 1 slots
 	uint64_t capacity;     // regular slots
 	unsigned int *overflow; // set to 1 if an insert gave up probing
 	unsigned long long *used; // number of slots created (counted per CTA)
+	// region mode (dir != nullptr): `capacity` slots are handed out in regions through `cursor`
+	region_entry *dir;
+	uint64_t dir_capacity;
+	unsigned long long *cursor; // slots handed out so far
+	unsigned long long *regions; // regions created so far
 };
 
 __device__ __forceinline__ uint64_t table_home(uint64_t hash, uint64_t capacity) { return __umul64hi(mix64(hash), capacity); }
@@ -152,6 +170,47 @@ __device__ __forceinline__ uint32_t table_insert_batch(const table_view &t, int 
 			break;
 	}
 	return created;
+}
+
+// The region of the objects identified by `key` (`leaves` consecutive slots).  One lane calls this per run.  Returns the
+// first slot, or ~0 when the table is too small (overflow raised); created = this call made the region, and the caller
+// must write the objects' hashes and representatives into its slots (magnitudes are added by every run of the region).
+__device__ __forceinline__ uint64_t region_acquire(const table_view &t, uint64_t key, uint32_t leaves, bool &created) {
+	created = false;
+	if (key == 0)
+		key = 1;
+	uint64_t i = __umul64hi(mix64(key), t.dir_capacity);
+	for (uint32_t probes = 0; probes <= TABLE_MAX_PROBES; ++probes) {
+		region_entry *e = t.dir + i;
+		unsigned long long seen = __ldcg(&e->key);
+		if (seen == 0) {
+			seen = atomicCAS(&e->key, 0ull, (unsigned long long)key);
+			if (seen == 0) { // this run creates the region
+				const unsigned long long base = atomicAdd(t.cursor, (unsigned long long)leaves);
+				if (base + leaves > t.capacity) {
+					*t.overflow = 1;
+					atomicExch(&e->base, ~0ull); // whoever waits for this region gives up too
+					return ~0ull;
+				}
+				atomicAdd(t.regions, 1ull);
+				atomicExch(&e->base, base + 1);
+				created = true;
+				return base;
+			}
+		}
+		if (seen == key) {
+			unsigned long long base;
+			while ((base = *(volatile unsigned long long *)&e->base) == 0) // published right after the creator's atomicAdd
+				;
+			return base == ~0ull ? ~0ull : base - 1;
+		}
+		if (++i == t.dir_capacity)
+			i = 0;
+		if ((probes & 63) == 63 && table_overflowed_lane(t))
+			return ~0ull;
+	}
+	*t.overflow = 1;
+	return ~0ull;
 }
 
 __device__ __forceinline__ bool slot_occupied(const table_slot &s, bool is_zero_slot) { return is_zero_slot ? s.rep != 0 : s.key != 0; }
