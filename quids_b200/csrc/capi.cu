@@ -351,7 +351,10 @@ __global__ void __launch_bounds__(256) key_changes_kernel(const uint32_t *keys, 
 
 // stable radix sort of n (u32 key, u64 value) pairs that sit in the first halves of sym->sort_keys /
 // sort_vals (each sized for 2 n); returns the sorted values (device)
-const uint64_t *sort_items(qb_ctx *ctx, qb_sym *sym, uint64_t n) {
+// Only the top SORT_KEY_BITS of the key are sorted on (3 passes instead of 4): the order only has to bring equal keys
+// together, and two different keys that agree on 24 bits merely interleave their (rare) items.
+constexpr int SORT_KEY_BITS = 24;
+const uint64_t *sort_items(qb_ctx *ctx, qb_sym *sym, uint64_t n, const uint32_t **sorted_keys = nullptr) {
 	cudaStream_t stream = ctx->stream;
 	const uint64_t tiles = div_up<uint64_t>(n, SORT_TILE);
 	sym->sort_hist.ensure(sizeof(uint32_t) * SORT_BINS * tiles, stream);
@@ -359,7 +362,7 @@ const uint64_t *sort_items(qb_ctx *ctx, qb_sym *sym, uint64_t n) {
 	uint32_t *keys[2] = {sym->sort_keys.as<uint32_t>(), sym->sort_keys.as<uint32_t>() + n};
 	uint64_t *vals[2] = {sym->sort_vals.as<uint64_t>(), sym->sort_vals.as<uint64_t>() + n};
 	int src = 0;
-	for (int shift = 0; shift < 32; shift += 8, src ^= 1) {
+	for (int shift = 32 - SORT_KEY_BITS; shift < 32; shift += 8, src ^= 1) {
 		radix_histogram_kernel<<<(unsigned)tiles, SORT_THREADS, 0, stream>>>(keys[src], n, shift, sym->sort_hist.as<uint32_t>(), tiles);
 		++ctx->launches;
 		exclusive_scan(ctx, widen_u32{sym->sort_hist.as<uint32_t>()}, sym->sort_base.as<uint64_t>(), SORT_BINS * tiles);
@@ -368,6 +371,8 @@ const uint64_t *sort_items(qb_ctx *ctx, qb_sym *sym, uint64_t n) {
 		++ctx->launches;
 	}
 	QB_CUDA(cudaGetLastError());
+	if (sorted_keys)
+		*sorted_keys = keys[src];
 	return vals[src];
 }
 
@@ -591,12 +596,16 @@ local_table build_local_table(qb_iter *it, int rule_id, const rule_ops *ops, con
 		L.item_keys = sym->sort_keys.as<uint32_t>();
 		L.item_vals = sym->sort_vals.as<uint64_t>();
 		ops->launch_group_items(rule, L);
-		L.items = sort_items(ctx, sym, n_groups);
+		const uint32_t *sorted_keys = nullptr;
+		L.items = sort_items(ctx, sym, n_groups, &sorted_keys);
 		// region mode (table.cuh): the rule sends every run to a region of consecutive slots found through a directory
 		// hashed by the run's identity.  Slots: one per child is always enough and needs no load factor.
 		region_mode = ops->region_size_limit > 0 && max_child_size < ops->region_size_limit;
 		if (region_mode) {
-			full_capacity = std::max<uint64_t>(1024, n_children);
+			// slots are handed to the warps in chunks of REGION_CHUNK: the tail of a chunk that cannot hold the next region
+			// (< group_capacity slots) and the last chunk of every warp stay empty
+			const uint64_t chunk_slack = std::min<uint64_t>(div_up<uint64_t>(n_groups, ITEM_CHUNK), (uint64_t)ctx->sm_count * 32) * REGION_CHUNK;
+			full_capacity = std::max<uint64_t>(1024, n_children + n_children / (REGION_CHUNK / ops->group_capacity - 1) + chunk_slack + REGION_CHUNK);
 			full_directory = 2 * n_groups + 1024;
 			auto hint = sym->region_ratio.find(rule_id);
 			have_history = hint != sym->region_ratio.end();
@@ -613,13 +622,14 @@ local_table build_local_table(qb_iter *it, int rule_id, const rule_ops *ops, con
 			// split per chunk of work items), far fewer than one per child: a prediction that needs no history.  It is
 			// not a bound (groups with equal keys may still hold different objects): an overflow falls back to the full size.
 			QB_CUDA(cudaMemsetAsync(ctx->small(DS_COUNT), 0, sizeof(uint64_t), stream));
-			key_changes_kernel<<<grid_for(n_groups, 256, ctx->grid_cap()), 256, 0, stream>>>(sym->sort_keys.as<uint32_t>(), n_groups,
+			key_changes_kernel<<<grid_for(n_groups, 256, ctx->grid_cap()), 256, 0, stream>>>(sorted_keys, n_groups,
 			                                                                              reinterpret_cast<unsigned long long *>(ctx->small(DS_COUNT)));
 			++ctx->launches;
 			ctx->fetch_small();
 			const double flushes = 1.25 * (double)(ctx->h_small[DS_COUNT] + 1 + div_up<uint64_t>(n_groups, ITEM_CHUNK)) + 4096;
 			if (region_mode) {
-				capacity = std::min<uint64_t>(full_capacity, std::max<uint64_t>(1024, (uint64_t)(flushes * ops->group_capacity)));
+				const uint64_t chunk_slack = std::min<uint64_t>(div_up<uint64_t>(n_groups, ITEM_CHUNK), (uint64_t)ctx->sm_count * 32) * REGION_CHUNK;
+				capacity = std::min<uint64_t>(full_capacity, std::max<uint64_t>(1024, (uint64_t)(flushes * ops->group_capacity * 1.15) + chunk_slack));
 				directory = std::min<uint64_t>(full_directory, (uint64_t)(2 * flushes));
 			} else {
 				capacity = std::min<uint64_t>(full_capacity, std::max<uint64_t>(1024, (uint64_t)(flushes * ops->group_capacity / opt.table_load)));

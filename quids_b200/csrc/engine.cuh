@@ -97,6 +97,7 @@ struct table_emitter {
 	const table_view &table;
 	uint64_t first_child; // index of child 0 of this parent in the symbolic order
 	uint32_t created = 0;
+	uint32_t regions = 0; // regions of the table created through this emitter (region mode)
 	__device__ table_emitter(const table_view &t, uint64_t first) : table(t), first_child(first) {}
 	__device__ void operator()(uint32_t child_id, uint64_t hash, uint32_t size, cplx mag) {
 		created += table_insert(table, hash, mag, rep_pack(first_child + child_id, size));
@@ -225,7 +226,7 @@ constexpr int ITEM_GROUP_BITS = 24;
 constexpr int POPULATE_COPIES = 4;  // parent copies one warp keeps in flight in the finalisation
 constexpr int STAGED_THREADS = 128; // kernels whose warps stage their parents in shared memory: 4 stages of 8 KB per CTA
 constexpr int ITEMS_BLOCKS_PER_SM = 5; // occupancy target of the sorted-order kernel (latency bound: ncu shows 29 % issue utilisation at 5)
-constexpr int ITEM_CHUNK = 128; // items one warp takes at a time
+constexpr int ITEM_CHUNK = 256; // items one warp takes at a time
 
 // one lane per kept parent writes the keys and values of its groups.  A warp takes 32 consecutive parents; when they
 // are consecutive in storage too (no parent truncation) and fit the stage, their bytes come to shared memory with one
@@ -264,8 +265,14 @@ __global__ void __launch_bounds__(STAGED_THREADS) group_items_kernel(const Rule 
 			continue;
 		// the parent's context is prepared here once (this lane already walks the object) instead of once
 		// per work item in the symbolic kernel, where 32 lanes would each chase a different object
-		rule.prepare(object, size, static_cast<typename Rule::ctx_t *>(L.parent_ctx)[p]);
-		rule.group_keys(object, size, count, L.item_keys + first);
+		typename Rule::ctx_t ctx;
+		rule.prepare(object, size, ctx);
+		static_cast<typename Rule::ctx_t *>(L.parent_ctx)[p] = ctx;
+		bool keyed = false;
+		if constexpr (Rule::has_group_keys_from_ctx)
+			keyed = rule.group_keys_from_ctx(ctx, count, L.item_keys + first);
+		if (!keyed)
+			rule.group_keys(object, size, count, L.item_keys + first);
 		for (uint32_t g = 0; g < count; ++g)
 			L.item_vals[first + g] = (p << ITEM_GROUP_BITS) | g;
 	}
@@ -290,7 +297,7 @@ __global__ void __launch_bounds__(SYMBOLIC_THREADS, ITEMS_BLOCKS_PER_SM) symboli
 	warp_slice &s = s_slices[threadIdx.x >> 5];
 	typename Rule::items_workspace_t &ws = s_workspace[threadIdx.x >> 5];
 	const unsigned lane = lane_id();
-	uint32_t created = 0;
+	uint32_t created = 0, regions = 0;
 	rule.init_warp(ws);
 	__syncwarp();
 
@@ -300,10 +307,14 @@ __global__ void __launch_bounds__(SYMBOLIC_THREADS, ITEMS_BLOCKS_PER_SM) symboli
 		if (table_overflowed(L.table))
 			break;
 		const uint64_t c0 = chunk * ITEM_CHUNK, c1 = min(c0 + (uint64_t)ITEM_CHUNK, L.n_groups);
+		uint64_t next_item = c0 + lane < c1 ? L.items[c0 + lane] : 0;
 		for (uint64_t b = c0; b < c1; b += 32) {
 			const uint32_t count = (uint32_t)min((uint64_t)32, c1 - b);
+			// the next batch's item is requested before this batch is processed: the gathers below depend on it, and
+			// two dependent round trips per batch were a fifth of the kernel's stalls
+			const uint64_t item = next_item;
+			next_item = b + 32 + lane < c1 ? L.items[b + 32 + lane] : 0;
 			if (lane < count) {
-				const uint64_t item = L.items[b + lane];
 				const uint64_t p = item >> ITEM_GROUP_BITS;
 				const uint32_t group = (uint32_t)(item & ((1u << ITEM_GROUP_BITS) - 1));
 				const uint64_t oid = L.kept ? L.kept[p] : p;
@@ -333,6 +344,7 @@ __global__ void __launch_bounds__(SYMBOLIC_THREADS, ITEMS_BLOCKS_PER_SM) symboli
 					table_emitter emit(L.table, s.child_begin[h]);
 					rule.template symbolic_warp<true>(L.it.objects + s.object[h], s.size[h], s.ctx[h], s.group[h], s.group_ctx[h], ws, emit);
 					created += emit.created;
+					regions += emit.regions;
 					if (lane > h && lane < e)
 						rule.continue_run(s.ctx[lane], s.group_ctx[lane], ws);
 					__syncwarp();
@@ -342,6 +354,7 @@ __global__ void __launch_bounds__(SYMBOLIC_THREADS, ITEMS_BLOCKS_PER_SM) symboli
 					table_emitter emit(L.table, s.child_begin[i]);
 					rule.template symbolic_warp<true>(L.it.objects + s.object[i], s.size[i], s.ctx[i], s.group[i], s.group_ctx[i], ws, emit);
 					created += emit.created;
+					regions += emit.regions;
 				}
 			}
 			__syncwarp();
@@ -349,10 +362,14 @@ __global__ void __launch_bounds__(SYMBOLIC_THREADS, ITEMS_BLOCKS_PER_SM) symboli
 		table_emitter emit(L.table, 0);
 		rule.flush_warp(ws, emit);
 		created += emit.created;
+		regions += emit.regions;
 	}
 	created = (uint32_t)warp_sum((uint64_t)created);
+	regions = (uint32_t)warp_sum((uint64_t)regions);
 	if (lane == 0 && created)
 		atomicAdd(L.table.used, (unsigned long long)created);
+	if (lane == 0 && regions)
+		atomicAdd(L.table.regions, (unsigned long long)regions);
 }
 
 // parent holding the first group of every chunk (one binary search per chunk, all in parallel, instead of

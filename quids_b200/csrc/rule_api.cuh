@@ -134,6 +134,9 @@ struct rule_base {
 	//     continue_run(ctx, group_ctx, workspace&)     this lane's group joins the open run (shared-memory atomics)
 	// The head of every stretch of equal identities still goes through symbolic_warp<true>.
 	static constexpr bool has_run_identity = false;
+	// optional: bool group_keys_from_ctx(ctx, num_groups, keys) -- the keys from the prepared context alone; false =
+	// not for this parent, group_keys() is called with the object
+	static constexpr bool has_group_keys_from_ctx = false;
 	// optional, with has_run_identity: the rule can send a run to a REGION of the table (table.cuh: region_acquire) when
 	// every object of the state is smaller than this many bytes (0 = the rule does not use regions)
 	static constexpr uint32_t region_size_limit = 0;

@@ -75,6 +75,25 @@ struct graph {
 	}
 };
 
+// the 2 n particle bytes (left[n] then right[n], each 0 or 1) of a graph of at most 32 nodes as one 64-bit mask: bit i =
+// left[i], bit n + i = right[i].  Aligned 32-bit loads + funnel shifts instead of one byte load per particle, then four
+// bytes become four bits with one multiplication ((b0 | b1<<8 | b2<<16 | b3<<24) * 0x00204081 has b0..b3 at bits 21..24).
+__device__ __forceinline__ uint64_t particle_mask(const uint8_t *object, uint32_t n) {
+	const uintptr_t first = reinterpret_cast<uintptr_t>(object) + 2;
+	const uint32_t *w = reinterpret_cast<const uint32_t *>(first & ~(uintptr_t)3);
+	const uint32_t shift = (uint32_t)(first & 3) * 8;
+	const uint32_t words = (2 * n + 3) / 4;
+	uint64_t mask = 0;
+	uint32_t lo = w[0];
+	for (uint32_t k = 0; k < words; ++k) {
+		const uint32_t hi = w[k + 1]; // at most 3 bytes past the particles: still inside the object (name_begin follows)
+		const uint32_t x = __funnelshift_r(lo, hi, shift);
+		mask |= (uint64_t)(((x & 0x01010101u) * 0x00204081u >> 21) & 0xfu) << (4 * k);
+		lo = hi;
+	}
+	return 2 * n < 64 ? mask & ((1ull << (2 * n)) - 1) : mask;
+}
+
 // qcgd.hpp:122-146
 __device__ inline uint64_t hash_graph(const uint8_t *object) {
 	graph g(object);
@@ -153,6 +172,7 @@ struct flip_workspace_t {
 	flip_root open_root;
 	uint64_t open_first_child;
 	uint32_t open_group, open_size;
+	region_chunk chunk; // this warp's private range of table slots
 };
 
 template <bool WANT_EQUAL>
@@ -282,6 +302,19 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 		return num_child > (uint32_t)FLIP_BLOCK ? num_child >> FLIP_LEVELS : 1;
 	}
 
+	// the same keys from a prepared context (n <= 64: the masks say everything group_keys reads from the object)
+	static constexpr bool has_group_keys_from_ctx = true;
+	__device__ bool group_keys_from_ctx(const flip_ctx &ctx, uint32_t num_groups, uint32_t *keys) const {
+		if (ctx.n > 64)
+			return false;
+		const uint64_t all = ctx.n == 64 ? ~0ull : ((1ull << ctx.n) - 1);
+		const uint64_t eligible = (WANT_EQUAL ? ~(ctx.left ^ ctx.right) : (ctx.left ^ ctx.right)) & all;
+		const uint64_t family = mix64(mix64(eligible + 0x9e3779b97f4a7c15ull * ctx.n) ^ (ctx.left & ~eligible));
+		for (uint32_t group = 0; group < num_groups; ++group)
+			keys[group] = (uint32_t)(mix64(family + 0x9e3779b97f4a7c15ull * ((group ^ ctx.prefix_bits) + 1)) >> 32);
+		return true;
+	}
+
 	__device__ void group_keys(const uint8_t *parent, uint32_t, uint32_t num_groups, uint32_t *keys) const {
 		graph g(parent);
 		uint64_t family = g.n;
@@ -311,6 +344,37 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 	__device__ void prepare(const uint8_t *parent, uint32_t, flip_ctx &ctx) const {
 		graph g(parent);
 		ctx.n = g.n;
+		if (g.n >= 1 && g.n <= 32) { // masks with a few word loads, everything else with bit operations
+			const uint64_t both = particle_mask(parent, g.n);
+			const uint64_t all = (1ull << g.n) - 1;
+			const uint64_t l = both & all, r = both >> g.n;
+			uint64_t hn = 0;
+			for (uint32_t i = 0; i < g.n; ++i)
+				hn = hash_combine(hn, g.atom_hash(g.name_begin(i)));
+			uint64_t elig = (WANT_EQUAL ? ~(l ^ r) : (l ^ r)) & all;
+			const uint32_t eligible = __popcll(elig), levels = min(eligible, (uint32_t)FLIP_LEVELS);
+			ctx.left = l;
+			ctx.right = r;
+			ctx.names_hash = hn;
+			ctx.eligible = (uint8_t)eligible;
+			ctx.levels = (uint8_t)levels;
+			uint32_t prefix_bits = 0, tree_bits = 0;
+			for (uint32_t seen = 0; elig; ++seen) { // eligible nodes in index order: the first eligible - levels are the prefix
+				const uint32_t i = __ffsll((long long)elig) - 1;
+				elig &= elig - 1;
+				const uint32_t bit = (uint32_t)((l >> i) & 1);
+				if (seen + levels >= eligible) {
+					ctx.pos[seen + levels - eligible] = (uint8_t)i;
+					tree_bits |= bit << (seen + levels - eligible);
+				} else {
+					prefix_bits |= bit << seen;
+				}
+			}
+			ctx.pos[levels] = (uint8_t)g.n;
+			ctx.prefix_bits = prefix_bits;
+			ctx.tree_bits = (uint8_t)tree_bits;
+			return;
+		}
 		uint64_t l = 0, r = 0, hn = 0;
 		uint32_t eligible = 0;
 		for (uint32_t i = 0; i < g.n; ++i) {
@@ -398,8 +462,10 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 
 	template <class WS>
 	__device__ void init_warp(WS &ws) const {
-		if (lane_id() == 0)
+		if (lane_id() == 0) {
 			ws.run_valid = 0;
+			ws.chunk.next = ws.chunk.end = 0;
+		}
 		if (lane_id() < 4)
 			ws.amp[lane_id()] = this->amp.f[lane_id()];
 	}
@@ -446,8 +512,9 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 				const uint64_t key = mix64(ws.run_eligible ^ mix64(ws.run_fixed + 0x9e3779b97f4a7c15ull * (ws.run_target + 1ull)) ^
 				                           mix64(ws.run_names ^ (0xc2b2ae3d27d4eb4full * ws.run_n)));
 				bool created;
-				base = region_acquire(emit.table, key, leaves, created);
+				base = region_acquire(emit.table, ws.chunk, key, leaves, created);
 				made = created;
+				emit.regions += created;
 			}
 			base = __shfl_sync(0xffffffffu, base, 0);
 			made = __shfl_sync(0xffffffffu, made, 0);

@@ -172,10 +172,17 @@ __device__ __forceinline__ uint32_t table_insert_batch(const table_view &t, int 
 	return created;
 }
 
+// Slots are handed out to the warps in chunks (one atomic on the shared cursor per REGION_CHUNK slots instead of one per
+// region: every creator hitting the same address was the top stall of the kernel); a warp fills its chunk front to back.
+constexpr uint32_t REGION_CHUNK = 1024;
+struct region_chunk {
+	unsigned long long next, end; // this warp's private range of slots
+};
+
 // The region of the objects identified by `key` (`leaves` consecutive slots).  One lane calls this per run.  Returns the
 // first slot, or ~0 when the table is too small (overflow raised); created = this call made the region, and the caller
 // must write the objects' hashes and representatives into its slots (magnitudes are added by every run of the region).
-__device__ __forceinline__ uint64_t region_acquire(const table_view &t, uint64_t key, uint32_t leaves, bool &created) {
+__device__ __forceinline__ uint64_t region_acquire(const table_view &t, region_chunk &mine, uint64_t key, uint32_t leaves, bool &created) {
 	created = false;
 	if (key == 0)
 		key = 1;
@@ -186,13 +193,18 @@ __device__ __forceinline__ uint64_t region_acquire(const table_view &t, uint64_t
 		if (seen == 0) {
 			seen = atomicCAS(&e->key, 0ull, (unsigned long long)key);
 			if (seen == 0) { // this run creates the region
-				const unsigned long long base = atomicAdd(t.cursor, (unsigned long long)leaves);
+				if (mine.next + leaves > mine.end) { // what is left of the old chunk stays empty
+					const unsigned long long want = leaves > REGION_CHUNK ? leaves : REGION_CHUNK;
+					mine.next = atomicAdd(t.cursor, want);
+					mine.end = mine.next + want;
+				}
+				const unsigned long long base = mine.next;
+				mine.next += leaves;
 				if (base + leaves > t.capacity) {
 					*t.overflow = 1;
 					atomicExch(&e->base, ~0ull); // whoever waits for this region gives up too
 					return ~0ull;
 				}
-				atomicAdd(t.regions, 1ull);
 				atomicExch(&e->base, base + 1);
 				created = true;
 				return base;
@@ -200,7 +212,7 @@ __device__ __forceinline__ uint64_t region_acquire(const table_view &t, uint64_t
 		}
 		if (seen == key) {
 			unsigned long long base;
-			while ((base = *(volatile unsigned long long *)&e->base) == 0) // published right after the creator's atomicAdd
+			while ((base = *(volatile unsigned long long *)&e->base) == 0) // published right after the creator found its slots
 				;
 			return base == ~0ull ? ~0ull : base - 1;
 		}
