@@ -57,48 +57,81 @@ def make_parents(n_parents, seed):
 
 
 class ClockSampler:
-    """samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)"""
+    """samples SM clocks and throttle reasons DURING the timed region: NVML in-process every ~2 ms (a step is a few
+    milliseconds, nvidia-smi -lms would not deliver one sample in time); nvidia-smi is the fallback"""
     FIELDS = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, device):
         self.device = device
-        self.samples = []
-        self.proc = None
+        self.sm, self.reasons, self.max_mhz = [], set(), None
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.source = None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            index = device
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if visible:
+                try:
+                    index = int(visible.split(",")[device])
+                except (ValueError, IndexError):
+                    index = device
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.source = "nvml"
+        except Exception:
+            self.nvml = None
+
+    def _loop_nvml(self):
+        n = self.nvml
+        names = {n.nvmlClocksEventReasonHwSlowdown: "hw_slowdown", n.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 n.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown", n.nvmlClocksEventReasonSwPowerCap: "sw_power_cap"}
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                break
+            time.sleep(0.002)
+
+    def _loop_smi(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=10).stdout
+            except (OSError, subprocess.TimeoutExpired):
+                break
+            f = [x.strip() for x in out.strip().split(",")]
+            if len(f) >= 6:
+                try:
+                    self.sm.append(float(f[0]))
+                    self.max_mhz = float(f[1])
+                except ValueError:
+                    pass
+                for name, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(name)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except OSError:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.samples.append(line.strip())
+        if self.nvml is None:
+            self.source = "nvidia-smi"
+        self.thread = threading.Thread(target=self._loop_nvml if self.nvml is not None else self._loop_smi, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        self.thread.join(timeout=2)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            f = [x.strip() for x in s.split(",")]
-            if len(f) < 6:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for name, v in zip(names, f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        self.stop_flag.set()
+        if self.thread is not None:
+            self.thread.join(timeout=15)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.sm), "source": self.source}
 
 
 def algorithmic_bytes(n_p, s_p, n_c, n_u, n_s, s_s):
