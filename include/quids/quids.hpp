@@ -155,6 +155,25 @@ namespace quids {
 		std::vector<double> params_;
 	};
 
+	/// an observable evaluated ON THE DEVICE: handle on a registered device observable (quids_b200.h: "qcgd_stats",
+	/// "qcgd_size", "qubit", "object_bytes").  it_t::average_value accepts it next to the reference's host closure
+	/// (observable_t); the state is then reduced in HBM instead of being downloaded.
+	class device_observable {
+	public:
+		device_observable(const char *name, std::initializer_list<double> params = {}) : params_(params) {
+			id_ = qb_observable_id(name);
+			if (id_ < 1)
+				throw std::runtime_error(std::string("quids: no device observable registered under the name ") + name);
+		}
+		int id() const { return id_; }
+		int values() const { return qb_observable_values(id_); }
+		const std::vector<double> &params() const { return params_; }
+
+	private:
+		int id_;
+		std::vector<double> params_;
+	};
+
 	/// iteration (wave function), quids.hpp:149-335: state in HBM + lazily synchronised host mirror
 	class iteration {
 	public:
@@ -195,6 +214,17 @@ namespace quids {
 			for (size_t oid = 0; oid < num_object; ++oid)
 				avg += observable(&objects[object_begin[oid]], &objects[object_begin[oid]] + object_size[oid]) * std::norm(magnitude[oid]);
 			return avg;
+		}
+		/// the same sum for a device observable: one reduction kernel over the state in HBM, nothing is downloaded.
+		/// Observables with several values per object fill `values` (up to 4) and return the first.
+		PROBA_TYPE average_value(const device_observable &observable, double *values = nullptr) const {
+			to_device();
+			double out[4] = {0, 0, 0, 0};
+			detail::check(qb_iter_average_value(handle_, observable.id(), observable.params().data(), (uint32_t)observable.params().size(), out, 4));
+			if (values)
+				for (int k = 0; k < observable.values(); ++k)
+					values[k] = out[k];
+			return (PROBA_TYPE)out[0];
 		}
 		/// read-write access, quids.hpp:242-246: the pointers alias the host mirror; the state is uploaded again before the next simulate
 		void get_object(size_t const object_id, char *&object_begin_, uint &object_size_, mag_t *&mag) {

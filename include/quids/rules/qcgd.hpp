@@ -186,10 +186,19 @@ namespace quids::rules::qcgd {
 					d += graphs::left(b, i) + graphs::right(b, i);
 				return d / (2 * n);
 			};
-			const PROBA_TYPE avg_size = iter.average_value([](char const *b, char const *) { return (PROBA_TYPE)graphs::num_nodes(b); });
-			const PROBA_TYPE avg_size2 = iter.average_value([](char const *b, char const *) { return (PROBA_TYPE)graphs::num_nodes(b) * graphs::num_nodes(b); });
-			const PROBA_TYPE avg_density = iter.average_value([&](char const *b, char const *) { return density(b); });
-			const PROBA_TYPE avg_density2 = iter.average_value([&](char const *b, char const *) { return density(b) * density(b); });
+			PROBA_TYPE avg_size, avg_size2, avg_density, avg_density2;
+			if constexpr (std::is_same<PROBA_TYPE, double>::value) {
+				// the four averages in ONE reduction over the state in HBM (device observable "qcgd_stats"); nothing is downloaded
+				static const quids::device_observable stats("qcgd_stats");
+				double v[4];
+				iter.average_value(stats, v);
+				avg_size = v[0], avg_size2 = v[1], avg_density = v[2], avg_density2 = v[3];
+			} else { // float build: accumulate in PROBA_TYPE on the host mirror, like the reference
+				avg_size = iter.average_value([](char const *b, char const *) { return (PROBA_TYPE)graphs::num_nodes(b); });
+				avg_size2 = iter.average_value([](char const *b, char const *) { return (PROBA_TYPE)graphs::num_nodes(b) * graphs::num_nodes(b); });
+				avg_density = iter.average_value([&](char const *b, char const *) { return density(b); });
+				avg_density2 = iter.average_value([&](char const *b, char const *) { return density(b) * density(b); });
+			}
 			PROBA_TYPE std_dev_size = avg_size2 - avg_size * avg_size;
 			std_dev_size = std_dev_size < quids::tolerance ? 0 : std::sqrt(avg_size2);
 			PROBA_TYPE std_dev_density = avg_density2 - avg_density * avg_density;

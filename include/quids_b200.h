@@ -168,6 +168,15 @@ int qb_modifier_id(const char *name); /* >= 1, or QB_ERR_UNKNOWN_RULE */
 /* quids::simulate(it_t&, modifier_t)  quids.hpp:436-438 / apply_modifier :973-980 */
 int qb_apply_modifier(qb_iter *it, int modifier_id, const double *params, uint32_t num_params);
 
+/* iteration::average_value(observable) (quids.hpp:208-234: sum over the objects of observable(begin, end) * |mag|^2) for an
+ * observable registered on the device (the reference's observable_t is a host closure; the drop-in headers keep that
+ * overload, evaluated on the host mirror).  An observable produces qb_observable_values(id) <= 4 numbers per object in
+ * one pass: "qcgd_stats" = {nodes, nodes^2, density, density^2} of utils::serialize (qcgd.hpp:309-372), "qcgd_size",
+ * "qubit" (params: [bit]) = probability that the qubit is set, "object_bytes". */
+int qb_observable_id(const char *name); /* >= 1, or QB_ERR_UNKNOWN_RULE */
+int qb_observable_values(int observable_id);
+int qb_iter_average_value(const qb_iter *it, int observable_id, const double *params, uint32_t num_params, double *values, uint32_t capacity);
+
 /* quids::simulate(it_t&, rule_t const*, it_t&, sy_it_t&, size_t max_num_object, debug_t)  quids.hpp:448-543 */
 int qb_simulate(qb_iter *it, int rule_id, const double *params, uint32_t num_params, qb_iter *next,
                 qb_sym *sym, uint64_t max_num_object, const qb_options *opt, qb_step_cb cb, void *user);

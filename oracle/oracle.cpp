@@ -623,6 +623,34 @@ int orc_hash_objects(const orc_state *s, int rule_id, const double *params, uint
 
 int orc_apply_modifier(orc_state *s, int modifier_id, const double *params) { return apply_modifier(s->s, modifier_id, params); }
 
+/* quids.hpp:208-234 with the observables of qcgd utils::serialize (qcgd.hpp:319-345): a plain sequential sum */
+int orc_average_value(const orc_state *s, int observable_id, const double *params, double *value) {
+	double avg = 0;
+	for (size_t i = 0; i < s->s.n(); ++i) {
+		const uint8_t *o = s->s.obj(i);
+		const uint32_t size = s->s.size(i);
+		double v = 0;
+		if (observable_id >= ORC_OBS_QCGD_SIZE && observable_id <= ORC_OBS_QCGD_SQUARED_DENSITY) {
+			const uint32_t n = (uint32_t)o[0] | ((uint32_t)o[1] << 8);
+			double density = 0;
+			for (uint32_t k = 0; k < n; ++k)
+				density += o[2 + k] + o[2 + n + k];
+			density /= 2 * (double)n;
+			v = observable_id == ORC_OBS_QCGD_SIZE ? (double)n : observable_id == ORC_OBS_QCGD_SQUARED_SIZE ? (double)n * n : observable_id == ORC_OBS_QCGD_DENSITY ? density : density * density;
+		} else if (observable_id == ORC_OBS_QUBIT) {
+			const uint64_t bit = (uint64_t)params[0];
+			v = bit < size && o[bit] ? 1 : 0;
+		} else if (observable_id == ORC_OBS_BYTES) {
+			v = size;
+		} else {
+			return -1;
+		}
+		avg += v * std::norm(s->s.mag[i]);
+	}
+	*value = avg;
+	return 0;
+}
+
 int orc_simulate(orc_state *in, int rule_id, const double *params, orc_state *out, uint64_t max_num_object, double tolerance, uint64_t *counters) {
 	if (max_num_object == 0)
 		return -2;

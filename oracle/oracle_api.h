@@ -70,6 +70,18 @@ int orc_hash_objects(const orc_state *s, int rule_id, const double *params, uint
 /* in place, quids.hpp:973-980 */
 int orc_apply_modifier(orc_state *s, int modifier_id, const double *params);
 
+/* observables (params are doubles) */
+enum {
+	ORC_OBS_QCGD_SIZE            = 1, /* number of nodes                       qcgd.hpp:319-321 */
+	ORC_OBS_QCGD_SQUARED_SIZE    = 2, /* its square                            qcgd.hpp:322-325 */
+	ORC_OBS_QCGD_DENSITY         = 3, /* particles / (2 nodes)                 qcgd.hpp:326-335 */
+	ORC_OBS_QCGD_SQUARED_DENSITY = 4, /* its square                            qcgd.hpp:336-345 */
+	ORC_OBS_QUBIT                = 5, /* params: [bit]; 1 when the qubit is set (byte != 0 inside the object), else 0 */
+	ORC_OBS_BYTES                = 6  /* size of the object in bytes */
+};
+/* iteration::average_value, quids.hpp:208-234: sum over the objects of observable(begin, end) * norm(magnitude) */
+int orc_average_value(const orc_state *s, int observable_id, const double *params, double *value);
+
 /* one rule iteration, quids.hpp:448-543, simple truncation.
  * max_num_object: UINT64_MAX = no truncation (0 = auto budget is NOT supported: returns -2).
  * counters[0] = N_c (sy_it.num_object), counters[1] = N_u (num_object_after_interferences). */

@@ -173,6 +173,29 @@ int orc_apply_modifier(orc_state *s, int modifier_id, const double *params) {
 	return 0;
 }
 
+/* the reference's own iteration::average_value with the lambdas of its utils::serialize (qcgd.hpp:319-345) */
+int orc_average_value(const orc_state *s, int observable_id, const double *params, double *value) {
+	namespace graphs = quids::rules::qcgd::graphs;
+	auto density = [](char const *object_begin) {
+		PROBA_TYPE num_nodes = graphs::num_nodes(object_begin);
+		PROBA_TYPE d = 0;
+		for (auto i = 0; i < num_nodes; ++i)
+			d += graphs::left(object_begin, i) + graphs::right(object_begin, i);
+		return d / (2 * num_nodes);
+	};
+	const uint64_t bit = params ? (uint64_t)params[0] : 0;
+	switch (observable_id) {
+	case ORC_OBS_QCGD_SIZE: *value = s->it.average_value([](char const *b, char const *) { return (PROBA_TYPE)graphs::num_nodes(b); }); break;
+	case ORC_OBS_QCGD_SQUARED_SIZE: *value = s->it.average_value([](char const *b, char const *) { PROBA_TYPE n = graphs::num_nodes(b); return n * n; }); break;
+	case ORC_OBS_QCGD_DENSITY: *value = s->it.average_value([&](char const *b, char const *) { return density(b); }); break;
+	case ORC_OBS_QCGD_SQUARED_DENSITY: *value = s->it.average_value([&](char const *b, char const *) { PROBA_TYPE d = density(b); return d * d; }); break;
+	case ORC_OBS_QUBIT: *value = s->it.average_value([bit](char const *b, char const *e) { return (PROBA_TYPE)(bit < (uint64_t)(e - b) && b[bit] ? 1 : 0); }); break;
+	case ORC_OBS_BYTES: *value = s->it.average_value([](char const *b, char const *e) { return (PROBA_TYPE)(e - b); }); break;
+	default: return -1;
+	}
+	return 0;
+}
+
 int orc_simulate(orc_state *in, int rule_id, const double *params, orc_state *out, uint64_t max_num_object, double tolerance, uint64_t *counters) {
 	if (max_num_object == 0)
 		return -2;

@@ -101,6 +101,9 @@ def lib():
         "qb_rule_id": (i32, [C.c_char_p]),
         "qb_modifier_id": (i32, [C.c_char_p]),
         "qb_apply_modifier": (i32, [vp, i32, P(dbl), u32]),
+        "qb_observable_id": (i32, [C.c_char_p]),
+        "qb_observable_values": (i32, [i32]),
+        "qb_iter_average_value": (i32, [vp, i32, P(dbl), u32, P(dbl), u32]),
         "qb_simulate": (i32, [vp, i32, P(dbl), u32, vp, vp, u64, P(qb_options), STEP_CB, vp]),
         "qb_hash_objects": (i32, [vp, i32, P(dbl), u32, vp]),
         "qb_comm_unique_id": (i32, [vp]),
@@ -432,6 +435,20 @@ class Iteration:
     def pop(self, n=1, normalize=True):
         self._flush()
         _check(lib().qb_iter_pop(self.handle, n, 1 if normalize else 0))
+
+    def average_value(self, observable, *params):
+        """iteration::average_value (quids.hpp:208-234) for a registered DEVICE observable: the sum over the objects
+        of observable(object) * |mag|^2, reduced in HBM.  Returns a float, or a list for observables that produce
+        several values per object ("qcgd_stats": nodes, nodes^2, density, density^2)."""
+        self._flush()
+        oid = lib().qb_observable_id(observable.encode())
+        if oid < 1:
+            raise QuidsError(f"unknown observable {observable!r}")
+        k = lib().qb_observable_values(oid)
+        out = (C.c_double * k)()
+        p = (C.c_double * max(1, len(params)))(*[float(x) for x in params])
+        _check(lib().qb_iter_average_value(self.handle, oid, p, len(params), out, k))
+        return out[0] if k == 1 else list(out)
 
     def normalize(self):
         self._flush()

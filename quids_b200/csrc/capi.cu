@@ -40,6 +40,17 @@ static std::vector<modifier_ops> &modifier_registry() {
 	static std::vector<modifier_ops> r;
 	return r;
 }
+static std::vector<observable_ops> &observable_registry() {
+	static std::vector<observable_ops> r;
+	return r;
+}
+int register_observable(const observable_ops &ops) {
+	observable_registry().push_back(ops);
+	return (int)observable_registry().size();
+}
+const observable_ops *find_observable(int id) {
+	return id >= 1 && (size_t)id <= observable_registry().size() ? &observable_registry()[id - 1] : nullptr;
+}
 int register_rule(const rule_ops &ops) {
 	rule_registry().push_back(ops);
 	return (int)rule_registry().size();
@@ -62,6 +73,7 @@ enum { // u64 words of the small device scratch
 	DS_SELECT_GT = 5, // and 6
 	DS_CURSOR = 7,    // region mode: slots handed out
 	DS_REGIONS = 8,   // region mode: regions created
+	DS_CHILD_RANGE = 9, // two u32: largest child count, ~smallest
 	DS_WORDS = 10
 };
 
@@ -76,6 +88,7 @@ struct qb_ctx {
 	dev_buf scan_ws;
 	dev_buf partials;
 	dev_buf select;
+	dev_buf select_cand; // keys still in the race after two digits of a radix select (select.cuh)
 
 	cudaStream_t copy_in = nullptr, copy_out = nullptr; // host <-> device transfers that overlap the compute stream (qb_iter_*_async)
 	cudaEvent_t fence = nullptr;
@@ -224,25 +237,35 @@ void exclusive_scan(qb_ctx *ctx, F f, uint64_t *out, uint64_t n) {
 template <class KeyFn>
 void select_threshold(qb_ctx *ctx, comm_ops *comm, KeyFn key_of, uint64_t n, uint64_t k) {
 	ctx->select.ensure(sizeof(select_state), ctx->stream);
-	select_state init;
-	memset(&init, 0, sizeof init);
-	init.k = k;
-	QB_CUDA(cudaMemcpyAsync(ctx->select.ptr, &init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
-	ctx->sync(); // `init` lives on this stack frame
+	// after two digits (24 bits) the keys still in the race are copied to a dense buffer and the four remaining digits
+	// read only that: 3 passes over all the keys instead of 6 (select.cuh).  Not worth a launch for small inputs.
+	const bool filter = n >= (1ull << 18);
+	const uint64_t cand_capacity = filter ? n / 32 + 1024 : 0;
+	if (filter)
+		ctx->select_cand.ensure(sizeof(uint64_t) * cand_capacity, ctx->stream);
+	select_state *st = ctx->select.as<select_state>();
+	select_init_kernel<<<1, SCAN_THREADS, 0, ctx->stream>>>(st, k, cand_capacity);
+	++ctx->launches;
 	ctx->select_k = k;
-	const int grid = grid_for(n, 256, ctx->grid_cap());
+	const int grid = grid_for(div_up<uint64_t>(n, SELECT_ITEMS), 256, ctx->grid_cap());
+	const uint64_t *cand = nullptr;
 	int shift = 64;
-	while (shift > 0) {
+	for (int pass = 0; shift > 0; ++pass) {
 		const int bits = shift >= SELECT_MAX_BITS ? SELECT_MAX_BITS : shift;
 		shift -= bits;
 		if (n > 0) {
-			select_histogram_kernel<<<grid, 256, 0, ctx->stream>>>(key_of, n, ctx->select.as<select_state>(), shift, bits);
+			select_histogram_kernel<<<grid, 256, 0, ctx->stream>>>(key_of, n, st, shift, bits, cand);
 			++ctx->launches;
 		}
 		if (comm)
-			comm->allreduce_u64_device(ctx->select.as<select_state>()->hist, SELECT_BINS);
-		select_pick_kernel<<<1, SCAN_THREADS, 0, ctx->stream>>>(ctx->select.as<select_state>(), shift, bits);
+			comm->allreduce_u64_device(st->hist, SELECT_BINS);
+		select_pick_kernel<<<1, SCAN_THREADS, 0, ctx->stream>>>(st, shift, bits);
 		++ctx->launches;
+		if (filter && pass == 1) {
+			select_filter_kernel<<<grid, 256, 0, ctx->stream>>>(key_of, n, st, ctx->select_cand.as<uint64_t>());
+			++ctx->launches;
+			cand = ctx->select_cand.as<uint64_t>();
+		}
 	}
 	QB_CUDA(cudaGetLastError());
 }
@@ -274,11 +297,18 @@ uint64_t select_keep(qb_ctx *ctx, comm_ops *comm, KeyFn key_of, uint64_t n, OutF
 		kept = mine[0] + need;
 	}
 	if (n > 0) {
-		const uint64_t tiles = div_up<uint64_t>(n, COMPACT_TILE);
-		for (int pass = 0; pass < 2; ++pass) {
+		const uint64_t tiles = div_up<uint64_t>(n, SELECT_TILE);
+		const select_state *sel = ctx->select.as<select_state>();
+		if (n < (1ull << 31)) { // both kinds in one pass (two 31-bit running counts in one look-back word)
 			scan_state st = ctx->scan(tiles);
-			select_compact_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, ctx->stream>>>(key_of, n, ctx->select.as<select_state>(), pass, out, st);
+			select_compact_kernel<2><<<(unsigned)tiles, SCAN_THREADS, 0, ctx->stream>>>(key_of, n, sel, out, st);
 			++ctx->launches;
+		} else {
+			scan_state st = ctx->scan(tiles);
+			select_compact_kernel<0><<<(unsigned)tiles, SCAN_THREADS, 0, ctx->stream>>>(key_of, n, sel, out, st);
+			st = ctx->scan(tiles);
+			select_compact_kernel<1><<<(unsigned)tiles, SCAN_THREADS, 0, ctx->stream>>>(key_of, n, sel, out, st);
+			ctx->launches += 2;
 		}
 	}
 	QB_CUDA(cudaGetLastError());
@@ -426,6 +456,7 @@ struct local_table {
 	const uint64_t *kept = nullptr;
 	uint64_t n_children = 0;
 	uint32_t max_child_size = 0;
+	uint32_t uniform_fanout = 0; // != 0: every parent of the state has this many children
 	double workspace = 0; // automatic budget: bytes the symbolic workspace of the kept parents was counted for
 	uint64_t n_unique = 0; // entries kept by the compaction
 	table_view table{};
@@ -458,13 +489,14 @@ local_table build_local_table(qb_iter *it, int rule_id, const rule_ops *ops, con
 			L.num_groups = it->num_groups.as<uint32_t>();
 		}
 		L.max_child_size = reinterpret_cast<unsigned int *>(ctx->small(DS_MAX_CHILD_SIZE));
+		L.child_count_range = reinterpret_cast<unsigned int *>(ctx->small(DS_CHILD_RANGE));
 		ops->launch_num_child(rule, L);
 		timer.end(QB_PHASE_NUM_CHILD);
 	}
 
 	// child index ranges of a set of kept parents (quids.hpp:666-671: a serial loop in the reference)
 	uint64_t n_groups = 0;
-	uint32_t max_child_size = 0;
+	uint32_t max_child_size = 0, uniform_fanout = 0;
 	const uint64_t *group_begin = nullptr;
 	auto index_children = [&](const uint64_t *kept, uint64_t n_parents) -> uint64_t {
 		it->child_begin.ensure(sizeof(uint64_t) * (n_parents + 1), stream);
@@ -478,7 +510,12 @@ local_table build_local_table(qb_iter *it, int rule_id, const rule_ops *ops, con
 		QB_CUDA(cudaMemcpyAsync(&ctx->h_small[DS_COUNT], it->child_begin.as<uint64_t>() + n_parents, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
 		QB_CUDA(cudaMemcpyAsync(&ctx->h_small[DS_USED], group_begin + n_parents, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
 		QB_CUDA(cudaMemcpyAsync(&ctx->h_small[DS_MAX_CHILD_SIZE], ctx->small(DS_MAX_CHILD_SIZE), sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+		QB_CUDA(cudaMemcpyAsync(&ctx->h_small[DS_CHILD_RANGE], ctx->small(DS_CHILD_RANGE), sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
 		ctx->sync();
+		{
+			const uint32_t largest = (uint32_t)ctx->h_small[DS_CHILD_RANGE], smallest = ~(uint32_t)(ctx->h_small[DS_CHILD_RANGE] >> 32);
+			uniform_fanout = largest == smallest ? largest : 0;
+		}
 		n_groups = ctx->h_small[DS_USED];
 		max_child_size = (uint32_t)ctx->h_small[DS_MAX_CHILD_SIZE];
 		return ctx->h_small[DS_COUNT];
@@ -542,6 +579,7 @@ local_table build_local_table(qb_iter *it, int rule_id, const rule_ops *ops, con
 		timer.end(QB_PHASE_NUM_CHILD);
 	}
 	R.max_child_size = max_child_size;
+	R.uniform_fanout = uniform_fanout;
 	sym->n_children = R.n_children;
 	it->n_symbolic = R.n_children;
 	if (global_sum(comm, R.n_children) == 0) {
@@ -834,6 +872,7 @@ void finalize_and_normalize(qb_iter *it, const rule_ops *ops, const void *rule, 
 			a.child_begin = it->child_begin.as<uint64_t>();
 			a.kept = R.kept;
 			a.n_parents = R.n_parents;
+			a.uniform_fanout = R.uniform_fanout;
 			a.align = opt.align_byte_length;
 			a.next_size = next->size.as<uint32_t>();
 			a.next_padded = sym->padded.as<uint32_t>();
@@ -850,6 +889,7 @@ void finalize_and_normalize(qb_iter *it, const rule_ops *ops, const void *rule, 
 			a.child_begin = it->child_begin.as<uint64_t>();
 			a.kept = R.kept;
 			a.n_parents = R.n_parents;
+			a.uniform_fanout = R.uniform_fanout;
 			a.align = opt.align_byte_length;
 			a.next_size = next->size.as<uint32_t>();
 			a.next_padded = sym->padded.as<uint32_t>();
@@ -1151,6 +1191,7 @@ int qb_ctx_destroy(qb_ctx *ctx) {
 		ctx->scan_ws.release();
 		ctx->partials.release();
 		ctx->select.release();
+		ctx->select_cand.release();
 		cudaStreamDestroy(ctx->stream);
 		delete ctx;
 	});
@@ -1547,6 +1588,52 @@ int qb_apply_modifier(qb_iter *it, int modifier_id, const double *params, uint32
 		++ctx->launches;
 		QB_CUDA(cudaGetLastError());
 		ctx->sync();
+	});
+}
+
+int qb_observable_id(const char *name) {
+	if (name)
+		for (size_t i = 0; i < observable_registry().size(); ++i)
+			if (!strcmp(observable_registry()[i].name, name))
+				return (int)i + 1;
+	g_last_error = std::string("unknown observable: ") + (name ? name : "(null)");
+	return QB_ERR_UNKNOWN_RULE;
+}
+
+int qb_observable_values(int observable_id) {
+	const observable_ops *ops = find_observable(observable_id);
+	return ops ? ops->values : QB_ERR_UNKNOWN_RULE;
+}
+
+// iteration::average_value (quids.hpp:208-234) for a registered device observable: sum of observable(object) * |mag|^2
+int qb_iter_average_value(const qb_iter *cit, int observable_id, const double *params, uint32_t num_params, double *values, uint32_t capacity) {
+	return guarded([&] {
+		qb_iter *it = const_cast<qb_iter *>(cit);
+		QB_REQUIRE(it && values, QB_ERR_ARG, "qb_iter_average_value: null argument");
+		const observable_ops *ops = find_observable(observable_id);
+		QB_REQUIRE(ops, QB_ERR_UNKNOWN_RULE, "unknown observable id");
+		QB_REQUIRE(capacity >= (uint32_t)ops->values, QB_ERR_ARG, std::string("observable ") + ops->name + " produces " + std::to_string(ops->values) + " values");
+		alignas(16) unsigned char storage[RULE_STORAGE_BYTES];
+		int rc = ops->make(params, num_params, storage);
+		QB_REQUIRE(rc == QB_OK, rc, std::string("bad parameters for observable ") + ops->name);
+		for (int k = 0; k < ops->values; ++k)
+			values[k] = 0;
+		if (it->n == 0)
+			return;
+		qb_ctx *ctx = it->ctx;
+		ctx->use();
+		it->settle();
+		ctx->partials.ensure(sizeof(double) * (size_t)ctx->grid_cap() * OBSERVABLE_MAX_VALUES, ctx->stream);
+		const int grid = ops->launch(storage, it->view(), ctx->partials.as<double>(), ctx->stream, ctx->sm_count);
+		++ctx->launches;
+		QB_REQUIRE(grid <= ctx->grid_cap(), QB_ERR_CUDA, "observable grid larger than the partial buffer");
+		for (int k = 0; k < ops->values; ++k) { // fixed-order second stage, one value after the other
+			norm_total_kernel<<<1, SCAN_THREADS, 0, ctx->stream>>>(ctx->partials.as<double>() + (size_t)k * grid, grid, reinterpret_cast<double *>(ctx->small(DS_TOTAL)));
+			++ctx->launches;
+			ctx->fetch_small();
+			memcpy(&values[k], &ctx->h_small[DS_TOTAL], sizeof(double));
+		}
+		QB_CUDA(cudaGetLastError());
 	});
 }
 

@@ -27,6 +27,7 @@ struct engine_launch {
 	uint32_t *num_childs;
 	uint32_t *num_groups; // only for rules with warp_groups
 	unsigned int *max_child_size;
+	unsigned int *child_count_range; // [0] = largest child count, [1] = ~smallest
 
 	// symbolic
 	const uint64_t *child_begin; // exclusive scan of num_childs over the kept parents, n_parents + 1 entries
@@ -69,12 +70,12 @@ inline int resident_grid(const void *kernel, int threads, int sm_count) {
 
 template <class Rule>
 __global__ void __launch_bounds__(ENGINE_THREADS) num_child_kernel(const Rule rule, iter_view it, uint32_t *num_childs, uint32_t *num_groups,
-                                                                 unsigned int *max_child_size) {
-	__shared__ unsigned int s_max;
+                                                                 unsigned int *max_child_size, unsigned int *child_count_range) {
+	__shared__ unsigned int s_max, s_count_max, s_count_min_inv;
 	if (threadIdx.x == 0)
-		s_max = 0;
+		s_max = s_count_max = s_count_min_inv = 0;
 	__syncthreads();
-	unsigned int local_max = 0;
+	unsigned int local_max = 0, count_max = 0, count_min_inv = 0;
 	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
 	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < it.n; i += stride) {
 		uint32_t count, bound;
@@ -85,11 +86,21 @@ __global__ void __launch_bounds__(ENGINE_THREADS) num_child_kernel(const Rule ru
 		if (Rule::warp_groups)
 			num_groups[i] = rule.get_num_group(parent, size, count);
 		local_max = max(local_max, bound);
+		count_max = max(count_max, count);
+		count_min_inv = max(count_min_inv, ~count);
 	}
 	atomicMax(&s_max, local_max);
+	atomicMax(&s_count_max, count_max);
+	atomicMax(&s_count_min_inv, count_min_inv);
 	__syncthreads();
-	if (threadIdx.x == 0 && s_max)
-		atomicMax(max_child_size, s_max);
+	if (threadIdx.x == 0) {
+		if (s_max)
+			atomicMax(max_child_size, s_max);
+		// largest and (inverted) smallest child count: equal = every parent has the same fan-out, and the parent of child c
+		// is c / fan-out, no search (finalize_meta_kernel)
+		atomicMax(child_count_range, s_count_max);
+		atomicMax(child_count_range + 1, s_count_min_inv);
+	}
 }
 
 // children -> interference table, straight from registers
@@ -129,8 +140,10 @@ template <class Rule>
 __global__ void __launch_bounds__(SYMBOLIC_THREADS, 5) symbolic_kernel(const Rule rule, const engine_launch L) {
 	typedef typename Rule::ctx_t ctx_t;
 	constexpr int CHUNK = Rule::warp_groups ? 32 : SYMBOLIC_CHUNK;
+	constexpr int BATCH = Rule::parents_per_batch; // parents whose contexts one warp holds at a time
+	static_assert(BATCH >= 1 && BATCH <= 32, "one lane per staged parent");
 	struct warp_slice {
-		ctx_t ctx[32];
+		ctx_t ctx[BATCH];
 		uint64_t group_begin[33];
 		uint64_t child_begin[32];
 		uint64_t object[32]; // byte offset of the parent
@@ -163,8 +176,8 @@ __global__ void __launch_bounds__(SYMBOLIC_THREADS, 5) symbolic_kernel(const Rul
 		if (p_hi > p_lo && L.group_begin[p_hi] == c1)
 			--p_hi;
 
-		for (uint64_t g0 = p_lo; g0 <= p_hi; g0 += 32) {
-			const uint32_t count = (uint32_t)min((uint64_t)32, p_hi + 1 - g0);
+		for (uint64_t g0 = p_lo; g0 <= p_hi; g0 += BATCH) {
+			const uint32_t count = (uint32_t)min((uint64_t)BATCH, p_hi + 1 - g0);
 			if (lane < count) {
 				const uint64_t p = g0 + lane;
 				const uint64_t oid = L.kept ? L.kept[p] : p;
@@ -182,6 +195,12 @@ __global__ void __launch_bounds__(SYMBOLIC_THREADS, 5) symbolic_kernel(const Rul
 			if (lane == 0)
 				s.group_begin[count] = L.group_begin[g0 + count];
 			__syncwarp();
+			if constexpr (Rule::warp_prepare) { // contexts built by the whole warp, one parent after the other
+				for (uint32_t j = 0; j < count; ++j)
+					if (s.group_begin[j + 1] > s.group_begin[j])
+						rule.prepare_warp(L.it.objects + s.object[j], s.size[j], s.ctx[j]);
+				__syncwarp();
+			}
 
 			const uint64_t lo = max(c0, s.group_begin[0]), hi = min(c1, s.group_begin[count]);
 			if constexpr (Rule::warp_groups) {
@@ -202,7 +221,9 @@ __global__ void __launch_bounds__(SYMBOLIC_THREADS, 5) symbolic_kernel(const Rul
 					created += emit.created;
 				}
 			} else {
-				for (uint64_t c = lo + lane; c < hi; c += 32) { // one child per lane: the loop body of quids.hpp:705-719
+				// one child per lane: the loop body of quids.hpp:705-719.  (Collecting a lane's 4 children and inserting them as one
+				// batch was measured 2.7x SLOWER on split_merge: the child walks then no longer overlap the inserts' round trips.)
+				for (uint64_t c = lo + lane; c < hi; c += 32) {
 					const uint32_t j = (uint32_t)upper_bound_u64(s.group_begin, count + 1, c) - 1;
 					table_emitter emit(L.table, s.child_begin[j]);
 					cplx mag = s.mag[j];
@@ -490,6 +511,140 @@ __global__ void __launch_bounds__(ENGINE_THREADS) populate_kernel(const Rule rul
 	}
 }
 
+// ---- finalisation of rules WITHOUT edit_child (children of any size, e.g. split_merge): staged ------------------------
+// One lane per child running populate_child_simple straight on global memory costs one L1 wavefront per lane for
+// every 1/2/4-byte access of the walk (32 different parents, 32 different children per warp instruction).  Here a
+// warp takes 32 consecutive survivors and, for as many of them as fit its two stages,
+//   1. fetches their parents into shared memory, one bulk copy (cp.async.bulk, mbarrier) per parent;
+//   2. builds the children in shared memory, one lane per child, padding zeroed (same 16-byte phase as their place in
+//      the next state, so the rule's alignment assumptions hold);
+//   3. writes the children -- consecutive in the next state, hence ONE contiguous byte range -- with a single bulk
+//      store (cp.async.bulk shared -> global; the < 16-byte head and tail by the lanes).
+// A child or parent too large for a stage is built in place by one lane.
+constexpr uint32_t POPULATE_PARENT_STAGE = 8704;  // 32 parents of 256 bytes (widened to 16-byte bounds) at a stride of 272
+constexpr uint32_t POPULATE_CHILD_STAGE = 9728;
+struct __align__(16) populate_stage {
+	uint8_t parents[POPULATE_PARENT_STAGE];
+	uint8_t children[POPULATE_CHILD_STAGE];
+	unsigned long long mbar;
+	unsigned long long pad_;
+};
+
+__device__ __forceinline__ uint32_t warp_inclusive_sum(uint32_t v) {
+	const unsigned lane = lane_id();
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const uint32_t up = __shfl_up_sync(0xffffffffu, v, o);
+		if (lane >= (unsigned)o)
+			v += up;
+	}
+	return v;
+}
+
+template <class Rule>
+__global__ void __launch_bounds__(STAGED_THREADS) populate_staged_kernel(const Rule rule, const engine_launch L) {
+	extern __shared__ __align__(16) uint8_t s_populate[];
+	populate_stage &st = reinterpret_cast<populate_stage *>(s_populate)[threadIdx.x >> 5];
+	const unsigned lane = lane_id();
+	const uint32_t bar = smem_addr(&st.mbar);
+	if (lane == 0) {
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncwarp();
+	uint32_t phase = 0;
+	const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+	const uint64_t batches = div_up<uint64_t>(L.n_survivors, 32);
+	for (uint64_t batch = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; batch < batches; batch += warps) {
+		const uint64_t mine = batch * 32 + lane;
+		const bool valid = mine < L.n_survivors;
+		const uint8_t *parent = L.it.objects;
+		uint64_t dst = 0;
+		uint32_t psize = 0, csize = 0, cbytes = 0, child_id = 0, lead = 0, pbytes = 0, pslot = 0;
+		if (valid) {
+			const uint64_t oid = L.survivor_parent[mine];
+			parent = L.it.objects + L.it.begin[oid];
+			psize = L.it.size[oid];
+			dst = L.next_begin[mine];
+			cbytes = (uint32_t)(L.next_begin[mine + 1] - dst);
+			csize = L.next_size[mine];
+			child_id = L.survivor_child[mine];
+			lead = (uint32_t)(reinterpret_cast<uintptr_t>(parent) & 15);
+			pbytes = (lead + psize + 15u) & ~15u;
+			// the lanes walk their parents in step: equal strides that are a multiple of 128 bytes (fresh 12-node graphs:
+			// 256) would put every lane on the same bank (ncu: 7e8 conflicts); an odd multiple of 16 spreads them over 8
+			pslot = (pbytes & 16u) ? pbytes : pbytes + 16;
+		}
+		const uint32_t count = __popc(__ballot_sync(0xffffffffu, valid));
+		const uint32_t p_incl = warp_inclusive_sum(pslot), c_incl = warp_inclusive_sum(cbytes);
+		uint32_t start = 0;
+		while (start < count) {
+			const uint32_t p0 = __shfl_sync(0xffffffffu, p_incl - pslot, start), c0 = __shfl_sync(0xffffffffu, c_incl - cbytes, start);
+			const uint64_t dst0 = __shfl_sync(0xffffffffu, dst, start);
+			uint8_t *out = L.next_objects + dst0;
+			const uint32_t clead = (uint32_t)(reinterpret_cast<uintptr_t>(out) & 15);
+			const bool fits = lane >= start && lane < count && p_incl - p0 <= POPULATE_PARENT_STAGE && clead + (c_incl - c0) <= POPULATE_CHILD_STAGE;
+			const uint32_t m = __popc(__ballot_sync(0xffffffffu, fits)); // both sums grow with the lane: the lanes that fit are start .. start + m - 1
+			if (m == 0) { // too large for the stages: built in place
+				if (lane == start) {
+					uint8_t *child = L.next_objects + dst;
+					rule.populate_child_simple(parent, psize, child, child_id);
+					for (uint32_t b = csize; b < cbytes; ++b)
+						child[b] = 0;
+				}
+				__syncwarp();
+				++start;
+				continue;
+			}
+			const uint32_t end = start + m;
+			const bool in = lane >= start && lane < end;
+			// 1. parents -> shared memory
+			const uint32_t total = (uint32_t)warp_sum((uint64_t)(in ? pbytes : 0u));
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the lanes' earlier reads of the stage come first
+			__syncwarp();
+			if (lane == start)
+				asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
+			__syncwarp();
+			uint8_t *staged = st.parents + (p_incl - pslot - p0);
+			if (in)
+				asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(staged)), "l"(parent - lead),
+				             "r"(pbytes), "r"(bar)
+				             : "memory");
+			uint32_t done = 0;
+			while (!done)
+				asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+			phase ^= 1;
+			// 2. children built in shared memory
+			if (in) {
+				uint8_t *child = st.children + clead + (c_incl - cbytes - c0);
+				rule.populate_child_simple(staged + lead, psize, child, child_id);
+				for (uint32_t b = csize; b < cbytes; ++b)
+					child[b] = 0;
+			}
+			// 3. one contiguous range of the next state
+			const uint32_t len = __shfl_sync(0xffffffffu, c_incl, end - 1) - c0;
+			const uint8_t *from = st.children + clead;
+			const uint32_t head = min(len, (16u - clead) & 15u), body = (len - head) & ~15u, tail = len - head - body;
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the children become visible to the copy engine
+			__syncwarp();
+			if (lane == 0 && body) {
+				asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + head), "r"(smem_addr(from + head)), "r"(body) : "memory");
+				asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+			}
+			if (lane < head)
+				out[lane] = from[lane];
+			if (lane < tail)
+				out[head + body + lane] = from[head + body + lane];
+			if (lane == 0 && body)
+				asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // the stage may be overwritten
+			__syncwarp();
+			start = end;
+		}
+	}
+	if (lane == 0)
+		asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 template <class Rule>
 __global__ void __launch_bounds__(ENGINE_THREADS) hash_kernel(const Rule rule, iter_view it, uint64_t *hashes) {
 	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -509,6 +664,40 @@ __global__ void __launch_bounds__(ENGINE_THREADS) modifier_kernel(const Modifier
 	}
 }
 
+// sum over the objects of observable(object) * |mag|^2 (quids.hpp:208-234), K values per object in one pass over the
+// state; per-CTA partial sums (fixed order inside a CTA), summed in CTA order by observable_total_kernel
+template <class Observable>
+__global__ void __launch_bounds__(ENGINE_THREADS) observable_kernel(const Observable observable, iter_view it, double *partial) {
+	constexpr int K = Observable::values;
+	__shared__ double s_part[ENGINE_THREADS / 32][K];
+	double local[K];
+#pragma unroll
+	for (int k = 0; k < K; ++k)
+		local[k] = 0;
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < it.n; i += stride) {
+		double value[K];
+		observable(it.objects + it.begin[i], it.size[i], value);
+		const double weight = cnorm(it.mag[i]);
+#pragma unroll
+		for (int k = 0; k < K; ++k)
+			local[k] += value[k] * weight;
+	}
+#pragma unroll
+	for (int k = 0; k < K; ++k) {
+		local[k] = warp_sum(local[k]);
+		if (lane_id() == 0)
+			s_part[threadIdx.x >> 5][k] = local[k];
+	}
+	__syncthreads();
+	if (threadIdx.x < K) {
+		double sum = 0;
+		for (int w = 0; w < ENGINE_THREADS / 32; ++w)
+			sum += s_part[w][threadIdx.x];
+		partial[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = sum;
+	}
+}
+
 // ---- glue -------------------------------------------------------------------------------------------
 inline int grid_for(uint64_t n, int threads, int cap) {
 	uint64_t g = div_up<uint64_t>(n, threads);
@@ -523,7 +712,7 @@ struct rule_glue {
 
 	static void num_child(const void *rule, const engine_launch &L) {
 		int grid = grid_for(L.it.n, ENGINE_THREADS, resident_grid((const void *)num_child_kernel<Rule>, ENGINE_THREADS, L.sm_count));
-		num_child_kernel<Rule><<<grid, ENGINE_THREADS, 0, L.stream>>>(*static_cast<const Rule *>(rule), L.it, L.num_childs, L.num_groups, L.max_child_size);
+		num_child_kernel<Rule><<<grid, ENGINE_THREADS, 0, L.stream>>>(*static_cast<const Rule *>(rule), L.it, L.num_childs, L.num_groups, L.max_child_size, L.child_count_range);
 		++*L.launch_counter;
 	}
 	static uint64_t symbolic_chunks(uint64_t n_groups) { return div_up<uint64_t>(n_groups, Rule::warp_groups ? 32 : SYMBOLIC_CHUNK); }
@@ -554,8 +743,21 @@ struct rule_glue {
 		}
 	}
 	static void populate(const void *rule, const engine_launch &L) {
-		int grid = grid_for(L.n_survivors, ENGINE_THREADS, resident_grid((const void *)populate_kernel<Rule>, ENGINE_THREADS, L.sm_count));
-		populate_kernel<Rule><<<grid, ENGINE_THREADS, 0, L.stream>>>(*static_cast<const Rule *>(rule), L);
+		if constexpr (Rule::has_edit_child) {
+			int grid = grid_for(L.n_survivors, ENGINE_THREADS, resident_grid((const void *)populate_kernel<Rule>, ENGINE_THREADS, L.sm_count));
+			populate_kernel<Rule><<<grid, ENGINE_THREADS, 0, L.stream>>>(*static_cast<const Rule *>(rule), L);
+		} else {
+			constexpr size_t smem = sizeof(populate_stage) * (STAGED_THREADS / 32);
+			static int per_sm = 0; // CTAs of this kernel one SM holds (shared-memory bound)
+			if (per_sm == 0) {
+				QB_CUDA(cudaFuncSetAttribute((const void *)populate_staged_kernel<Rule>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+				QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)populate_staged_kernel<Rule>, STAGED_THREADS, smem));
+				if (per_sm < 1)
+					per_sm = 1;
+			}
+			int grid = grid_for(L.n_survivors, STAGED_THREADS, per_sm * L.sm_count);
+			populate_staged_kernel<Rule><<<grid, STAGED_THREADS, smem, L.stream>>>(*static_cast<const Rule *>(rule), L);
+		}
 		++*L.launch_counter;
 	}
 	static void hash(const void *rule, const engine_launch &L) {
@@ -594,6 +796,20 @@ struct modifier_glue {
 	}
 };
 
+template <class Observable>
+struct observable_glue {
+	static_assert(sizeof(Observable) <= RULE_STORAGE_BYTES, "device observables are passed by value");
+	static_assert(Observable::values >= 1 && Observable::values <= OBSERVABLE_MAX_VALUES, "values per object");
+	static int launch(const void *observable, const iter_view &it, double *partial, cudaStream_t stream, int sm_count) {
+		int grid = grid_for(it.n, ENGINE_THREADS, resident_grid((const void *)observable_kernel<Observable>, ENGINE_THREADS, sm_count));
+		observable_kernel<Observable><<<grid, ENGINE_THREADS, 0, stream>>>(*static_cast<const Observable *>(observable), it, partial);
+		return grid;
+	}
+};
+
+#define QB_REGISTER_OBSERVABLE(NAME, TYPE, MAKE) \
+	static const int qb_observable_registered_##NAME = \
+	    ::qb::register_observable(::qb::observable_ops{#NAME, TYPE::values, MAKE, ::qb::observable_glue<TYPE>::launch})
 #define QB_REGISTER_RULE(NAME, TYPE, MAKE) static const int qb_rule_registered_##NAME = ::qb::register_rule(::qb::rule_glue<TYPE>::ops(#NAME, MAKE))
 #define QB_REGISTER_MODIFIER(NAME, TYPE, MAKE) \
 	static const int qb_modifier_registered_##NAME = ::qb::register_modifier(::qb::modifier_ops{#NAME, MAKE, ::qb::modifier_glue<TYPE>::launch})

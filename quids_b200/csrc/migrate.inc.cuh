@@ -156,6 +156,7 @@ uint64_t count_children(qb_iter *it, const rule_ops *ops, const void *rule) {
 		L.num_groups = it->num_groups.as<uint32_t>();
 	}
 	L.max_child_size = reinterpret_cast<unsigned int *>(ctx->small(DS_MAX_CHILD_SIZE));
+	L.child_count_range = reinterpret_cast<unsigned int *>(ctx->small(DS_CHILD_RANGE));
 	ops->launch_num_child(rule, L);
 	it->child_begin.ensure(sizeof(uint64_t) * (it->n + 1), stream);
 	exclusive_scan(ctx, counts_through{it->num_childs.as<uint32_t>(), nullptr}, it->child_begin.as<uint64_t>(), it->n);

@@ -9,7 +9,7 @@
 
 namespace qb {
 
-constexpr int COMPACT_ITEMS = 4;
+constexpr int COMPACT_ITEMS = 8; // warp-striped (scan.cuh): 2048 elements per tile
 constexpr int COMPACT_TILE = SCAN_THREADS * COMPACT_ITEMS;
 
 __device__ __forceinline__ uint64_t key_of_norm(double norm) { return (uint64_t)__double_as_longlong(norm); }
@@ -25,67 +25,105 @@ __global__ void __launch_bounds__(SCAN_THREADS) table_compact_kernel(table_view 
 	const uint64_t base = (uint64_t)tile * COMPACT_TILE;
 	bool keep[COMPACT_ITEMS];
 	uint64_t key[COMPACT_ITEMS];
+	ulonglong2 lo[COMPACT_ITEMS], hi[COMPACT_ITEMS];
 #pragma unroll
-	for (int j = 0; j < COMPACT_ITEMS; ++j) {
-		const uint64_t i = base + (uint64_t)j * SCAN_THREADS + threadIdx.x;
-		keep[j] = false;
-		key[j] = 0;
+	for (int j = 0; j < COMPACT_ITEMS; ++j) { // all loads first: two 16-byte halves of every slot
+		const uint64_t i = warp_striped_index<COMPACT_ITEMS>(base, j);
+		lo[j] = hi[j] = make_ulonglong2(0, 0);
 		if (i < n) {
-			const ulonglong2 lo = reinterpret_cast<const ulonglong2 *>(t.slots + i)[0]; // key, re
-			const ulonglong2 hi = reinterpret_cast<const ulonglong2 *>(t.slots + i)[1]; // im, rep
-			// a slot is occupied once it has a representative (set by whoever created it; never 0): true for hashed slots,
-			// for the dedicated slot of the hash 0, and for region slots (whose object may hash to 0)
-			const bool occupied = hi.y != 0;
-			const double norm = cnorm(cplx{__longlong_as_double((long long)lo.y), __longlong_as_double((long long)hi.x)});
-			keep[j] = occupied && norm > tolerance;
-			key[j] = key_of_norm(norm);
+			lo[j] = __ldcs(reinterpret_cast<const ulonglong2 *>(t.slots + i));     // key, re
+			hi[j] = __ldcs(reinterpret_cast<const ulonglong2 *>(t.slots + i) + 1); // im, rep
 		}
 	}
-	uint32_t rank[COMPACT_ITEMS], total;
-	block_rank_striped<COMPACT_ITEMS>(keep, rank, total);
+#pragma unroll
+	for (int j = 0; j < COMPACT_ITEMS; ++j) {
+		// a slot is occupied once it has a representative (set by whoever created it; never 0): true for hashed slots,
+		// for the dedicated slot of the hash 0, and for region slots (whose object may hash to 0)
+		const bool occupied = hi[j].y != 0;
+		const double norm = cnorm(cplx{__longlong_as_double((long long)lo[j].y), __longlong_as_double((long long)hi[j].x)});
+		keep[j] = occupied && norm > tolerance;
+		key[j] = key_of_norm(norm);
+	}
+	uint32_t rank[COMPACT_ITEMS], unused_rank[COMPACT_ITEMS], total, unused_total;
+	block_rank_warp_striped<COMPACT_ITEMS, false>(keep, keep, rank, unused_rank, total, unused_total);
 	const uint64_t before = scan_lookback(st, tile, total);
 #pragma unroll
 	for (int j = 0; j < COMPACT_ITEMS; ++j)
 		if (keep[j]) {
 			const uint64_t dst = before + rank[j];
 			ukey[dst] = key[j];
-			uslot[dst] = (uint32_t)(base + (uint64_t)j * SCAN_THREADS + threadIdx.x);
+			uslot[dst] = (uint32_t)warp_striped_index<COMPACT_ITEMS>(base, j);
 		}
 	if (base + COMPACT_TILE >= n && threadIdx.x == 0)
 		*count = before + total;
 }
 
 // ---- keep the elements selected by a finished radix select --------------------------------------------
-// pass 0: key >  threshold                      -> out[rank]
-// pass 1: key == threshold, first `k` of them   -> out[count_gt + rank]
-template <class KeyFn, class OutFn>
-__global__ void __launch_bounds__(SCAN_THREADS) select_compact_kernel(KeyFn key_of, uint64_t n, const select_state *sel, int pass, OutFn out, scan_state st) {
+//   key >  threshold                      -> out[rank among those]
+//   key == threshold, first `k` of them   -> out[count_gt + rank among those]
+// The look-back of a single-pass compaction advances ~32 tiles per L2 round trip (about 8e7 tiles/s measured on B200), so
+// a tile must carry >= 100 KB of input to stream at HBM speed: a CTA owns 16384 keys.  Pass A reads the keys ONCE, keeps
+// two bits per key in registers and counts; one look-back per CTA; pass B ranks the kept keys row by row from the
+// saved bits (no memory traffic but the output; a first version that ranked sub-tile by sub-tile with block-wide
+// scans needed 128 registers and 2 instructions per key: 9 ms for 1.3e9 keys, ncu profiles/select_compact_r1i).
+// MODE 2: both kinds in one launch; the look-back carries the two running counts packed in one word (31 bits each),
+// so this mode is for n < 2^31.  MODE 0 / 1: one kind per launch (any n).
+constexpr int SELECT_ROWS = 64; // rows of 32 keys one warp owns (one bit per row and lane in a 64-bit register)
+constexpr uint64_t SELECT_TILE = (uint64_t)SCAN_WARPS * 32 * SELECT_ROWS;
+
+// Warp w of the CTA owns the SELECT_ROWS * 32 consecutive keys starting at tile_base + w * 32 * SELECT_ROWS, row r of lane
+// l = that + r * 32 + l.  Element order = (warp, row, lane), so a kept key's rank is: CTA prefix (look-back) + warp prefix
+// (one block scan) + kept keys of earlier rows (running count of ballots) + earlier lanes of its row.
+template <int MODE, class KeyFn, class OutFn>
+__global__ void __launch_bounds__(SCAN_THREADS, 4) select_compact_kernel(KeyFn key_of, uint64_t n, const select_state *sel, OutFn out, scan_state st) {
 	const unsigned int tile = scan_take_ticket(st);
 	const uint64_t threshold = sel->prefix, need = sel->k, count_gt = sel->count_gt;
-	const uint64_t base = (uint64_t)tile * COMPACT_TILE;
-	bool keep[COMPACT_ITEMS];
+	const unsigned lane = lane_id();
+	const uint64_t first = (uint64_t)tile * SELECT_TILE + (uint64_t)(threadIdx.x >> 5) * (32 * SELECT_ROWS) + lane;
+	uint64_t gt_bits = 0, eq_bits = 0;
+	constexpr int IN_FLIGHT = 8;
+#pragma unroll 1
+	for (int r0 = 0; r0 < SELECT_ROWS; r0 += IN_FLIGHT) {
+		uint64_t key[IN_FLIGHT];
 #pragma unroll
-	for (int j = 0; j < COMPACT_ITEMS; ++j) {
-		const uint64_t i = base + (uint64_t)j * SCAN_THREADS + threadIdx.x;
-		keep[j] = false;
-		if (i < n) {
-			const uint64_t key = key_of(i);
-			keep[j] = pass == 0 ? key > threshold : key == threshold;
+		for (int j = 0; j < IN_FLIGHT; ++j) {
+			const uint64_t i = first + (uint64_t)(r0 + j) * 32;
+			key[j] = i < n ? key_of(i) : 0;
+		}
+#pragma unroll
+		for (int j = 0; j < IN_FLIGHT; ++j) {
+			const uint64_t i = first + (uint64_t)(r0 + j) * 32;
+			const bool gt = i < n && MODE != 1 && key[j] > threshold;
+			const bool eq = i < n && MODE != 0 && key[j] == threshold;
+			gt_bits |= (uint64_t)gt << (r0 + j);
+			eq_bits |= (uint64_t)eq << (r0 + j);
 		}
 	}
-	uint32_t rank[COMPACT_ITEMS], total;
-	block_rank_striped<COMPACT_ITEMS>(keep, rank, total);
-	const uint64_t before = scan_lookback(st, tile, total);
-#pragma unroll
-	for (int j = 0; j < COMPACT_ITEMS; ++j)
-		if (keep[j]) {
-			const uint64_t r = before + rank[j];
-			const uint64_t i = base + (uint64_t)j * SCAN_THREADS + threadIdx.x;
-			if (pass == 0)
-				out(r, i);
-			else if (r < need)
-				out(count_gt + r, i);
+	// CTA totals -> one look-back; the exclusive prefix of a warp's first thread is the warp's prefix
+	uint64_t cta_total;
+	const uint64_t mine = ((uint64_t)__popcll(eq_bits) << 32) | (uint64_t)__popcll(gt_bits);
+	const uint64_t warp_prefix = __shfl_sync(0xffffffffu, block_exclusive_sum(mine, cta_total), 0);
+	const uint32_t total_gt = (uint32_t)cta_total, total_eq = (uint32_t)(cta_total >> 32);
+	const uint64_t aggregate = MODE == 2 ? ((uint64_t)total_eq << 31) | total_gt : MODE == 0 ? total_gt : total_eq;
+	const uint64_t before = scan_lookback(st, tile, aggregate);
+	uint64_t run_gt = (MODE == 2 ? before & 0x7fffffffull : before) + (uint32_t)warp_prefix;
+	uint64_t run_eq = (MODE == 2 ? before >> 31 : before) + (warp_prefix >> 32);
+	// rows with nothing kept cost two votes
+	unsigned rows_left = __ballot_sync(0xffffffffu, (gt_bits | eq_bits) != 0) ? SELECT_ROWS : 0;
+	for (int r = 0; r < (int)rows_left; ++r) {
+		const bool gt = (gt_bits >> r) & 1, eq = (eq_bits >> r) & 1;
+		const unsigned vg = __ballot_sync(0xffffffffu, gt), ve = __ballot_sync(0xffffffffu, eq);
+		if (vg | ve) {
+			const unsigned lt = (1u << lane) - 1;
+			const uint64_t i = first + (uint64_t)r * 32;
+			if (gt)
+				out(run_gt + __popc(vg & lt), i);
+			if (eq && run_eq + __popc(ve & lt) < need)
+				out(count_gt + run_eq + __popc(ve & lt), i);
+			run_gt += __popc(vg);
+			run_eq += __popc(ve);
 		}
+	}
 }
 
 // ---- finalisation metadata (quids.hpp:933-942) ---------------------------------------------------------
@@ -98,6 +136,7 @@ struct finalize_args {
 	const uint64_t *child_begin;
 	const uint64_t *kept;
 	uint64_t n_parents;
+	uint32_t uniform_fanout; // != 0: every kept parent has this many children (parent of child c = c / fan-out)
 	uint32_t align;
 	uint32_t *next_size;
 	uint32_t *next_padded;
@@ -125,7 +164,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) finalize_meta_kernel(finalize_ar
 		const cplx mag{__longlong_as_double((long long)lo.y), __longlong_as_double((long long)hi.x)};
 		const uint64_t index = rep_index(hi.y);
 		const uint32_t size = rep_size(hi.y);
-		const uint64_t p = upper_bound_u64(a.child_begin, a.n_parents + 1, index) - 1;
+		const uint64_t p = a.uniform_fanout ? index / a.uniform_fanout : upper_bound_u64(a.child_begin, a.n_parents + 1, index) - 1;
 		a.survivor_parent[s] = a.kept ? a.kept[p] : p;
 		a.survivor_child[s] = (uint32_t)(index - a.child_begin[p]);
 		a.next_size[s] = size;
@@ -157,6 +196,7 @@ struct finalize_record_args {
 	const uint64_t *child_begin;
 	const uint64_t *kept;
 	uint64_t n_parents;
+	uint32_t uniform_fanout; // != 0: every kept parent has this many children (parent of child c = c / fan-out)
 	uint32_t align;
 	uint32_t *next_size;
 	uint32_t *next_padded;
@@ -175,7 +215,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) finalize_meta_records_kernel(fin
 		const cplx mag{r.re, r.im};
 		const uint64_t index = rep_index(r.rep);
 		const uint32_t size = rep_size(r.rep);
-		const uint64_t p = upper_bound_u64(a.child_begin, a.n_parents + 1, index) - 1;
+		const uint64_t p = a.uniform_fanout ? index / a.uniform_fanout : upper_bound_u64(a.child_begin, a.n_parents + 1, index) - 1;
 		a.survivor_parent[s] = a.kept ? a.kept[p] : p;
 		a.survivor_child[s] = (uint32_t)(index - a.child_begin[p]);
 		a.next_size[s] = size;

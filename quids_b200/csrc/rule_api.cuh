@@ -75,6 +75,10 @@ struct rule_base {
 	__device__ const Derived &self() const { return *static_cast<const Derived *>(this); }
 
 	__device__ void prepare(const uint8_t *, uint32_t, no_ctx &) const {}
+	// optional: the context of a parent is built by a whole warp -- prepare_warp(parent, parent_size, ctx&) is called by all
+	// 32 lanes with the same arguments after prepare() -- and, for large contexts, fewer parents are staged at a time
+	static constexpr bool warp_prepare = false;
+	static constexpr int parents_per_batch = 32;
 
 	__device__ uint64_t hasher(const uint8_t *object, uint32_t size) const { return murmur_bytes(object, size); }
 
@@ -191,10 +195,24 @@ struct modifier_ops {
 	void (*launch)(const void *modifier, const iter_view &it, cudaStream_t stream, int sm_count);
 };
 
+// ---- observables: f(begin, end) -> value, averaged with weights |mag|^2 (iteration::average_value, quids.hpp:208-234)
+// as a device functor producing `values` numbers per object in one pass:
+//     static constexpr int values;   __device__ void operator()(const uint8_t *object, uint32_t size, double *out) const
+constexpr int OBSERVABLE_MAX_VALUES = 4;
+struct observable_ops {
+	const char *name;
+	int values;
+	int (*make)(const double *params, uint32_t num_params, void *storage);
+	// partial[k * grid + block] = this CTA's share of value k; returns the grid used
+	int (*launch)(const void *observable, const iter_view &it, double *partial, cudaStream_t stream, int sm_count);
+};
+
 constexpr size_t RULE_STORAGE_BYTES = 256;
 
 int register_rule(const rule_ops &ops);
 int register_modifier(const modifier_ops &ops);
+int register_observable(const observable_ops &ops);
+const observable_ops *find_observable(int id);
 const rule_ops *find_rule(int id);
 const modifier_ops *find_modifier(int id);
 

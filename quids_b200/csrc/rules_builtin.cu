@@ -68,4 +68,10 @@ QB_REGISTER_MODIFIER(step, qcgd::step_modifier<false>, make_empty<qcgd::step_mod
 QB_REGISTER_MODIFIER(reversed_step, qcgd::step_modifier<true>, make_empty<qcgd::step_modifier<true>>);
 QB_REGISTER_MODIFIER(phase, qc::phase, make_phase);
 
+// ---- observables ----------------------------------------------------------------------------------------------------------
+QB_REGISTER_OBSERVABLE(qcgd_stats, qcgd::stats_observable, make_empty<qcgd::stats_observable>);
+QB_REGISTER_OBSERVABLE(qcgd_size, qcgd::size_observable, make_empty<qcgd::size_observable>);
+QB_REGISTER_OBSERVABLE(qubit, qc::bit_observable, make_bit<qc::bit_observable>);
+QB_REGISTER_OBSERVABLE(object_bytes, qc::bytes_observable, make_empty<qc::bytes_observable>);
+
 } // namespace qb

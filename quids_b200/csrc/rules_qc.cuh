@@ -43,6 +43,21 @@ struct hadamard_fused : hadamard {
 		size = parent_size;
 		const uint8_t flip = (uint8_t)!child_id;
 		const uint32_t b = (uint32_t)bit;
+		if ((reinterpret_cast<uintptr_t>(parent) & 7) == 0 && (parent_size & 7) == 0) {
+			// a register of 8 k qubits on an 8-byte boundary: the murmur words are the object's own 64-bit words (little
+			// endian), and the flipped qubit is one XOR into the word that holds it -- 3 loads for 24 qubits instead of 24
+			const uint64_t *words = reinterpret_cast<const uint64_t *>(parent);
+			const uint32_t flip_word = b >> 3;
+			const uint64_t flip_bits = (uint64_t)flip << (8 * (b & 7));
+			uint64_t h = 0xc70f6907ull ^ ((uint64_t)parent_size * MURMUR_MUL);
+			for (uint32_t k = 0; k < parent_size / 8; ++k) {
+				const uint64_t w = words[k] ^ (k == flip_word ? flip_bits : 0);
+				h ^= shift_mix(w * MURMUR_MUL) * MURMUR_MUL;
+				h *= MURMUR_MUL;
+			}
+			h = shift_mix(h) * MURMUR_MUL;
+			return shift_mix(h);
+		}
 		return murmur_bytes([=](uint32_t i) { return (uint8_t)(parent[i] ^ (i == b ? flip : 0)); }, parent_size);
 	}
 };
@@ -91,6 +106,19 @@ struct phase {
 		if (b[0] & 1)
 			mag = cmul(mag, rot);
 	}
+};
+
+// ---- observables ------------------------------------------------------------------------------------------------------
+// probability that a qubit is set: observable = object[bit] (a driver would write it as a lambda for average_value)
+struct bit_observable {
+	static constexpr int values = 1;
+	uint64_t bit;
+	__device__ void operator()(const uint8_t *object, uint32_t size, double *out) const { out[0] = bit < size && object[bit] ? 1.0 : 0.0; }
+};
+// size of the object in bytes
+struct bytes_observable {
+	static constexpr int values = 1;
+	__device__ void operator()(const uint8_t *, uint32_t size, double *out) const { out[0] = (double)size; }
 };
 
 } // namespace qc

@@ -1002,16 +1002,149 @@ struct split_merge : rule_base<split_merge> {
 	}
 };
 
+// What all the children of one parent share in the symbolic phase, computed ONCE per parent by a whole warp (lane i =
+// node i) and kept in shared memory: the particle masks, the split / merge site masks, and for every node the (first
+// hash, number of atoms) of each name it can contribute to a child -- its own, the two halves of its split, its merge
+// with the next node (node n-1: with node 0, the wrap-around merge).  A child is then a walk over these tables:
+// no access to the object, no dependent loads, 1-3 hash folds per node.
+constexpr uint32_t SPLIT_MERGE_MAX_NODES = 32;
+struct split_merge_ctx {
+	uint32_t n; // 0: not prepared (more than 32 nodes): the children walk the object itself
+	uint32_t left, right, split, merge;
+	uint32_t most_left_zero; // qcgd.hpp:709-749: where the left half of a first split goes
+	// [0] the node's own name; [1] split site: left half, merge site (and node n-1): the merged name; [2] split site: right half
+	uint64_t hash[3][SPLIT_MERGE_MAX_NODES]; // first hash of the name
+	uint16_t len[3][SPLIT_MERGE_MAX_NODES];  // its number of atoms
+};
+
 struct split_merge_fused : split_merge {
 	static constexpr bool needs_scratch = false;
+	typedef split_merge_ctx ctx_t;
+	static constexpr bool warp_prepare = true;
+	static constexpr int parents_per_batch = 8; // 1 KB of context per parent
 
-	__device__ uint64_t symbolic(const uint8_t *parent, uint32_t, const no_ctx &, uint32_t child_id, uint8_t *, uint32_t &size, cplx &mag) const {
-		graph g(parent);
-		split_merge_plan pl = plan_split_merge<true>(g, child_id, amp, mag);
-		hash_emitter out(g);
-		walk_split_merge(g, pl, out);
-		size = out.size();
-		return out.hash();
+	__device__ void prepare(const uint8_t *, uint32_t, split_merge_ctx &ctx) const { ctx.n = 0; }
+
+	// all 32 lanes, same arguments
+	__device__ void prepare_warp(const uint8_t *parent, uint32_t, split_merge_ctx &ctx) const {
+		const graph g(parent);
+		const uint32_t n = g.n, i = lane_id();
+		if (n == 0 || n > SPLIT_MERGE_MAX_NODES) {
+			if (i == 0)
+				ctx.n = 0;
+			return;
+		}
+		const bool here = i < n;
+		const uint32_t l = __ballot_sync(0xffffffffu, here && g.left(i)), r = __ballot_sync(0xffffffffu, here && g.right(i));
+		const uint32_t split = l & r;
+		const uint32_t merge = ~split & l & (r >> 1) & ~(l >> 1) & (n > 1 ? (0xffffffffu >> (33 - n)) : 0u); // i + 1 < n
+		const bool wrap_merge = !(split & 1) && n > 1 && (r & 1) && ((l >> (n - 1)) & 1) && !((r >> (n - 1)) & 1);
+		if (i == 0) {
+			ctx.n = n;
+			ctx.left = l;
+			ctx.right = r;
+			ctx.split = split;
+			ctx.merge = merge;
+			ctx.most_left_zero = !(g.get(0).kind >= 0 && g.get(1).hmlz > 0);
+		}
+		if (!here)
+			return;
+		const uint32_t begin = g.name_begin(i), len = g.name_begin(i + 1) - begin;
+		const atom first = g.get(begin);
+		ctx.hash[0][i] = first.hash;
+		ctx.len[0][i] = (uint16_t)len;
+		if ((split >> i) & 1) { // operations::left / right, qcgd.hpp:194-208
+			if (first.kind >= 0) {
+				ctx.hash[1][i] = g.atom_hash(begin + 1);
+				ctx.len[1][i] = (uint16_t)(first.kind - 1);
+				ctx.hash[2][i] = g.atom_hash(begin + first.kind);
+				ctx.len[2][i] = (uint16_t)(len - first.kind);
+			} else {
+				ctx.hash[1][i] = hash_combine(first.hash, (uint64_t)(int64_t)DOT_L);
+				ctx.hash[2][i] = hash_combine(first.hash, (uint64_t)(int64_t)DOT_R);
+				ctx.len[1][i] = ctx.len[2][i] = (uint16_t)(len + 1);
+			}
+		} else if (((merge >> i) & 1) || (wrap_merge && i == n - 1)) { // operations::merge, qcgd.hpp:181-192
+			const uint32_t j = i + 1 < n ? i + 1 : 0;
+			const uint32_t other = g.name_begin(j), other_len = g.name_begin(j + 1) - other;
+			const atom second = g.get(other);
+			if (first.kind == DOT_L && second.kind == DOT_R && g.atom_hash(begin + 1) == g.atom_hash(other + 1)) { // X.l v X.r -> X
+				ctx.hash[1][i] = g.atom_hash(begin + 1);
+				ctx.len[1][i] = (uint16_t)(len - 1);
+			} else {
+				ctx.hash[1][i] = hash_combine(first.hash, second.hash);
+				ctx.len[1][i] = (uint16_t)(len + other_len + 1);
+			}
+		}
+	}
+
+	__device__ uint64_t symbolic(const uint8_t *parent, uint32_t, const split_merge_ctx &ctx, uint32_t child_id, uint8_t *, uint32_t &size, cplx &mag) const {
+		const uint32_t n = ctx.n;
+		if (n == 0) { // not prepared: walk the object (same result)
+			graph g(parent);
+			split_merge_plan pl = plan_split_merge<true>(g, child_id, amp, mag);
+			hash_emitter out(g);
+			walk_split_merge(g, pl, out);
+			size = out.size();
+			return out.hash();
+		}
+		const uint32_t left = ctx.left, right = ctx.right, split = ctx.split, merge = ctx.merge;
+		uint64_t hn = 0, hl = 0, hr = 0;
+		uint32_t index = 0, atoms = 0, bits = child_id;
+		// one node of the child: selects, no branches (the lanes of a warp are different children of the same few parents
+		// and would take every path of a branchy walk one after the other: 2560 instructions per child, ncu
+		// profiles/split_merge_sym_r1i, against ~800 this way)
+		auto node = [&](bool l, bool r, uint32_t which, uint32_t i) {
+			const uint64_t with_l = hash_combine_index(hl, index), with_r = hash_combine_index(hr, index);
+			hl = l ? with_l : hl;
+			hr = r ? with_r : hr;
+			hn = hash_combine(hn, ctx.hash[which][i]);
+			atoms += ctx.len[which][i];
+			++index;
+		};
+		// the wrap-around sites first (qcgd.hpp:647-668); a first split that is not taken leaves its bit to the walk
+		const bool first_split = (split & 1) && (bits & 1);
+		bool last_merge = !(split & 1) && n > 1 && (right & 1) && ((left >> (n - 1)) & 1) && !((right >> (n - 1)) & 1);
+		bool overflow = false;
+		if (first_split) {
+			mag = cmul(mag, amp.get(true, false));
+			bits >>= 1;
+			if (ctx.most_left_zero)
+				node(true, false, 1, 0);
+			else
+				overflow = true; // the left half goes to the end
+			node(false, true, 2, 0);
+		}
+		if (last_merge) {
+			last_merge = bits & 1;
+			mag = cmul(mag, amp.get(last_merge, true));
+			bits >>= 1;
+			if (last_merge)
+				node(true, true, 1, n - 1);
+		}
+		// the general walk: every iteration emits exactly one node of the child -- the node itself, a merge (consumes two
+		// nodes), or one half of a split (the right half is `pending` for the next iteration)
+		const uint32_t end = n - last_merge;
+		bool pending = false;
+		for (uint32_t i = (uint32_t)first_split + last_merge; i < end;) {
+			const bool is_split = (split >> i) & 1, is_merge = (merge >> i) & 1;
+			const bool site = (is_split || is_merge) && !pending;
+			const bool taken = site && (bits & 1);
+			if (site) {
+				mag = cmul(mag, amp.get(taken, is_merge));
+				bits >>= 1;
+			}
+			const bool l = pending ? false : (taken ? true : (bool)((left >> i) & 1));
+			const bool r = pending ? true : (taken ? is_merge : (bool)((right >> i) & 1));
+			node(l, r, pending ? 2u : (taken ? 1u : 0u), i);
+			const bool left_half = taken && is_split;
+			i += left_half ? 0u : (taken ? 2u : 1u); // a taken merge swallows node i + 1 (:816)
+			pending = left_half;
+		}
+		if (overflow)
+			node(true, false, 1, 0);
+		size = 4 + 4 * index + 16 * atoms;
+		return hash_combine(hash_combine(hn, hl), hr);
 	}
 };
 
@@ -1044,6 +1177,29 @@ struct step_modifier {
 			up[i] = up[i - 1];
 		up[0] = last;
 	}
+};
+
+// ---- observables of utils::serialize (qcgd.hpp:309-372) -----------------------------------------------------------------
+// number of nodes; its square; density = (number of particles) / (2 n); its square -- the four averages of one
+// serialize() call in a single pass over the state
+struct stats_observable {
+	static constexpr int values = 4;
+	__device__ void operator()(const uint8_t *object, uint32_t, double *out) const {
+		const uint32_t n = *reinterpret_cast<const uint16_t *>(object);
+		const double nodes = (double)n;
+		double density = 0; // the reference adds left + right per node in a PROBA_TYPE, then divides by 2 n (:329-334)
+		for (uint32_t i = 0; i < n; ++i)
+			density += (double)(object[2 + i] + object[2 + n + i]);
+		density /= 2 * nodes;
+		out[0] = nodes;
+		out[1] = nodes * nodes;
+		out[2] = density;
+		out[3] = density * density;
+	}
+};
+struct size_observable {
+	static constexpr int values = 1;
+	__device__ void operator()(const uint8_t *object, uint32_t, double *out) const { out[0] = (double)*reinterpret_cast<const uint16_t *>(object); }
 };
 
 } // namespace qcgd

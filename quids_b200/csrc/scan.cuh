@@ -186,4 +186,70 @@ __device__ __forceinline__ void block_rank_striped(const bool (&keep)[ITEMS], ui
 	__syncthreads();
 }
 
+// ---- ranks for a stream compaction with WARP-STRIPED items: warp w of the CTA owns the 32 * ITEMS consecutive
+// elements starting at tile_base + w * 32 * ITEMS, item j of lane l = that + j * 32 + l (every load of a warp is one
+// coalesced row), so a tile can be as long as the registers allow (ITEMS is not bounded by the warp width).  Two
+// predicates are ranked at once (`a` and `b`, exclusive of each other or not); ranks are in element order.
+template <int ITEMS>
+__device__ __forceinline__ uint64_t warp_striped_index(uint64_t tile_base, int j) {
+	return tile_base + (uint64_t)(threadIdx.x >> 5) * (32 * ITEMS) + (uint64_t)j * 32 + (threadIdx.x & 31);
+}
+
+template <int ITEMS, bool TWO>
+__device__ __forceinline__ void block_rank_warp_striped(const bool (&a)[ITEMS], const bool (&b)[ITEMS], uint32_t (&rank_a)[ITEMS], uint32_t (&rank_b)[ITEMS],
+                                                        uint32_t &total_a, uint32_t &total_b) {
+	__shared__ uint32_t s_a[SCAN_WARPS], s_b[SCAN_WARPS];
+	__shared__ uint32_t s_total_a, s_total_b;
+	const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+	const unsigned lt = (1u << lane) - 1;
+	uint32_t run_a = 0, run_b = 0;
+#pragma unroll
+	for (int j = 0; j < ITEMS; ++j) {
+		const unsigned ba = __ballot_sync(0xffffffffu, a[j]);
+		rank_a[j] = run_a + __popc(ba & lt);
+		run_a += __popc(ba);
+		if (TWO) {
+			const unsigned bb = __ballot_sync(0xffffffffu, b[j]);
+			rank_b[j] = run_b + __popc(bb & lt);
+			run_b += __popc(bb);
+		}
+	}
+	if (lane == 0) {
+		s_a[warp] = run_a;
+		s_b[warp] = run_b;
+	}
+	__syncthreads();
+	if (warp == 0) {
+		const uint32_t ca = lane < SCAN_WARPS ? s_a[lane] : 0, cb = lane < SCAN_WARPS ? s_b[lane] : 0;
+		uint32_t ia = ca, ib = cb;
+#pragma unroll
+		for (int o = 1; o < SCAN_WARPS; o <<= 1) {
+			const uint32_t ua = __shfl_up_sync(0xffffffffu, ia, o), ub = __shfl_up_sync(0xffffffffu, ib, o);
+			if (lane >= (unsigned)o) {
+				ia += ua;
+				ib += ub;
+			}
+		}
+		if (lane < SCAN_WARPS) {
+			s_a[lane] = ia - ca;
+			s_b[lane] = ib - cb;
+		}
+		if (lane == SCAN_WARPS - 1) {
+			s_total_a = ia;
+			s_total_b = ib;
+		}
+	}
+	__syncthreads();
+	const uint32_t off_a = s_a[warp], off_b = s_b[warp];
+#pragma unroll
+	for (int j = 0; j < ITEMS; ++j) {
+		rank_a[j] += off_a;
+		if (TWO)
+			rank_b[j] += off_b;
+	}
+	total_a = s_total_a;
+	total_b = s_total_b;
+	__syncthreads();
+}
+
 } // namespace qb

@@ -20,6 +20,7 @@ REF_SO = os.path.join(ORACLE_DIR, "_ref", "libquids_ref.so")
 
 RULE_HADAMARD, RULE_ERASE_CREATE, RULE_COIN, RULE_SPLIT_MERGE = 1, 2, 3, 4
 MOD_CNOT, MOD_XGATE, MOD_YGATE, MOD_ZGATE, MOD_STEP, MOD_REVERSED_STEP, MOD_PHASE = 1, 2, 3, 4, 5, 6, 7
+OBS_QCGD_SIZE, OBS_QCGD_SQUARED_SIZE, OBS_QCGD_DENSITY, OBS_QCGD_SQUARED_DENSITY, OBS_QUBIT, OBS_BYTES = 1, 2, 3, 4, 5, 6
 NO_TRUNCATION = 2**64 - 1
 
 QCGD_RULES = (RULE_ERASE_CREATE, RULE_COIN, RULE_SPLIT_MERGE)
@@ -150,6 +151,21 @@ class Oracle:
             rc = self.lib.orc_hash_objects(h, rule_id, pr.ctypes.data, out.ctypes.data)
             assert rc == 0
             return out
+        finally:
+            self._free(h)
+
+    def average_value(self, p: Packed, observable_id, params=()) -> float:
+        """iteration::average_value (quids.hpp:208-234) with one of the ORC_OBS_* observables"""
+        h = self._new()
+        try:
+            self._load(h, p)
+            pr = self._params(params)
+            out = C.c_double()
+            self.lib.orc_average_value.restype = C.c_int
+            self.lib.orc_average_value.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_double)]
+            rc = self.lib.orc_average_value(h, observable_id, pr.ctypes.data, C.byref(out))
+            assert rc == 0
+            return out.value
         finally:
             self._free(h)
 

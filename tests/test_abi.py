@@ -34,6 +34,10 @@ def test_registry_names(library):
         assert library.qb_rule_id(name.encode()) >= 1
     for name in ("cnot", "xgate", "ygate", "zgate", "step", "reversed_step", "phase"):
         assert library.qb_modifier_id(name.encode()) >= 1
+    for name, values in (("qcgd_stats", 4), ("qcgd_size", 1), ("qubit", 1), ("object_bytes", 1)):
+        oid = library.qb_observable_id(name.encode())
+        assert oid >= 1 and library.qb_observable_values(oid) == values
+    assert library.qb_observable_id(b"no_such_observable") == -3
     assert library.qb_rule_id(b"no_such_rule") == -3
     assert b"no_such_rule" in library.qb_last_error()
 

@@ -579,3 +579,29 @@ def test_float_magnitudes_at_the_boundary(gpu, port):
     sizes, mags_out, data = nxt.download_packed()
     got = orc.Packed(sizes, m32.astype(np.float64), data, nxt.total_proba)
     orc.assert_same_state(got, port.hash_objects(got, rid), want, port.hash_objects(want, rid), True, rtol=1e-5, what="float boundary")
+
+
+def test_device_observables_vs_oracle(gpu, port):
+    """iteration::average_value (quids.hpp:208-234) as a device reduction (qb_iter_average_value) against the checker:
+    the four averages of utils::serialize in one pass ("qcgd_stats"), a qubit probability, sizes; 1e-12 relative"""
+    import quids_b200 as qb
+    rng = np.random.default_rng(12)
+    g = port.qcgd_random_state(9, 5000, 6)
+    g.mags[:] = rng.normal(size=g.mags.shape) / 70
+    grown, _, _ = port.simulate(g, orc.RULE_SPLIT_MERGE, [0.3, 0.2, 0.1], tolerance=1e-18)
+    it = gpu()._load(grown)
+    stats = it.average_value("qcgd_stats")
+    for got, oid in zip(stats, (orc.OBS_QCGD_SIZE, orc.OBS_QCGD_SQUARED_SIZE, orc.OBS_QCGD_DENSITY, orc.OBS_QCGD_SQUARED_DENSITY)):
+        want = port.average_value(grown, oid)
+        assert abs(got - want) <= 1e-12 * abs(want), (oid, got, want)
+    assert abs(it.average_value("qcgd_size") - port.average_value(grown, orc.OBS_QCGD_SIZE)) <= 1e-12 * stats[0]
+    assert abs(it.average_value("object_bytes") - port.average_value(grown, orc.OBS_BYTES)) <= 1e-12 * port.average_value(grown, orc.OBS_BYTES)
+    reg = orc.Packed.from_objects([bytes(rng.integers(0, 2, size=l, dtype=np.uint8)) for l in rng.integers(3, 9, size=3000)], rng.normal(size=3000) + 1j * rng.normal(size=3000))
+    it = gpu("", align=0)._load(reg)
+    for bit in (0, 2, 7):
+        want = port.average_value(reg, orc.OBS_QUBIT, [bit])
+        assert abs(it.average_value("qubit", bit) - want) <= 1e-12 * want
+    # an empty state averages to 0; an unknown observable fails loudly
+    assert qb.Iteration().average_value("qcgd_size") == 0.0
+    with pytest.raises(qb.QuidsError):
+        it.average_value("no_such_observable")

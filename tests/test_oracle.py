@@ -120,3 +120,26 @@ def test_modifiers_match_live_reference(port, reference):
         assert a.objects() == b.objects()
         assert np.array_equal(a.mags, b.mags)
         st = a
+
+
+def test_average_value_port_matches_reference(port):
+    """iteration::average_value (quids.hpp:208-234) with the observables of utils::serialize (qcgd.hpp:319-345):
+    restatement against the reference's own average_value where the reference checker was built"""
+    rng = np.random.default_rng(11)
+    g = port.qcgd_random_state(9, 400, 6)
+    g.mags[:] = rng.normal(size=g.mags.shape) / 20
+    grown, _, _ = port.simulate(g, orc.RULE_SPLIT_MERGE, [0.3, 0.2, 0.1], tolerance=1e-18)  # graphs of several sizes
+    reg = orc.Packed.from_objects([bytes(rng.integers(0, 2, size=l, dtype=np.uint8)) for l in rng.integers(3, 9, size=300)], rng.normal(size=300) + 1j * rng.normal(size=300))
+    # hand-checked: two 2-node graphs, |mag|^2 = 0.25 and 0.75
+    two = port.qcgd_random_state(2, 2, 1)
+    two.mags[:] = [[0.5, 0], [0, math.sqrt(0.75)]]
+    assert abs(port.average_value(two, orc.OBS_QCGD_SIZE) - 2.0) < 1e-15
+    assert abs(port.average_value(two, orc.OBS_BYTES) - 44.0) < 1e-13
+    if not orc.have_reference():
+        pytest.skip("oracle/_ref not built here")
+    ref = orc.Oracle(orc.REF_SO)
+    for st, ids in ((grown, (orc.OBS_QCGD_SIZE, orc.OBS_QCGD_SQUARED_SIZE, orc.OBS_QCGD_DENSITY, orc.OBS_QCGD_SQUARED_DENSITY, orc.OBS_BYTES)), (reg, (orc.OBS_QUBIT, orc.OBS_BYTES))):
+        for oid in ids:
+            for params in ([0], [2], [7]) if oid == orc.OBS_QUBIT else ([],):
+                a, b = port.average_value(st, oid, params), ref.average_value(st, oid, params)
+                assert abs(a - b) <= 1e-12 * max(1.0, abs(b)), (oid, params, a, b)
