@@ -428,10 +428,17 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--large-parents", type=int, default=10**8, help="N = 1 only: also time this many parents on the one GPU (0 = skip)")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: whatever the libraries print on file descriptor 1 meanwhile (NCCL's version
+    # banner, for one) goes to stderr; the line itself is written to the saved descriptor by print()
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(saved, "w")
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":

@@ -391,12 +391,17 @@ const uint64_t *sort_items(qb_ctx *ctx, qb_sym *sym, uint64_t n, const uint32_t 
 	sym->sort_base.ensure(sizeof(uint64_t) * (SORT_BINS * tiles + 1), stream);
 	uint32_t *keys[2] = {sym->sort_keys.as<uint32_t>(), sym->sort_keys.as<uint32_t>() + n};
 	uint64_t *vals[2] = {sym->sort_vals.as<uint64_t>(), sym->sort_vals.as<uint64_t>() + n};
+	static bool stage_allowed = false; // the scatter kernel sorts a tile in 58 KB of shared memory
+	if (!stage_allowed) {
+		QB_CUDA(cudaFuncSetAttribute((const void *)radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SORT_STAGE_BYTES));
+		stage_allowed = true;
+	}
 	int src = 0;
 	for (int shift = 32 - SORT_KEY_BITS; shift < 32; shift += 8, src ^= 1) {
 		radix_histogram_kernel<<<(unsigned)tiles, SORT_THREADS, 0, stream>>>(keys[src], n, shift, sym->sort_hist.as<uint32_t>(), tiles);
 		++ctx->launches;
 		exclusive_scan(ctx, widen_u32{sym->sort_hist.as<uint32_t>()}, sym->sort_base.as<uint64_t>(), SORT_BINS * tiles);
-		radix_scatter_kernel<<<(unsigned)tiles, SORT_THREADS, 0, stream>>>(keys[src], vals[src], n, shift, sym->sort_base.as<uint64_t>(), tiles,
+		radix_scatter_kernel<<<(unsigned)tiles, SORT_THREADS, SORT_STAGE_BYTES, stream>>>(keys[src], vals[src], n, shift, sym->sort_base.as<uint64_t>(), tiles,
 		                                                                   keys[src ^ 1], vals[src ^ 1]);
 		++ctx->launches;
 	}

@@ -157,6 +157,27 @@ struct __align__(32) exchange_record { // a locally unique child, on its way to 
 
 __device__ __forceinline__ uint32_t owner_of(uint64_t hash, uint32_t world) { return (uint32_t)__umul64hi(mix64(hash ^ 0x9e3779b97f4a7c15ull), (uint64_t)world); }
 
+// The partition kernels below count and rank elements by a key with only `world` (2..8) values: one shared-memory atomic
+// per ELEMENT would have 256 threads hammering 2 addresses (1.5 ms for 1.5e7 records, QB_DIST_TRACE).  The lanes of a
+// warp with the same key are merged first: one atomic per (warp, key).
+struct warp_group {
+	unsigned peers;  // lanes of this warp with the same key (0 for a lane without element)
+	uint32_t rank;   // this lane's rank among them
+	uint32_t size;
+	bool leader;
+};
+__device__ __forceinline__ warp_group warp_group_by(bool valid, uint32_t key) {
+	warp_group g{0, 0, 0, false};
+	const unsigned active = __ballot_sync(0xffffffffu, valid);
+	if (valid) {
+		g.peers = __match_any_sync(active, key);
+		g.rank = __popc(g.peers & ((1u << lane_id()) - 1));
+		g.size = __popc(g.peers);
+		g.leader = g.rank == 0;
+	}
+	return g;
+}
+
 // counts[owner] over the locally unique children (shared-memory histogram per CTA: a global atomic per
 // element on `world` addresses would serialise in L2)
 __global__ void __launch_bounds__(256) owner_count_kernel(table_view t, const uint32_t *uslot, uint64_t n, uint32_t world, unsigned long long *counts) {
@@ -165,8 +186,14 @@ __global__ void __launch_bounds__(256) owner_count_kernel(table_view t, const ui
 		s_counts[i] = 0;
 	__syncthreads();
 	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-		atomicAdd(&s_counts[owner_of(t.slots[uslot[i]].key, world)], 1u);
+	for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n; base += stride) {
+		const uint64_t i = base + threadIdx.x;
+		const bool valid = i < n;
+		const uint32_t o = valid ? owner_of(t.slots[uslot[i]].key, world) : 0;
+		const warp_group g = warp_group_by(valid, o);
+		if (g.leader)
+			atomicAdd(&s_counts[o], g.size);
+	}
 	__syncthreads();
 	for (uint32_t i = threadIdx.x; i < world; i += blockDim.x)
 		if (s_counts[i])
@@ -177,27 +204,43 @@ constexpr int SCATTER_TILE = 2048; // elements one CTA places per round: `world`
 
 // records grouped by owner: cursor[owner] starts at the owner's offset.  Per tile: histogram in shared
 // memory, one global atomicAdd per owner reserves the tile's range, ranks inside the tile come from
-// shared-memory atomics.
+// shared-memory atomics (one per warp and owner).
 __global__ void __launch_bounds__(256) owner_scatter_kernel(table_view t, const uint32_t *uslot, uint64_t n, uint32_t world, unsigned long long *cursor,
                                                             exchange_record *out) {
-	extern __shared__ unsigned long long s_base[]; // [world] tile base, then [world] running rank (as u64 for alignment)
-	unsigned long long *s_rank = s_base + world;
+	extern __shared__ unsigned long long s_base[]; // [world] tile base (u64), then [world] counts and [world] running ranks (u32)
+	unsigned int *s_count = reinterpret_cast<unsigned int *>(s_base + world), *s_rank = s_count + world;
 	for (uint64_t tile = (uint64_t)blockIdx.x * SCATTER_TILE; tile < n; tile += (uint64_t)gridDim.x * SCATTER_TILE) {
-		for (uint32_t i = threadIdx.x; i < 2 * world; i += blockDim.x)
-			s_base[i] = 0;
+		for (uint32_t i = threadIdx.x; i < world; i += blockDim.x)
+			s_count[i] = s_rank[i] = 0;
 		__syncthreads();
 		const uint64_t end = min(tile + (uint64_t)SCATTER_TILE, n);
-		for (uint64_t i = tile + threadIdx.x; i < end; i += blockDim.x)
-			atomicAdd(&s_base[owner_of(t.slots[uslot[i]].key, world)], 1ull);
+		for (uint64_t base = tile; base < end; base += blockDim.x) {
+			const uint64_t i = base + threadIdx.x;
+			const bool valid = i < end;
+			const uint32_t o = valid ? owner_of(t.slots[uslot[i]].key, world) : 0;
+			const warp_group g = warp_group_by(valid, o);
+			if (g.leader)
+				atomicAdd(&s_count[o], g.size);
+		}
 		__syncthreads();
 		for (uint32_t o = threadIdx.x; o < world; o += blockDim.x)
-			s_base[o] = s_base[o] ? atomicAdd(&cursor[o], s_base[o]) : 0;
+			s_base[o] = s_count[o] ? atomicAdd(&cursor[o], (unsigned long long)s_count[o]) : 0;
 		__syncthreads();
-		for (uint64_t i = tile + threadIdx.x; i < end; i += blockDim.x) {
-			const table_slot s = t.slots[uslot[i]];
-			const uint32_t o = owner_of(s.key, world);
-			const unsigned long long at = s_base[o] + atomicAdd(&s_rank[o], 1ull);
-			out[at] = exchange_record{s.key, s.re, s.im, s.rep};
+		for (uint64_t base = tile; base < end; base += blockDim.x) {
+			const uint64_t i = base + threadIdx.x;
+			const bool valid = i < end;
+			table_slot s{};
+			if (valid)
+				s = t.slots[uslot[i]];
+			const uint32_t o = valid ? owner_of(s.key, world) : 0;
+			const warp_group g = warp_group_by(valid, o);
+			unsigned int first = 0;
+			if (g.leader)
+				first = atomicAdd(&s_rank[o], g.size);
+			if (valid) {
+				first = __shfl_sync(g.peers, first, __ffs(g.peers) - 1);
+				out[s_base[o] + first + g.rank] = exchange_record{s.key, s.re, s.im, s.rep};
+			}
 		}
 		__syncthreads();
 	}
@@ -210,42 +253,62 @@ __global__ void __launch_bounds__(256) owner_scatter_kernel(table_view t, const 
 __device__ __forceinline__ uint64_t owner_rep_pack(uint64_t position, uint64_t hash) { return ((mix64(position ^ hash) >> 56) << 56) | (position + 1); }
 __device__ __forceinline__ uint64_t owner_rep_position(uint64_t rep) { return (rep & ((1ull << 56) - 1)) - 1; }
 
+// Four records per thread and round: all their key loads go out before any is resolved, so a thread has four DRAM round
+// trips in flight instead of one (the table is far larger than L2 and the records arrive in no useful order).
 __global__ void __launch_bounds__(256) record_insert_kernel(table_view t, const exchange_record *records, uint64_t n) {
-	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	constexpr int N = 4;
+	const uint64_t threads = (uint64_t)gridDim.x * blockDim.x;
 	unsigned int created = 0;
-	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-		const exchange_record r = records[i];
-		table_slot *s;
-		if (r.hash == 0) {
-			s = t.slots + t.capacity;
-		} else {
-			uint64_t at = table_home(r.hash, t.capacity);
-			uint32_t probes = 0;
-			while (true) {
-				s = t.slots + at;
-				unsigned long long seen = __ldcg(&s->key);
-				if (seen == 0) {
-					seen = atomicCAS(&s->key, 0ull, (unsigned long long)r.hash);
-					if (seen == 0) {
-						++created;
-						break;
-					}
-				}
-				if (seen == r.hash)
-					break;
-				if (++at == t.capacity)
-					at = 0;
-				if (++probes > TABLE_MAX_PROBES) {
-					*t.overflow = 1;
-					s = nullptr;
-					break;
+	for (uint64_t first = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; first < n; first += threads * N) {
+		exchange_record r[N];
+		uint64_t at[N];
+		unsigned pending = 0;
+#pragma unroll
+		for (int q = 0; q < N; ++q) {
+			const uint64_t i = first + (uint64_t)q * threads;
+			if (i < n) {
+				r[q] = records[i];
+				if (r[q].hash == 0) { // the dedicated slot
+					table_slot *s = t.slots + t.capacity;
+					atomicAdd(&s->re, r[q].re);
+					atomicAdd(&s->im, r[q].im);
+					atomicMax(&s->rep, (unsigned long long)owner_rep_pack(i, 0));
+				} else {
+					at[q] = table_home(r[q].hash, t.capacity);
+					pending |= 1u << q;
 				}
 			}
 		}
-		if (s) {
-			atomicAdd(&s->re, r.re);
-			atomicAdd(&s->im, r.im);
-			atomicMax(&s->rep, (unsigned long long)owner_rep_pack(i, r.hash));
+		for (uint32_t round = 0; pending; ++round) {
+			unsigned long long seen[N];
+#pragma unroll
+			for (int q = 0; q < N; ++q)
+				if (pending & (1u << q))
+					seen[q] = __ldcg(&t.slots[at[q]].key);
+#pragma unroll
+			for (int q = 0; q < N; ++q)
+				if (pending & (1u << q)) {
+					table_slot *s = t.slots + at[q];
+					if (seen[q] == 0) {
+						seen[q] = atomicCAS(&s->key, 0ull, (unsigned long long)r[q].hash);
+						if (seen[q] == 0) {
+							++created;
+							seen[q] = r[q].hash;
+						}
+					}
+					if (seen[q] == r[q].hash) {
+						atomicAdd(&s->re, r[q].re);
+						atomicAdd(&s->im, r[q].im);
+						atomicMax(&s->rep, (unsigned long long)owner_rep_pack(first + (uint64_t)q * threads, r[q].hash));
+						pending &= ~(1u << q);
+					} else if (++at[q] == t.capacity) {
+						at[q] = 0;
+					}
+				}
+			if (round > TABLE_MAX_PROBES) {
+				*t.overflow = 1;
+				break;
+			}
 		}
 	}
 	created = (unsigned int)warp_sum((uint64_t)created);
@@ -261,9 +324,13 @@ __global__ void __launch_bounds__(256) return_count_kernel(table_view t, const u
 		s_counts[i] = 0;
 	__syncthreads();
 	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-		const uint64_t position = owner_rep_position(t.slots[slot[i]].rep);
-		atomicAdd(&s_counts[(uint32_t)upper_bound_u64(recv_begin, world + 1, position) - 1], 1u);
+	for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n; base += stride) {
+		const uint64_t i = base + threadIdx.x;
+		const bool valid = i < n;
+		const uint32_t src = valid ? (uint32_t)upper_bound_u64(recv_begin, world + 1, owner_rep_position(t.slots[slot[i]].rep)) - 1 : 0;
+		const warp_group g = warp_group_by(valid, src);
+		if (g.leader)
+			atomicAdd(&s_counts[src], g.size);
 	}
 	__syncthreads();
 	for (uint32_t i = threadIdx.x; i < world; i += blockDim.x)
@@ -274,26 +341,40 @@ __global__ void __launch_bounds__(256) return_count_kernel(table_view t, const u
 __global__ void __launch_bounds__(256) return_scatter_kernel(table_view t, const uint32_t *slot, uint64_t n, const uint64_t *recv_begin, uint32_t world,
                                                              const exchange_record *received, unsigned long long *cursor, survivor_record *out) {
 	extern __shared__ unsigned long long s_base[];
-	unsigned long long *s_rank = s_base + world;
+	unsigned int *s_count = reinterpret_cast<unsigned int *>(s_base + world), *s_rank = s_count + world;
 	for (uint64_t tile = (uint64_t)blockIdx.x * SCATTER_TILE; tile < n; tile += (uint64_t)gridDim.x * SCATTER_TILE) {
-		for (uint32_t i = threadIdx.x; i < 2 * world; i += blockDim.x)
-			s_base[i] = 0;
+		for (uint32_t i = threadIdx.x; i < world; i += blockDim.x)
+			s_count[i] = s_rank[i] = 0;
 		__syncthreads();
 		const uint64_t end = min(tile + (uint64_t)SCATTER_TILE, n);
-		for (uint64_t i = tile + threadIdx.x; i < end; i += blockDim.x) {
-			const uint64_t position = owner_rep_position(t.slots[slot[i]].rep);
-			atomicAdd(&s_base[(uint32_t)upper_bound_u64(recv_begin, world + 1, position) - 1], 1ull);
+		for (uint64_t base = tile; base < end; base += blockDim.x) {
+			const uint64_t i = base + threadIdx.x;
+			const bool valid = i < end;
+			const uint32_t src = valid ? (uint32_t)upper_bound_u64(recv_begin, world + 1, owner_rep_position(t.slots[slot[i]].rep)) - 1 : 0;
+			const warp_group g = warp_group_by(valid, src);
+			if (g.leader)
+				atomicAdd(&s_count[src], g.size);
 		}
 		__syncthreads();
 		for (uint32_t o = threadIdx.x; o < world; o += blockDim.x)
-			s_base[o] = s_base[o] ? atomicAdd(&cursor[o], s_base[o]) : 0;
+			s_base[o] = s_count[o] ? atomicAdd(&cursor[o], (unsigned long long)s_count[o]) : 0;
 		__syncthreads();
-		for (uint64_t i = tile + threadIdx.x; i < end; i += blockDim.x) {
-			const table_slot s = t.slots[slot[i]];
-			const uint64_t position = owner_rep_position(s.rep);
-			const uint32_t src = (uint32_t)upper_bound_u64(recv_begin, world + 1, position) - 1;
-			const unsigned long long at = s_base[src] + atomicAdd(&s_rank[src], 1ull);
-			out[at] = survivor_record{received[position].rep, s.re, s.im};
+		for (uint64_t base = tile; base < end; base += blockDim.x) {
+			const uint64_t i = base + threadIdx.x;
+			const bool valid = i < end;
+			table_slot s{};
+			if (valid)
+				s = t.slots[slot[i]];
+			const uint64_t position = valid ? owner_rep_position(s.rep) : 0;
+			const uint32_t src = valid ? (uint32_t)upper_bound_u64(recv_begin, world + 1, position) - 1 : 0;
+			const warp_group g = warp_group_by(valid, src);
+			unsigned int first = 0;
+			if (g.leader)
+				first = atomicAdd(&s_rank[src], g.size);
+			if (valid) {
+				first = __shfl_sync(g.peers, first, __ffs(g.peers) - 1);
+				out[s_base[src] + first + g.rank] = survivor_record{received[position].rep, s.re, s.im};
+			}
 		}
 		__syncthreads();
 	}

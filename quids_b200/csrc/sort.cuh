@@ -44,12 +44,25 @@ static __global__ void __launch_bounds__(SORT_THREADS) radix_histogram_kernel(co
 	hist[(uint64_t)threadIdx.x * tiles + blockIdx.x] = s_hist[threadIdx.x];
 }
 
-// base[digit * tiles + tile] = exclusive scan of hist (position of the tile's first element with that digit)
+// base[digit * tiles + tile] = exclusive scan of hist (position of the tile's first element with that digit).
+// The tile is first sorted by digit in SHARED memory (rank = digit start inside the tile + the warp's base + the rank among
+// the warp's elements), then written out in that order: consecutive threads hold consecutive elements of one digit, i.e.
+// consecutive destinations -- runs of ~16 elements (128-byte value runs) instead of one scattered 8-byte store per lane.
+struct sort_stage {
+	uint64_t vals[SORT_TILE];
+	uint64_t base[SORT_BINS];  // base[digit * tiles + tile] - digit start inside the tile
+	uint32_t keys[SORT_TILE];
+	unsigned int count[SORT_WARPS][SORT_BINS]; // per warp: elements seen so far per digit, then the warp's base inside the tile
+	unsigned int start[SORT_BINS];             // first local position of every digit
+};
+constexpr size_t SORT_STAGE_BYTES = sizeof(sort_stage);
+
 static __global__ void __launch_bounds__(SORT_THREADS) radix_scatter_kernel(const uint32_t *keys_in, const uint64_t *vals_in, uint64_t n, int shift,
                                                                             const uint64_t *base, uint64_t tiles, uint32_t *keys_out, uint64_t *vals_out) {
-	__shared__ unsigned int s_count[SORT_WARPS][SORT_BINS]; // per warp: elements seen so far per digit, then the warp's base
+	extern __shared__ __align__(16) uint8_t s_sort_raw[];
+	sort_stage &st = *reinterpret_cast<sort_stage *>(s_sort_raw);
 	for (int i = threadIdx.x; i < SORT_WARPS * SORT_BINS; i += SORT_THREADS)
-		(&s_count[0][0])[i] = 0;
+		(&st.count[0][0])[i] = 0;
 	__syncthreads();
 	const unsigned warp = threadIdx.x >> 5, lane = lane_id();
 	const unsigned lt = (1u << lane) - 1;
@@ -65,23 +78,27 @@ static __global__ void __launch_bounds__(SORT_THREADS) radix_scatter_kernel(cons
 		offset[r] = 0;
 		if (valid) {
 			const unsigned peers = __match_any_sync(active, digit);
-			const unsigned before = s_count[warp][digit]; // rows are processed in order by the same warp
+			const unsigned before = st.count[warp][digit]; // rows are processed in order by the same warp
 			offset[r] = before + __popc(peers & lt);
 			__syncwarp(active);
 			if ((peers & lt) == 0)
-				s_count[warp][digit] = before + __popc(peers);
+				st.count[warp][digit] = before + __popc(peers);
 		}
 		__syncwarp();
 	}
 	__syncthreads();
-	// per digit: exclusive prefix over the warps (thread d handles digit d)
+	// per digit (thread d handles digit d): exclusive prefix over the warps, then over the digits
 	{
 		unsigned run = 0;
 		for (int w = 0; w < SORT_WARPS; ++w) {
-			const unsigned c = s_count[w][threadIdx.x];
-			s_count[w][threadIdx.x] = run;
+			const unsigned c = st.count[w][threadIdx.x];
+			st.count[w][threadIdx.x] = run;
 			run += c;
 		}
+		uint64_t tile_total;
+		const uint32_t begin = (uint32_t)block_exclusive_sum((uint64_t)run, tile_total);
+		st.start[threadIdx.x] = begin;
+		st.base[threadIdx.x] = base[(uint64_t)threadIdx.x * tiles + blockIdx.x] - begin;
 	}
 	__syncthreads();
 #pragma unroll
@@ -89,10 +106,19 @@ static __global__ void __launch_bounds__(SORT_THREADS) radix_scatter_kernel(cons
 		const uint64_t i = sort_element(blockIdx.x, warp, r, lane);
 		if (i < n) {
 			const unsigned digit = (key[r] >> shift) & (SORT_BINS - 1);
-			const uint64_t dst = base[(uint64_t)digit * tiles + blockIdx.x] + s_count[warp][digit] + offset[r];
-			keys_out[dst] = key[r];
-			vals_out[dst] = vals_in[i];
+			const uint32_t q = st.start[digit] + st.count[warp][digit] + offset[r];
+			st.keys[q] = key[r];
+			st.vals[q] = vals_in[i];
 		}
+	}
+	__syncthreads();
+	const uint64_t tile_begin = (uint64_t)blockIdx.x * SORT_TILE;
+	const uint32_t in_tile = (uint32_t)min((uint64_t)SORT_TILE, n - tile_begin);
+	for (uint32_t q = threadIdx.x; q < in_tile; q += SORT_THREADS) {
+		const uint32_t k = st.keys[q];
+		const uint64_t dst = st.base[(k >> shift) & (SORT_BINS - 1)] + q;
+		keys_out[dst] = k;
+		vals_out[dst] = st.vals[q];
 	}
 }
 

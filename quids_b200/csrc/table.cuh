@@ -112,6 +112,8 @@ __device__ __forceinline__ bool table_insert(const table_view &t, uint64_t hash,
 	if (hash == 0)
 		return table_insert_zero_hash(t, mag, rep);
 	const uint64_t home = table_home(hash, t.capacity);
+	// (claiming the home slot with the compare-and-swap straight away, without looking first, was measured: no gain on
+	// split_merge, 15 % slower on the hadamard doubling step -- a failed or redundant CAS costs more than the load it saves)
 	return table_insert_from(t, hash, mag, rep, home, __ldcg(&t.slots[home].key));
 }
 

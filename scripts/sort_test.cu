@@ -18,12 +18,13 @@ int main() {
 		uint64_t stiles = (SORT_BINS * tiles + SCAN_TILE - 1) / SCAN_TILE; cudaMalloc(&ws, 8 * (stiles + 2));
 		cudaMemcpy(k[0], keys.data(), 4 * n, cudaMemcpyHostToDevice); cudaMemcpy(v[0], vals.data(), 8 * n, cudaMemcpyHostToDevice);
 		int src = 0;
+		cudaFuncSetAttribute((const void *)radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SORT_STAGE_BYTES);
 		for (int shift = 0; shift < 32; shift += 8, src ^= 1) {
 			radix_histogram_kernel<<<tiles, SORT_THREADS>>>(k[src], n, shift, hist, tiles);
 			cudaMemset(ws, 0, 8 * (stiles + 2));
 			scan_state st{ws + 1, (unsigned int *)ws};
 			exclusive_scan_kernel<<<stiles, SCAN_THREADS>>>(widen{hist}, base, (uint64_t)SORT_BINS * tiles, st);
-			radix_scatter_kernel<<<tiles, SORT_THREADS>>>(k[src], v[src], n, shift, base, tiles, k[src ^ 1], v[src ^ 1]);
+			radix_scatter_kernel<<<tiles, SORT_THREADS, SORT_STAGE_BYTES>>>(k[src], v[src], n, shift, base, tiles, k[src ^ 1], v[src ^ 1]);
 		}
 		std::vector<uint32_t> ok(n); std::vector<uint64_t> ov(n);
 		cudaMemcpy(ok.data(), k[src], 4 * n, cudaMemcpyDeviceToHost); cudaMemcpy(ov.data(), v[src], 8 * n, cudaMemcpyDeviceToHost);
