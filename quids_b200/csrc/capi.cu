@@ -1042,25 +1042,37 @@ void simulate_dist(qb_iter *it, int rule_id, const rule_ops *ops, const void *ru
 	table_view owner{};
 	uint64_t n_owner_unique = 0;
 	if (n_recv > 0) {
-		const uint64_t capacity = std::max<uint64_t>(1024, (uint64_t)std::ceil((double)n_recv / 0.5));
-		QB_REQUIRE(capacity + 1 <= 0xffffffffull, QB_ERR_CAPACITY, "owner table would need more than 2^32 slots");
-		cm->owner_table.ensure((capacity + 1) * sizeof(table_slot), stream);
-		QB_CUDA(cudaMemsetAsync(cm->owner_table.ptr, 0, (capacity + 1) * sizeof(table_slot), stream));
-		QB_CUDA(cudaMemsetAsync(ctx->small(DS_COUNT), 0, 4 * sizeof(uint64_t), stream));
-		owner = table_view{cm->owner_table.as<table_slot>(), capacity, reinterpret_cast<unsigned int *>(ctx->small(DS_OVERFLOW)),
-		                   reinterpret_cast<unsigned long long *>(ctx->small(DS_USED))};
-		record_insert_kernel<<<grid_for(n_recv, 256, ctx->grid_cap()), 256, 0, stream>>>(owner, cm->recv.as<exchange_record>(), n_recv);
-		++ctx->launches;
+		// every rank sends each of its objects once, so an object arrives up to `world` times: the table is sized from the share
+		// of the records that created a slot in the previous call (x 1.25), at most for "every record is a new object"; a
+		// table that turns out too small is redone at that size
+		const uint64_t full_capacity = std::max<uint64_t>(1024, (uint64_t)std::ceil((double)n_recv / 0.5));
+		uint64_t capacity = full_capacity;
+		if (cm->owner_unique_ratio > 0)
+			capacity = std::min<uint64_t>(full_capacity, std::max<uint64_t>(1024, (uint64_t)((cm->owner_unique_ratio * 1.25 * (double)n_recv + 1024) / 0.5)));
+		QB_REQUIRE(full_capacity + 1 <= 0xffffffffull, QB_ERR_CAPACITY, "owner table would need more than 2^32 slots");
 		cm->okey.ensure(sizeof(uint64_t) * n_recv, stream);
 		cm->oslot.ensure(sizeof(uint32_t) * n_recv, stream);
-		const uint64_t tiles = div_up<uint64_t>(capacity + 1, COMPACT_TILE);
-		scan_state st = ctx->scan(tiles);
-		table_compact_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, stream>>>(owner, opt.tolerance, cm->okey.as<uint64_t>(), cm->oslot.as<uint32_t>(),
-		                                                                    reinterpret_cast<unsigned long long *>(ctx->small(DS_COUNT)), st);
-		++ctx->launches;
-		QB_CUDA(cudaGetLastError());
-		ctx->fetch_small();
-		QB_REQUIRE(ctx->h_small[DS_OVERFLOW] == 0, QB_ERR_CAPACITY, "owner table overflow");
+		for (int attempt = 0;; ++attempt) {
+			cm->owner_table.ensure((capacity + 1) * sizeof(table_slot), stream);
+			QB_CUDA(cudaMemsetAsync(cm->owner_table.ptr, 0, (capacity + 1) * sizeof(table_slot), stream));
+			QB_CUDA(cudaMemsetAsync(ctx->small(DS_COUNT), 0, 4 * sizeof(uint64_t), stream));
+			owner = table_view{cm->owner_table.as<table_slot>(), capacity, reinterpret_cast<unsigned int *>(ctx->small(DS_OVERFLOW)),
+			                   reinterpret_cast<unsigned long long *>(ctx->small(DS_USED))};
+			record_insert_kernel<<<grid_for(n_recv, 256, ctx->grid_cap()), 256, 0, stream>>>(owner, cm->recv.as<exchange_record>(), n_recv);
+			++ctx->launches;
+			const uint64_t tiles = div_up<uint64_t>(capacity + 1, COMPACT_TILE);
+			scan_state st = ctx->scan(tiles);
+			table_compact_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, stream>>>(owner, opt.tolerance, cm->okey.as<uint64_t>(), cm->oslot.as<uint32_t>(),
+			                                                                    reinterpret_cast<unsigned long long *>(ctx->small(DS_COUNT)), st);
+			++ctx->launches;
+			QB_CUDA(cudaGetLastError());
+			ctx->fetch_small();
+			if (ctx->h_small[DS_OVERFLOW] == 0)
+				break;
+			QB_REQUIRE(capacity < full_capacity && attempt == 0, QB_ERR_CAPACITY, "owner table overflow");
+			capacity = full_capacity;
+		}
+		cm->owner_unique_ratio = (double)ctx->h_small[DS_USED] / (double)n_recv;
 		n_owner_unique = ctx->h_small[DS_COUNT];
 	}
 	timer.end(QB_PHASE_OWNER);

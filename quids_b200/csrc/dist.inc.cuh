@@ -83,6 +83,7 @@ struct qb_comm {
 	ncclComm_t nccl = nullptr;
 	dev_buf scratch; // small device staging for host-value collectives
 	dev_buf send, recv, owner_table, okey, oslot, ret_send, ret_recv, cursors;
+	double owner_unique_ratio = 0; // slots created / records received by the owner table of the last call (0 = no call yet)
 };
 
 namespace {
