@@ -390,6 +390,10 @@ def run_ours(args):
     roofline = {"bound": "hbm", "kernel": "symbolic_items_kernel<erase_create> (child generation in sorted order, on-chip family accumulation, interference-table insert)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": sym_bytes, "kernel_ms": sym_ms, "kernel_share_of_step": sym_ms / ms_per_step,
+                # what the kernel really moves: the (hash, magnitude) pairs of the algorithmic count are merged on chip and never
+                # written, so `frac` can pass 1; this is the DRAM traffic of the ncu capture over the live kernel time
+                "traffic_gbs": (traffic / (sym_ms / 1e3) / 1e9) if traffic else None,
+                "traffic_frac": (traffic / (sym_ms / 1e3) / 1e9 / peak) if traffic else None,
                 "dominant_phase": dominant, "phase_ms": phase_ms,
                 "whole_iteration": {"algorithmic_bytes": total_bytes, "achieved": total_bytes / (ms_per_step / 1e3) / 1e9,
                                     "frac": total_bytes / (ms_per_step / 1e3) / 1e9 / peak}}

@@ -605,3 +605,43 @@ def test_device_observables_vs_oracle(gpu, port):
     assert qb.Iteration().average_value("qcgd_size") == 0.0
     with pytest.raises(qb.QuidsError):
         it.average_value("no_such_observable")
+
+
+def test_split_merge_wide_and_huge_graphs_vs_oracle(gpu, port):
+    """split_merge outside its fast paths: graphs of more than 32 nodes (the children walk the object instead of the
+    per-parent context) and objects larger than the finalisation's shared-memory stages (built in place), mixed with
+    ordinary graphs in the same warp batches; two iterations, so that the second one meets grown names"""
+    from quids_b200 import qcgd
+    rng = np.random.default_rng(21)
+
+    def graph(n, splits, merges, wrap):
+        g = bytearray(qcgd.fresh_graph(n).tobytes())
+        for i in splits:  # both particles: a split site
+            g[2 + i] = g[2 + n + i] = 1
+        for i in merges:  # left at i, right (and no left) at i + 1: a merge site
+            g[2 + i], g[2 + n + i + 1] = 1, 1
+        if wrap:  # right at node 0, left without right at the last node: the wrap-around merge
+            g[2 + n + 0], g[2 + n - 1] = 1, 1
+        return bytes(g)
+
+    objs = [graph(40, [3, 20], [10, 30], True), graph(40, [0, 17], [5], False), graph(33, [32], [1, 8], False),
+            graph(700, [3, 400], [10, 650], True), graph(600, [0], [100], False)]
+    for _ in range(40):  # ordinary 12-node graphs around them
+        n = 12
+        g = bytearray(qcgd.fresh_graph(n).tobytes())
+        g[2:2 + 2 * n] = bytes(rng.integers(0, 2, size=2 * n, dtype=np.uint8))
+        objs.insert(int(rng.integers(0, len(objs) + 1)), bytes(g))
+    mags = rng.normal(size=len(objs)) + 1j * rng.normal(size=len(objs))
+    st = orc.Packed.from_objects(objs, mags / np.linalg.norm(mags))
+    params = [0.3, 0.2, 0.1]
+    for suffix in ("", "_generic"):
+        state = st
+        for iteration in range(2):
+            want, nc, nu = port.simulate(state, orc.RULE_SPLIT_MERGE, params, tolerance=1e-18)
+            got, gc, gu = gpu(suffix).simulate(state, orc.RULE_SPLIT_MERGE, params, tol=1e-18)
+            assert (gc, gu) == (nc, nu), (suffix, iteration)
+            orc.assert_same_state(got, port.hash_objects(got, orc.RULE_SPLIT_MERGE), want, port.hash_objects(want, orc.RULE_SPLIT_MERGE), True,
+                                  what=f"split_merge{suffix} wide/huge iteration {iteration}")
+            # second iteration: the grown graphs with fresh random magnitudes (iterating on the coherent result would un-split
+            # everything and leave residues of cancelled sums, for which a relative tolerance means nothing)
+            state = orc.Packed(want.sizes, np.random.default_rng(5).normal(size=want.mags.shape) / 10, want.data)

@@ -143,3 +143,35 @@ def test_average_value_port_matches_reference(port):
             for params in ([0], [2], [7]) if oid == orc.OBS_QUBIT else ([],):
                 a, b = port.average_value(st, oid, params), ref.average_value(st, oid, params)
                 assert abs(a - b) <= 1e-12 * max(1.0, abs(b)), (oid, params, a, b)
+
+
+def test_split_merge_wide_graphs_port_matches_reference(port):
+    """graphs of 33-700 nodes with hand-placed split / merge / wrap-around sites (the inputs of the GPU test of the same
+    name): the restatement against the reference, two iterations"""
+    if not orc.have_reference():
+        pytest.skip("oracle/_ref not built here")
+    from quids_b200 import qcgd
+
+    def graph(n, splits, merges, wrap):
+        g = bytearray(qcgd.fresh_graph(n).tobytes())
+        for i in splits:
+            g[2 + i] = g[2 + n + i] = 1
+        for i in merges:
+            g[2 + i], g[2 + n + i + 1] = 1, 1
+        if wrap:
+            g[2 + n + 0], g[2 + n - 1] = 1, 1
+        return bytes(g)
+
+    objs = [graph(40, [3, 20], [10, 30], True), graph(40, [0, 17], [5], False), graph(33, [32], [1, 8], False),
+            graph(700, [3, 400], [10, 650], True), graph(600, [0], [100], False)]
+    ref = orc.Oracle(orc.REF_SO)
+    state = orc.Packed.from_objects(objs, [0.2, 0.4j, 0.4, 0.6, 0.5])
+    for _ in range(2):
+        a, ac, au = port.simulate(state, orc.RULE_SPLIT_MERGE, [0.3, 0.2, 0.1], tolerance=1e-18)
+        b, bc, bu = ref.simulate(state, orc.RULE_SPLIT_MERGE, [0.3, 0.2, 0.1], tolerance=1e-18)
+        assert (ac, au) == (bc, bu)
+        orc.assert_same_state(a, port.hash_objects(a, orc.RULE_SPLIT_MERGE), b, ref.hash_objects(b, orc.RULE_SPLIT_MERGE), True, what="wide graphs")
+        # the grown graphs with fresh random magnitudes: iterating on the coherent result would un-split everything and leave
+        # residues of cancelled sums, for which a relative tolerance means nothing
+        rng = np.random.default_rng(5)
+        state = orc.Packed(b.sizes, rng.normal(size=b.mags.shape) / 10, b.data)
