@@ -299,7 +299,8 @@ uint64_t select_keep(qb_ctx *ctx, comm_ops *comm, KeyFn key_of, uint64_t n, OutF
 	if (n > 0) {
 		const uint64_t tiles = div_up<uint64_t>(n, SELECT_TILE);
 		const select_state *sel = ctx->select.as<select_state>();
-		if (n < (1ull << 31)) { // both kinds in one pass (two 31-bit running counts in one look-back word)
+		// QB_SELECT_TWO_PASS: developer / test knob that forces the path of inputs of 2^31 keys and more
+		if (n < (1ull << 31) && !getenv("QB_SELECT_TWO_PASS")) { // both kinds in one pass (two 31-bit running counts in one look-back word)
 			scan_state st = ctx->scan(tiles);
 			select_compact_kernel<2><<<(unsigned)tiles, SCAN_THREADS, 0, ctx->stream>>>(key_of, n, sel, out, st);
 			++ctx->launches;
@@ -391,10 +392,10 @@ const uint64_t *sort_items(qb_ctx *ctx, qb_sym *sym, uint64_t n, const uint32_t 
 	sym->sort_base.ensure(sizeof(uint64_t) * (SORT_BINS * tiles + 1), stream);
 	uint32_t *keys[2] = {sym->sort_keys.as<uint32_t>(), sym->sort_keys.as<uint32_t>() + n};
 	uint64_t *vals[2] = {sym->sort_vals.as<uint64_t>(), sym->sort_vals.as<uint64_t>() + n};
-	static bool stage_allowed = false; // the scatter kernel sorts a tile in 58 KB of shared memory
-	if (!stage_allowed) {
+	static bool stage_allowed[MAX_DEVICES] = {}; // the scatter kernel sorts a tile in 58 KB of shared memory: a per-device opt-in
+	if (!stage_allowed[ctx->device % MAX_DEVICES]) {
 		QB_CUDA(cudaFuncSetAttribute((const void *)radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SORT_STAGE_BYTES));
-		stage_allowed = true;
+		stage_allowed[ctx->device % MAX_DEVICES] = true;
 	}
 	int src = 0;
 	for (int shift = 32 - SORT_KEY_BITS; shift < 32; shift += 8, src ^= 1) {

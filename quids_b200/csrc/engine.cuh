@@ -58,6 +58,7 @@ struct engine_launch {
 };
 
 constexpr int ENGINE_THREADS = 256;
+constexpr int MAX_DEVICES = 64; // per-device launch state (one context per GPU; several contexts may live in one process)
 constexpr int SYMBOLIC_CHUNK = 128; // groups of children handled by one warp per loop iteration
 
 inline int resident_grid(const void *kernel, int threads, int sm_count) {
@@ -752,7 +753,11 @@ struct rule_glue {
 			populate_kernel<Rule><<<grid, ENGINE_THREADS, 0, L.stream>>>(*static_cast<const Rule *>(rule), L);
 		} else {
 			constexpr size_t smem = sizeof(populate_stage) * (STAGED_THREADS / 32);
-			static int per_sm = 0; // CTAs of this kernel one SM holds (shared-memory bound)
+			// CTAs of this kernel one SM holds (shared-memory bound); the opt-in to more than 48 KB is a per-DEVICE attribute
+			static int per_sm_of_device[MAX_DEVICES] = {};
+			int device = 0;
+			QB_CUDA(cudaGetDevice(&device));
+			int &per_sm = per_sm_of_device[device % MAX_DEVICES];
 			if (per_sm == 0) {
 				QB_CUDA(cudaFuncSetAttribute((const void *)populate_staged_kernel<Rule>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 				QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)populate_staged_kernel<Rule>, STAGED_THREADS, smem));

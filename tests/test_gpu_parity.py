@@ -645,3 +645,42 @@ def test_split_merge_wide_and_huge_graphs_vs_oracle(gpu, port):
             # second iteration: the grown graphs with fresh random magnitudes (iterating on the coherent result would un-split
             # everything and leave residues of cancelled sums, for which a relative tolerance means nothing)
             state = orc.Packed(want.sizes, np.random.default_rng(5).normal(size=want.mags.shape) / 10, want.data)
+
+
+@pytest.mark.parametrize("two_pass", [False, True])
+def test_truncation_at_scale_vs_oracle(gpu, port, two_pass):
+    """7e5 unique children, k = 1e5: the radix select on its large-input path (candidates of the first two digits copied
+    out, one-pass compaction; with QB_SELECT_TWO_PASS the compaction of inputs beyond 2^31 keys), against the checker;
+    then the same with equal magnitudes everywhere, where the candidates do not fit and every pass reads all the keys"""
+    import os
+    params = [PI / 4, 0.1, 0.2]
+    base = port.qcgd_random_state(12, 6000, 13, 1.0)
+    rng = np.random.default_rng(6)
+    mags = rng.normal(size=(base.n, 2))
+    mags /= np.sqrt((mags ** 2).sum())
+    st = orc.Packed(base.sizes, mags, base.data)
+    k = 100000
+    if two_pass:
+        os.environ["QB_SELECT_TWO_PASS"] = "1"
+    try:
+        full, _, nu = port.simulate(st, orc.RULE_ERASE_CREATE, params, tolerance=1e-18)
+        assert nu >= (1 << 18)
+        want, wc, wu = port.simulate(st, orc.RULE_ERASE_CREATE, params, k, 1e-18)
+        got, gc, gu = gpu().simulate(st, orc.RULE_ERASE_CREATE, params, k, 1e-18)
+        assert (gc, gu) == (wc, wu)
+        orc.assert_same_truncated(got, port.hash_objects(got, orc.RULE_ERASE_CREATE), want, port.hash_objects(want, orc.RULE_ERASE_CREATE), full,
+                                  port.hash_objects(full, orc.RULE_ERASE_CREATE), k, True, what="truncation at scale")
+        # exact ties: every parent has the same magnitude, the children a few hundred distinct ones
+        tied = port.qcgd_random_state(12, 6000, 3)
+        full, _, nu = port.simulate(tied, orc.RULE_ERASE_CREATE, [PI / 4, 0, 0], tolerance=1e-18)
+        got, gc, gu = gpu().simulate(tied, orc.RULE_ERASE_CREATE, [PI / 4, 0, 0], k, 1e-18)
+        assert gu == nu and got.n == k
+        kf = orc.keyed(full, port.hash_objects(full, orc.RULE_ERASE_CREATE), True)
+        f, ff = math.sqrt(got.total_proba), math.sqrt(full.total_proba)
+        probs = np.sort(np.abs(full.cmags) ** 2)[::-1]
+        for h, (o, m) in orc.keyed(got, port.hash_objects(got, orc.RULE_ERASE_CREATE), True).items():
+            assert h in kf and kf[h][0] == o
+            assert abs(m * f - kf[h][1] * ff) <= 1e-12 * abs(m * f)
+            assert abs(kf[h][1]) ** 2 >= probs[k - 1] * (1 - 1e-12)
+    finally:
+        os.environ.pop("QB_SELECT_TWO_PASS", None)
