@@ -194,6 +194,13 @@ def main():
     # equal magnitudes: the ties at the threshold must be shared out between the ranks, exactly k kept
     tied = port.qcgd_random_state(7, 300, 9)
     run_case(comm, port, tied, orc.RULE_ERASE_CREATE, [math.pi / 4, 0, 0], 777, 1e-18, True, "ties across ranks")
+    # at scale: 7e5 unique children, so that every rank's share takes the large-input path of the global select (candidates
+    # copied out after two all-reduced digits), once with distinct probabilities and once saturated with ties
+    big = port.qcgd_random_state(12, 6000, 13, 1.0)
+    big_mags = np.random.default_rng(6).normal(size=(big.n, 2))
+    big = orc.Packed(big.sizes, big_mags / np.sqrt((big_mags ** 2).sum()), big.data)
+    run_case(comm, port, big, orc.RULE_ERASE_CREATE, [math.pi / 4, 0.1, 0.2], 100000, 1e-18, True, "global select at scale")
+    run_case(comm, port, port.qcgd_random_state(12, 6000, 3), orc.RULE_ERASE_CREATE, [math.pi / 4, 0, 0], 100000, 1e-18, True, "global select at scale, ties")
     # load balancing at the head of mpi::simulate (quids_mpi.hpp:442-500): skewed shares, same result
     for rid in orc.QCGD_RULES:
         run_case(comm, port, state, rid, p, orc.NO_TRUNCATION, 1e-18, True, f"rule {rid} skewed shares, equalize by children", share=skewed_share, equalize=2)
