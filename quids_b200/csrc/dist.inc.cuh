@@ -136,15 +136,24 @@ struct comm_ops {
 		recv.ensure(record_bytes * std::max<uint64_t>(1, n_recv), c->ctx->stream);
 		QB_NCCL(nccl().GroupStart());
 		uint64_t send_off = 0, recv_off = 0;
+		const void *self_from = nullptr;
+		void *self_to = nullptr;
 		for (int r = 0; r < c->world; ++r) {
-			if (send_counts[r])
-				QB_NCCL(nccl().Send((const char *)send + send_off * record_bytes, send_counts[r] * record_bytes, ncclUint8, r, c->nccl, c->ctx->stream));
-			if (recv_counts[r])
-				QB_NCCL(nccl().Recv(recv.as<char>() + recv_off * record_bytes, recv_counts[r] * record_bytes, ncclUint8, r, c->nccl, c->ctx->stream));
+			if (r == c->rank) { // what stays on this GPU is a plain device copy, not a send to oneself
+				self_from = (const char *)send + send_off * record_bytes;
+				self_to = recv.as<char>() + recv_off * record_bytes;
+			} else {
+				if (send_counts[r])
+					QB_NCCL(nccl().Send((const char *)send + send_off * record_bytes, send_counts[r] * record_bytes, ncclUint8, r, c->nccl, c->ctx->stream));
+				if (recv_counts[r])
+					QB_NCCL(nccl().Recv(recv.as<char>() + recv_off * record_bytes, recv_counts[r] * record_bytes, ncclUint8, r, c->nccl, c->ctx->stream));
+			}
 			send_off += send_counts[r];
 			recv_off += recv_counts[r];
 		}
 		QB_NCCL(nccl().GroupEnd());
+		if (send_counts[c->rank])
+			QB_CUDA(cudaMemcpyAsync(self_to, self_from, send_counts[c->rank] * record_bytes, cudaMemcpyDeviceToDevice, c->ctx->stream));
 		return recv_counts;
 	}
 };
