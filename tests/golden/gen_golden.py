@@ -3,7 +3,7 @@
 Run in the build container (needs /root/reference, compiled by oracle/Makefile into
 oracle/_ref/libquids_ref.so):
 
-    python tests/golden/gen_golden.py
+    python tests/golden/gen_golden.py [fixture names; default: all]
 
 Each fixture is a "script": an initial packed state and a list of operations (rule iterations and
 modifiers); the state after every operation, its hashes (rule->hasher), N_c, N_u and total_proba
@@ -21,6 +21,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 import orc  # noqa: E402
 
 PI = math.pi
@@ -41,7 +42,12 @@ def canon(p: orc.Packed, qcgd: bool) -> orc.Packed:
     return orc.Packed(p.sizes, p.mags, data, p.total_proba)
 
 
+ONLY = set(sys.argv[1:])  # fixture names to (re)generate; none given = all
+
+
 def run_script(R: orc.Oracle, name, init: orc.Packed, ops, hash_rule, qcgd):
+    if ONLY and name not in ONLY:
+        return
     out = {"ops": json.dumps({"ops": ops, "hash_rule": hash_rule, "qcgd": qcgd})}
     init = canon(init, qcgd)
     out["init_sizes"], out["init_mags"], out["init_data"] = init.sizes, init.mags, init.data
@@ -141,6 +147,31 @@ def main():
     base = R.qcgd_random_state(9, 12, 21)
     for nm, rid, pr in (("erase_create", EC, [0.4, 0.3, 0.2]), ("coin", COIN, [0.4, 0.3, 0.2]), ("split_merge", SM, [0.4, 0.3, 0.2])):
         run_script(R, f"qcgd_random9_{nm}", base, [rule(rid, pr, tol=1e-18), mod(orc.MOD_STEP), rule(rid, pr, tol=1e-18)], EC, True)
+
+    # 8. split_merge outside the GPU path's fast paths: graphs of 33-700 nodes with hand-placed split, merge and wrap-around
+    #    sites (objects up to 14 KB) among ordinary 12-node graphs
+    from quids_b200 import qcgd
+
+    def graph(n, splits, merges, wrap):
+        g = bytearray(qcgd.fresh_graph(n).tobytes())
+        for i in splits:
+            g[2 + i] = g[2 + n + i] = 1
+        for i in merges:
+            g[2 + i], g[2 + n + i + 1] = 1, 1
+        if wrap:
+            g[2 + n + 0], g[2 + n - 1] = 1, 1
+        return bytes(g)
+
+    rng = np.random.default_rng(21)
+    objs = [graph(40, [3, 20], [10, 30], True), graph(40, [0, 17], [5], False), graph(33, [32], [1, 8], False),
+            graph(700, [3, 400], [10, 650], True), graph(600, [0], [100], False)]
+    for _ in range(20):
+        g = bytearray(qcgd.fresh_graph(12).tobytes())
+        g[2:2 + 24] = bytes(rng.integers(0, 2, size=24, dtype=np.uint8))
+        objs.insert(int(rng.integers(0, len(objs) + 1)), bytes(g))
+    mags = rng.normal(size=len(objs)) + 1j * rng.normal(size=len(objs))
+    init = orc.Packed.from_objects(objs, mags / np.linalg.norm(mags))
+    run_script(R, "qcgd_wide_split_merge", init, [rule(SM, [0.3, 0.2, 0.1], tol=1e-18)], EC, True)
 
 
 if __name__ == "__main__":
