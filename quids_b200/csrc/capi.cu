@@ -1004,22 +1004,27 @@ void simulate_dist(qb_iter *it, int rule_id, const rule_ops *ops, const void *ru
 	// 2. partition the locally unique children by owner
 	timer.begin(QB_PHASE_OWNER);
 	const uint64_t n_local = R.n_unique;
-	cm->cursors.ensure(sizeof(uint64_t) * 2 * (world + 1), stream);
-	unsigned long long *counts = cm->cursors.as<unsigned long long>(), *cursor = counts + world + 1;
-	QB_CUDA(cudaMemsetAsync(counts, 0, sizeof(uint64_t) * 2 * (world + 1), stream));
+	const uint32_t sub = owner_sub_buckets(world), bins = world * sub; // records grouped by (owner, region of the owner's table)
+	cm->cursors.ensure(sizeof(uint64_t) * 2 * (bins + 1), stream);
+	unsigned long long *counts = cm->cursors.as<unsigned long long>(), *cursor = counts + bins + 1;
+	QB_CUDA(cudaMemsetAsync(counts, 0, sizeof(uint64_t) * 2 * (bins + 1), stream));
 	std::vector<uint64_t> send_counts(world, 0);
 	const int grid_local = grid_for(n_local, 256, ctx->grid_cap());
 	if (n_local > 0) {
-		owner_count_kernel<<<grid_local, 256, sizeof(unsigned int) * world, stream>>>(R.table, sym->uslot.as<uint32_t>(), n_local, world, counts);
+		owner_count_kernel<<<grid_local, 256, sizeof(unsigned int) * bins, stream>>>(R.table, sym->uslot.as<uint32_t>(), n_local, world, sub, counts);
 		++ctx->launches;
-		QB_CUDA(cudaMemcpyAsync(send_counts.data(), counts, sizeof(uint64_t) * world, cudaMemcpyDeviceToHost, stream));
+		std::vector<uint64_t> bin_counts(bins, 0), offsets(bins, 0);
+		QB_CUDA(cudaMemcpyAsync(bin_counts.data(), counts, sizeof(uint64_t) * bins, cudaMemcpyDeviceToHost, stream));
 		ctx->sync();
-		std::vector<uint64_t> offsets(world, 0);
-		for (uint32_t r = 1; r < world; ++r)
-			offsets[r] = offsets[r - 1] + send_counts[r - 1];
-		QB_CUDA(cudaMemcpyAsync(cursor, offsets.data(), sizeof(uint64_t) * world, cudaMemcpyHostToDevice, stream));
+		for (uint32_t b = 0; b < bins; ++b) {
+			send_counts[b / sub] += bin_counts[b];
+			if (b > 0)
+				offsets[b] = offsets[b - 1] + bin_counts[b - 1];
+		}
+		QB_CUDA(cudaMemcpyAsync(cursor, offsets.data(), sizeof(uint64_t) * bins, cudaMemcpyHostToDevice, stream));
 		cm->send.ensure(sizeof(exchange_record) * n_local, stream);
-		owner_scatter_kernel<<<grid_for(div_up<uint64_t>(n_local, SCATTER_TILE) * 256, 256, ctx->grid_cap()), 256, 2 * sizeof(unsigned long long) * world, stream>>>(R.table, sym->uslot.as<uint32_t>(), n_local, world, cursor, cm->send.as<exchange_record>());
+		owner_scatter_kernel<<<grid_for(div_up<uint64_t>(n_local, SCATTER_TILE) * 256, 256, ctx->grid_cap()), 256, 2 * sizeof(unsigned long long) * bins, stream>>>(
+		    R.table, sym->uslot.as<uint32_t>(), n_local, world, sub, cursor, cm->send.as<exchange_record>());
 		++ctx->launches;
 		ctx->sync(); // `offsets` lives on this stack frame
 	}

@@ -167,6 +167,23 @@ struct __align__(32) exchange_record { // a locally unique child, on its way to 
 
 __device__ __forceinline__ uint32_t owner_of(uint64_t hash, uint32_t world) { return (uint32_t)__umul64hi(mix64(hash ^ 0x9e3779b97f4a7c15ull), (uint64_t)world); }
 
+// Inside the segment a rank sends to one owner, the records are grouped by the TOP BITS of the mix that also places them in
+// the owner's table (table_home = mulhi(mix64(hash), capacity) grows with mix64(hash)): the owner then walks every
+// source's segment as one sweep over its table, and the slots it touches at any moment are a few tens of MB -- L2
+// resident (21 ps per insert) instead of anywhere in a GB of DRAM (100 ps, scripts/table_bench.cu).
+// number of regions (a power of two, at most 256) such that world * regions <= 2048 bins: 32 KB of shared memory in the
+// scatter kernel
+inline uint32_t owner_sub_buckets(uint32_t world) {
+	uint32_t sub = 256;
+	while (sub > 1 && world * sub > 2048)
+		sub >>= 1;
+	return sub;
+}
+__device__ __forceinline__ uint32_t owner_bin(uint64_t hash, uint32_t world, uint32_t sub) {
+	const uint32_t region = sub > 1 ? (uint32_t)__umul64hi(mix64(hash), (uint64_t)sub) : 0u; // the top log2(sub) bits
+	return owner_of(hash, world) * sub + region;
+}
+
 // The partition kernels below count and rank elements by a key with only `world` (2..8) values: one shared-memory atomic
 // per ELEMENT would have 256 threads hammering 2 addresses (1.5 ms for 1.5e7 records, QB_DIST_TRACE).  The lanes of a
 // warp with the same key are merged first: one atomic per (warp, key).
@@ -188,53 +205,55 @@ __device__ __forceinline__ warp_group warp_group_by(bool valid, uint32_t key) {
 	return g;
 }
 
-// counts[owner] over the locally unique children (shared-memory histogram per CTA: a global atomic per
-// element on `world` addresses would serialise in L2)
-__global__ void __launch_bounds__(256) owner_count_kernel(table_view t, const uint32_t *uslot, uint64_t n, uint32_t world, unsigned long long *counts) {
+// counts[bin] over the locally unique children, bin = owner * sub + sub-bucket (shared-memory histogram per CTA: a global
+// atomic per element would serialise in L2)
+__global__ void __launch_bounds__(256) owner_count_kernel(table_view t, const uint32_t *uslot, uint64_t n, uint32_t world, uint32_t sub, unsigned long long *counts) {
 	extern __shared__ unsigned int s_counts[];
-	for (uint32_t i = threadIdx.x; i < world; i += blockDim.x)
+	const uint32_t bins = world * sub;
+	for (uint32_t i = threadIdx.x; i < bins; i += blockDim.x)
 		s_counts[i] = 0;
 	__syncthreads();
 	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
 	for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n; base += stride) {
 		const uint64_t i = base + threadIdx.x;
 		const bool valid = i < n;
-		const uint32_t o = valid ? owner_of(t.slots[uslot[i]].key, world) : 0;
-		const warp_group g = warp_group_by(valid, o);
+		const uint32_t b = valid ? owner_bin(t.slots[uslot[i]].key, world, sub) : 0;
+		const warp_group g = warp_group_by(valid, b);
 		if (g.leader)
-			atomicAdd(&s_counts[o], g.size);
+			atomicAdd(&s_counts[b], g.size);
 	}
 	__syncthreads();
-	for (uint32_t i = threadIdx.x; i < world; i += blockDim.x)
+	for (uint32_t i = threadIdx.x; i < bins; i += blockDim.x)
 		if (s_counts[i])
 			atomicAdd(&counts[i], (unsigned long long)s_counts[i]);
 }
 
-constexpr int SCATTER_TILE = 2048; // elements one CTA places per round: `world` global atomics per tile
+constexpr int SCATTER_TILE = 2048; // elements one CTA places per round: at most one global atomic per bin and tile
 
-// records grouped by owner: cursor[owner] starts at the owner's offset.  Per tile: histogram in shared
-// memory, one global atomicAdd per owner reserves the tile's range, ranks inside the tile come from
-// shared-memory atomics (one per warp and owner).
-__global__ void __launch_bounds__(256) owner_scatter_kernel(table_view t, const uint32_t *uslot, uint64_t n, uint32_t world, unsigned long long *cursor,
+// records grouped by bin: cursor[bin] starts at the bin's offset (owner-major, so every owner's records are contiguous).
+// Per tile: histogram in shared memory, one global atomicAdd per bin reserves the tile's range, ranks inside the tile
+// come from shared-memory atomics (one per warp and bin).
+__global__ void __launch_bounds__(256) owner_scatter_kernel(table_view t, const uint32_t *uslot, uint64_t n, uint32_t world, uint32_t sub, unsigned long long *cursor,
                                                             exchange_record *out) {
-	extern __shared__ unsigned long long s_base[]; // [world] tile base (u64), then [world] counts and [world] running ranks (u32)
-	unsigned int *s_count = reinterpret_cast<unsigned int *>(s_base + world), *s_rank = s_count + world;
+	extern __shared__ unsigned long long s_base[]; // [bins] tile base (u64), then [bins] counts and [bins] running ranks (u32)
+	const uint32_t bins = world * sub;
+	unsigned int *s_count = reinterpret_cast<unsigned int *>(s_base + bins), *s_rank = s_count + bins;
 	for (uint64_t tile = (uint64_t)blockIdx.x * SCATTER_TILE; tile < n; tile += (uint64_t)gridDim.x * SCATTER_TILE) {
-		for (uint32_t i = threadIdx.x; i < world; i += blockDim.x)
+		for (uint32_t i = threadIdx.x; i < bins; i += blockDim.x)
 			s_count[i] = s_rank[i] = 0;
 		__syncthreads();
 		const uint64_t end = min(tile + (uint64_t)SCATTER_TILE, n);
 		for (uint64_t base = tile; base < end; base += blockDim.x) {
 			const uint64_t i = base + threadIdx.x;
 			const bool valid = i < end;
-			const uint32_t o = valid ? owner_of(t.slots[uslot[i]].key, world) : 0;
-			const warp_group g = warp_group_by(valid, o);
+			const uint32_t b = valid ? owner_bin(t.slots[uslot[i]].key, world, sub) : 0;
+			const warp_group g = warp_group_by(valid, b);
 			if (g.leader)
-				atomicAdd(&s_count[o], g.size);
+				atomicAdd(&s_count[b], g.size);
 		}
 		__syncthreads();
-		for (uint32_t o = threadIdx.x; o < world; o += blockDim.x)
-			s_base[o] = s_count[o] ? atomicAdd(&cursor[o], (unsigned long long)s_count[o]) : 0;
+		for (uint32_t b = threadIdx.x; b < bins; b += blockDim.x)
+			s_base[b] = s_count[b] ? atomicAdd(&cursor[b], (unsigned long long)s_count[b]) : 0;
 		__syncthreads();
 		for (uint64_t base = tile; base < end; base += blockDim.x) {
 			const uint64_t i = base + threadIdx.x;
@@ -242,14 +261,14 @@ __global__ void __launch_bounds__(256) owner_scatter_kernel(table_view t, const 
 			table_slot s{};
 			if (valid)
 				s = t.slots[uslot[i]];
-			const uint32_t o = valid ? owner_of(s.key, world) : 0;
-			const warp_group g = warp_group_by(valid, o);
+			const uint32_t b = valid ? owner_bin(s.key, world, sub) : 0;
+			const warp_group g = warp_group_by(valid, b);
 			unsigned int first = 0;
 			if (g.leader)
-				first = atomicAdd(&s_rank[o], g.size);
+				first = atomicAdd(&s_rank[b], g.size);
 			if (valid) {
 				first = __shfl_sync(g.peers, first, __ffs(g.peers) - 1);
-				out[s_base[o] + first + g.rank] = exchange_record{s.key, s.re, s.im, s.rep};
+				out[s_base[b] + first + g.rank] = exchange_record{s.key, s.re, s.im, s.rep};
 			}
 		}
 		__syncthreads();
@@ -263,10 +282,11 @@ __global__ void __launch_bounds__(256) owner_scatter_kernel(table_view t, const 
 __device__ __forceinline__ uint64_t owner_rep_pack(uint64_t position, uint64_t hash) { return ((mix64(position ^ hash) >> 56) << 56) | (position + 1); }
 __device__ __forceinline__ uint64_t owner_rep_position(uint64_t rep) { return (rep & ((1ull << 56) - 1)) - 1; }
 
-// Four records per thread and round: all their key loads go out before any is resolved, so a thread has four DRAM round
-// trips in flight instead of one (the table is far larger than L2 and the records arrive in no useful order).
+// Two records per thread and round: their key loads go out before either is resolved.  Not more: the records of a source
+// arrive grouped by table region (owner_bin), and the narrower the window of records in flight, the smaller the part of
+// the table it touches -- it has to stay L2 resident.
 __global__ void __launch_bounds__(256) record_insert_kernel(table_view t, const exchange_record *records, uint64_t n) {
-	constexpr int N = 4;
+	constexpr int N = 2;
 	const uint64_t threads = (uint64_t)gridDim.x * blockDim.x;
 	unsigned int created = 0;
 	for (uint64_t first = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; first < n; first += threads * N) {
