@@ -25,6 +25,22 @@ def owner_of(h: int, world: int) -> int:  # dist.inc.cuh owner_of: mulhi(mix64(h
     return (mix64(h ^ 0x9e3779b97f4a7c15) * world) >> 64
 
 
+def owner_sub_buckets(world: int) -> int:  # dist.inc.cuh owner_sub_buckets: world * regions <= 2048 bins
+    sub = 256
+    while sub > 1 and world * sub > 2048:
+        sub >>= 1
+    return sub
+
+
+def owner_bin(h: int, world: int, sub: int) -> int:  # dist.inc.cuh owner_bin: owner-major, region of the owner's table inside
+    region = (mix64(h) * sub) >> 64 if sub > 1 else 0
+    return owner_of(h, world) * sub + region
+
+
+def table_home(h: int, capacity: int) -> int:  # table.cuh table_home
+    return (mix64(h) * capacity) >> 64
+
+
 def share_ties(need: int, eq_counts, rank: int) -> int:
     """ties at the threshold are served to the lower ranks first (capi.cu select_keep)"""
     before = sum(eq_counts[:rank])

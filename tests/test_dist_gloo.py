@@ -25,6 +25,29 @@ def test_owner_function_is_balanced_and_total():
         assert counts.max() < 1.1 * len(hashes) / world
 
 
+def test_exchange_bins_group_the_records_by_owner_then_by_table_region():
+    """the records a rank sends are ordered by bin = owner * regions + region (dist.inc.cuh): every owner's records stay
+    contiguous, and inside an owner's segment the home slot in the owner's table never decreases from one region to
+    the next, whatever the capacity -- which is what lets the owner's inserts sweep its table"""
+    rng = np.random.default_rng(3)
+    hashes = [int(h) for h in rng.integers(0, 2**63, size=5000, dtype=np.int64).astype(np.uint64)] + [0, 1, 2**64 - 1]
+    assert [dist_model.owner_sub_buckets(w) for w in (1, 2, 8, 9, 16, 64, 4096)] == [256, 256, 256, 128, 128, 32, 1]
+    for world in (2, 8, 12):
+        sub = dist_model.owner_sub_buckets(world)
+        assert world * sub <= 2048
+        order = sorted(hashes, key=lambda h: dist_model.owner_bin(h, world, sub))
+        owners = [dist_model.owner_of(h, world) for h in order]
+        assert owners == sorted(owners), "an owner's records must be contiguous"
+        for capacity in (1024, 999983, 31000000):
+            for o in range(world):
+                segment = [h for h in order if dist_model.owner_of(h, world) == o]
+                regions = [dist_model.owner_bin(h, world, sub) for h in segment]
+                homes = [dist_model.table_home(h, capacity) for h in segment]
+                for a in range(1, len(segment)):
+                    if regions[a] != regions[a - 1]:  # crossing into the next region: every home there is at or above the last one's
+                        assert min(homes[a:]) >= max(x for x, r in zip(homes[:a], regions[:a]) if r == regions[a - 1])
+
+
 def test_tie_sharing_serves_lower_ranks_first():
     assert [dist_model.share_ties(5, [2, 2, 4], r) for r in range(3)] == [2, 2, 1]
     assert [dist_model.share_ties(0, [2, 2, 4], r) for r in range(3)] == [0, 0, 0]
