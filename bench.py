@@ -176,7 +176,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    parents = CPU_SAMPLE_PARENTS
+    parents = args.cpu_sample_parents
     rate, o, nc, secs = cpu_reference_rate(parents, 0, steps=args.steps, warmup=args.warmup)
     sample = f"{parents} random 12-node parents ({nc} children) per step, erase_create(pi/4), max_num_object={parents}"
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -401,10 +401,10 @@ def run_ours(args):
     # ---- CPU baseline beside it (bounded sample, rank 0, N = 1 only) ----------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu:
-        rate, o, nc_cpu, secs = cpu_reference_rate(CPU_SAMPLE_PARENTS, seed=0, steps=3, warmup=1)
+        rate, o, nc_cpu, secs = cpu_reference_rate(args.cpu_sample_parents, seed=0, steps=3, warmup=1)
         cpu = {"value": rate, "unit": UNIT, "cores": o.num_threads, "kind": o.kind,
-               "sample": f"{CPU_SAMPLE_PARENTS} parents of the same generator ({nc_cpu} children, {secs:.2f} s per step, 3 steps after 1 warm-up), "
-                         f"erase_create(pi/4), max_num_object={CPU_SAMPLE_PARENTS}"}
+               "sample": f"{args.cpu_sample_parents} parents of the same generator ({nc_cpu} children, {secs:.2f} s per step, 3 steps after 1 warm-up), "
+                         f"erase_create(pi/4), max_num_object={args.cpu_sample_parents}"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -430,6 +430,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--parents", type=int, default=10**7, help="parents per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-sample-parents", type=int, default=CPU_SAMPLE_PARENTS, help="parents of the bounded CPU sample (cpu_baseline and --impl reference)")
     ap.add_argument("--large-parents", type=int, default=10**8, help="N = 1 only: also time this many parents on the one GPU (0 = skip)")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: whatever the libraries print on file descriptor 1 meanwhile (NCCL's version
