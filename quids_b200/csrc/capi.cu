@@ -1113,8 +1113,8 @@ void simulate_dist(qb_iter *it, int rule_id, const rule_ops *ops, const void *ru
 	QB_CUDA(cudaMemsetAsync(counts, 0, sizeof(uint64_t) * 2 * (world + 1), stream));
 	std::vector<uint64_t> back_counts(world, 0);
 	if (n_owner_survivors > 0) {
-		// recv_begin on the device: reuse the tail of the cursor buffer after the counts are read
-		dev_buf begin_dev;
+		// recv_begin on the device
+		dev_buf &begin_dev = cm->recv_begin; // kept across calls: a local buffer would cost a cudaMalloc and a synchronising cudaFree per step
 		begin_dev.ensure(sizeof(uint64_t) * (world + 1), stream);
 		QB_CUDA(cudaMemcpyAsync(begin_dev.ptr, recv_begin.data(), sizeof(uint64_t) * (world + 1), cudaMemcpyHostToDevice, stream));
 		const int grid_back = grid_for(n_owner_survivors, 256, ctx->grid_cap());

@@ -82,7 +82,7 @@ struct qb_comm {
 	int world = 1, rank = 0;
 	ncclComm_t nccl = nullptr;
 	dev_buf scratch; // small device staging for host-value collectives
-	dev_buf send, recv, owner_table, okey, oslot, ret_send, ret_recv, cursors;
+	dev_buf send, recv, owner_table, okey, oslot, ret_send, ret_recv, cursors, recv_begin;
 	double owner_unique_ratio = 0; // slots created / records received by the owner table of the last call (0 = no call yet)
 };
 
