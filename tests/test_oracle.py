@@ -175,3 +175,27 @@ def test_split_merge_wide_graphs_port_matches_reference(port):
         # residues of cancelled sums, for which a relative tolerance means nothing
         rng = np.random.default_rng(5)
         state = orc.Packed(b.sizes, rng.normal(size=b.mags.shape) / 10, b.data)
+
+
+def test_port_matches_live_reference_on_random_rule_sequences(port, reference):
+    """random sequences of QCGD rules and steps on small random states (25 seeds): the restatement follows the reference
+    through grown names, merges back and interference, one operation at a time from the reference's state"""
+    rng = np.random.default_rng(2024)
+    for seed in range(25):
+        n_node, n_graphs = int(rng.integers(2, 8)), int(rng.integers(1, 6))
+        state = reference.qcgd_random_state(n_node, n_graphs, 100 + seed)
+        mags = rng.normal(size=(state.n, 2))
+        state = orc.Packed(state.sizes, mags / np.sqrt((mags ** 2).sum()), state.data)
+        for step in range(4):
+            rule_id = int(rng.choice(orc.QCGD_RULES))
+            params = [float(x) for x in rng.uniform(-1.5, 1.5, size=3)]
+            ra, nca, nua = reference.simulate(state, rule_id, params, tolerance=1e-18)
+            rb, ncb, nub = port.simulate(state, rule_id, params, tolerance=1e-18)
+            assert (nca, nua) == (ncb, nub), (seed, step, rule_id)
+            orc.assert_same_state(rb, port.hash_objects(rb, rule_id, params), ra, reference.hash_objects(ra, rule_id, params), True, rtol=1e-10,
+                                  what=f"seed {seed} step {step} rule {rule_id}")
+            mod_id = int(rng.choice([orc.MOD_STEP, orc.MOD_REVERSED_STEP]))
+            state = reference.apply_modifier(ra, mod_id)
+            assert port.apply_modifier(ra, mod_id).objects() == state.objects()
+            if state.n > 1500 or state.n == 0:
+                break
