@@ -160,8 +160,9 @@ namespace quids::mpi {
 		friend void simulate(mpi_it_t &, quids::rule_t const *, mpi_it_t &, mpi_sy_it_t &, communicator &, size_t, quids::debug_t);
 	};
 
-	/// quids::mpi::simulate (quids_mpi.hpp:423-598).  max_num_object counts objects over all ranks; 0 and -1 both mean
-	/// "no truncation" here (the reference's automatic budget is SURVEY 8(f) item 2).
+	/// quids::mpi::simulate (quids_mpi.hpp:423-598).  max_num_object counts objects over all ranks; -1 = no truncation;
+	/// 0 (the default, as in the reference) = automatic budget: every rank keeps the most probable of its parents whose
+	/// workspace fits its GPU, and the ranks agree on how many children the next states can hold (capi.cu simulate_dist).
 	void inline simulate(mpi_it_t &iteration, quids::rule_t const *rule, mpi_it_t &next_iteration, mpi_sy_it_t &symbolic_iteration, communicator &comm,
 	                     size_t max_num_object = 0, quids::debug_t mid_step_function = [](const char *) {}) {
 		iteration.to_device();
@@ -170,7 +171,7 @@ namespace quids::mpi {
 		opt.equalize_inbalance = equalize_inbalance;
 		opt.min_equalize_step = min_equalize_step;
 		opt.min_equalize_size = min_equalize_size;
-		const uint64_t k = (max_num_object == 0 || max_num_object == std::numeric_limits<size_t>::max()) ? QB_NO_TRUNCATION : (uint64_t)max_num_object;
+		const uint64_t k = max_num_object == std::numeric_limits<size_t>::max() ? QB_NO_TRUNCATION : (uint64_t)max_num_object;
 		double node = 1;
 		quids::detail::check(qb_simulate_dist(iteration.handle_, rule->id(), rule->params().data(), (uint32_t)rule->params().size(), next_iteration.handle_,
 		                                      symbolic_iteration.handle_, comm.handle(), k, &opt, mid_step_function ? quids::detail::forward_step : nullptr,

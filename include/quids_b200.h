@@ -50,7 +50,8 @@ typedef struct qb_comm qb_comm; /* stands where MPI_Comm stands in quids_mpi.hpp
  * Here the budget is the GPU memory left after the safety margin (cudaMemGetInfo, or qb_options.memory_budget): the most
  * probable parents whose symbolic workspace (interference table at its safe size, compacted lists, work items) fits are
  * kept, then as many of the most probable children as the next state has room for.  QB_ERR_CAPACITY only when not even
- * one parent's children fit.  The distributed path needs an explicit max_num_object. */
+ * one parent's children fit.  On the distributed path the budget is per rank for the parents and agreed between
+ * the ranks for the children (qb_simulate_dist). */
 
 /* the mutable namespace globals of the reference that influence one call (quids.hpp:60-75) */
 typedef struct qb_options {
@@ -192,7 +193,10 @@ int qb_comm_create(qb_ctx *ctx, int world_size, int rank, const uint8_t id[128],
 int qb_comm_destroy(qb_comm *comm);
 /* quids::mpi::simulate quids_mpi.hpp:423-598: hash-ownership interference over NCCL all-to-allv,
  * global top-k, global normalisation.  next->total_proba is the global sum; node_total_proba is
- * this rank's share (quids_mpi.hpp:67,892). */
+ * this rank's share (quids_mpi.hpp:67,892).  max_num_object counts objects over ALL ranks; 0 = automatic
+ * budget (per-rank parent budget, children: what the ranks agree their next states can hold).
+ * Errors are collective: if any rank fails (a table overflow on its share, an allocation), EVERY rank
+ * returns a non-zero status from the same call -- no rank is left waiting in a collective. */
 int qb_simulate_dist(qb_iter *it, int rule_id, const double *params, uint32_t num_params, qb_iter *next,
                      qb_sym *sym, qb_comm *comm, uint64_t max_num_object, const qb_options *opt,
                      qb_step_cb cb, void *user, double *node_total_proba);

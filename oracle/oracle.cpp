@@ -563,6 +563,7 @@ extern "C" {
 
 const char *orc_kind(void) { return "port"; }
 int orc_num_threads(void) { return 1; }
+int orc_set_num_threads(int) { return 1; }
 
 orc_state *orc_state_create(void) { return new orc_state(); }
 void orc_state_destroy(orc_state *s) { delete s; }
@@ -587,6 +588,28 @@ int orc_state_store(const orc_state *s, uint32_t *sizes, double *mags, uint8_t *
 	}
 	if (!s->s.bytes.empty())
 		memcpy(bytes, s->s.bytes.data(), s->s.bytes.size());
+	return 0;
+}
+
+int orc_state_pop(orc_state *s, uint64_t n, int normalize) {
+	state_t &st = s->s;
+	if (n > st.n())
+		return -1;
+	if (n < 1) /* quids.hpp:195-196 */
+		return 0;
+	const size_t left = st.n() - n;
+	st.bytes.resize(st.begin[left]);
+	st.begin.resize(left + 1);
+	st.mag.resize(left);
+	if (normalize) { /* quids.hpp:985-1017 */
+		st.total_proba = 0;
+		for (size_t i = 0; i < left; ++i)
+			st.total_proba += std::norm(st.mag[i]);
+		const double f = std::sqrt(st.total_proba);
+		if (left > 0 && f != 1)
+			for (size_t i = 0; i < left; ++i)
+				st.mag[i] /= f;
+	}
 	return 0;
 }
 

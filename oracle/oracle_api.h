@@ -49,6 +49,10 @@ typedef struct orc_state orc_state;
 const char *orc_kind(void);
 /* number of host threads the implementation will use for orc_simulate */
 int orc_num_threads(void);
+/* ask for `n` host threads in the following orc_simulate calls (n <= 0: all the cores of the machine); returns what
+ * orc_num_threads() now reports.  torch.distributed.run exports OMP_NUM_THREADS=1 to its workers: bench.py's
+ * reference arm undoes that here.  The port is single-threaded and always returns 1. */
+int orc_set_num_threads(int n);
 
 orc_state *orc_state_create(void);
 void orc_state_destroy(orc_state *s);
@@ -59,6 +63,10 @@ uint64_t orc_state_num_bytes(const orc_state *s); /* sum of object sizes, no pad
 double orc_state_total_proba(const orc_state *s);
 /* copy the state out, packed, in storage order */
 int orc_state_store(const orc_state *s, uint32_t *sizes, double *mags, uint8_t *bytes);
+
+/* iteration::pop (quids.hpp:194-203): drop the last n objects, then (normalize != 0) iteration::normalize (quids.hpp:985-1017):
+ * total_proba = sum of |mag|^2 over what is left, magnitudes divided by its square root unless that is exactly 1 */
+int orc_state_pop(orc_state *s, uint64_t n, int normalize);
 
 /* n_graphs fresh n_node graphs (make_graph, qcgd.hpp:214-230) with magnitude (re, im), then
  * left/right bits drawn with glibc srand(seed); rand()&1 in the order of qcgd.hpp:114-120,232-240 */

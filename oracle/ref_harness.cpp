@@ -74,6 +74,10 @@ extern "C" {
 
 const char *orc_kind(void) { return "reference"; }
 int orc_num_threads(void) { return omp_get_max_threads(); }
+int orc_set_num_threads(int n) {
+	omp_set_num_threads(n > 0 ? n : omp_get_num_procs());
+	return omp_get_max_threads();
+}
 
 orc_state *orc_state_create(void) { return new orc_state(); }
 void orc_state_destroy(orc_state *s) { delete s; }
@@ -121,6 +125,13 @@ int orc_state_store(const orc_state *s, uint32_t *sizes, double *mags, uint8_t *
 		memcpy(bytes + off, b, size);
 		off += size;
 	}
+	return 0;
+}
+
+int orc_state_pop(orc_state *s, uint64_t n, int normalize) {
+	if (n > s->it.num_object)
+		return -1;
+	s->it.pop(n, normalize != 0);
 	return 0;
 }
 

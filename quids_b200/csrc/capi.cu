@@ -90,6 +90,7 @@ struct qb_ctx {
 	dev_buf select;
 	dev_buf select_cand; // keys still in the race after two digits of a radix select (select.cuh)
 
+	size_t l2_fetch_granularity_before = 0; // cudaLimitMaxL2FetchGranularity as found by qb_ctx_create (restored by qb_ctx_destroy)
 	cudaStream_t copy_in = nullptr, copy_out = nullptr; // host <-> device transfers that overlap the compute stream (qb_iter_*_async)
 	cudaEvent_t fence = nullptr;
 
@@ -157,8 +158,8 @@ struct qb_sym {
 	cudaEvent_t ev[2 * QB_PHASE_COUNT] = {};
 	bool ev_used[QB_PHASE_COUNT] = {};
 	float phase_ms[QB_PHASE_COUNT] = {};
-	std::map<int, double> unique_ratio; // per rule id: slots created / children of the last call (sizes the next table)
-	std::map<int, std::pair<double, double>> region_ratio; // region mode: (slots handed out, regions created) / children of the last call
+	std::map<uint64_t, double> unique_ratio; // per (rule id, parameters), see rule_history_key(): slots created / children of the last call (sizes the next table)
+	std::map<uint64_t, std::pair<double, double>> region_ratio; // region mode: (slots handed out, regions created) / children of the last call
 	uint64_t table_capacity = 0;        // of the last call
 	int table_attempts = 0;
 
@@ -432,6 +433,18 @@ void scale_state(qb_ctx *ctx, cplx *mag, uint64_t n, double total) {
 	++ctx->launches;
 }
 
+// what the table-size history of a symbolic iteration is filed under: the rule AND its parameters (erase_create(0.1) and
+// erase_create(pi/4) on the same state create very different numbers of slots: amplitudes that vanish prune children)
+uint64_t rule_history_key(int rule_id, const double *params, uint32_t num_params) {
+	uint64_t h = mix64((uint64_t)rule_id + 0x9e3779b97f4a7c15ull);
+	for (uint32_t i = 0; i < num_params; ++i) {
+		uint64_t bits;
+		memcpy(&bits, &params[i], sizeof bits);
+		h = mix64(h ^ bits) + i;
+	}
+	return h;
+}
+
 void resolve_options(const qb_options *in, qb_options &opt) {
 	qb_options_default(&opt);
 	if (in)
@@ -469,8 +482,9 @@ struct local_table {
 	int empty_from = -1; // >= 0: nothing to do from label `empty_from` on (no parents / no children)
 };
 
-local_table build_local_table(qb_iter *it, int rule_id, const rule_ops *ops, const void *rule, qb_sym *sym, uint64_t max_num_object, bool automatic,
-                              const qb_options &opt, double compaction_tolerance, phase_timer &timer, const stepper &step, engine_launch &L, comm_ops *comm) {
+local_table build_local_table(qb_iter *it, uint64_t rule_id, const rule_ops *ops, const void *rule, qb_sym *sym, uint64_t max_num_object, bool automatic,
+                              const qb_options &opt, double compaction_tolerance, phase_timer &timer, const stepper &step, engine_launch &L, comm_ops *comm,
+                              bool *past_collectives = nullptr) {
 	qb_ctx *ctx = it->ctx;
 	cudaStream_t stream = ctx->stream;
 	local_table R;
@@ -530,6 +544,8 @@ local_table build_local_table(qb_iter *it, int rule_id, const rule_ops *ops, con
 	// ---- 2a. automatic budget (max_num_object = 0, quids.hpp:459-485): keep the most probable parents whose
 	//          symbolic workspace fits in the GPU memory left after the safety margin.  The reference bisects
 	//          over get_truncated_mem_size (:574-589); here the count shrinks by the ratio budget / need until it fits.
+	bool parents_chosen = false;
+	R.n_parents = it->n;
 	if (automatic && it->n > 0) {
 		const double budget = automatic_budget(ctx, sym, nullptr, opt);
 		uint64_t k = it->n;
@@ -539,7 +555,8 @@ local_table build_local_table(qb_iter *it, int rule_id, const rule_ops *ops, con
 			const uint64_t children = index_children(kept, k);
 			// interference table at its safe size + the compacted (key, slot) lists + sorted work items and parent contexts
 			need = (std::ceil((double)children / opt.table_load) + 2) * sizeof(table_slot) + 12.0 * (double)children +
-			       (ops->has_group_key ? 24.0 * (double)n_groups + (double)ops->ctx_bytes * (double)k : 0.0) + 16.0 * (double)k;
+			       (ops->has_group_key ? 24.0 * (double)n_groups + (double)ops->ctx_bytes * (double)k : 0.0) + 16.0 * (double)k +
+			       (comm ? 140.0 * (double)children : 0.0); // distributed path: send + receive buffers, owner table and its compacted lists
 			if (need <= budget || k <= 1)
 				break;
 			k = std::max<uint64_t>(1, std::min<uint64_t>(k - 1, (uint64_t)((double)k * std::min(0.9, budget / need))));
@@ -552,8 +569,14 @@ local_table build_local_table(qb_iter *it, int rule_id, const rule_ops *ops, con
 		QB_REQUIRE(need <= budget, QB_ERR_CAPACITY,
 		           "max_num_object = 0 (automatic budget): the children of a single parent need about " + std::to_string((uint64_t)(need / 1e6)) +
 		               " MB of workspace, " + std::to_string((uint64_t)(std::max(0.0, budget) / 1e6)) + " MB are available after the safety margin");
-		if (k < it->n)
-			max_num_object = k;
+		if (k < it->n) {
+			if (comm) { // distributed path: every rank keeps what ITS memory holds (as the reference does, quids_mpi.hpp:505-537)
+				parents_chosen = true;
+				R.n_parents = k;
+				R.kept = kept;
+			} else
+				max_num_object = k;
+		}
 		R.workspace = need;
 	}
 
@@ -561,8 +584,7 @@ local_table build_local_table(qb_iter *it, int rule_id, const rule_ops *ops, con
 	//         over ALL ranks on the distributed path, so that the result equals the single-GPU one ---------
 	step("truncate_symbolic - prepare");
 	step("truncate_symbolic");
-	R.n_parents = it->n;
-	if (max_num_object < n_global) {
+	if (!parents_chosen && max_num_object < n_global) {
 		timer.begin(QB_PHASE_PRE_TRUNCATE);
 		sym->kept.ensure(sizeof(uint64_t) * std::max<uint64_t>(1, std::min<uint64_t>(it->n, max_num_object)), stream);
 		if (opt.simple_truncation) {
@@ -595,6 +617,8 @@ local_table build_local_table(qb_iter *it, int rule_id, const rule_ops *ops, con
 	QB_REQUIRE(R.n_children <= REP_MAX_INDEX, QB_ERR_CAPACITY, "more than 2^40 children in one iteration");
 	QB_REQUIRE(max_child_size <= REP_MAX_SIZE, QB_ERR_CAPACITY, "child objects of 16 MiB or more are not supported");
 	step("symbolic_iteration");
+	if (past_collectives) // nothing below talks to the other ranks: what fails from here on is agreed on by the caller
+		*past_collectives = true;
 	if (R.n_children == 0) // this rank has nothing to contribute (distributed path only)
 		return R;
 
@@ -681,8 +705,15 @@ local_table build_local_table(qb_iter *it, int rule_id, const rule_ops *ops, con
 		}
 		timer.end(QB_PHASE_PRE_TRUNCATE);
 	}
+	// mid_step_function labels of compute_collisions (quids.hpp:754,784,810), single-GPU path: the reference's phases map to
+	// prepare = table (and directory) clear, insert = the fused child-generation + table-insert kernel, finalize = compaction by
+	// tolerance; "symbolic_iteration" before them covers the ordering of the work items.  A redo after a table overflow does not
+	// repeat the labels (their order is part of the API): its time is attributed to "finalize".
+	const bool collision_labels = comm == nullptr;
 	for (sym->table_attempts = 1;; ++sym->table_attempts) {
 		QB_REQUIRE(capacity + 1 <= 0xffffffffull, QB_ERR_CAPACITY, "interference table would need more than 2^32 slots");
+		if (collision_labels && sym->table_attempts == 1)
+			step("compute_collisions - prepare");
 		timer.begin(QB_PHASE_TABLE_CLEAR);
 		const size_t table_bytes = (capacity + 1) * sizeof(table_slot);
 		sym->table.ensure(table_bytes, stream);
@@ -702,6 +733,8 @@ local_table build_local_table(qb_iter *it, int rule_id, const rule_ops *ops, con
 		timer.end(QB_PHASE_TABLE_CLEAR);
 
 		// children -> (hash, magnitude) -> table (quids.hpp:705-719 fused with :785-809)
+		if (collision_labels && sym->table_attempts == 1)
+			step("compute_collisions - insert");
 		timer.begin(QB_PHASE_SYMBOLIC);
 		L.table = R.table;
 		if (sorted_order)
@@ -712,6 +745,8 @@ local_table build_local_table(qb_iter *it, int rule_id, const rule_ops *ops, con
 		timer.end(QB_PHASE_SYMBOLIC);
 
 		// unique children above the tolerance (quids.hpp:819-823)
+		if (collision_labels && sym->table_attempts == 1)
+			step("compute_collisions - finalize");
 		timer.begin(QB_PHASE_COMPACT);
 		uint64_t scan_slots = capacity; // hashed table: every slot may be occupied; regions: only the slots handed out
 		if (region_mode) {
@@ -764,7 +799,7 @@ struct survivor_source {
 
 void finalize_and_normalize(qb_iter *it, const rule_ops *ops, const void *rule, qb_iter *next, qb_sym *sym, const qb_options &opt, const local_table &R,
                             const survivor_source &src, uint64_t n_survivors, phase_timer &timer, const stepper &step, engine_launch &L, comm_ops *comm,
-                            double *node_total_proba);
+                            double *node_total_proba, bool inject_failure = false);
 
 void finish_empty(qb_ctx *ctx, qb_iter *next, const stepper &step, phase_timer &timer, int from) {
 	// the label sequences of the reference's early outs (quids.hpp:650-651,729-731,908-909,989-990)
@@ -781,7 +816,7 @@ void finish_empty(qb_ctx *ctx, qb_iter *next, const stepper &step, phase_timer &
 	timer.collect();
 }
 
-void simulate(qb_iter *it, int rule_id, const rule_ops *ops, const void *rule, qb_iter *next, qb_sym *sym, uint64_t max_num_object, const qb_options &opt,
+void simulate(qb_iter *it, uint64_t rule_id, const rule_ops *ops, const void *rule, qb_iter *next, qb_sym *sym, uint64_t max_num_object, const qb_options &opt,
               qb_step_cb cb, void *user) {
 	qb_ctx *ctx = it->ctx;
 	QB_REQUIRE(next->ctx == ctx && sym->ctx == ctx, QB_ERR_ARG, "iteration, next iteration and symbolic iteration belong to different contexts");
@@ -808,10 +843,7 @@ void simulate(qb_iter *it, int rule_id, const rule_ops *ops, const void *rule, q
 		finish_empty(ctx, next, step, timer, R.empty_from);
 		return;
 	}
-	sym->n_unique = R.n_unique;
-	step("compute_collisions - prepare");
-	step("compute_collisions - insert");
-	step("compute_collisions - finalize");
+	sym->n_unique = R.n_unique; // (the compute_collisions labels were emitted inside build_local_table, around the phases they name)
 
 	// ---- 7. child truncation: the max_num_object most probable (quids.hpp:866-900) ---------------------
 	step("truncate - prepare");
@@ -852,9 +884,16 @@ void simulate(qb_iter *it, int rule_id, const rule_ops *ops, const void *rule, q
 
 void finalize_and_normalize(qb_iter *it, const rule_ops *ops, const void *rule, qb_iter *next, qb_sym *sym, const qb_options &opt, const local_table &R,
                             const survivor_source &src, uint64_t n_survivors, phase_timer &timer, const stepper &step, engine_launch &L, comm_ops *comm,
-                            double *node_total_proba) {
+                            double *node_total_proba, bool inject_failure) {
 	qb_ctx *ctx = it->ctx;
 	cudaStream_t stream = ctx->stream;
+	comm_ops::pending_error err; // distributed path: a failure of this rank's finalisation is agreed on at the normalisation sum
+	auto guarded_phase = [&](auto &&f) {
+		if (comm)
+			err.run(f);
+		else
+			f();
+	};
 
 	// ---- 8. finalisation (quids.hpp:905-968) ------------------------------------------------------------
 	step("prepare_final");
@@ -862,6 +901,9 @@ void finalize_and_normalize(qb_iter *it, const rule_ops *ops, const void *rule, 
 	next->n = n_survivors;
 	next->n_bytes = 0;
 	double local_total = 0;
+	guarded_phase([&] {
+	if (inject_failure)
+		throw qb::error(QB_ERR_CAPACITY, "injected failure in phase finalize");
 	next->begin.ensure(sizeof(uint64_t) * (n_survivors + 1), stream);
 	if (n_survivors > 0) {
 		next->size.ensure(sizeof(uint32_t) * n_survivors, stream);
@@ -917,8 +959,10 @@ void finalize_and_normalize(qb_iter *it, const rule_ops *ops, const void *rule, 
 	} else {
 		QB_CUDA(cudaMemsetAsync(next->begin.ptr, 0, sizeof(uint64_t), stream));
 	}
+	});
 
 	step("final");
+	guarded_phase([&] {
 	if (n_survivors > 0) {
 		L.n_survivors = n_survivors;
 		L.survivor_parent = sym->survivor_parent.as<uint64_t>();
@@ -929,12 +973,13 @@ void finalize_and_normalize(qb_iter *it, const rule_ops *ops, const void *rule, 
 		ops->launch_populate(rule, L);
 		QB_CUDA(cudaGetLastError());
 	}
+	});
 	timer.end(QB_PHASE_FINALIZE);
 
 	// ---- 9. normalisation (quids.hpp:985-1017, quids_mpi.hpp:870-895); total_proba keeps the pre-normalisation sum
 	step("normalize");
 	timer.begin(QB_PHASE_NORMALIZE);
-	const double total = comm ? comm->sum_f64(local_total) : local_total;
+	const double total = comm ? comm->sum_f64_agreed(local_total, err, "the finalisation") : local_total;
 	next->total_proba = total;
 	if (node_total_proba)
 		*node_total_proba = total > 0 ? local_total / total : 0; // quids_mpi.hpp:892
@@ -951,12 +996,17 @@ void finalize_and_normalize(qb_iter *it, const rule_ops *ops, const void *rule, 
 // ======================================================================================================
 // one rule iteration over the GPUs of a communicator (see dist.inc.cuh for the protocol)
 // ======================================================================================================
-void simulate_dist(qb_iter *it, int rule_id, const rule_ops *ops, const void *rule, qb_iter *next, qb_sym *sym, qb_comm *cm, uint64_t max_num_object,
+void simulate_dist(qb_iter *it, uint64_t rule_id, const rule_ops *ops, const void *rule, qb_iter *next, qb_sym *sym, qb_comm *cm, uint64_t max_num_object,
                    const qb_options &opt, qb_step_cb cb, void *user, double *node_total_proba) {
 	qb_ctx *ctx = it->ctx;
 	QB_REQUIRE(next->ctx == ctx && sym->ctx == ctx && cm->ctx == ctx, QB_ERR_ARG, "handles belong to different contexts");
 	QB_REQUIRE(next != it, QB_ERR_ARG, "next_iteration must be a different object from iteration");
-	QB_REQUIRE(max_num_object != 0, QB_ERR_UNSUPPORTED, "the distributed path needs an explicit max_num_object (or QB_NO_TRUNCATION)");
+	// max_num_object = 0 (the reference's default, quids_mpi.hpp:423): automatic budget.  Parents: every rank keeps the most
+	// probable of ITS parents whose workspace fits its GPU (per rank, as in the reference, :505-537).  Children: the global
+	// top-k with k = what the ranks can hold, agreed by all ranks (below, after the owner merge).
+	const bool automatic = max_num_object == 0;
+	if (automatic)
+		max_num_object = QB_NO_TRUNCATION;
 	ctx->use();
 	it->settle();
 	next->settle();
@@ -964,8 +1014,15 @@ void simulate_dist(qb_iter *it, int rule_id, const rule_ops *ops, const void *ru
 	stepper step{ctx, cb, user};
 	phase_timer timer(sym, opt.profile != 0);
 	comm_ops comm{cm};
+	comm_ops::pending_error err; // see dist.inc.cuh: a failure on one rank is agreed on at the next count exchange
 	const uint32_t world = (uint32_t)cm->world;
 	const bool trace = getenv("QB_DIST_TRACE") != nullptr; // developer aid: wall-clock of every distributed sub-step (drains the stream)
+	// test knob: "<rank>:<phase>" makes that rank fail in that phase (local, partition, owner, return, finalize)
+	const char *inject = getenv("QB_DIST_INJECT_FAILURE");
+	auto injected = [&](const char *phase) {
+		if (inject && atoi(inject) == cm->rank && strchr(inject, ':') && !strcmp(strchr(inject, ':') + 1, phase))
+			throw qb::error(QB_ERR_CAPACITY, std::string("injected failure in phase ") + phase);
+	};
 	auto t_last = std::chrono::steady_clock::now();
 	auto mark = [&](const char *what) {
 		if (!trace) return;
@@ -991,9 +1048,21 @@ void simulate_dist(qb_iter *it, int rule_id, const rule_ops *ops, const void *ru
 	L.launch_counter = &ctx->launches;
 	L.it = it->view();
 
-	// 1. local children, merged locally; the tolerance applies to GLOBAL sums only: keep every occupied slot
-	local_table R = build_local_table(it, rule_id, ops, rule, sym, max_num_object, false, opt, -1.0, timer, step, L, &comm);
-	if (R.empty_from >= 0) {
+	// 1. local children, merged locally; the tolerance applies to GLOBAL sums only: keep every occupied slot.
+	//    (The collectives inside -- global counts, the all-reduced select of the parents -- come BEFORE the data-dependent part,
+	//    the interference table; what fails there is caught and agreed on at the count exchange of step 3.)
+	local_table R;
+	bool past_collectives = false;
+	try {
+		R = build_local_table(it, rule_id, ops, rule, sym, max_num_object, automatic, opt, -1.0, timer, step, L, &comm, &past_collectives);
+		injected("local");
+	} catch (const qb::error &e) {
+		if (!past_collectives)
+			throw;
+		err.status = e.status;
+		err.what = e.what();
+	}
+	if (err.ok() && R.empty_from >= 0) {
 		finish_empty(ctx, next, step, timer, R.empty_from);
 		if (node_total_proba) *node_total_proba = 0;
 		return;
@@ -1003,39 +1072,46 @@ void simulate_dist(qb_iter *it, int rule_id, const rule_ops *ops, const void *ru
 
 	// 2. partition the locally unique children by owner
 	timer.begin(QB_PHASE_OWNER);
-	const uint64_t n_local = R.n_unique;
+	const uint64_t n_local = err.ok() ? R.n_unique : 0;
 	const uint32_t sub = owner_sub_buckets(world), bins = world * sub; // records grouped by (owner, region of the owner's table)
-	cm->cursors.ensure(sizeof(uint64_t) * 2 * (bins + 1), stream);
-	unsigned long long *counts = cm->cursors.as<unsigned long long>(), *cursor = counts + bins + 1;
-	QB_CUDA(cudaMemsetAsync(counts, 0, sizeof(uint64_t) * 2 * (bins + 1), stream));
+	unsigned long long *counts = nullptr, *cursor = nullptr;
 	std::vector<uint64_t> send_counts(world, 0);
-	const int grid_local = grid_for(n_local, 256, ctx->grid_cap());
-	if (n_local > 0) {
-		owner_count_kernel<<<grid_local, 256, sizeof(unsigned int) * bins, stream>>>(R.table, sym->uslot.as<uint32_t>(), n_local, world, sub, counts);
-		++ctx->launches;
-		std::vector<uint64_t> bin_counts(bins, 0), offsets(bins, 0);
-		QB_CUDA(cudaMemcpyAsync(bin_counts.data(), counts, sizeof(uint64_t) * bins, cudaMemcpyDeviceToHost, stream));
-		ctx->sync();
-		for (uint32_t b = 0; b < bins; ++b) {
-			send_counts[b / sub] += bin_counts[b];
-			if (b > 0)
-				offsets[b] = offsets[b - 1] + bin_counts[b - 1];
+	err.run([&] {
+		cm->cursors.ensure(sizeof(uint64_t) * 2 * (bins + 1), stream);
+		counts = cm->cursors.as<unsigned long long>();
+		cursor = counts + bins + 1;
+		QB_CUDA(cudaMemsetAsync(counts, 0, sizeof(uint64_t) * 2 * (bins + 1), stream));
+		injected("partition");
+		if (n_local > 0) {
+			const int grid_local = grid_for(n_local, 256, ctx->grid_cap());
+			owner_count_kernel<<<grid_local, 256, sizeof(unsigned int) * bins, stream>>>(R.table, sym->uslot.as<uint32_t>(), n_local, world, sub, counts);
+			++ctx->launches;
+			std::vector<uint64_t> bin_counts(bins, 0), offsets(bins, 0);
+			QB_CUDA(cudaMemcpyAsync(bin_counts.data(), counts, sizeof(uint64_t) * bins, cudaMemcpyDeviceToHost, stream));
+			ctx->sync();
+			for (uint32_t b = 0; b < bins; ++b) {
+				send_counts[b / sub] += bin_counts[b];
+				if (b > 0)
+					offsets[b] = offsets[b - 1] + bin_counts[b - 1];
+			}
+			QB_CUDA(cudaMemcpyAsync(cursor, offsets.data(), sizeof(uint64_t) * bins, cudaMemcpyHostToDevice, stream));
+			cm->send.ensure(sizeof(exchange_record) * n_local, stream);
+			owner_scatter_kernel<<<grid_for(div_up<uint64_t>(n_local, SCATTER_TILE) * 256, 256, ctx->grid_cap()), 256, 2 * sizeof(unsigned long long) * bins, stream>>>(
+			    R.table, sym->uslot.as<uint32_t>(), n_local, world, sub, cursor, cm->send.as<exchange_record>());
+			++ctx->launches;
+			ctx->sync(); // `offsets` lives on this stack frame
 		}
-		QB_CUDA(cudaMemcpyAsync(cursor, offsets.data(), sizeof(uint64_t) * bins, cudaMemcpyHostToDevice, stream));
-		cm->send.ensure(sizeof(exchange_record) * n_local, stream);
-		owner_scatter_kernel<<<grid_for(div_up<uint64_t>(n_local, SCATTER_TILE) * 256, 256, ctx->grid_cap()), 256, 2 * sizeof(unsigned long long) * bins, stream>>>(
-		    R.table, sym->uslot.as<uint32_t>(), n_local, world, sub, cursor, cm->send.as<exchange_record>());
-		++ctx->launches;
-		ctx->sync(); // `offsets` lives on this stack frame
-	}
+	});
+	if (!err.ok())
+		std::fill(send_counts.begin(), send_counts.end(), 0);
 
 	mark("partition by owner");
-	// 3. all-to-allv of the records
+	// 3. all-to-allv of the records (its count exchange is the agreement point of steps 1 and 2)
 	timer.end(QB_PHASE_OWNER);
 	step("compute_collisions - com");
 	timer.begin(QB_PHASE_EXCHANGE);
 	uint64_t n_recv = 0;
-	std::vector<uint64_t> recv_counts = comm.alltoallv(cm->send.ptr, send_counts, cm->recv, sizeof(exchange_record), n_recv);
+	std::vector<uint64_t> recv_counts = comm.alltoallv(cm->send.ptr, send_counts, cm->recv, sizeof(exchange_record), n_recv, &err, "the local interference step");
 	timer.end(QB_PHASE_EXCHANGE);
 	std::vector<uint64_t> recv_begin(world + 1, 0);
 	for (uint32_t r = 0; r < world; ++r)
@@ -1047,7 +1123,10 @@ void simulate_dist(qb_iter *it, int rule_id, const rule_ops *ops, const void *ru
 	timer.begin(QB_PHASE_OWNER);
 	table_view owner{};
 	uint64_t n_owner_unique = 0;
-	if (n_recv > 0) {
+	err.run([&] {
+		injected("owner");
+		if (n_recv == 0)
+			return;
 		// every rank sends each of its objects once, so an object arrives up to `world` times: the table is sized from the share
 		// of the records that created a slot in the previous call (x 1.25), at most for "every record is a new object"; a
 		// table that turns out too small is redone at that size
@@ -1080,10 +1159,32 @@ void simulate_dist(qb_iter *it, int rule_id, const rule_ops *ops, const void *ru
 		}
 		cm->owner_unique_ratio = (double)ctx->h_small[DS_USED] / (double)n_recv;
 		n_owner_unique = ctx->h_small[DS_COUNT];
-	}
+	});
 	timer.end(QB_PHASE_OWNER);
 	step("compute_collisions - finalize");
-	const uint64_t n_unique_global = comm.sum_u64(n_owner_unique);
+	// automatic budget, children (quids.hpp:510-536): what this rank's next state has room for; all ranks then keep the global
+	// top-k with k = half of (ranks x the smallest room): the survivors spread evenly over the ranks of their representatives
+	// (pseudo-random choice, dist.inc.cuh), a factor 2 of head room covers the spread
+	uint64_t room = 0;
+	if (automatic)
+		err.run([&] {
+			const double budget = automatic_budget(ctx, sym, next, opt, R.workspace);
+			const double per_object = (double)((R.max_child_size + 7u) & ~7u) + 48.0 + sizeof(survivor_record) * 2;
+			room = budget > 0 ? (uint64_t)(budget / per_object) : 0;
+			QB_REQUIRE(room >= 1, QB_ERR_CAPACITY, "max_num_object = 0 (automatic budget): no room left for a next state on this rank");
+		});
+	uint64_t n_unique_global = 0;
+	{
+		const uint64_t mine[2] = {n_owner_unique, automatic ? room : ~0ull};
+		std::vector<uint64_t> all = comm.allgather_agreed(mine, 2, err, "the owner-side interference step");
+		uint64_t min_room = ~0ull;
+		for (uint32_t r = 0; r < world; ++r) {
+			n_unique_global += all[2 * r];
+			min_room = std::min(min_room, all[2 * r + 1]);
+		}
+		if (automatic)
+			max_num_object = std::max<uint64_t>(1, (uint64_t)((double)min_room * world / 2));
+	}
 	sym->n_unique = n_owner_unique; // this rank's share; qb_comm_allreduce_u64 gives the total (get_total_num_object_after_interferences)
 
 	mark("owner merge + compact");
@@ -1110,40 +1211,45 @@ void simulate_dist(qb_iter *it, int rule_id, const rule_ops *ops, const void *ru
 	mark("global select");
 	// 6. survivors go back to the rank of their representative
 	timer.begin(QB_PHASE_OWNER);
-	QB_CUDA(cudaMemsetAsync(counts, 0, sizeof(uint64_t) * 2 * (world + 1), stream));
 	std::vector<uint64_t> back_counts(world, 0);
-	if (n_owner_survivors > 0) {
-		// recv_begin on the device
-		dev_buf &begin_dev = cm->recv_begin; // kept across calls: a local buffer would cost a cudaMalloc and a synchronising cudaFree per step
-		begin_dev.ensure(sizeof(uint64_t) * (world + 1), stream);
-		QB_CUDA(cudaMemcpyAsync(begin_dev.ptr, recv_begin.data(), sizeof(uint64_t) * (world + 1), cudaMemcpyHostToDevice, stream));
-		const int grid_back = grid_for(n_owner_survivors, 256, ctx->grid_cap());
-		return_count_kernel<<<grid_back, 256, sizeof(unsigned int) * world, stream>>>(owner, owner_survivor_slot, n_owner_survivors, begin_dev.as<uint64_t>(), world, counts);
-		++ctx->launches;
-		QB_CUDA(cudaMemcpyAsync(back_counts.data(), counts, sizeof(uint64_t) * world, cudaMemcpyDeviceToHost, stream));
-		ctx->sync();
-		std::vector<uint64_t> offsets(world, 0);
-		for (uint32_t r = 1; r < world; ++r)
-			offsets[r] = offsets[r - 1] + back_counts[r - 1];
-		QB_CUDA(cudaMemcpyAsync(cursor, offsets.data(), sizeof(uint64_t) * world, cudaMemcpyHostToDevice, stream));
-		cm->ret_send.ensure(sizeof(survivor_record) * n_owner_survivors, stream);
-		return_scatter_kernel<<<grid_for(div_up<uint64_t>(n_owner_survivors, SCATTER_TILE) * 256, 256, ctx->grid_cap()), 256, 2 * sizeof(unsigned long long) * world, stream>>>(owner, owner_survivor_slot, n_owner_survivors, begin_dev.as<uint64_t>(), world,
-		                                                     cm->recv.as<exchange_record>(), cursor, cm->ret_send.as<survivor_record>());
-		++ctx->launches;
-		ctx->sync();
-	}
+	err.run([&] {
+		injected("return");
+		QB_CUDA(cudaMemsetAsync(counts, 0, sizeof(uint64_t) * 2 * (world + 1), stream));
+		if (n_owner_survivors > 0) {
+			// recv_begin on the device
+			dev_buf &begin_dev = cm->recv_begin; // kept across calls: a local buffer would cost a cudaMalloc and a synchronising cudaFree per step
+			begin_dev.ensure(sizeof(uint64_t) * (world + 1), stream);
+			QB_CUDA(cudaMemcpyAsync(begin_dev.ptr, recv_begin.data(), sizeof(uint64_t) * (world + 1), cudaMemcpyHostToDevice, stream));
+			const int grid_back = grid_for(n_owner_survivors, 256, ctx->grid_cap());
+			return_count_kernel<<<grid_back, 256, sizeof(unsigned int) * world, stream>>>(owner, owner_survivor_slot, n_owner_survivors, begin_dev.as<uint64_t>(), world, counts);
+			++ctx->launches;
+			QB_CUDA(cudaMemcpyAsync(back_counts.data(), counts, sizeof(uint64_t) * world, cudaMemcpyDeviceToHost, stream));
+			ctx->sync();
+			std::vector<uint64_t> offsets(world, 0);
+			for (uint32_t r = 1; r < world; ++r)
+				offsets[r] = offsets[r - 1] + back_counts[r - 1];
+			QB_CUDA(cudaMemcpyAsync(cursor, offsets.data(), sizeof(uint64_t) * world, cudaMemcpyHostToDevice, stream));
+			cm->ret_send.ensure(sizeof(survivor_record) * n_owner_survivors, stream);
+			return_scatter_kernel<<<grid_for(div_up<uint64_t>(n_owner_survivors, SCATTER_TILE) * 256, 256, ctx->grid_cap()), 256, 2 * sizeof(unsigned long long) * world, stream>>>(owner, owner_survivor_slot, n_owner_survivors, begin_dev.as<uint64_t>(), world,
+			                                                     cm->recv.as<exchange_record>(), cursor, cm->ret_send.as<survivor_record>());
+			++ctx->launches;
+			ctx->sync();
+		}
+	});
+	if (!err.ok())
+		std::fill(back_counts.begin(), back_counts.end(), 0);
 	timer.end(QB_PHASE_OWNER);
 	step("compute_collisions - com");
 	timer.begin(QB_PHASE_EXCHANGE);
 	uint64_t n_survivors = 0;
-	comm.alltoallv(cm->ret_send.ptr, back_counts, cm->ret_recv, sizeof(survivor_record), n_survivors);
+	comm.alltoallv(cm->ret_send.ptr, back_counts, cm->ret_recv, sizeof(survivor_record), n_survivors, &err, "the return of the survivors");
 	timer.end(QB_PHASE_EXCHANGE);
 
 	mark("return survivors");
 	// 7. every rank rebuilds the survivors whose representative it generated, then global normalisation
 	survivor_source src;
 	src.records = cm->ret_recv.as<survivor_record>();
-	finalize_and_normalize(it, ops, rule, next, sym, opt, R, src, n_survivors, timer, step, L, &comm, node_total_proba);
+	finalize_and_normalize(it, ops, rule, next, sym, opt, R, src, n_survivors, timer, step, L, &comm, node_total_proba, inject && atoi(inject) == cm->rank && strstr(inject, ":finalize"));
 	mark("finalize + normalize");
 }
 
@@ -1191,9 +1297,15 @@ int qb_ctx_create(int device, qb_ctx **out) {
 		QB_CUDA(cudaSetDevice(device));
 		qb_ctx *ctx = new qb_ctx();
 		ctx->device = device;
-		// the interference table is hit at random, one 32-byte slot at a time: do not let L2 widen the fills
-		cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
-		cudaGetLastError();
+		// the interference table is hit at random, one 32-byte slot at a time: do not let L2 widen the fills.  The limit is
+		// device-wide (it also applies to other libraries in this process): the value found here is put back by qb_ctx_destroy,
+		// and QB_KEEP_L2_FETCH_GRANULARITY=1 leaves it alone altogether
+		if (!getenv("QB_KEEP_L2_FETCH_GRANULARITY")) {
+			if (cudaDeviceGetLimit(&ctx->l2_fetch_granularity_before, cudaLimitMaxL2FetchGranularity) != cudaSuccess)
+				ctx->l2_fetch_granularity_before = 0;
+			cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
+			cudaGetLastError();
+		}
 		QB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
 		QB_CUDA(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
 		QB_CUDA(cudaHostAlloc((void **)&ctx->h_small, DS_WORDS * sizeof(uint64_t), cudaHostAllocDefault));
@@ -1216,6 +1328,10 @@ int qb_ctx_destroy(qb_ctx *ctx) {
 		ctx->select.release();
 		ctx->select_cand.release();
 		cudaStreamDestroy(ctx->stream);
+		if (ctx->l2_fetch_granularity_before) {
+			cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, ctx->l2_fetch_granularity_before);
+			cudaGetLastError();
+		}
 		delete ctx;
 	});
 }
@@ -1671,7 +1787,7 @@ int qb_simulate(qb_iter *it, int rule_id, const double *params, uint32_t num_par
 		QB_REQUIRE(rc == QB_OK, rc, std::string("bad parameters for rule ") + ops->name);
 		qb_options opt;
 		resolve_options(opt_in, opt);
-		simulate(it, rule_id, ops, storage, next, sym, max_num_object, opt, cb, user);
+		simulate(it, rule_history_key(rule_id, params, num_params), ops, storage, next, sym, max_num_object, opt, cb, user);
 	});
 }
 
@@ -1753,11 +1869,11 @@ int qb_simulate_dist(qb_iter *it, int rule_id, const double *params, uint32_t nu
 		qb_options opt;
 		resolve_options(opt_in, opt);
 		if (comm->world == 1) { // quids_mpi.hpp:439-440
-			simulate(it, rule_id, ops, storage, next, sym, max_num_object, opt, cb, user);
+			simulate(it, rule_history_key(rule_id, params, num_params), ops, storage, next, sym, max_num_object, opt, cb, user);
 			if (node_total_proba) *node_total_proba = 1;
 			return;
 		}
-		simulate_dist(it, rule_id, ops, storage, next, sym, comm, max_num_object, opt, cb, user, node_total_proba);
+		simulate_dist(it, rule_history_key(rule_id, params, num_params), ops, storage, next, sym, comm, max_num_object, opt, cb, user, node_total_proba);
 	});
 }
 

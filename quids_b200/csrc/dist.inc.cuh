@@ -107,6 +107,70 @@ struct comm_ops {
 		c->ctx->sync();
 		return out;
 	}
+	// ---- agreement on errors.  A failure that only ONE rank sees (a table that overflows on its share of the data, a failed
+	// allocation) must not leave the other ranks waiting in the next collective for ever: every phase of the distributed
+	// iteration runs under a pending_error, and the status word travels with the next count exchange the protocol does
+	// anyway (no extra synchronisation); if any rank reports a failure, ALL ranks throw, with the failing rank's status.
+	struct pending_error {
+		int status = QB_OK;
+		std::string what;
+		bool ok() const { return status == QB_OK; }
+		template <class F>
+		void run(F &&f) { // runs f unless an earlier phase already failed; remembers the first failure
+			if (!ok())
+				return;
+			try {
+				f();
+			} catch (const qb::error &e) {
+				status = e.status;
+				what = e.what();
+			} catch (const std::exception &e) {
+				status = QB_ERR_ARG;
+				what = e.what();
+			}
+		}
+	};
+	// all-gather of n values per rank with the status word appended; throws on every rank if any rank failed
+	std::vector<uint64_t> allgather_agreed(const uint64_t *values, size_t n, pending_error &err, const char *phase) {
+		std::vector<uint64_t> mine(values, values + n);
+		mine.push_back((uint64_t)(uint32_t)err.status);
+		std::vector<uint64_t> all = allgather_u64(mine.data(), n + 1);
+		std::vector<uint64_t> out;
+		out.reserve(n * c->world);
+		int failed_rank = -1, failed_status = QB_OK;
+		for (int r = 0; r < c->world; ++r) {
+			const int st = (int)(uint32_t)all[(size_t)r * (n + 1) + n];
+			if (st != QB_OK && failed_rank < 0) {
+				failed_rank = r;
+				failed_status = st;
+			}
+			out.insert(out.end(), all.begin() + (size_t)r * (n + 1), all.begin() + (size_t)r * (n + 1) + n);
+		}
+		if (failed_rank >= 0) {
+			if (!err.ok())
+				throw qb::error(err.status, err.what + " [rank " + std::to_string(c->rank) + ", " + phase + "; every rank of the communicator stops]");
+			throw qb::error(failed_status, std::string("quids::mpi::simulate: rank ") + std::to_string(failed_rank) + " failed during " + phase +
+			                                   " (status " + std::to_string(failed_status) + "); this rank stops too");
+		}
+		return out;
+	}
+	uint64_t sum_u64_agreed(uint64_t v, pending_error &err, const char *phase) {
+		uint64_t total = 0;
+		for (uint64_t x : allgather_agreed(&v, 1, err, phase))
+			total += x;
+		return total;
+	}
+	double sum_f64_agreed(double v, pending_error &err, const char *phase) {
+		uint64_t bits;
+		memcpy(&bits, &v, 8);
+		double total = 0;
+		for (uint64_t x : allgather_agreed(&bits, 1, err, phase)) {
+			double d;
+			memcpy(&d, &x, 8);
+			total += d;
+		}
+		return total;
+	}
 	uint64_t sum_u64(uint64_t v) {
 		uint64_t total = 0;
 		for (uint64_t x : allgather_u64(&v, 1))
@@ -125,15 +189,20 @@ struct comm_ops {
 		return total;
 	}
 	// all-to-allv of fixed-size records: send_counts[r] records go to rank r (contiguous, rank order)
-	std::vector<uint64_t> alltoallv(const void *send, const std::vector<uint64_t> &send_counts, dev_buf &recv, size_t record_bytes, uint64_t &n_recv) {
-		std::vector<uint64_t> matrix = allgather_u64(send_counts.data(), c->world); // matrix[src * world + dst]
+	std::vector<uint64_t> alltoallv(const void *send, const std::vector<uint64_t> &send_counts, dev_buf &recv, size_t record_bytes, uint64_t &n_recv,
+	                                pending_error *err = nullptr, const char *phase = "") {
+		pending_error none;
+		std::vector<uint64_t> matrix = allgather_agreed(send_counts.data(), c->world, err ? *err : none, phase); // matrix[src * world + dst]
 		std::vector<uint64_t> recv_counts(c->world);
 		n_recv = 0;
 		for (int src = 0; src < c->world; ++src) {
 			recv_counts[src] = matrix[(size_t)src * c->world + c->rank];
 			n_recv += recv_counts[src];
 		}
-		recv.ensure(record_bytes * std::max<uint64_t>(1, n_recv), c->ctx->stream);
+		// the receive buffer may have to grow, and that can fail on one rank only: agree once more before anything is posted
+		pending_error grow;
+		grow.run([&] { recv.ensure(record_bytes * std::max<uint64_t>(1, n_recv), c->ctx->stream); });
+		sum_u64_agreed(0, grow, "allocation of a receive buffer");
 		QB_NCCL(nccl().GroupStart());
 		uint64_t send_off = 0, recv_off = 0;
 		const void *self_from = nullptr;

@@ -58,9 +58,43 @@ def all_to_all(lists):
     return out
 
 
-def model_simulate(port: orc.Oracle, mine: orc.Packed, all_parent_norms_fn, rule_id, params, k, tol):
-    """returns (next state of this rank as Packed, N_c total, N_u total)"""
+class RankFailure(RuntimeError):
+    pass
+
+
+class Pending:
+    """dist.inc.cuh pending_error / allgather_agreed: a phase that fails on one rank is remembered, the status word travels
+    with the next exchange of the protocol, and EVERY rank raises there -- nobody is left waiting in a collective"""
+
+    def __init__(self):
+        self.error = None
+
+    def run(self, fn):
+        if self.error is None:
+            try:
+                return fn()
+            except Exception as e:  # noqa: BLE001 -- the model treats any failure of a phase alike
+                self.error = str(e) or type(e).__name__
+        return None
+
+    def agree(self, phase):
+        world = dist.get_world_size()
+        status = [None] * world
+        dist.all_gather_object(status, self.error)
+        for r, e in enumerate(status):
+            if e is not None:
+                raise RankFailure(self.error + f" [rank {dist.get_rank()}, {phase}]" if self.error is not None else f"rank {r} failed during {phase}; this rank stops too")
+
+
+def model_simulate(port: orc.Oracle, mine: orc.Packed, all_parent_norms_fn, rule_id, params, k, tol, fail=None):
+    """returns (next state of this rank as Packed, N_c total, N_u total); fail = (rank, phase) injects a failure of that rank
+    in "local", "owner" or "return" (the test knob QB_DIST_INJECT_FAILURE of capi.cu)"""
     rank, world = dist.get_rank(), dist.get_world_size()
+    pending = Pending()
+
+    def inject(phase):
+        if fail is not None and fail == (rank, phase):
+            raise MemoryError(f"injected failure in phase {phase}")
 
     # parent pre-truncation over ALL ranks (quids.hpp:613-642 applied to the gathered state)
     norms = np.abs(mine.cmags) ** 2
@@ -80,19 +114,23 @@ def model_simulate(port: orc.Oracle, mine: orc.Packed, all_parent_norms_fn, rule
     kept = orc.Packed.from_objects([objs[i] for i in keep], mine.cmags[keep])
 
     # 1. local children merged locally; tolerance -1 keeps every locally unique child
-    if kept.n:
+    def local_phase():
+        inject("local")
+        if not kept.n:
+            return 0, []
         local, nc, _ = port.simulate(kept, rule_id, params, orc.NO_TRUNCATION, -1.0)
         scale = np.sqrt(local.total_proba)
         lh = port.hash_objects(local, rule_id, params)
-        records = [(int(h), complex(m) * scale, o) for h, m, o in zip(lh.tolist(), local.cmags.tolist(), local.objects())]
-    else:
-        nc, records = 0, []
+        return nc, [(int(h), complex(m) * scale, o) for h, m, o in zip(lh.tolist(), local.cmags.tolist(), local.objects())]
+
+    nc, records = pending.run(local_phase) or (0, [])
 
     # 2-3. partition by owner, all-to-allv (the object bytes ride along here only so that the model can
     #      hand them back; on the GPUs the representative's index travels and the origin rebuilds the bytes)
     outgoing = [[] for _ in range(world)]
     for h, m, o in records:
         outgoing[owner_of(h, world)].append((h, m, o))
+    pending.agree("the local interference step")  # rides on the count exchange of the all-to-allv
     incoming = all_to_all(outgoing)
 
     # 4. owner: merge, first record seen is the representative; tolerance on the global sum
@@ -104,6 +142,8 @@ def model_simulate(port: orc.Oracle, mine: orc.Packed, all_parent_norms_fn, rule
             else:
                 merged[h] = [m, src, o]
     alive = {h: v for h, v in merged.items() if abs(v[0]) ** 2 > tol}
+    pending.run(lambda: inject("owner"))
+    pending.agree("the owner-side interference step")  # rides on the all-gather of the unique counts
 
     # 5. global top-k with ties shared out in rank order
     my_norms = np.array([v[0].real ** 2 + v[0].imag ** 2 for v in alive.values()])
@@ -125,6 +165,8 @@ def model_simulate(port: orc.Oracle, mine: orc.Packed, all_parent_norms_fn, rule
     back = [[] for _ in range(world)]
     for h, (m, src, o) in survivors:
         back[src].append((m, o))
+    pending.run(lambda: inject("return"))
+    pending.agree("the return of the survivors")
     mine_back = [x for recs in all_to_all(back) for x in recs]
 
     # 7. global normalisation

@@ -176,6 +176,73 @@ def run_case(comm, port, state, rid, params, k, tol, qcgd, what, share=share, eq
     print(f"ok {what}: N_c={nc} N_u={nu} N_s={got.n}", flush=True)
 
 
+def failure_cases(comm, port, state):
+    """a failure that only ONE rank sees must surface as an error on EVERY rank from the same call (no rank left waiting in
+    a collective), and the communicator must stay usable (capacity checks are data dependent per rank)"""
+    rank = dist.get_rank()
+    qb.config.tolerance, qb.config.align_byte_length, qb.config.equalize = 1e-18, 8, 0
+    mine = share(state, rank, dist.get_world_size())
+    rule = qb.Rule("erase_create", 0.37, 0.21, -0.4)
+    for phase in ("local", "partition", "owner", "return", "finalize"):
+        it, nxt, sym = qb.Iteration(), qb.Iteration(), qb.SymbolicIteration()
+        it.upload_packed(mine.sizes, mine.mags, mine.data)
+        os.environ["QB_DIST_INJECT_FAILURE"] = f"1:{phase}"
+        try:
+            qb.mpi_simulate(it, rule, nxt, sym, comm, 900)
+            raised = None
+        except qb.QuidsError as e:
+            raised = str(e)
+        finally:
+            del os.environ["QB_DIST_INJECT_FAILURE"]
+        assert raised is not None, f"rank {rank}: no error although rank 1 failed in phase {phase}"
+        assert ("injected failure" in raised) == (rank == 1), raised
+        assert rank == 1 or "rank 1 failed" in raised, raised
+    if rank == 0:
+        print("ok failure on one rank stops every rank", flush=True)
+    run_case(comm, port, state, orc.RULE_ERASE_CREATE, [0.37, 0.21, -0.4], 900, 1e-18, True, "communicator usable after agreed failures")
+
+
+def automatic_budget_cases(comm, port, state):
+    """max_num_object = 0 on the distributed path (the reference's default, quids_mpi.hpp:423): per-rank parent budget, children
+    budget agreed between the ranks.  With all parents kept, the result must be the oracle's top-k for the k that was agreed."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    qb.config.tolerance, qb.config.align_byte_length, qb.config.equalize = 1e-18, 8, 0
+    mine = share(state, rank, world)
+    rid, params = orc.RULE_ERASE_CREATE, [0.37, 0.21, -0.4]
+    full, nc_full, nu_full = port.simulate(state, rid, params, orc.NO_TRUNCATION, 1e-18)
+    truncated = 0
+    try:
+        for budget in (1 << 31, 40 << 20, 20 << 20, 10 << 20, 5 << 20, 3 << 20):
+            qb.config.memory_budget = budget
+            it, nxt, sym = qb.Iteration(), qb.Iteration(), qb.SymbolicIteration()
+            it.upload_packed(mine.sizes, mine.mags, mine.data)
+            try:
+                qb.mpi_simulate(it, qb.Rule(RULE_NAMES[rid], *params), nxt, sym, comm, 0)
+            except qb.QuidsError as e:
+                assert "automatic budget" in str(e) or "failed during" in str(e), str(e)
+                break
+            counts = comm.allreduce_u64([sym.num_object, sym.num_object_after_interferences, nxt.num_object])
+            gathered = [None] * world
+            dist.all_gather_object(gathered, (*nxt.download_packed(), nxt.total_proba))
+            if rank != 0 or int(counts[0]) != nc_full:
+                continue  # parents were cut per rank: no single-process counterpart
+            k = int(counts[2])
+            assert int(counts[1]) == nu_full and 1 <= k <= nu_full
+            got = orc.Packed(np.concatenate([g[0] for g in gathered]), np.concatenate([g[1] for g in gathered]), np.concatenate([g[2] for g in gathered]), gathered[0][3])
+            want, _, _ = port.simulate(state, rid, params, k, 1e-18)
+            hg, hw = port.hash_objects(got, rid), port.hash_objects(want, rid)
+            if k == nu_full:
+                orc.assert_same_state(got, hg, want, hw, True, what=f"automatic budget {budget}")
+            else:
+                truncated += 1
+                orc.assert_same_truncated(got, hg, want, hw, full, port.hash_objects(full, rid), k, True, what=f"automatic budget {budget}")
+    finally:
+        qb.config.memory_budget = 0
+    if rank == 0:
+        assert truncated >= 1, "no budget of the sweep truncated the children"
+        print(f"ok automatic budget on the distributed path ({truncated} truncating budgets)", flush=True)
+
+
 def main():
     dist.init_process_group("gloo")
     rank = dist.get_rank()
@@ -207,6 +274,8 @@ def main():
     run_case(comm, port, state, orc.RULE_ERASE_CREATE, p, 900, 1e-18, True, "skewed shares, equalize by objects, children truncated", share=skewed_share,
              equalize=1)
     migration_cases(comm, port)
+    failure_cases(comm, port, state)
+    automatic_budget_cases(comm, port, state)
     # one rank empty: fewer objects than ranks
     tiny = orc.Packed.from_objects([bytes([0, 1, 0, 1])], [1.0])
     run_case(comm, port, tiny, orc.RULE_HADAMARD, [2], orc.NO_TRUNCATION, 1e-30, False, "single object, other ranks empty")

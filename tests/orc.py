@@ -88,6 +88,8 @@ class Oracle:
         vp, u64, u32, dbl, i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_double, C.c_int
         L.orc_kind.restype = C.c_char_p
         L.orc_num_threads.restype = i32
+        L.orc_set_num_threads.restype = i32
+        L.orc_set_num_threads.argtypes = [i32]
         L.orc_state_create.restype = vp
         L.orc_state_destroy.argtypes = [vp]
         L.orc_state_load.argtypes = [vp, u64, vp, vp, vp]
@@ -105,6 +107,13 @@ class Oracle:
         L.orc_last_simulate_seconds.restype = dbl
         self.kind = L.orc_kind().decode()
         self.num_threads = L.orc_num_threads()
+
+    def set_num_threads(self, n=0):
+        """host threads of the following simulate calls (0 = every core: len(os.sched_getaffinity(0)))"""
+        if n <= 0:
+            n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        self.num_threads = self.lib.orc_set_num_threads(int(n))
+        return self.num_threads
 
     # -- state handles ------------------------------------------------------------------
     def _new(self):
@@ -169,6 +178,22 @@ class Oracle:
         finally:
             self._free(h)
 
+    def pop(self, p: Packed, n=1, normalize=True) -> Packed:
+        """iteration::pop (quids.hpp:194-203)"""
+        h = self._new()
+        try:
+            self._load(h, p)
+            self.lib.orc_state_total_proba.restype = C.c_double
+            self.lib.orc_state_pop.argtypes = [C.c_void_p, C.c_uint64, C.c_int]
+            rc = self.lib.orc_state_pop(h, n, 1 if normalize else 0)
+            assert rc == 0, rc
+            out = self._store(h)
+            if not normalize or n < 1:
+                out.total_proba = p.total_proba
+            return out
+        finally:
+            self._free(h)
+
     def apply_modifier(self, p: Packed, modifier_id, params=()) -> Packed:
         h = self._new()
         try:
@@ -214,6 +239,12 @@ class LoadedState:
 
     def store(self) -> Packed:
         return self.o._store(self.h)
+
+    def apply_modifier(self, modifier_id, params=()):
+        """in place (quids.hpp:973-980)"""
+        pr = self.o._params(params)
+        rc = self.o.lib.orc_apply_modifier(self.h, modifier_id, pr.ctypes.data)
+        assert rc == 0, rc
 
     def simulate_into(self, out: "LoadedState", rule_id, params=(), max_num_object=NO_TRUNCATION, tolerance=1e-30):
         """returns (N_c, N_u, seconds inside simulate)"""

@@ -114,6 +114,51 @@ def test_two_rank_protocol_matches_single_process(port):
     assert all(p.exitcode == 0 for p in procs)
 
 
+def _failure_worker(rank, world, port_number, results):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port_number))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    port = orc.Oracle(orc.PORT_SO)
+    state = port.qcgd_random_state(6, 60, 2)
+    objs = state.objects()
+    idx = [i for i in range(state.n) if i % world == rank]
+    mine = orc.Packed.from_objects([objs[i] for i in idx], state.cmags[idx])
+    seen = []
+    for phase in ("local", "owner", "return"):
+        try:
+            dist_model.model_simulate(port, mine, None, orc.RULE_ERASE_CREATE, [0.3, 0.2, 0.1], 100, 1e-18, fail=(1, phase))
+            seen.append((phase, None))
+        except dist_model.RankFailure as e:
+            seen.append((phase, str(e)))
+    # the protocol is still in step on every rank: a clean iteration goes through
+    nxt, nc, nu = dist_model.model_simulate(port, mine, None, orc.RULE_ERASE_CREATE, [0.3, 0.2, 0.1], 100, 1e-18)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (seen, nxt.n))
+    if rank == 0:
+        results.put(gathered)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_failure_on_one_rank_is_agreed_on_by_all():
+    """an overflow / allocation failure that only rank 1 sees: every rank raises from the same call, none hangs
+    (dist.inc.cuh allgather_agreed; the GPU counterpart is tests/dist_worker.py::failure_cases)"""
+    ctx = mp.get_context("spawn")
+    results = ctx.Queue()
+    procs = [ctx.Process(target=_failure_worker, args=(r, 2, 29535, results)) for r in range(2)]
+    for p in procs:
+        p.start()
+    gathered = results.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+    assert all(p.exitcode == 0 for p in procs)
+    for rank, (seen, n_after) in enumerate(gathered):
+        assert [ph for ph, _ in seen] == ["local", "owner", "return"]
+        for phase, message in seen:
+            assert message is not None, f"rank {rank} went on although rank 1 failed in {phase}"
+            assert ("injected failure" in message) == (rank == 1), message
+    assert sum(n for _, n in gathered) == 100
+
+
 def test_pairing_and_shares_of_the_migration_logic():
     assert dist_model.make_equal_pairs([5, 9, 1, 7]) == [3, 2, 1, 0]
     assert dist_model.make_equal_pairs([4, 4, 4]) == [2, 1, 0]  # the middle rank is alone

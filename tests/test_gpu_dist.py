@@ -21,7 +21,8 @@ def test_two_gpu_parity_with_single_process_oracle():
     assert out.returncode == 0, out.stdout[-4000:]
     assert "ok ties across ranks" in out.stdout
     for what in ("distribute_objects", "gather_objects", "send_objects / receive_objects", "equalize by objects", "equalize by children",
-                 "rule iteration after distribute_objects"):
+                 "rule iteration after distribute_objects", "failure on one rank stops every rank", "communicator usable after agreed failures",
+                 "automatic budget on the distributed path"):
         assert f"ok {what}" in out.stdout, out.stdout[-4000:]
 
 

@@ -199,3 +199,14 @@ def test_port_matches_live_reference_on_random_rule_sequences(port, reference):
             assert port.apply_modifier(ra, mod_id).objects() == state.objects()
             if state.n > 1500 or state.n == 0:
                 break
+
+
+def test_pop_port_matches_reference(port, reference):
+    """iteration::pop + normalize (quids.hpp:194-203, 985-1017): the restatement against the reference's own method"""
+    base = port.qcgd_random_state(5, 30, 3)
+    rng = np.random.default_rng(2)
+    st = orc.Packed(base.sizes, rng.normal(size=(30, 2)), base.data)
+    for n, normalize in ((1, True), (1, False), (7, True), (0, True), (29, True), (30, True), (30, False)):
+        a, b = port.pop(st, n, normalize), reference.pop(st, n, normalize)
+        assert a.n == b.n == 30 - n and a.objects() == b.objects()
+        assert np.allclose(a.mags, b.mags, rtol=1e-15, atol=0) and abs(a.total_proba - b.total_proba) <= 1e-15
