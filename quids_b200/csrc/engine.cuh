@@ -42,6 +42,7 @@ struct engine_launch {
 	uint64_t n_children;
 	uint64_t n_groups;
 	table_view table;
+	bin_view bins;           // records != nullptr: one-child-per-lane rules send their children to the bins of table.cuh instead of the table
 	uint8_t *scratch;        // needs_scratch rules: scratch_stride bytes per resident thread
 	uint32_t scratch_stride;
 
@@ -226,12 +227,14 @@ __global__ void __launch_bounds__(SYMBOLIC_THREADS, 5) symbolic_kernel(const Rul
 				// batch was measured 2.7x SLOWER on split_merge: the child walks then no longer overlap the inserts' round trips.)
 				for (uint64_t c = lo + lane; c < hi; c += 32) {
 					const uint32_t j = (uint32_t)upper_bound_u64(s.group_begin, count + 1, c) - 1;
-					table_emitter emit(L.table, s.child_begin[j]);
 					cplx mag = s.mag[j];
 					uint32_t size;
-					const uint64_t hash = rule.symbolic(L.it.objects + s.object[j], s.size[j], s.ctx[j], (uint32_t)(c - s.group_begin[j]), scratch, size, mag);
-					emit((uint32_t)(c - s.group_begin[j]), hash, size, mag);
-					created += emit.created;
+					const uint32_t child_id = (uint32_t)(c - s.group_begin[j]);
+					const uint64_t hash = rule.symbolic(L.it.objects + s.object[j], s.size[j], s.ctx[j], child_id, scratch, size, mag);
+					if (L.bins.records) // a large table: the child goes to the bin of its table region (table.cuh), bin_insert_kernel does the rest
+						created += bin_emit(L.bins, L.table, hash, mag, rep_pack(s.child_begin[j] + child_id, size));
+					else
+						created += table_insert(L.table, hash, mag, rep_pack(s.child_begin[j] + child_id, size));
 				}
 			}
 			__syncwarp();
@@ -258,6 +261,21 @@ constexpr int ITEM_CHUNK = 256; // items one warp takes at a time
 // are consecutive in storage too (no parent truncation) and fit the stage, their bytes come to shared memory with one
 // bulk copy and the lanes walk their object there: 32 lanes chasing 32 different objects in global memory cost one
 // L1 wavefront per lane and load, the copy costs none.
+// what a work item needs from its parent, written ONCE per kept parent by group_items_kernel: the symbolic kernel then does
+// one gather per item (this record) instead of a chain item -> kept -> begin / size / magnitude / child_begin / context
+// (ncu r1: long-scoreboard bound, 4.4x the compulsory traffic)
+template <class Rule>
+struct __align__(16) item_parent {
+	typename Rule::ctx_t ctx;
+	cplx mag;
+	uint64_t child_begin;
+	uint64_t object; // byte offset of the parent in the state
+	uint32_t size;
+	uint32_t pad_;
+};
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 template <class Rule>
 __global__ void __launch_bounds__(STAGED_THREADS) group_items_kernel(const Rule rule, const engine_launch L) {
 	__shared__ warp_stage s_stage[STAGED_THREADS / 32];
@@ -291,9 +309,15 @@ __global__ void __launch_bounds__(STAGED_THREADS) group_items_kernel(const Rule 
 			continue;
 		// the parent's context is prepared here once (this lane already walks the object) instead of once
 		// per work item in the symbolic kernel, where 32 lanes would each chase a different object
-		typename Rule::ctx_t ctx;
-		rule.prepare(object, size, ctx);
-		static_cast<typename Rule::ctx_t *>(L.parent_ctx)[p] = ctx;
+		item_parent<Rule> record;
+		rule.prepare(object, size, record.ctx);
+		record.mag = L.it.mag[oid];
+		record.child_begin = L.child_begin[p];
+		record.object = off;
+		record.size = size;
+		record.pad_ = 0;
+		static_cast<item_parent<Rule> *>(L.parent_ctx)[p] = record;
+		const typename Rule::ctx_t &ctx = record.ctx;
 		bool keyed = false;
 		if constexpr (Rule::has_group_keys_from_ctx)
 			keyed = rule.group_keys_from_ctx(ctx, count, L.item_keys + first);
@@ -333,25 +357,29 @@ __global__ void __launch_bounds__(SYMBOLIC_THREADS, ITEMS_BLOCKS_PER_SM) symboli
 		if (table_overflowed(L.table))
 			break;
 		const uint64_t c0 = chunk * ITEM_CHUNK, c1 = min(c0 + (uint64_t)ITEM_CHUNK, L.n_groups);
+		const item_parent<Rule> *parents = static_cast<const item_parent<Rule> *>(L.parent_ctx);
 		uint64_t next_item = c0 + lane < c1 ? L.items[c0 + lane] : 0;
 		for (uint64_t b = c0; b < c1; b += 32) {
 			const uint32_t count = (uint32_t)min((uint64_t)32, c1 - b);
-			// the next batch's item is requested before this batch is processed: the gathers below depend on it, and
-			// two dependent round trips per batch were a fifth of the kernel's stalls
+			// the next batch's item is requested before this batch is processed, and its parent record is pulled into L2:
+			// the gather below depends on the item, and dependent round trips to DRAM were the kernel's top stall
 			const uint64_t item = next_item;
 			next_item = b + 32 + lane < c1 ? L.items[b + 32 + lane] : 0;
+			if (b + 32 + lane < c1) {
+				const char *ahead = reinterpret_cast<const char *>(parents + (next_item >> ITEM_GROUP_BITS));
+				prefetch_l2(ahead);
+				prefetch_l2(ahead + sizeof(item_parent<Rule>) - 1);
+			}
 			if (lane < count) {
 				const uint64_t p = item >> ITEM_GROUP_BITS;
 				const uint32_t group = (uint32_t)(item & ((1u << ITEM_GROUP_BITS) - 1));
-				const uint64_t oid = L.kept ? L.kept[p] : p;
-				const uint64_t off = L.it.begin[oid];
-				const uint32_t sz = L.it.size[oid];
-				s.child_begin[lane] = L.child_begin[p];
-				s.object[lane] = off;
-				s.size[lane] = sz;
+				const item_parent<Rule> &record = parents[p];
+				s.ctx[lane] = record.ctx;
+				s.child_begin[lane] = record.child_begin;
+				s.object[lane] = record.object;
+				s.size[lane] = record.size;
 				s.group[lane] = group;
-				s.ctx[lane] = static_cast<const typename Rule::ctx_t *>(L.parent_ctx)[p];
-				rule.prepare_group(s.ctx[lane], group, L.it.mag[oid], s.group_ctx[lane]);
+				rule.prepare_group(s.ctx[lane], group, record.mag, s.group_ctx[lane]);
 			}
 			__syncwarp();
 			if constexpr (Rule::has_run_identity) {
@@ -389,6 +417,10 @@ __global__ void __launch_bounds__(SYMBOLIC_THREADS, ITEMS_BLOCKS_PER_SM) symboli
 		rule.flush_warp(ws, emit);
 		created += emit.created;
 		regions += emit.regions;
+	}
+	{
+		table_emitter emit(L.table, 0);
+		rule.finish_warp(ws, emit); // whatever the rule keeps per warp across chunks (the unused part of its range of table slots)
 	}
 	created = (uint32_t)warp_sum((uint64_t)created);
 	regions = (uint32_t)warp_sum((uint64_t)regions);
@@ -786,7 +818,7 @@ struct rule_glue {
 		o.warp_groups = Rule::warp_groups;
 		o.has_group_key = Rule::has_group_key;
 		o.region_size_limit = Rule::region_size_limit;
-		o.ctx_bytes = sizeof(typename Rule::ctx_t);
+		o.ctx_bytes = sizeof(item_parent<Rule>); // per kept parent in sorted order
 		o.group_capacity = Rule::group_capacity;
 		o.launch_group_items = group_items;
 		o.launch_symbolic_items = symbolic_items;

@@ -151,6 +151,9 @@ struct rule_base {
 	__device__ void init_warp(workspace_t &) const {}
 	template <class Emit>
 	__device__ void flush_warp(workspace_t &, Emit &) const {}
+	// optional: called once per warp when the sorted-order kernel ends (after the last flush_warp)
+	template <class WS, class Emit>
+	__device__ void finish_warp(WS &, Emit &) const {}
 };
 
 // ---- modifiers: f(begin, end, mag&) in place (quids.hpp:86,973-980) as a device functor

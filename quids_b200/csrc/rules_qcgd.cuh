@@ -503,39 +503,48 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 	__device__ void flush_warp(WS &ws, Emit &emit) const {
 		__syncwarp();
 		if (ws.run_valid && emit.table.dir) {
-			// region mode: one directory probe for the whole run, then the run's magnitudes land on consecutive slots
+			// region mode: one directory probe for the whole run, then the run's objects land on consecutive slots
 			const uint32_t lane = lane_id(), leaves = ws.run_leaves;
 			spread_run(ws);
-			unsigned long long base = 0;
-			int made = 0;
+			region_grant grant{~0ull, nullptr, 0, 0, false};
 			if (lane == 0) {
 				const uint64_t key = mix64(ws.run_eligible ^ mix64(ws.run_fixed + 0x9e3779b97f4a7c15ull * (ws.run_target + 1ull)) ^
 				                           mix64(ws.run_names ^ (0xc2b2ae3d27d4eb4full * ws.run_n)));
-				bool created;
-				base = region_acquire(emit.table, ws.chunk, key, leaves, created);
-				made = created;
-				emit.regions += created;
+				grant = region_acquire(emit.table, ws.chunk, key, leaves);
+				emit.regions += grant.created;
 			}
-			base = __shfl_sync(0xffffffffu, base, 0);
-			made = __shfl_sync(0xffffffffu, made, 0);
+			const unsigned long long base = __shfl_sync(0xffffffffu, grant.base, 0);
+			const int made = __shfl_sync(0xffffffffu, (int)grant.created, 0);
+			const unsigned long long retire_from = __shfl_sync(0xffffffffu, grant.retire_from, 0), retire_count = __shfl_sync(0xffffffffu, grant.retire_count, 0);
+			if (retire_count)
+				region_retire(emit.table, retire_from, retire_count);
 			if (base != ~0ull) {
 				table_slot *slots = emit.table.slots + base;
-				if (made) { // first run of these objects anywhere: their hashes (tree of the opening group) and representatives
+				if (made) {
+					// first run of these objects anywhere: it writes the slots WHOLE -- hash (tree of the opening group), summed
+					// magnitude, representative -- one full 32-byte sector per object, then publishes the region
 					expand_full<false>(ws.open_ctx, ws.open_root, ws);
 					const uint32_t levels = ws.open_ctx.levels, tree_bits = ws.open_ctx.tree_bits;
 					const uint32_t shift = ws.open_ctx.eligible - levels; // child_id = group | leaf << shift
 					const uint64_t names_hash = ws.open_ctx.names_hash;
-					for (uint32_t leaf = lane; leaf < leaves; leaf += 32) {
-						table_slot *s = slots + (leaf ^ tree_bits);
-						s->key = hash_combine(hash_combine(names_hash, ws.hl[leaf]), ws.hr[leaf]);
-						s->rep = rep_pack(ws.open_first_child + (ws.open_group | (leaf << shift)), ws.open_size);
+					for (uint32_t slot = lane; slot < leaves; slot += 32) {
+						const uint32_t leaf = slot ^ tree_bits;
+						const unsigned long long key = hash_combine(hash_combine(names_hash, ws.hl[leaf]), ws.hr[leaf]);
+						const unsigned long long rep = rep_pack(ws.open_first_child + (ws.open_group | (leaf << shift)), ws.open_size);
+						ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(slots + slot);
+						dst[0] = make_ulonglong2(key, (unsigned long long)__double_as_longlong(ws.acc_re[slot]));
+						dst[1] = make_ulonglong2((unsigned long long)__double_as_longlong(ws.acc_im[slot]), rep);
 					}
-					if (lane == 0)
+					__syncwarp();
+					if (lane == 0) {
+						region_publish(grant);
 						emit.created += leaves;
-				}
-				for (uint32_t i = lane; i < leaves; i += 32) {
-					atomicAdd(&slots[i].re, ws.acc_re[i]); // results unused -> RED.ADD.F64 on consecutive sectors
-					atomicAdd(&slots[i].im, ws.acc_im[i]);
+					}
+				} else {
+					for (uint32_t i = lane; i < leaves; i += 32) {
+						atomicAdd(&slots[i].re, ws.acc_re[i]); // results unused -> RED.ADD.F64 on consecutive sectors
+						atomicAdd(&slots[i].im, ws.acc_im[i]);
+					}
 				}
 			}
 		} else if (ws.run_valid) {
@@ -559,6 +568,17 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 		if (lane_id() == 0)
 			ws.run_valid = 0;
 		__syncwarp();
+	}
+
+	// the warp is done: what it did not use of its last range of table slots must read as empty (table.cuh, region_retire)
+	template <class WS, class Emit>
+	__device__ void finish_warp(WS &ws, Emit &emit) const {
+		__syncwarp();
+		if (emit.table.dir && ws.chunk.end > ws.chunk.next)
+			region_retire(emit.table, ws.chunk.next, ws.chunk.end - ws.chunk.next);
+		__syncwarp();
+		if (lane_id() == 0)
+			ws.chunk.next = ws.chunk.end = 0;
 	}
 
 	// full expansion of one group: tree states (hash folds and magnitudes) of all its leaves in ws

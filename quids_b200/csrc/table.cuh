@@ -176,16 +176,27 @@ __device__ __forceinline__ uint32_t table_insert_batch(const table_view &t, int 
 
 // Slots are handed out to the warps in chunks (one atomic on the shared cursor per REGION_CHUNK slots instead of one per
 // region: every creator hitting the same address was the top stall of the kernel); a warp fills its chunk front to back.
+//
+// The slots of region mode are NOT cleared before the kernel (round 1 did: a memset of the whole table, then read-modify-write
+// RED.F64 into the zeroed sectors = 32 B written + 32 B fetched + 32 B written back per slot).  The run that CREATES a region
+// writes its slots whole -- hash, summed magnitude, representative: full 32-byte sectors, no fetch -- and only then publishes
+// the region's base in the directory (region_publish); a later run of the same objects waits for the base and adds with
+// RED.F64.  What a warp leaves unused of its chunk (the tail that cannot hold the next region, the rest of its last chunk)
+// is zeroed by that warp (region_retire), so that every slot below the cursor is either a written object or empty.
 constexpr uint32_t REGION_CHUNK = 1024;
 struct region_chunk {
 	unsigned long long next, end; // this warp's private range of slots
 };
+struct region_grant {
+	unsigned long long base;       // first slot of the region, ~0 = the table is too small (overflow raised)
+	region_entry *entry;           // created: the directory entry to publish once the slots are written
+	unsigned long long retire_from, retire_count; // slots of the warp's previous chunk to zero (region_retire)
+	bool created;
+};
 
-// The region of the objects identified by `key` (`leaves` consecutive slots).  One lane calls this per run.  Returns the
-// first slot, or ~0 when the table is too small (overflow raised); created = this call made the region, and the caller
-// must write the objects' hashes and representatives into its slots (magnitudes are added by every run of the region).
-__device__ __forceinline__ uint64_t region_acquire(const table_view &t, region_chunk &mine, uint64_t key, uint32_t leaves, bool &created) {
-	created = false;
+// The region of the objects identified by `key` (`leaves` consecutive slots).  ONE lane calls this per run.
+__device__ __forceinline__ region_grant region_acquire(const table_view &t, region_chunk &mine, uint64_t key, uint32_t leaves) {
+	region_grant g{~0ull, nullptr, 0, 0, false};
 	if (key == 0)
 		key = 1;
 	uint64_t i = __umul64hi(mix64(key), t.dir_capacity);
@@ -196,37 +207,187 @@ __device__ __forceinline__ uint64_t region_acquire(const table_view &t, region_c
 			seen = atomicCAS(&e->key, 0ull, (unsigned long long)key);
 			if (seen == 0) { // this run creates the region
 				if (mine.next + leaves > mine.end) { // what is left of the old chunk stays empty
+					g.retire_from = mine.next;
+					g.retire_count = mine.end - mine.next;
 					const unsigned long long want = leaves > REGION_CHUNK ? leaves : REGION_CHUNK;
 					mine.next = atomicAdd(t.cursor, want);
 					mine.end = mine.next + want;
+					if (mine.end > t.capacity) { // the new chunk does not fit: nothing of it may be touched
+						mine.end = mine.next;
+						*t.overflow = 1;
+						atomicExch(&e->base, ~0ull); // whoever waits for this region gives up too
+						return g;
+					}
 				}
-				const unsigned long long base = mine.next;
+				g.base = mine.next;
 				mine.next += leaves;
-				if (base + leaves > t.capacity) {
-					*t.overflow = 1;
-					atomicExch(&e->base, ~0ull); // whoever waits for this region gives up too
-					return ~0ull;
-				}
-				atomicExch(&e->base, base + 1);
-				created = true;
-				return base;
+				g.entry = e;
+				g.created = true;
+				return g;
 			}
 		}
 		if (seen == key) {
 			unsigned long long base;
-			while ((base = *(volatile unsigned long long *)&e->base) == 0) // published right after the creator found its slots
-				;
-			return base == ~0ull ? ~0ull : base - 1;
+			while ((base = *(volatile unsigned long long *)&e->base) == 0) // published once the creator has written the slots
+				if (table_overflowed_lane(t))
+					return g;
+			__threadfence(); // the slots written before the publication are visible to what follows
+			g.base = base == ~0ull ? ~0ull : base - 1;
+			return g;
 		}
 		if (++i == t.dir_capacity)
 			i = 0;
 		if ((probes & 63) == 63 && table_overflowed_lane(t))
-			return ~0ull;
+			return g;
 	}
 	*t.overflow = 1;
-	return ~0ull;
+	return g;
+}
+
+// the creator's slots are written: let the other runs of the same objects in (one lane, after a __syncwarp of the writers)
+__device__ __forceinline__ void region_publish(const region_grant &g) {
+	__threadfence();
+	atomicExch(&g.entry->base, g.base + 1);
+}
+
+// zero slots [from, from + count) (whole warp): the unused part of a chunk
+__device__ __forceinline__ void region_retire(const table_view &t, unsigned long long from, unsigned long long count) {
+	const unsigned long long end = from + count < t.capacity ? from + count : t.capacity;
+	for (unsigned long long i = from + lane_id(); i < end; i += 32) {
+		ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(t.slots + i);
+		dst[0] = make_ulonglong2(0, 0);
+		dst[1] = make_ulonglong2(0, 0);
+	}
 }
 
 __device__ __forceinline__ bool slot_occupied(const table_slot &s, bool is_zero_slot) { return is_zero_slot ? s.rep != 0 : s.key != 0; }
+
+// ---- BINNED inserts (rules whose children come in no useful order: split_merge, hadamard, any rule written with the four
+// reference methods only).  A table larger than L2 hit at random costs one DRAM round trip per probe and one read-modify-write
+// of a 32-byte sector per child: 60-70 ps per insert, latency bound (profiles/table_bench_r1.txt, the kernel sat at 16 % of
+// DRAM throughput).  The reference's answer is to partition the children by hash prefix so that every bucket's map is
+// cache resident (utils/algorithm.hpp:170-227, quids.hpp:755-809); this is its counterpart:
+//   pass 1  the child-generation kernel does not touch the table: a child's (hash, magnitude, representative) record goes to
+//           the bin of its table REGION -- bin = mulhi(mix64(hash), bins), the top bits of the very mix that places it in the
+//           table (table_home grows with mix64(hash)), so bin b holds exactly the children of slots [b, b + 1) * capacity / bins.
+//           One L2 atomic on the bin's cursor (cursors are 32 bytes apart) and one 32-byte store per child, fire and forget:
+//           the kernel is bound by the rule's own arithmetic, not by table round trips;
+//   pass 2  bin_insert_kernel streams the bins IN ORDER with all CTAs: at any moment the slots being touched are a few
+//           consecutive regions, tens of MB, L2 resident -- each slot's sector comes from DRAM once and goes back once.
+// A bin that is full (equal hashes concentrate: every record of a hash lands in the same bin) sends its record straight to
+// the table, as before: the bins are an ordering device, the table's semantics are untouched.
+struct __align__(32) bin_record {
+	unsigned long long hash;
+	double re, im;
+	unsigned long long rep;
+};
+constexpr uint32_t BIN_CURSOR_STRIDE = 4; // u64 words between two cursors: one 32-byte sector each
+
+struct bin_view {
+	bin_record *records;        // bins * bin_capacity records; nullptr = no binning
+	unsigned long long *cursor; // cursor[bin * BIN_CURSOR_STRIDE] = records sent to the bin so far (may exceed bin_capacity)
+	uint32_t bins;
+	uint32_t bin_capacity;
+};
+
+__device__ __forceinline__ bool bin_emit(const bin_view &b, const table_view &t, uint64_t hash, cplx mag, uint64_t rep) {
+	if (hash == 0)
+		return table_insert_zero_hash(t, mag, rep);
+	const uint32_t bin = (uint32_t)__umul64hi(mix64(hash), (uint64_t)b.bins);
+	const unsigned long long at = atomicAdd(&b.cursor[(size_t)bin * BIN_CURSOR_STRIDE], 1ull);
+	if (at < b.bin_capacity) {
+		ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(b.records + (size_t)bin * b.bin_capacity + at);
+		__stcs(dst, make_ulonglong2(hash, (unsigned long long)__double_as_longlong(mag.re)));
+		__stcs(dst + 1, make_ulonglong2((unsigned long long)__double_as_longlong(mag.im), rep));
+		return false;
+	}
+	return table_insert(t, hash, mag, rep); // the bin is full
+}
+
+constexpr int BIN_INSERT_THREADS = 256;
+constexpr int BIN_INSERT_BATCH = 2; // records per thread and round: their key loads go out together
+
+// all CTAs walk the bins in order, BIN_INSERT_THREADS * BIN_INSERT_BATCH consecutive records per CTA and round
+static __global__ void __launch_bounds__(BIN_INSERT_THREADS) bin_insert_kernel(bin_view b, table_view t) {
+	constexpr int N = BIN_INSERT_BATCH;
+	constexpr uint32_t TILE = BIN_INSERT_THREADS * N;
+	const uint32_t tiles_per_bin = (b.bin_capacity + TILE - 1) / TILE;
+	const uint64_t tiles = (uint64_t)b.bins * tiles_per_bin;
+	uint32_t created = 0;
+	for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+		const uint32_t bin = (uint32_t)(tile / tiles_per_bin);
+		const uint32_t first = (uint32_t)(tile % tiles_per_bin) * TILE;
+		const unsigned long long sent = __ldcg(&b.cursor[(size_t)bin * BIN_CURSOR_STRIDE]);
+		const uint32_t filled = sent < b.bin_capacity ? (uint32_t)sent : b.bin_capacity;
+		if (first >= filled)
+			continue;
+		if (table_overflowed_lane(t))
+			break;
+		const bin_record *records = b.records + (size_t)bin * b.bin_capacity;
+		uint64_t hash[N];
+		cplx mag[N];
+		uint64_t rep[N];
+		int count = 0;
+#pragma unroll
+		for (int q = 0; q < N; ++q) {
+			const uint32_t i = first + q * BIN_INSERT_THREADS + threadIdx.x;
+			hash[q] = 0;
+			if (i < filled) {
+				const ulonglong2 lo = __ldcs(reinterpret_cast<const ulonglong2 *>(records + i));
+				const ulonglong2 hi = __ldcs(reinterpret_cast<const ulonglong2 *>(records + i) + 1);
+				hash[q] = lo.x;
+				mag[q] = cplx{__longlong_as_double((long long)lo.y), __longlong_as_double((long long)hi.x)};
+				rep[q] = hi.y;
+				count = q + 1;
+			}
+		}
+		// entries past `filled` keep hash 0 with a zero magnitude: they must not reach the dedicated slot of the hash 0
+		// (records with hash 0 never enter a bin, bin_emit), so the batch skips them
+		uint64_t slot[N];
+		uint32_t pending = 0;
+#pragma unroll
+		for (int q = 0; q < N; ++q)
+			if (q < count && hash[q] != 0) {
+				slot[q] = table_home(hash[q], t.capacity);
+				pending |= 1u << q;
+			}
+		for (uint32_t round = 0; pending; ++round) {
+			unsigned long long seen[N];
+#pragma unroll
+			for (int q = 0; q < N; ++q)
+				if (pending & (1u << q))
+					seen[q] = __ldcg(&t.slots[slot[q]].key);
+#pragma unroll
+			for (int q = 0; q < N; ++q)
+				if (pending & (1u << q)) {
+					table_slot *s = t.slots + slot[q];
+					if (seen[q] == 0) {
+						seen[q] = atomicCAS(&s->key, 0ull, (unsigned long long)hash[q]);
+						if (seen[q] == 0) {
+							s->rep = rep[q];
+							++created;
+							seen[q] = hash[q];
+						}
+					}
+					if (seen[q] == hash[q]) {
+						atomicAdd(&s->re, mag[q].re);
+						atomicAdd(&s->im, mag[q].im);
+						pending &= ~(1u << q);
+					} else if (++slot[q] == t.capacity) {
+						slot[q] = 0;
+					}
+				}
+			if (round > TABLE_MAX_PROBES) {
+				*t.overflow = 1;
+				break;
+			}
+			if ((round & 63) == 63 && table_overflowed_lane(t))
+				break;
+		}
+	}
+	created = (uint32_t)warp_sum((uint64_t)created);
+	if (lane_id() == 0 && created)
+		atomicAdd(t.used, (unsigned long long)created);
+}
 
 } // namespace qb
