@@ -65,6 +65,9 @@ typedef struct qb_options {
 	uint32_t seed;             /* probabilistic truncation: seed of the counter-based generator (the reference seeds from rand()) */
 	int32_t locality_sort;     /* engine knob: process the child groups in the order of the rule's group key so that equal
 	                              objects are merged on chip before the table; 0 off, 1 when there are >= 2^16 groups (default), 2 always */
+	int32_t binned_inserts;    /* engine knob: one-child-per-lane rules send their children to the table through bins ordered by table region
+	                              (cache-resident inserts, the reference's bucket partition quids.hpp:755-809); 0 off, 1 when the table
+	                              is larger than L2 (default), 2 always */
 	uint64_t memory_budget;    /* engine knob: bytes the automatic budget (max_num_object = 0) may spend on the symbolic workspace and
 	                              on the next state; 0 = measured (cudaMemGetInfo minus safety_margin of the GPU) */
 	/* load balancing at the head of quids::mpi::simulate (quids_mpi.hpp:442-500); only qb_simulate_dist reads these */
@@ -150,6 +153,7 @@ enum {
 	QB_PHASE_NORMALIZE,     /* quids.hpp:985-1017                                             */
 	QB_PHASE_EXCHANGE,      /* distributed: all-to-allv of records and survivors   quids_mpi.hpp:741-743,842 */
 	QB_PHASE_OWNER,         /* distributed: owner-side merge, tolerance, return lists   quids_mpi.hpp:762-830 */
+	QB_PHASE_INSERT,        /* binned inserts: the children's records reach the table region by region   quids.hpp:755-809 */
 	QB_PHASE_COUNT
 };
 int qb_sym_phase_ms(const qb_sym *sym, float *ms /* [QB_PHASE_COUNT] */);

@@ -27,7 +27,7 @@ CSRC = os.path.join(_HERE, "csrc")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "quids_b200.h")
 
 NO_TRUNCATION = 2**64 - 1
-PHASES = ("num_child", "pre_truncate", "table_clear", "symbolic", "compact", "truncate", "finalize", "normalize", "exchange", "owner")
+PHASES = ("num_child", "pre_truncate", "table_clear", "symbolic", "compact", "truncate", "finalize", "normalize", "exchange", "owner", "insert")
 
 
 class QuidsError(RuntimeError):
@@ -47,7 +47,7 @@ def build(verbose=False):
 
 class qb_options(C.Structure):
     _fields_ = [("tolerance", C.c_double), ("align_byte_length", C.c_uint32), ("simple_truncation", C.c_int32),
-                ("table_load", C.c_double), ("profile", C.c_int32), ("safety_margin", C.c_float), ("seed", C.c_uint32), ("locality_sort", C.c_int32), ("memory_budget", C.c_uint64),
+                ("table_load", C.c_double), ("profile", C.c_int32), ("safety_margin", C.c_float), ("seed", C.c_uint32), ("locality_sort", C.c_int32), ("binned_inserts", C.c_int32), ("memory_budget", C.c_uint64),
                 ("equalize", C.c_int32), ("equalize_inbalance", C.c_float), ("min_equalize_step", C.c_float), ("min_equalize_size", C.c_uint64)]
 
 
@@ -160,6 +160,7 @@ class _Globals:
     min_equalize_step = 0.2    # quids::mpi::min_equalize_step
     min_equalize_size = 100    # quids::mpi::min_equalize_size
     locality_sort = 1          # engine knob: 0 off, 1 auto, 2 always
+    binned_inserts = 1         # engine knob: 0 off, 1 when the table is larger than L2, 2 always
 
     def options(self):
         o = qb_options()
@@ -172,6 +173,7 @@ class _Globals:
         o.seed = self.seed
         o.profile = 1 if self.profile else 0
         o.locality_sort = self.locality_sort
+        o.binned_inserts = self.binned_inserts
         o.memory_budget = self.memory_budget
         o.equalize = self.equalize
         o.equalize_inbalance = self.equalize_inbalance

@@ -154,7 +154,7 @@ struct qb_iter {
 struct qb_sym {
 	qb_ctx *ctx;
 	uint64_t n_children = 0, n_unique = 0; // quids.hpp:344-346
-	dev_buf table, directory, ukey, uslot, sslot, kept, scratch, survivor_parent, survivor_child, padded, chunk_parent, sort_keys, sort_vals, sort_hist, sort_base, parent_ctx;
+	dev_buf table, directory, ukey, uslot, sslot, kept, scratch, survivor_parent, survivor_child, padded, chunk_parent, sort_keys, sort_vals, sort_hist, sort_base, parent_ctx, bin_records, bin_cursor;
 	cudaEvent_t ev[2 * QB_PHASE_COUNT] = {};
 	bool ev_used[QB_PHASE_COUNT] = {};
 	float phase_ms[QB_PHASE_COUNT] = {};
@@ -164,7 +164,7 @@ struct qb_sym {
 	int table_attempts = 0;
 
 	uint64_t device_bytes() const {
-		return table.cap + directory.cap + ukey.cap + uslot.cap + sslot.cap + kept.cap + scratch.cap + survivor_parent.cap + survivor_child.cap + padded.cap + chunk_parent.cap + sort_keys.cap + sort_vals.cap + sort_hist.cap + sort_base.cap + parent_ctx.cap;
+		return table.cap + directory.cap + ukey.cap + uslot.cap + sslot.cap + kept.cap + scratch.cap + survivor_parent.cap + survivor_child.cap + padded.cap + chunk_parent.cap + sort_keys.cap + sort_vals.cap + sort_hist.cap + sort_base.cap + parent_ctx.cap + bin_records.cap + bin_cursor.cap;
 	}
 };
 
@@ -172,6 +172,8 @@ struct qb_sym {
 
 // ---- helpers --------------------------------------------------------------------------------------------
 namespace {
+
+constexpr size_t BINNED_MIN_TABLE_BYTES = 96u << 20; // below this the table (mostly) stays in the 126 MB L2 by itself
 
 struct phase_timer {
 	qb_sym *sym;
@@ -451,6 +453,8 @@ void resolve_options(const qb_options *in, qb_options &opt) {
 		opt = *in;
 	if (!(opt.table_load > 0 && opt.table_load <= 0.95))
 		opt.table_load = 0.75;
+	if (in == nullptr || opt.binned_inserts < 0 || opt.binned_inserts > 2)
+		opt.binned_inserts = 1;
 }
 
 // ======================================================================================================
@@ -717,8 +721,26 @@ local_table build_local_table(qb_iter *it, uint64_t rule_id, const rule_ops *ops
 		timer.begin(QB_PHASE_TABLE_CLEAR);
 		const size_t table_bytes = (capacity + 1) * sizeof(table_slot);
 		sym->table.ensure(table_bytes, stream);
-		QB_CUDA(cudaMemsetAsync(sym->table.ptr, 0, table_bytes, stream));
+		if (!region_mode) // regions are written whole by the runs that create them, what stays unused is zeroed by its warp (table.cuh)
+			QB_CUDA(cudaMemsetAsync(sym->table.ptr, 0, table_bytes, stream));
 		QB_CUDA(cudaMemsetAsync(ctx->small(DS_COUNT), 0, 4 * sizeof(uint64_t), stream)); // count, overflow, total, used
+		// binned inserts (table.cuh): one-child-per-lane rules whose table is far larger than L2 send their children to the bin of
+		// their table region first.  Bins: regions of about 2 MB of table; capacity: the mean + 5 % + 1024 (hashes are mixed, the
+		// spread of a bin is its square root; a bin that overflows because equal hashes pile up inserts directly).
+		L.bins = bin_view{nullptr, nullptr, 0, 0};
+		const bool binned = !sorted_order && !ops->warp_groups && opt.binned_inserts != 0 &&
+		                    (opt.binned_inserts > 1 || table_bytes >= (size_t)BINNED_MIN_TABLE_BYTES) && n_children >= 4096;
+		if (binned) {
+			uint32_t bins = 64;
+			while (bins < 16384 && (table_bytes / bins) > (size_t)(2u << 20))
+				bins <<= 1;
+			const uint64_t bin_capacity = n_children / bins + n_children / bins / 20 + 1024;
+			QB_REQUIRE(bin_capacity < (1ull << 32), QB_ERR_CAPACITY, "more than 2^32 children per bin");
+			sym->bin_records.ensure(sizeof(bin_record) * bins * bin_capacity, stream);
+			sym->bin_cursor.ensure(sizeof(uint64_t) * BIN_CURSOR_STRIDE * bins, stream);
+			QB_CUDA(cudaMemsetAsync(sym->bin_cursor.ptr, 0, sizeof(uint64_t) * BIN_CURSOR_STRIDE * bins, stream));
+			L.bins = bin_view{sym->bin_records.as<bin_record>(), sym->bin_cursor.as<unsigned long long>(), bins, (uint32_t)bin_capacity};
+		}
 		R.table = table_view{sym->table.as<table_slot>(), capacity, reinterpret_cast<unsigned int *>(ctx->small(DS_OVERFLOW)),
 		                     reinterpret_cast<unsigned long long *>(ctx->small(DS_USED))};
 		if (region_mode) {
@@ -743,6 +765,20 @@ local_table build_local_table(qb_iter *it, uint64_t rule_id, const rule_ops *ops
 			ops->launch_symbolic(rule, L);
 		QB_CUDA(cudaGetLastError());
 		timer.end(QB_PHASE_SYMBOLIC);
+		if (binned) { // pass 2: the bins reach the table in order, the slots in flight stay L2 resident
+			timer.begin(QB_PHASE_INSERT);
+			static int per_sm_of_device[MAX_DEVICES] = {};
+			int &per_sm = per_sm_of_device[ctx->device % MAX_DEVICES];
+			if (per_sm == 0) {
+				QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)bin_insert_kernel, BIN_INSERT_THREADS, 0));
+				if (per_sm < 1) per_sm = 1;
+			}
+			const uint64_t tiles = (uint64_t)L.bins.bins * div_up<uint64_t>(L.bins.bin_capacity, BIN_INSERT_THREADS * BIN_INSERT_BATCH);
+			bin_insert_kernel<<<(unsigned)std::min<uint64_t>(tiles, (uint64_t)per_sm * ctx->sm_count), BIN_INSERT_THREADS, 0, stream>>>(L.bins, R.table);
+			++ctx->launches;
+			QB_CUDA(cudaGetLastError());
+			timer.end(QB_PHASE_INSERT);
+		}
 
 		// unique children above the tolerance (quids.hpp:819-823)
 		if (collision_labels && sym->table_attempts == 1)
@@ -756,12 +792,11 @@ local_table build_local_table(qb_iter *it, uint64_t rule_id, const rule_ops *ops
 		const uint64_t bound = std::min<uint64_t>(n_children, scan_slots + 1);
 		sym->ukey.ensure(sizeof(uint64_t) * bound, stream);
 		sym->uslot.ensure(sizeof(uint32_t) * bound, stream);
-		const uint64_t tiles = div_up<uint64_t>(scan_slots + 1, COMPACT_TILE);
-		scan_state st = ctx->scan(tiles);
-		table_view scanned = R.table;
-		scanned.capacity = scan_slots; // slot `scan_slots` was never handed out: empty unless it is the hashed table's slot for hash 0
-		table_compact_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, stream>>>(scanned, compaction_tolerance, sym->ukey.as<uint64_t>(), sym->uslot.as<uint32_t>(),
-		                                                                    reinterpret_cast<unsigned long long *>(ctx->small(DS_COUNT)), st);
+		// hashed table: every slot + the dedicated slot of the hash 0; regions: exactly the slots handed out (nothing beyond was written or zeroed)
+		const uint64_t scan_n = region_mode ? scan_slots : scan_slots + 1;
+		const uint64_t tiles = div_up<uint64_t>(std::max<uint64_t>(scan_n, 1), COMPACT_TILE);
+		table_compact_kernel<<<(unsigned)std::min<uint64_t>(tiles, (uint64_t)ctx->sm_count * 16), SCAN_THREADS, 0, stream>>>(
+		    R.table, scan_n, compaction_tolerance, sym->ukey.as<uint64_t>(), sym->uslot.as<uint32_t>(), reinterpret_cast<unsigned long long *>(ctx->small(DS_COUNT)));
 		++ctx->launches;
 		QB_CUDA(cudaGetLastError());
 		timer.end(QB_PHASE_COMPACT);
@@ -777,7 +812,7 @@ local_table build_local_table(qb_iter *it, uint64_t rule_id, const rule_ops *ops
 		// the prediction was too small (the kernels stop early once an insert gives up): redo at the always-safe full size
 		capacity = full_capacity;
 		directory = full_directory;
-		for (int p : {QB_PHASE_TABLE_CLEAR, QB_PHASE_SYMBOLIC, QB_PHASE_COMPACT})
+		for (int p : {QB_PHASE_TABLE_CLEAR, QB_PHASE_SYMBOLIC, QB_PHASE_INSERT, QB_PHASE_COMPACT})
 			timer.restart(p); // report the attempt that counted
 	}
 	R.n_unique = ctx->h_small[DS_COUNT];
@@ -1146,9 +1181,8 @@ void simulate_dist(qb_iter *it, uint64_t rule_id, const rule_ops *ops, const voi
 			record_insert_kernel<<<grid_for(n_recv, 256, ctx->grid_cap()), 256, 0, stream>>>(owner, cm->recv.as<exchange_record>(), n_recv);
 			++ctx->launches;
 			const uint64_t tiles = div_up<uint64_t>(capacity + 1, COMPACT_TILE);
-			scan_state st = ctx->scan(tiles);
-			table_compact_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, stream>>>(owner, opt.tolerance, cm->okey.as<uint64_t>(), cm->oslot.as<uint32_t>(),
-			                                                                    reinterpret_cast<unsigned long long *>(ctx->small(DS_COUNT)), st);
+			table_compact_kernel<<<(unsigned)std::min<uint64_t>(tiles, (uint64_t)ctx->sm_count * 16), SCAN_THREADS, 0, stream>>>(
+			    owner, capacity + 1, opt.tolerance, cm->okey.as<uint64_t>(), cm->oslot.as<uint32_t>(), reinterpret_cast<unsigned long long *>(ctx->small(DS_COUNT)));
 			++ctx->launches;
 			QB_CUDA(cudaGetLastError());
 			ctx->fetch_small();
@@ -1268,6 +1302,7 @@ void qb_options_default(qb_options *opt) {
 	opt->table_load = 0;
 	opt->profile = 0;
 	opt->locality_sort = 1;
+	opt->binned_inserts = 1;
 	opt->safety_margin = 0.2f; // SAFETY_MARGIN, quids.hpp:33-35
 	opt->memory_budget = 0;
 	opt->equalize = 0;

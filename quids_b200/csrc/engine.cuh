@@ -331,8 +331,8 @@ __global__ void __launch_bounds__(STAGED_THREADS) group_items_kernel(const Rule 
 // every warp takes ITEM_CHUNK consecutive items of the sorted order; one lane per item prepares its
 // parent's context and the group's root, then all lanes produce one group after the other with
 // ACCUMULATE = true; what the rule still holds at the end of the chunk is flushed
-template <class Rule>
-__global__ void __launch_bounds__(SYMBOLIC_THREADS, ITEMS_BLOCKS_PER_SM) symbolic_items_kernel(const Rule rule, const engine_launch L) {
+template <class Rule, int BLOCKS_PER_SM>
+__global__ void __launch_bounds__(SYMBOLIC_THREADS, BLOCKS_PER_SM) symbolic_items_kernel(const Rule rule, const engine_launch L) {
 	typedef typename Rule::ctx_t ctx_t;
 	struct warp_slice {
 		ctx_t ctx[32];
@@ -774,8 +774,19 @@ struct rule_glue {
 	static void symbolic_items(const void *rule, const engine_launch &L) {
 		if constexpr (Rule::has_group_key) {
 			const uint64_t warps = div_up<uint64_t>(L.n_groups, ITEM_CHUNK);
-			int grid = grid_for(warps * 32, SYMBOLIC_THREADS, resident_grid((const void *)symbolic_items_kernel<Rule>, SYMBOLIC_THREADS, L.sm_count));
-			symbolic_items_kernel<Rule><<<grid, SYMBOLIC_THREADS, 0, L.stream>>>(*static_cast<const Rule *>(rule), L);
+			// occupancy target: the register budget follows from it (5 CTAs of 4 warps: 96 registers).  QB_ITEMS_BLOCKS is a developer
+			// knob for A/B runs (4: 128 registers, no spills; 6: 80 registers)
+			static const int blocks = getenv("QB_ITEMS_BLOCKS") ? atoi(getenv("QB_ITEMS_BLOCKS")) : ITEMS_BLOCKS_PER_SM;
+			auto launch = [&](auto kernel) {
+				int grid = grid_for(warps * 32, SYMBOLIC_THREADS, resident_grid((const void *)kernel, SYMBOLIC_THREADS, L.sm_count));
+				kernel<<<grid, SYMBOLIC_THREADS, 0, L.stream>>>(*static_cast<const Rule *>(rule), L);
+			};
+			if (blocks == 4)
+				launch(symbolic_items_kernel<Rule, 4>);
+			else if (blocks == 6)
+				launch(symbolic_items_kernel<Rule, 6>);
+			else
+				launch(symbolic_items_kernel<Rule, ITEMS_BLOCKS_PER_SM>);
 			++*L.launch_counter;
 		}
 	}

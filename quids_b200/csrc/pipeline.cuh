@@ -15,47 +15,54 @@ constexpr int COMPACT_TILE = SCAN_THREADS * COMPACT_ITEMS;
 __device__ __forceinline__ uint64_t key_of_norm(double norm) { return (uint64_t)__double_as_longlong(norm); }
 
 // ---- interference result -> dense list of unique children above the tolerance ------------------------
-// One streaming pass over the table (two 16-byte loads per 32-byte slot, coalesced), stable
-// compaction ranked by decoupled look-back.  Replaces the partition by `norm(mag) > tolerance` of
-// quids.hpp:819-823; the strict > and norm = re*re + im*im (separately rounded) are kept.
-__global__ void __launch_bounds__(SCAN_THREADS) table_compact_kernel(table_view t, double tolerance, uint64_t *ukey, uint32_t *uslot,
-                                                                     unsigned long long *count, scan_state st) {
-	const unsigned int tile = scan_take_ticket(st);
-	const uint64_t n = t.capacity + 1;
-	const uint64_t base = (uint64_t)tile * COMPACT_TILE;
-	bool keep[COMPACT_ITEMS];
-	uint64_t key[COMPACT_ITEMS];
-	ulonglong2 lo[COMPACT_ITEMS], hi[COMPACT_ITEMS];
+// One streaming pass over the table (two 16-byte loads per 32-byte slot, coalesced).  Replaces the partition by
+// `norm(mag) > tolerance` of quids.hpp:819-823; the strict > and norm = re*re + im*im (separately rounded) are kept.
+// The kept entries of a tile go to out[base .. base + total) with base = ONE atomicAdd on the output cursor per tile: the
+// order of the list is the order in which the tiles asked, i.e. arbitrary -- as arbitrary as the order of the table itself
+// (which child created which slot) and of the reference's own list (quids.hpp:819, an unstable parallel partition).
+// Round 1 ranked the tiles with a decoupled look-back instead (stable order): the look-back chain advances about 8e7
+// tiles/s, and a table of 1.3e9 slots has 6.5e5 tiles of 2048 -- 8 ms of pure serialisation out of 16 ms for the kernel.
+// `n` = slots to scan (a hashed table: capacity + 1 with the dedicated slot of the hash 0; regions: the slots handed out).
+__global__ void __launch_bounds__(SCAN_THREADS) table_compact_kernel(table_view t, uint64_t n, double tolerance, uint64_t *ukey, uint32_t *uslot,
+                                                                     unsigned long long *count) {
+	__shared__ unsigned long long s_base;
+	for (uint64_t base = (uint64_t)blockIdx.x * COMPACT_TILE; base < n; base += (uint64_t)gridDim.x * COMPACT_TILE) {
+		bool keep[COMPACT_ITEMS];
+		uint64_t key[COMPACT_ITEMS];
+		ulonglong2 lo[COMPACT_ITEMS], hi[COMPACT_ITEMS];
 #pragma unroll
-	for (int j = 0; j < COMPACT_ITEMS; ++j) { // all loads first: two 16-byte halves of every slot
-		const uint64_t i = warp_striped_index<COMPACT_ITEMS>(base, j);
-		lo[j] = hi[j] = make_ulonglong2(0, 0);
-		if (i < n) {
-			lo[j] = __ldcs(reinterpret_cast<const ulonglong2 *>(t.slots + i));     // key, re
-			hi[j] = __ldcs(reinterpret_cast<const ulonglong2 *>(t.slots + i) + 1); // im, rep
+		for (int j = 0; j < COMPACT_ITEMS; ++j) { // all loads first: two 16-byte halves of every slot
+			const uint64_t i = warp_striped_index<COMPACT_ITEMS>(base, j);
+			lo[j] = hi[j] = make_ulonglong2(0, 0);
+			if (i < n) {
+				lo[j] = __ldcs(reinterpret_cast<const ulonglong2 *>(t.slots + i));     // key, re
+				hi[j] = __ldcs(reinterpret_cast<const ulonglong2 *>(t.slots + i) + 1); // im, rep
+			}
 		}
-	}
 #pragma unroll
-	for (int j = 0; j < COMPACT_ITEMS; ++j) {
-		// a slot is occupied once it has a representative (set by whoever created it; never 0): true for hashed slots,
-		// for the dedicated slot of the hash 0, and for region slots (whose object may hash to 0)
-		const bool occupied = hi[j].y != 0;
-		const double norm = cnorm(cplx{__longlong_as_double((long long)lo[j].y), __longlong_as_double((long long)hi[j].x)});
-		keep[j] = occupied && norm > tolerance;
-		key[j] = key_of_norm(norm);
-	}
-	uint32_t rank[COMPACT_ITEMS], unused_rank[COMPACT_ITEMS], total, unused_total;
-	block_rank_warp_striped<COMPACT_ITEMS, false>(keep, keep, rank, unused_rank, total, unused_total);
-	const uint64_t before = scan_lookback(st, tile, total);
-#pragma unroll
-	for (int j = 0; j < COMPACT_ITEMS; ++j)
-		if (keep[j]) {
-			const uint64_t dst = before + rank[j];
-			ukey[dst] = key[j];
-			uslot[dst] = (uint32_t)warp_striped_index<COMPACT_ITEMS>(base, j);
+		for (int j = 0; j < COMPACT_ITEMS; ++j) {
+			// a slot is occupied once it has a representative (set by whoever created it; never 0): true for hashed slots,
+			// for the dedicated slot of the hash 0, and for region slots (whose object may hash to 0)
+			const bool occupied = hi[j].y != 0;
+			const double norm = cnorm(cplx{__longlong_as_double((long long)lo[j].y), __longlong_as_double((long long)hi[j].x)});
+			keep[j] = occupied && norm > tolerance;
+			key[j] = key_of_norm(norm);
 		}
-	if (base + COMPACT_TILE >= n && threadIdx.x == 0)
-		*count = before + total;
+		uint32_t rank[COMPACT_ITEMS], unused_rank[COMPACT_ITEMS], total, unused_total;
+		block_rank_warp_striped<COMPACT_ITEMS, false>(keep, keep, rank, unused_rank, total, unused_total);
+		if (threadIdx.x == 0)
+			s_base = total ? atomicAdd(count, (unsigned long long)total) : 0;
+		__syncthreads();
+		const uint64_t before = s_base;
+#pragma unroll
+		for (int j = 0; j < COMPACT_ITEMS; ++j)
+			if (keep[j]) {
+				const uint64_t dst = before + rank[j];
+				ukey[dst] = key[j];
+				uslot[dst] = (uint32_t)warp_striped_index<COMPACT_ITEMS>(base, j);
+			}
+		__syncthreads(); // s_base is reused by the next tile
+	}
 }
 
 // ---- keep the elements selected by a finished radix select --------------------------------------------
