@@ -66,8 +66,9 @@ typedef struct qb_options {
 	int32_t locality_sort;     /* engine knob: process the child groups in the order of the rule's group key so that equal
 	                              objects are merged on chip before the table; 0 off, 1 when there are >= 2^16 groups (default), 2 always */
 	int32_t binned_inserts;    /* engine knob: one-child-per-lane rules send their children to the table through bins ordered by table region
-	                              (cache-resident inserts, the reference's bucket partition quids.hpp:755-809); 0 off, 1 when the table
-	                              is larger than L2 (default), 2 always */
+	                              (the reference's bucket partition, quids.hpp:755-809); 0 off (default: measured SLOWER on B200 when most
+	                              children are unique -- a first touch costs the same DRAM round trip in any order),
+	                              1 when the table is larger than L2, 2 always */
 	uint64_t memory_budget;    /* engine knob: bytes the automatic budget (max_num_object = 0) may spend on the symbolic workspace and
 	                              on the next state; 0 = measured (cudaMemGetInfo minus safety_margin of the GPU) */
 	/* load balancing at the head of quids::mpi::simulate (quids_mpi.hpp:442-500); only qb_simulate_dist reads these */

@@ -454,7 +454,7 @@ void resolve_options(const qb_options *in, qb_options &opt) {
 	if (!(opt.table_load > 0 && opt.table_load <= 0.95))
 		opt.table_load = 0.75;
 	if (in == nullptr || opt.binned_inserts < 0 || opt.binned_inserts > 2)
-		opt.binned_inserts = 1;
+		opt.binned_inserts = 0;
 }
 
 // ======================================================================================================
@@ -1302,7 +1302,7 @@ void qb_options_default(qb_options *opt) {
 	opt->table_load = 0;
 	opt->profile = 0;
 	opt->locality_sort = 1;
-	opt->binned_inserts = 1;
+	opt->binned_inserts = 0;
 	opt->safety_margin = 0.2f; // SAFETY_MARGIN, quids.hpp:33-35
 	opt->memory_budget = 0;
 	opt->equalize = 0;

@@ -498,6 +498,11 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 		}
 	}
 
+	// identity of a run's objects -> key of their region in the directory
+	__device__ static uint64_t region_key(uint64_t eligible, uint64_t fixed, uint32_t target, uint64_t names, uint32_t n) {
+		return mix64(eligible ^ mix64(fixed + 0x9e3779b97f4a7c15ull * (target + 1ull)) ^ mix64(names ^ (0xc2b2ae3d27d4eb4full * n)));
+	}
+
 	// the objects of the current run go to the global table, four per lane at a time
 	template <class WS, class Emit>
 	__device__ void flush_warp(WS &ws, Emit &emit) const {
@@ -508,9 +513,7 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 			spread_run(ws);
 			region_grant grant{~0ull, nullptr, 0, 0, false};
 			if (lane == 0) {
-				const uint64_t key = mix64(ws.run_eligible ^ mix64(ws.run_fixed + 0x9e3779b97f4a7c15ull * (ws.run_target + 1ull)) ^
-				                           mix64(ws.run_names ^ (0xc2b2ae3d27d4eb4full * ws.run_n)));
-				grant = region_acquire(emit.table, ws.chunk, key, leaves);
+				grant = region_acquire(emit.table, ws.chunk, region_key(ws.run_eligible, ws.run_fixed, ws.run_target, ws.run_names, ws.run_n), leaves);
 				emit.regions += grant.created;
 			}
 			const unsigned long long base = __shfl_sync(0xffffffffu, grant.base, 0);
@@ -656,6 +659,7 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 		}
 		if (emit.table.dir) { // region mode: hashes and representatives are only needed if this run creates the region (flush_warp)
 			if (lane == 0) {
+				region_prefetch(emit.table, region_key(eligible, fixed, target, ctx.names_hash, ctx.n)); // probed when the run is flushed
 				ws.open_ctx = ctx;
 				ws.open_root = root;
 				ws.open_first_child = emit.first_child;

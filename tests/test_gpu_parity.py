@@ -42,6 +42,19 @@ def test_golden_vectors_with_parent_ordering(gpu, port, name):
         qb.config.locality_sort = 1
 
 
+@pytest.mark.parametrize("name", golden_util.fixtures())
+def test_golden_vectors_with_binned_inserts(gpu, port, name):
+    """children sent to the table through bins ordered by table region (table.cuh, an engine knob that is off by default):
+    the same results, for the rules written with the four reference methods and for the fused ones"""
+    import quids_b200 as qb
+    qb.config.binned_inserts = 2
+    try:
+        for suffix in ("", "_generic"):
+            assert golden_util.replay(name, gpu(suffix), port) > 0
+    finally:
+        qb.config.binned_inserts = 0
+
+
 @pytest.mark.parametrize("align", [0, 4, 8, 16])
 def test_golden_vectors_other_alignments(gpu, port, align):
     for name in ("qc_example", "qcgd_example_seed1", "qcgd_truncate_children"):
