@@ -9,7 +9,7 @@
 #include <stdexcept>
 #include <string>
 
-#include "../../include/quids_b200.h"
+#include "../../quids_b200.h"
 
 namespace qb {
 

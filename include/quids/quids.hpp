@@ -11,8 +11,10 @@
 //     QB_REGISTER_RULE) plus the constructor arguments of the reference class.  The rule classes of
 //     rules/quantum_computer.hpp and rules/qcgd.hpp keep their names and constructors.
 //   * a modifier_t is likewise a handle (the reference's is a std::function host closure); the
-//     factories cnot/Xgate/Ygate/Zgate and qcgd::step / reversed_step keep their names.  A host
-//     lambda is NOT accepted: there is no CPU fallback.
+//     factories cnot/Xgate/Ygate/Zgate and qcgd::step / reversed_step keep their names.  The LAMBDA path
+//     (simulate(it, callable)) takes __device__ callables: include quids/device/lambda.cuh and compile the
+//     driver with nvcc (extended lambdas).  A HOST lambda is not accepted: there is no CPU fallback.
+//   * user-written rules and modifiers are device code too: quids/device/plugin.cuh, examples/custom_rule.cu.
 //   * simple_truncation defaults to true (the probabilistic mode is not reproducible even in the
 //     reference).  false selects the probabilistic truncation of the reference
 //     (keep the smallest u / |mag|^2) with a counter-based generator seeded by quids::truncation_seed.
@@ -247,6 +249,9 @@ namespace quids {
 			to_device();
 			return handle_;
 		}
+		/// tell the mirror that device code changed the state behind device_handle() (objects / magnitudes in place, or the
+		/// whole state): the public counters are refreshed and the host copy is fetched again on the next read
+		void device_modified() { after_device_write(); }
 
 	protected:
 		friend void simulate(it_t &iteration, modifier_t const &rule);

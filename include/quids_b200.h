@@ -130,7 +130,13 @@ int qb_iter_wait(const qb_iter *it);
 /* iteration::append (quids.hpp:174-188) for a whole state at once, HBM to HBM: the objects of `other` are appended to
  * `it` with their magnitudes (no normalisation; total_proba of `it` is kept) */
 int qb_iter_append_state(qb_iter *it, const qb_iter *other);
+/* the four arrays of the state in HBM (quids.hpp:266-276 layout: objects, object_begin u64[n+1], object_size u32[n], magnitude
+ * 2 x f64 [n]), for device code that reads or modifies a state in place (quids/device/plugin.cuh: modifier lambdas); the
+ * pointers are invalidated by the next call that resizes the state */
 int qb_iter_device_ptrs(const qb_iter *it, void **objects, void **object_begin, void **object_size, void **magnitude);
+/* the context a state belongs to, and the CUDA device / stream of a context (device plug-ins launch on that stream) */
+qb_ctx *qb_iter_ctx(const qb_iter *it);
+int qb_ctx_device(const qb_ctx *ctx);
 /* pop(n, normalize) quids.hpp:194-203 */
 int qb_iter_pop(qb_iter *it, uint64_t n, int normalize);
 /* normalize() quids.hpp:985-1017 */

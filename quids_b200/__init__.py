@@ -91,6 +91,8 @@ def lib():
         "qb_iter_counts": (i32, [vp, P(u64), P(u64), P(dbl)]),
         "qb_iter_download": (i32, [vp, vp, vp, vp, vp]),
         "qb_iter_device_ptrs": (i32, [vp, P(vp), P(vp), P(vp), P(vp)]),
+        "qb_iter_ctx": (vp, [vp]),
+        "qb_ctx_device": (i32, [vp]),
         "qb_iter_pop": (i32, [vp, u64, i32]),
         "qb_iter_normalize": (i32, [vp]),
         "qb_sym_create": (i32, [vp, P(vp)]),

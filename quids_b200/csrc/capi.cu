@@ -7,7 +7,7 @@
 #include <mutex>
 #include <vector>
 
-#include "engine.cuh"
+#include <quids/device/engine.cuh>
 #include "pipeline.cuh"
 #include "sort.cuh"
 
@@ -1621,12 +1621,17 @@ int qb_iter_download(const qb_iter *it, uint8_t *objects, uint64_t *object_begin
 int qb_iter_device_ptrs(const qb_iter *it, void **objects, void **object_begin, void **object_size, void **magnitude) {
 	return guarded([&] {
 		QB_REQUIRE(it, QB_ERR_ARG, "null iteration");
+		it->ctx->use();
+		it->settle(); // what the caller enqueues on the context's stream comes after the transfers in flight
 		if (objects) *objects = it->objects.ptr;
 		if (object_begin) *object_begin = it->begin.ptr;
 		if (object_size) *object_size = it->size.ptr;
 		if (magnitude) *magnitude = it->mag.ptr;
 	});
 }
+
+qb_ctx *qb_iter_ctx(const qb_iter *it) { return it ? it->ctx : nullptr; }
+int qb_ctx_device(const qb_ctx *ctx) { return ctx ? ctx->device : -1; }
 
 int qb_iter_append_state(qb_iter *it, const qb_iter *other) {
 	return guarded([&] {

@@ -2,10 +2,10 @@
 // selection, finalisation metadata, normalisation.  (Rule-dependent kernels: engine.cuh.)
 #pragma once
 
-#include "rule_api.cuh"
+#include <quids/device/rule_api.cuh>
 #include "scan.cuh"
 #include "select.cuh"
-#include "table.cuh"
+#include <quids/device/table.cuh>
 
 namespace qb {
 

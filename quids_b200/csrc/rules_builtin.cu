@@ -7,7 +7,7 @@
 #include <cmath>
 #include <complex>
 
-#include "engine.cuh"
+#include <quids/device/engine.cuh>
 #include "rules_qc.cuh"
 #include "rules_qcgd.cuh"
 

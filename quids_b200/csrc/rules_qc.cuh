@@ -2,7 +2,7 @@
 // (reference: src/rules/quantum_computer.hpp).  Objects are one byte per qubit (0/1).
 #pragma once
 
-#include "rule_api.cuh"
+#include <quids/device/rule_api.cuh>
 
 namespace qb {
 namespace qc {

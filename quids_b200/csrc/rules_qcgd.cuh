@@ -16,7 +16,7 @@
 // writes the child's bytes (finalisation).
 #pragma once
 
-#include "rule_api.cuh"
+#include <quids/device/rule_api.cuh>
 
 namespace qb {
 namespace qcgd {

@@ -9,7 +9,7 @@
 // value are read atomically with one volatile load and no fence is needed.
 #pragma once
 
-#include "common.cuh"
+#include <quids/device/common.cuh>
 
 namespace qb {
 

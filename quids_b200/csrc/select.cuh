@@ -11,7 +11,7 @@
 // (ties at the threshold are arbitrary in the reference; here the first ones in storage order win).
 #pragma once
 
-#include "common.cuh"
+#include <quids/device/common.cuh>
 #include "scan.cuh"
 
 namespace qb {

@@ -14,7 +14,7 @@
 // contiguous elements [w * 32 * ROUNDS, (w + 1) * 32 * ROUNDS), visited in rows of 32.
 #pragma once
 
-#include "common.cuh"
+#include <quids/device/common.cuh>
 #include "scan.cuh"
 
 namespace qb {
