@@ -689,6 +689,13 @@ __global__ void __launch_bounds__(ENGINE_THREADS) hash_kernel(const Rule rule, i
 		hashes[i] = rule.hasher(it.objects + it.begin[i], it.size[i]);
 }
 
+template <class Rule>
+__global__ void __launch_bounds__(ENGINE_THREADS) family_kernel(const Rule rule, iter_view it, uint64_t *family) {
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < it.n; i += stride)
+		family[i] = rule.family_key(it.objects + it.begin[i], it.size[i]);
+}
+
 template <class Modifier>
 __global__ void __launch_bounds__(ENGINE_THREADS) modifier_kernel(const Modifier modifier, iter_view it) {
 	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -817,6 +824,13 @@ struct rule_glue {
 		hash_kernel<Rule><<<grid, ENGINE_THREADS, 0, L.stream>>>(*static_cast<const Rule *>(rule), L.it, L.hashes);
 		++*L.launch_counter;
 	}
+	static void family(const void *rule, const engine_launch &L) {
+		if constexpr (Rule::has_family) {
+			int grid = grid_for(L.it.n, ENGINE_THREADS, resident_grid((const void *)family_kernel<Rule>, ENGINE_THREADS, L.sm_count));
+			family_kernel<Rule><<<grid, ENGINE_THREADS, 0, L.stream>>>(*static_cast<const Rule *>(rule), L.it, L.hashes);
+			++*L.launch_counter;
+		}
+	}
 	static rule_ops ops(const char *name, int (*make)(const double *, uint32_t, void *)) {
 		rule_ops o;
 		o.name = name;
@@ -833,6 +847,8 @@ struct rule_glue {
 		o.group_capacity = Rule::group_capacity;
 		o.launch_group_items = group_items;
 		o.launch_symbolic_items = symbolic_items;
+		o.has_family = Rule::has_family;
+		o.launch_family = family;
 		o.symbolic_grid = symbolic_grid;
 		o.symbolic_chunks = symbolic_chunks;
 		return o;

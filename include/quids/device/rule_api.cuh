@@ -145,6 +145,14 @@ struct rule_base {
 	// every object of the state is smaller than this many bytes (0 = the rule does not use regions)
 	static constexpr uint32_t region_size_limit = 0;
 
+	// optional, distributed path: a FAMILY is a set of objects closed under the rule -- every child of a member is a member --
+	// so that objects of different families never interfere.  family_key(parent, size) gives equal keys to the members of a
+	// family (a hash of what the rule leaves untouched).  quids::mpi::simulate then moves every PARENT to the rank that owns
+	// its family (parents are a few hundred bytes, their children thousands of records) and interference needs no exchange at
+	// all (route.inc.cuh).  Only used when every object of the state is smaller than region_size_limit.
+	static constexpr bool has_family = false;
+	__device__ uint64_t family_key(const uint8_t *, uint32_t) const { return 0; }
+
 	static constexpr bool has_group_key = false;
 	static constexpr uint32_t group_capacity = 1; // most children one group can hold (bounds what a run can send to the table)
 	__device__ void group_keys(const uint8_t *, uint32_t, uint32_t, uint32_t *) const {}
@@ -188,6 +196,8 @@ struct rule_ops {
 	size_t ctx_bytes;
 	void (*launch_group_items)(const void *rule, const engine_launch &L);
 	void (*launch_symbolic_items)(const void *rule, const engine_launch &L);
+	bool has_family;
+	void (*launch_family)(const void *rule, const engine_launch &L); // L.hashes[i] = family_key of object i
 	int (*symbolic_grid)(int sm_count); // CTAs the symbolic kernel is launched with at most (sizes the scratch)
 	uint64_t (*symbolic_chunks)(uint64_t n_groups); // work chunks of the symbolic kernel (sizes chunk_parent)
 };

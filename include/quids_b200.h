@@ -69,6 +69,8 @@ typedef struct qb_options {
 	                              (the reference's bucket partition, quids.hpp:755-809); 0 off (default: measured SLOWER on B200 when most
 	                              children are unique -- a first touch costs the same DRAM round trip in any order),
 	                              1 when the table is larger than L2, 2 always */
+	int32_t family_routing;    /* engine knob, qb_simulate_dist: rules with families (erase_create, coin) move the PARENTS to the rank that
+	                              owns their family, so that interference needs no exchange of children; 1 on (default), 0 off */
 	uint64_t memory_budget;    /* engine knob: bytes the automatic budget (max_num_object = 0) may spend on the symbolic workspace and
 	                              on the next state; 0 = measured (cudaMemGetInfo minus safety_margin of the GPU) */
 	/* load balancing at the head of quids::mpi::simulate (quids_mpi.hpp:442-500); only qb_simulate_dist reads these */

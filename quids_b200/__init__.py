@@ -47,7 +47,7 @@ def build(verbose=False):
 
 class qb_options(C.Structure):
     _fields_ = [("tolerance", C.c_double), ("align_byte_length", C.c_uint32), ("simple_truncation", C.c_int32),
-                ("table_load", C.c_double), ("profile", C.c_int32), ("safety_margin", C.c_float), ("seed", C.c_uint32), ("locality_sort", C.c_int32), ("binned_inserts", C.c_int32), ("memory_budget", C.c_uint64),
+                ("table_load", C.c_double), ("profile", C.c_int32), ("safety_margin", C.c_float), ("seed", C.c_uint32), ("locality_sort", C.c_int32), ("binned_inserts", C.c_int32), ("family_routing", C.c_int32), ("memory_budget", C.c_uint64),
                 ("equalize", C.c_int32), ("equalize_inbalance", C.c_float), ("min_equalize_step", C.c_float), ("min_equalize_size", C.c_uint64)]
 
 
@@ -163,6 +163,7 @@ class _Globals:
     min_equalize_size = 100    # quids::mpi::min_equalize_size
     locality_sort = 1          # engine knob: 0 off, 1 auto, 2 always
     binned_inserts = 0         # engine knob: 0 off (default), 1 when the table is larger than L2, 2 always
+    family_routing = 1         # engine knob, distributed path: parents routed to the owner of their family (erase_create, coin)
 
     def options(self):
         o = qb_options()
@@ -176,6 +177,7 @@ class _Globals:
         o.profile = 1 if self.profile else 0
         o.locality_sort = self.locality_sort
         o.binned_inserts = self.binned_inserts
+        o.family_routing = self.family_routing
         o.memory_budget = self.memory_budget
         o.equalize = self.equalize
         o.equalize_inbalance = self.equalize_inbalance

@@ -469,6 +469,14 @@ double automatic_budget(qb_ctx *ctx, const qb_sym *sym, const qb_iter *next, con
 		return (double)opt.memory_budget - (next ? workspace : 0.0);
 	size_t free_bytes = 0, total_bytes = 0;
 	QB_CUDA(cudaMemGetInfo(&free_bytes, &total_bytes));
+	{ // what the stream-ordered pool holds but nobody uses counts as free: the next allocation takes it first
+		cudaMemPool_t pool = nullptr;
+		uint64_t reserved = 0, used = 0;
+		if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess && cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+		    cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
+			free_bytes += reserved - used;
+		cudaGetLastError();
+	}
 	double reusable = next ? (double)(next->objects.cap + next->begin.cap + next->size.cap + next->mag.cap) : (double)sym->device_bytes();
 	return (double)free_bytes + reusable - (double)opt.safety_margin * (double)total_bytes;
 }
@@ -713,7 +721,7 @@ local_table build_local_table(qb_iter *it, uint64_t rule_id, const rule_ops *ops
 	// prepare = table (and directory) clear, insert = the fused child-generation + table-insert kernel, finalize = compaction by
 	// tolerance; "symbolic_iteration" before them covers the ordering of the work items.  A redo after a table overflow does not
 	// repeat the labels (their order is part of the API): its time is attributed to "finalize".
-	const bool collision_labels = comm == nullptr;
+	const bool collision_labels = comm == nullptr || comm->local_interference;
 	for (sym->table_attempts = 1;; ++sym->table_attempts) {
 		QB_REQUIRE(capacity + 1 <= 0xffffffffull, QB_ERR_CAPACITY, "interference table would need more than 2^32 slots");
 		if (collision_labels && sym->table_attempts == 1)
@@ -834,7 +842,7 @@ struct survivor_source {
 
 void finalize_and_normalize(qb_iter *it, const rule_ops *ops, const void *rule, qb_iter *next, qb_sym *sym, const qb_options &opt, const local_table &R,
                             const survivor_source &src, uint64_t n_survivors, phase_timer &timer, const stepper &step, engine_launch &L, comm_ops *comm,
-                            double *node_total_proba, bool inject_failure = false);
+                            double *node_total_proba, bool fail_injected = false);
 
 void finish_empty(qb_ctx *ctx, qb_iter *next, const stepper &step, phase_timer &timer, int from) {
 	// the label sequences of the reference's early outs (quids.hpp:650-651,729-731,908-909,989-990)
@@ -851,8 +859,19 @@ void finish_empty(qb_ctx *ctx, qb_iter *next, const stepper &step, phase_timer &
 	timer.collect();
 }
 
+// test knob QB_DIST_INJECT_FAILURE="<rank>:<phase>": that rank fails in that phase of the distributed iteration (phases of the
+// record-exchange path: local, partition, owner, return, finalize; of the family-routed path: route, local, finalize)
+void inject_failure(int rank, const char *phase) {
+	const char *inject = getenv("QB_DIST_INJECT_FAILURE");
+	if (inject && atoi(inject) == rank && strchr(inject, ':') && !strcmp(strchr(inject, ':') + 1, phase))
+		throw qb::error(QB_ERR_CAPACITY, std::string("injected failure in phase ") + phase);
+}
+
+// One rule iteration with the interference complete on this GPU: the single-GPU path (comm = nullptr), and the distributed path
+// after the parents were routed by family (route.inc.cuh) -- there only the scalars are collective: counts, the digit histograms
+// of the global top-k, the norm.
 void simulate(qb_iter *it, uint64_t rule_id, const rule_ops *ops, const void *rule, qb_iter *next, qb_sym *sym, uint64_t max_num_object, const qb_options &opt,
-              qb_step_cb cb, void *user) {
+              qb_step_cb cb, void *user, comm_ops *comm = nullptr, double *node_total_proba = nullptr) {
 	qb_ctx *ctx = it->ctx;
 	QB_REQUIRE(next->ctx == ctx && sym->ctx == ctx, QB_ERR_ARG, "iteration, next iteration and symbolic iteration belong to different contexts");
 	QB_REQUIRE(next != it, QB_ERR_ARG, "next_iteration must be a different object from iteration");
@@ -865,6 +884,7 @@ void simulate(qb_iter *it, uint64_t rule_id, const rule_ops *ops, const void *ru
 	cudaStream_t stream = ctx->stream;
 	stepper step{ctx, cb, user};
 	phase_timer timer(sym, opt.profile != 0);
+	comm_ops::pending_error err; // distributed path: a failure of this rank is agreed on at the next collective (dist.inc.cuh)
 
 	engine_launch L;
 	memset(&L, 0, sizeof L);
@@ -873,53 +893,96 @@ void simulate(qb_iter *it, uint64_t rule_id, const rule_ops *ops, const void *ru
 	L.launch_counter = &ctx->launches;
 	L.it = it->view();
 
-	local_table R = build_local_table(it, rule_id, ops, rule, sym, max_num_object, automatic, opt, opt.tolerance, timer, step, L, nullptr);
-	if (R.empty_from >= 0) {
+	local_table R;
+	if (comm) {
+		bool past_collectives = false;
+		try {
+			R = build_local_table(it, rule_id, ops, rule, sym, max_num_object, automatic, opt, opt.tolerance, timer, step, L, comm, &past_collectives);
+			inject_failure(comm->rank(), "local");
+		} catch (const qb::error &e) {
+			if (!past_collectives)
+				throw;
+			err.status = e.status;
+			err.what = e.what();
+		}
+	} else {
+		R = build_local_table(it, rule_id, ops, rule, sym, max_num_object, automatic, opt, opt.tolerance, timer, step, L, nullptr);
+	}
+	if (err.ok() && R.empty_from >= 0) {
 		finish_empty(ctx, next, step, timer, R.empty_from);
+		if (node_total_proba) *node_total_proba = 0;
 		return;
 	}
 	sym->n_unique = R.n_unique; // (the compute_collisions labels were emitted inside build_local_table, around the phases they name)
 
-	// ---- 7. child truncation: the max_num_object most probable (quids.hpp:866-900) ---------------------
+	// ---- 7. child truncation: the max_num_object most probable (quids.hpp:866-900), over all ranks on the distributed path
+	uint64_t room = 0;
+	if (automatic) {
+		// quids.hpp:510-536: as many children as the next state can hold.  Per survivor: its bytes (bounded by the largest
+		// child, padded) + object_begin 8 + size 4 + magnitude 16 + the finalisation's parent 8, child id 4, padded size 4, slot 4
+		auto fit = [&] {
+			const double budget = automatic_budget(ctx, sym, next, opt, R.workspace);
+			const double per_object = (double)((R.max_child_size + 7u) & ~7u) + 48.0;
+			room = budget > 0 ? (uint64_t)(budget / per_object) : 0;
+			QB_REQUIRE(room >= 1, QB_ERR_CAPACITY, "max_num_object = 0 (automatic budget): no room left for a next state after the interference table");
+		};
+		if (comm)
+			err.run(fit);
+		else
+			fit();
+		max_num_object = room;
+	}
+	uint64_t n_unique_global = R.n_unique;
+	if (comm) { // agreement point of the local interference step; the automatic budget becomes what the tightest rank allows
+		const uint64_t mine[2] = {err.ok() ? R.n_unique : 0, automatic ? room : ~0ull};
+		std::vector<uint64_t> all = comm->allgather_agreed(mine, 2, err, "the interference step");
+		n_unique_global = 0;
+		uint64_t min_room = ~0ull;
+		for (int r = 0; r < comm->world(); ++r) {
+			n_unique_global += all[2 * r];
+			min_room = std::min(min_room, all[2 * r + 1]);
+		}
+		if (automatic) // families are spread by hash, so are the survivors: a factor 2 of head room covers the spread
+			max_num_object = std::max<uint64_t>(1, (uint64_t)((double)min_room * comm->world() / 2));
+	}
 	step("truncate - prepare");
 	step("truncate");
 	uint64_t n_survivors = R.n_unique;
 	survivor_source src;
 	src.table = R.table;
 	src.slot = sym->uslot.as<uint32_t>();
-	if (automatic) {
-		// quids.hpp:510-536: as many children as the next state can hold.  Per survivor: its bytes (bounded by the largest
-		// child, padded) + object_begin 8 + size 4 + magnitude 16 + the finalisation's parent 8, child id 4, padded size 4, slot 4
-		const double budget = automatic_budget(ctx, sym, next, opt, R.workspace);
-		const double per_object = (double)((R.max_child_size + 7u) & ~7u) + 48.0;
-		const uint64_t fit = budget > 0 ? (uint64_t)(budget / per_object) : 0;
-		QB_REQUIRE(fit >= 1, QB_ERR_CAPACITY, "max_num_object = 0 (automatic budget): no room left for a next state after the interference table");
-		max_num_object = fit;
-	}
-	if (max_num_object < R.n_unique) {
+	if (max_num_object < n_unique_global) {
 		timer.begin(QB_PHASE_TRUNCATE);
-		sym->sslot.ensure(sizeof(uint32_t) * max_num_object, stream);
-		if (!opt.simple_truncation) {
+		sym->sslot.ensure(sizeof(uint32_t) * std::max<uint64_t>(1, std::min<uint64_t>(R.n_unique, max_num_object)), stream);
+		if (!opt.simple_truncation && R.n_unique > 0) {
 			randomize_keys_kernel<<<grid_for(R.n_unique, 256, ctx->grid_cap()), 256, 0, stream>>>(sym->ukey.as<uint64_t>(), R.table, sym->uslot.as<uint32_t>(),
 			                                                                                    R.n_unique, opt.seed);
 			++ctx->launches;
 		}
 		key_from_array keys{sym->ukey.as<uint64_t>()};
-		select_threshold(ctx, nullptr, keys, R.n_unique, max_num_object);
-		n_survivors = select_keep(ctx, nullptr, keys, R.n_unique, out_gather_u32{sym->sslot.as<uint32_t>(), sym->uslot.as<uint32_t>()});
+		select_threshold(ctx, comm, keys, R.n_unique, max_num_object);
+		n_survivors = select_keep(ctx, comm, keys, R.n_unique, out_gather_u32{sym->sslot.as<uint32_t>(), sym->uslot.as<uint32_t>()});
 		src.slot = sym->sslot.as<uint32_t>();
 		timer.end(QB_PHASE_TRUNCATE);
 	}
-	if (n_survivors == 0) {
+	if (n_survivors == 0 && !comm) {
 		finish_empty(ctx, next, step, timer, 7);
 		return;
 	}
-	finalize_and_normalize(it, ops, rule, next, sym, opt, R, src, n_survivors, timer, step, L, nullptr, nullptr);
+	bool fail_finalize = false;
+	if (comm) {
+		try {
+			inject_failure(comm->rank(), "finalize");
+		} catch (const qb::error &) {
+			fail_finalize = true;
+		}
+	}
+	finalize_and_normalize(it, ops, rule, next, sym, opt, R, src, n_survivors, timer, step, L, comm, node_total_proba, fail_finalize);
 }
 
 void finalize_and_normalize(qb_iter *it, const rule_ops *ops, const void *rule, qb_iter *next, qb_sym *sym, const qb_options &opt, const local_table &R,
                             const survivor_source &src, uint64_t n_survivors, phase_timer &timer, const stepper &step, engine_launch &L, comm_ops *comm,
-                            double *node_total_proba, bool inject_failure) {
+                            double *node_total_proba, bool fail_injected) {
 	qb_ctx *ctx = it->ctx;
 	cudaStream_t stream = ctx->stream;
 	comm_ops::pending_error err; // distributed path: a failure of this rank's finalisation is agreed on at the normalisation sum
@@ -937,7 +1000,7 @@ void finalize_and_normalize(qb_iter *it, const rule_ops *ops, const void *rule, 
 	next->n_bytes = 0;
 	double local_total = 0;
 	guarded_phase([&] {
-	if (inject_failure)
+	if (fail_injected)
 		throw qb::error(QB_ERR_CAPACITY, "injected failure in phase finalize");
 	next->begin.ensure(sizeof(uint64_t) * (n_survivors + 1), stream);
 	if (n_survivors > 0) {
@@ -1027,6 +1090,7 @@ void finalize_and_normalize(qb_iter *it, const rule_ops *ops, const void *rule, 
 }
 
 #include "migrate.inc.cuh"
+#include "route.inc.cuh"
 
 // ======================================================================================================
 // one rule iteration over the GPUs of a communicator (see dist.inc.cuh for the protocol)
@@ -1052,12 +1116,7 @@ void simulate_dist(qb_iter *it, uint64_t rule_id, const rule_ops *ops, const voi
 	comm_ops::pending_error err; // see dist.inc.cuh: a failure on one rank is agreed on at the next count exchange
 	const uint32_t world = (uint32_t)cm->world;
 	const bool trace = getenv("QB_DIST_TRACE") != nullptr; // developer aid: wall-clock of every distributed sub-step (drains the stream)
-	// test knob: "<rank>:<phase>" makes that rank fail in that phase (local, partition, owner, return, finalize)
-	const char *inject = getenv("QB_DIST_INJECT_FAILURE");
-	auto injected = [&](const char *phase) {
-		if (inject && atoi(inject) == cm->rank && strchr(inject, ':') && !strcmp(strchr(inject, ':') + 1, phase))
-			throw qb::error(QB_ERR_CAPACITY, std::string("injected failure in phase ") + phase);
-	};
+	auto injected = [&](const char *phase) { inject_failure(cm->rank, phase); };
 	auto t_last = std::chrono::steady_clock::now();
 	auto mark = [&](const char *what) {
 		if (!trace) return;
@@ -1074,6 +1133,30 @@ void simulate_dist(qb_iter *it, uint64_t rule_id, const rule_ops *ops, const voi
 		while ((1u << max_rounds) < world) ++max_rounds; // utils::log_2_upper_bound(size), quids_mpi.hpp:432
 		equalize_loop(it, cm, ops, rule, opt.equalize == 2, opt.min_equalize_size, opt.equalize_inbalance, opt.min_equalize_step, max_rounds);
 		mark("equalize");
+	}
+
+	// 0b. rules with families (rule_api.cuh): the PARENTS go to the rank that owns their family, and the iteration needs no
+	//     exchange of children at all (route.inc.cuh); otherwise the locally unique children are exchanged (below)
+	if (ops->has_family && ops->region_size_limit > 0 && opt.family_routing != 0) {
+		if (!cm->route)
+			cm->route = new route_buffers();
+		step("compute_collisions - com");
+		timer.begin(QB_PHASE_EXCHANGE);
+		const bool routed = route_by_family(it, cm, ops, rule, comm, *cm->route, trace);
+		timer.end(QB_PHASE_EXCHANGE);
+		mark("route parents by family");
+		if (routed) {
+			comm.local_interference = true;
+			float exchange_ms = 0;
+			if (opt.profile) { // simulate() resets the phase table: carry the routing time over
+				ctx->sync();
+				QB_CUDA(cudaEventElapsedTime(&exchange_ms, sym->ev[2 * QB_PHASE_EXCHANGE], sym->ev[2 * QB_PHASE_EXCHANGE + 1]));
+			}
+			simulate(it, rule_id, ops, rule, next, sym, automatic ? 0 : max_num_object, opt, cb, user, &comm, node_total_proba);
+			sym->phase_ms[QB_PHASE_EXCHANGE] = exchange_ms;
+			mark("local iteration on the owned families");
+			return;
+		}
 	}
 
 	engine_launch L;
@@ -1283,7 +1366,13 @@ void simulate_dist(qb_iter *it, uint64_t rule_id, const rule_ops *ops, const voi
 	// 7. every rank rebuilds the survivors whose representative it generated, then global normalisation
 	survivor_source src;
 	src.records = cm->ret_recv.as<survivor_record>();
-	finalize_and_normalize(it, ops, rule, next, sym, opt, R, src, n_survivors, timer, step, L, &comm, node_total_proba, inject && atoi(inject) == cm->rank && strstr(inject, ":finalize"));
+	bool fail_finalize = false;
+	try {
+		injected("finalize");
+	} catch (const qb::error &) {
+		fail_finalize = true;
+	}
+	finalize_and_normalize(it, ops, rule, next, sym, opt, R, src, n_survivors, timer, step, L, &comm, node_total_proba, fail_finalize);
 	mark("finalize + normalize");
 }
 
@@ -1303,6 +1392,7 @@ void qb_options_default(qb_options *opt) {
 	opt->profile = 0;
 	opt->locality_sort = 1;
 	opt->binned_inserts = 0;
+	opt->family_routing = 1;
 	opt->safety_margin = 0.2f; // SAFETY_MARGIN, quids.hpp:33-35
 	opt->memory_budget = 0;
 	opt->equalize = 0;
@@ -1343,6 +1433,13 @@ int qb_ctx_create(int device, qb_ctx **out) {
 		}
 		QB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
 		QB_CUDA(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
+		{ // dev_buf allocates stream-ordered from the device's default pool: keep what is freed cached instead of returning it to
+		  // the driver at every synchronisation (the tables of consecutive rule iterations are GB-sized and change size)
+			cudaMemPool_t pool = nullptr;
+			QB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+			uint64_t keep = ~0ull;
+			QB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+		}
 		QB_CUDA(cudaHostAlloc((void **)&ctx->h_small, DS_WORDS * sizeof(uint64_t), cudaHostAllocDefault));
 		ctx->d_small.ensure(DS_WORDS * sizeof(uint64_t), ctx->stream);
 		QB_CUDA(cudaMemsetAsync(ctx->d_small.ptr, 0, DS_WORDS * sizeof(uint64_t), ctx->stream));
@@ -1538,14 +1635,15 @@ int qb_iter_upload_async(qb_iter *it, uint64_t n, const uint8_t *objects, uint64
 		ctx->use();
 		transfer_events(it);
 		cudaStream_t s = ctx->copy_in;
-		// the old contents may still be in use: by kernels already enqueued, or by a download in flight
-		ctx->order_after_compute(s);
-		if (it->download_pending)
-			QB_CUDA(cudaStreamWaitEvent(s, it->downloaded, 0));
+		// buffers grow on the compute stream (stream-ordered allocation), BEFORE the copy stream is ordered after it
 		it->objects.ensure(num_bytes + 16, ctx->stream);
 		it->begin.ensure(sizeof(uint64_t) * (n + 1), ctx->stream);
 		it->size.ensure(sizeof(uint32_t) * (n ? n : 1), ctx->stream);
 		it->mag.ensure(sizeof(cplx) * (n ? n : 1), ctx->stream);
+		// the old contents may still be in use: by kernels already enqueued, or by a download in flight
+		ctx->order_after_compute(s);
+		if (it->download_pending)
+			QB_CUDA(cudaStreamWaitEvent(s, it->downloaded, 0));
 		if (num_bytes) QB_CUDA(cudaMemcpyAsync(it->objects.ptr, objects, num_bytes, cudaMemcpyHostToDevice, s));
 		if (n) {
 			QB_CUDA(cudaMemcpyAsync(it->begin.ptr, object_begin, sizeof(uint64_t) * (n + 1), cudaMemcpyHostToDevice, s));
@@ -1893,6 +1991,7 @@ int qb_comm_destroy(qb_comm *comm) {
 		comm->ctx->use();
 		comm->ctx->sync();
 		if (comm->nccl) nccl().CommDestroy(comm->nccl);
+		delete comm->route;
 		delete comm;
 	});
 }

@@ -77,6 +77,12 @@ static nccl_api &nccl() {
 			                                   std::to_string(__LINE__) + ")");                                                   \
 	} while (0)
 
+struct route_buffers { // route.inc.cuh: kept in the communicator across calls
+	dev_buf family, owner, counts, cursor;
+	dev_buf s_size, s_padded, s_mag, s_src, s_begin, s_bytes; // this rank's objects grouped by owner
+	dev_buf r_size, r_padded, r_mag, r_begin, r_bytes;        // what arrived: the state this rank owns
+};
+
 struct qb_comm {
 	qb_ctx *ctx = nullptr;
 	int world = 1, rank = 0;
@@ -84,12 +90,14 @@ struct qb_comm {
 	dev_buf scratch; // small device staging for host-value collectives
 	dev_buf send, recv, owner_table, okey, oslot, ret_send, ret_recv, cursors, recv_begin;
 	double owner_unique_ratio = 0; // slots created / records received by the owner table of the last call (0 = no call yet)
+	route_buffers *route = nullptr; // route.inc.cuh: parents grouped by family owner, and what arrived (created on first use)
 };
 
 namespace {
 
 struct comm_ops {
 	qb_comm *c;
+	bool local_interference = false; // the parents were routed by family (route.inc.cuh): interference is complete on every rank
 	qb_ctx *ctx() const { return c->ctx; }
 	int world() const { return c->world; }
 	int rank() const { return c->rank; }

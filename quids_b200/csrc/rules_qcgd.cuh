@@ -257,6 +257,19 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 			id.target = group, id.eligible = ~0ull, id.fixed = (uint64_t)lane_id();
 		return id;
 	}
+	// FAMILY (rule_api.cuh): a child keeps its parent's node count, eligible nodes, particles on the other nodes and names, so
+	// all of that is an invariant of the rule: parents that differ in any of it have no child in common.  (Graphs of more
+	// than 64 nodes have no masks: the caller only routes by family when every object is below region_size_limit.)
+	static constexpr bool has_family = true;
+	__device__ uint64_t family_key(const uint8_t *parent, uint32_t parent_size) const {
+		flip_ctx ctx;
+		prepare(parent, parent_size, ctx);
+		const uint64_t all = ctx.n >= 64 ? ~0ull : ((1ull << ctx.n) - 1);
+		const uint64_t eligible = (WANT_EQUAL ? ~(ctx.left ^ ctx.right) : (ctx.left ^ ctx.right)) & all;
+		const uint64_t fixed = ctx.left & ~eligible & all;
+		return mix64(eligible ^ mix64(fixed + 0x9e3779b97f4a7c15ull * (ctx.n + 1ull)) ^ mix64(ctx.names_hash ^ 0xc2b2ae3d27d4eb4full));
+	}
+
 	// this lane's group has the identity of the run that is open: its root joins the sum of its parent pattern
 	template <class WS>
 	__device__ void continue_run(const flip_ctx &ctx, const flip_root &root, WS &ws) const {

@@ -139,11 +139,12 @@ def want_tail(p: orc.Packed, n):
     return multiset(sizes, mags, p.data[begin:])
 
 
-def run_case(comm, port, state, rid, params, k, tol, qcgd, what, share=share, equalize=0):
+def run_case(comm, port, state, rid, params, k, tol, qcgd, what, share=share, equalize=0, family_routing=1):
     rank, world = dist.get_rank(), dist.get_world_size()
     qb.config.tolerance = tol
     qb.config.align_byte_length = 8
     qb.config.equalize = equalize
+    qb.config.family_routing = family_routing
     mine = share(state, rank, world)
     it, nxt, sym = qb.Iteration(), qb.Iteration(), qb.SymbolicIteration()
     it.upload_packed(mine.sizes, mine.mags, mine.data)
@@ -182,21 +183,24 @@ def failure_cases(comm, port, state):
     rank = dist.get_rank()
     qb.config.tolerance, qb.config.align_byte_length, qb.config.equalize = 1e-18, 8, 0
     mine = share(state, rank, dist.get_world_size())
-    rule = qb.Rule("erase_create", 0.37, 0.21, -0.4)
-    for phase in ("local", "partition", "owner", "return", "finalize"):
-        it, nxt, sym = qb.Iteration(), qb.Iteration(), qb.SymbolicIteration()
-        it.upload_packed(mine.sizes, mine.mags, mine.data)
-        os.environ["QB_DIST_INJECT_FAILURE"] = f"1:{phase}"
-        try:
-            qb.mpi_simulate(it, rule, nxt, sym, comm, 900)
-            raised = None
-        except qb.QuidsError as e:
-            raised = str(e)
-        finally:
-            del os.environ["QB_DIST_INJECT_FAILURE"]
-        assert raised is not None, f"rank {rank}: no error although rank 1 failed in phase {phase}"
-        assert ("injected failure" in raised) == (rank == 1), raised
-        assert rank == 1 or "rank 1 failed" in raised, raised
+    # the record-exchange path (a rule without families) and the family-routed path (erase_create), every phase of each
+    plans = [(qb.Rule("split_merge", 0.37, 0.21, -0.4), ("local", "partition", "owner", "return", "finalize")),
+             (qb.Rule("erase_create", 0.37, 0.21, -0.4), ("route", "local", "finalize"))]
+    for rule, phases in plans:
+        for phase in phases:
+            it, nxt, sym = qb.Iteration(), qb.Iteration(), qb.SymbolicIteration()
+            it.upload_packed(mine.sizes, mine.mags, mine.data)
+            os.environ["QB_DIST_INJECT_FAILURE"] = f"1:{phase}"
+            try:
+                qb.mpi_simulate(it, rule, nxt, sym, comm, 900)
+                raised = None
+            except qb.QuidsError as e:
+                raised = str(e)
+            finally:
+                del os.environ["QB_DIST_INJECT_FAILURE"]
+            assert raised is not None, f"rank {rank}: no error although rank 1 failed in phase {phase} of {rule.name}"
+            assert ("injected failure" in raised) == (rank == 1), raised
+            assert rank == 1 or "rank 1 failed" in raised, raised
     if rank == 0:
         print("ok failure on one rank stops every rank", flush=True)
     run_case(comm, port, state, orc.RULE_ERASE_CREATE, [0.37, 0.21, -0.4], 900, 1e-18, True, "communicator usable after agreed failures")
@@ -258,6 +262,16 @@ def main():
         run_case(comm, port, state, rid, p, orc.NO_TRUNCATION, 1e-18, True, f"rule {rid} no truncation")
         run_case(comm, port, state, rid, p, 900, 1e-18, True, f"rule {rid} children truncated")
         run_case(comm, port, state, rid, p, 250, 1e-18, True, f"rule {rid} parents and children truncated")
+        if rid != orc.RULE_SPLIT_MERGE:  # erase_create / coin went through the family routing above: the record exchange must agree
+            run_case(comm, port, state, rid, p, 900, 1e-18, True, f"rule {rid} children truncated, record exchange", family_routing=0)
+            run_case(comm, port, state, rid, p, 250, 1e-18, True, f"rule {rid} parents and children truncated, record exchange", family_routing=0)
+    # a ragged grown state (names of many shapes, nodes merged and split): families must still be closed under erase_create / coin
+    grown, _, _ = port.simulate(port.qcgd_random_state(9, 2000, 8), orc.RULE_SPLIT_MERGE, [0.4, 0.3, 0.2], orc.NO_TRUNCATION, 1e-18)
+    gm = np.random.default_rng(3).normal(size=(grown.n, 2))
+    grown = orc.Packed(grown.sizes, gm / np.sqrt((gm ** 2).sum()), grown.data)
+    for rid in (orc.RULE_ERASE_CREATE, orc.RULE_COIN):
+        run_case(comm, port, grown, rid, p, orc.NO_TRUNCATION, 1e-18, True, f"rule {rid} on a grown state, routed by family")
+        run_case(comm, port, grown, rid, p, 20000, 1e-18, True, f"rule {rid} on a grown state, routed by family, truncated")
     # equal magnitudes: the ties at the threshold must be shared out between the ranks, exactly k kept
     tied = port.qcgd_random_state(7, 300, 9)
     run_case(comm, port, tied, orc.RULE_ERASE_CREATE, [math.pi / 4, 0, 0], 777, 1e-18, True, "ties across ranks")
