@@ -276,132 +276,245 @@ __device__ __forceinline__ void region_retire(const table_view &t, unsigned long
 
 __device__ __forceinline__ bool slot_occupied(const table_slot &s, bool is_zero_slot) { return is_zero_slot ? s.rep != 0 : s.key != 0; }
 
-// ---- BINNED inserts (rules whose children come in no useful order: split_merge, hadamard, any rule written with the four
-// reference methods only).  A table larger than L2 hit at random costs one DRAM round trip per probe and one read-modify-write
-// of a 32-byte sector per child: 60-70 ps per insert, latency bound (profiles/table_bench_r1.txt, the kernel sat at 16 % of
-// DRAM throughput).  The reference's answer is to partition the children by hash prefix so that every bucket's map is
-// cache resident (utils/algorithm.hpp:170-227, quids.hpp:755-809); this is its counterpart:
-//   pass 1  the child-generation kernel does not touch the table: a child's (hash, magnitude, representative) record goes to
-//           the bin of its table REGION -- bin = mulhi(mix64(hash), bins), the top bits of the very mix that places it in the
-//           table (table_home grows with mix64(hash)), so bin b holds exactly the children of slots [b, b + 1) * capacity / bins.
-//           One L2 atomic on the bin's cursor (cursors are 32 bytes apart) and one 32-byte store per child, fire and forget:
-//           the kernel is bound by the rule's own arithmetic, not by table round trips;
-//   pass 2  bin_insert_kernel streams the bins IN ORDER with all CTAs: at any moment the slots being touched are a few
-//           consecutive regions, tens of MB, L2 resident -- each slot's sector comes from DRAM once and goes back once.
-// A bin that is full (equal hashes concentrate: every record of a hash lands in the same bin) sends its record straight to
-// the table, as before: the bins are an ordering device, the table's semantics are untouched.
+// ---- BINNED interference (rules whose children come in no useful order: split_merge, hadamard, any rule written with the
+// four reference methods only).  A table larger than L2 hit at random costs one DRAM round trip per probe and a read-modify-write
+// of a 32-byte sector per child: 60-70 ps per insert, latency bound.  The reference's answer is to partition the children by
+// hash prefix so that every bucket's map is cache resident (utils/algorithm.hpp:170-227, quids.hpp:755-809).  Two GPU
+// counterparts were built and measured (profiles/r2_*):
+//   A  bins = regions of the global table, inserted region by region so that the slots in flight stay in L2: no gain when
+//      most children are unique -- a FIRST touch of a slot costs the same DRAM round trip in any order (dropped);
+//   B  (this one) bins small enough that a bin's interference table fits in SHARED memory:
+//   pass 1  the child-generation kernel does not touch any table: a child's (hash, magnitude, representative) record goes to
+//           bin = mulhi(mix64(hash), bins): one L2 atomic on the bin's cursor and one 32-byte store, fire and forget -- the
+//           kernel is bound by the rule's own arithmetic.  ~1500 records per bin; the bins' open cache lines (one per bin) stay
+//           in L2, which merges the 32-byte stores into full lines before they reach DRAM;
+//   pass 2  bin_dedup_kernel: one CTA per bin builds the bin's table in 128 KB of shared memory (shared-memory atomics, no
+//           DRAM traffic at all), then writes the UNIQUE children as a dense array of table slots together with the compacted
+//           (norm key, slot) list of those above the tolerance: no table clear, no compaction pass, every byte streamed once.
+// Equal hashes always land in the same bin, so a bin can receive any number of records; what does not fit its fixed space goes
+// to a spill list that is sorted by bin (sort.cuh) and read back by the bin's CTA.  A bin with more UNIQUE hashes than its
+// table holds raises the overflow flag and the step is redone through the global table.
 struct __align__(32) bin_record {
 	unsigned long long hash;
 	double re, im;
 	unsigned long long rep;
 };
-constexpr uint32_t BIN_CURSOR_STRIDE = 4; // u64 words between two cursors: one 32-byte sector each
+constexpr uint32_t BIN_TABLE_SLOTS = 4096;                                  // shared-memory table of one bin (4 arrays of 8 bytes: 128 KB)
+constexpr uint32_t BIN_MEAN_RECORDS = 1536;                                 // records per bin the bin count aims at (load 0.375 if all unique)
+constexpr uint32_t BIN_CAPACITY = BIN_MEAN_RECORDS + 8 * 40 + 64;           // mean + 8 sigma of a Poisson(1536) + slack
+constexpr uint32_t BIN_MAX_UNIQUE = BIN_TABLE_SLOTS - BIN_TABLE_SLOTS / 8;  // beyond this load the bin gives up
 
 struct bin_view {
-	bin_record *records;        // bins * bin_capacity records; nullptr = no binning
-	unsigned long long *cursor; // cursor[bin * BIN_CURSOR_STRIDE] = records sent to the bin so far (may exceed bin_capacity)
+	bin_record *records;         // bins * BIN_CAPACITY records; nullptr = no binning
+	unsigned int *cursor;        // records sent to each bin so far (may exceed BIN_CAPACITY: the excess is in the spill list)
 	uint32_t bins;
-	uint32_t bin_capacity;
+	bin_record *spill;           // records that found their bin full
+	unsigned int *spill_bin;     // ... and the bin of each, shifted left by 8 (sort key, sort.cuh sorts on the top 24 bits)
+	unsigned long long *spill_cursor;
+	uint64_t spill_capacity;
 };
 
-__device__ __forceinline__ bool bin_emit(const bin_view &b, const table_view &t, uint64_t hash, cplx mag, uint64_t rep) {
-	if (hash == 0)
-		return table_insert_zero_hash(t, mag, rep);
-	const uint32_t bin = (uint32_t)__umul64hi(mix64(hash), (uint64_t)b.bins);
-	const unsigned long long at = atomicAdd(&b.cursor[(size_t)bin * BIN_CURSOR_STRIDE], 1ull);
-	if (at < b.bin_capacity) {
-		ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(b.records + (size_t)bin * b.bin_capacity + at);
-		__stcs(dst, make_ulonglong2(hash, (unsigned long long)__double_as_longlong(mag.re)));
-		__stcs(dst + 1, make_ulonglong2((unsigned long long)__double_as_longlong(mag.im), rep));
-		return false;
-	}
-	return table_insert(t, hash, mag, rep); // the bin is full
+__device__ __forceinline__ void bin_store(bin_record *dst, uint64_t hash, cplx mag, uint64_t rep) {
+	ulonglong2 *d = reinterpret_cast<ulonglong2 *>(dst);
+	__stcg(d, make_ulonglong2(hash, (unsigned long long)__double_as_longlong(mag.re)));
+	__stcg(d + 1, make_ulonglong2((unsigned long long)__double_as_longlong(mag.im), rep));
 }
 
-constexpr int BIN_INSERT_THREADS = 256;
-constexpr int BIN_INSERT_BATCH = 2; // records per thread and round: their key loads go out together
-
-// all CTAs walk the bins in order, BIN_INSERT_THREADS * BIN_INSERT_BATCH consecutive records per CTA and round
-static __global__ void __launch_bounds__(BIN_INSERT_THREADS) bin_insert_kernel(bin_view b, table_view t) {
-	constexpr int N = BIN_INSERT_BATCH;
-	constexpr uint32_t TILE = BIN_INSERT_THREADS * N;
-	const uint32_t tiles_per_bin = (b.bin_capacity + TILE - 1) / TILE;
-	const uint64_t tiles = (uint64_t)b.bins * tiles_per_bin;
-	uint32_t created = 0;
-	for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-		const uint32_t bin = (uint32_t)(tile / tiles_per_bin);
-		const uint32_t first = (uint32_t)(tile % tiles_per_bin) * TILE;
-		const unsigned long long sent = __ldcg(&b.cursor[(size_t)bin * BIN_CURSOR_STRIDE]);
-		const uint32_t filled = sent < b.bin_capacity ? (uint32_t)sent : b.bin_capacity;
-		if (first >= filled)
-			continue;
-		if (table_overflowed_lane(t))
-			break;
-		const bin_record *records = b.records + (size_t)bin * b.bin_capacity;
-		uint64_t hash[N];
-		cplx mag[N];
-		uint64_t rep[N];
-		int count = 0;
-#pragma unroll
-		for (int q = 0; q < N; ++q) {
-			const uint32_t i = first + q * BIN_INSERT_THREADS + threadIdx.x;
-			hash[q] = 0;
-			if (i < filled) {
-				const ulonglong2 lo = __ldcs(reinterpret_cast<const ulonglong2 *>(records + i));
-				const ulonglong2 hi = __ldcs(reinterpret_cast<const ulonglong2 *>(records + i) + 1);
-				hash[q] = lo.x;
-				mag[q] = cplx{__longlong_as_double((long long)lo.y), __longlong_as_double((long long)hi.x)};
-				rep[q] = hi.y;
-				count = q + 1;
-			}
-		}
-		// entries past `filled` keep hash 0 with a zero magnitude: they must not reach the dedicated slot of the hash 0
-		// (records with hash 0 never enter a bin, bin_emit), so the batch skips them
-		uint64_t slot[N];
-		uint32_t pending = 0;
-#pragma unroll
-		for (int q = 0; q < N; ++q)
-			if (q < count && hash[q] != 0) {
-				slot[q] = table_home(hash[q], t.capacity);
-				pending |= 1u << q;
-			}
-		for (uint32_t round = 0; pending; ++round) {
-			unsigned long long seen[N];
-#pragma unroll
-			for (int q = 0; q < N; ++q)
-				if (pending & (1u << q))
-					seen[q] = __ldcg(&t.slots[slot[q]].key);
-#pragma unroll
-			for (int q = 0; q < N; ++q)
-				if (pending & (1u << q)) {
-					table_slot *s = t.slots + slot[q];
-					if (seen[q] == 0) {
-						seen[q] = atomicCAS(&s->key, 0ull, (unsigned long long)hash[q]);
-						if (seen[q] == 0) {
-							s->rep = rep[q];
-							++created;
-							seen[q] = hash[q];
-						}
-					}
-					if (seen[q] == hash[q]) {
-						atomicAdd(&s->re, mag[q].re);
-						atomicAdd(&s->im, mag[q].im);
-						pending &= ~(1u << q);
-					} else if (++slot[q] == t.capacity) {
-						slot[q] = 0;
-					}
-				}
-			if (round > TABLE_MAX_PROBES) {
-				*t.overflow = 1;
-				break;
-			}
-			if ((round & 63) == 63 && table_overflowed_lane(t))
-				break;
+// returns true when the record created a slot right away (only the dedicated slot of the hash 0 does)
+__device__ __forceinline__ bool bin_emit(const bin_view &b, const table_view &t, uint64_t hash, cplx mag, uint64_t rep) {
+	if (hash == 0) // 0 marks an empty slot of the shared-memory tables: the hash 0 keeps its dedicated global slot
+		return table_insert_zero_hash(t, mag, rep);
+	const uint32_t bin = (uint32_t)__umul64hi(mix64(hash), (uint64_t)b.bins);
+	const unsigned int at = atomicAdd(&b.cursor[bin], 1u);
+	if (at < BIN_CAPACITY) {
+		bin_store(b.records + (size_t)bin * BIN_CAPACITY + at, hash, mag, rep);
+	} else {
+		const unsigned long long s = atomicAdd(b.spill_cursor, 1ull);
+		if (s < b.spill_capacity) {
+			bin_store(b.spill + s, hash, mag, rep);
+			b.spill_bin[s] = bin << 8;
+		} else {
+			*t.overflow = 1;
 		}
 	}
-	created = (uint32_t)warp_sum((uint64_t)created);
-	if (lane_id() == 0 && created)
-		atomicAdd(t.used, (unsigned long long)created);
+	return false;
+}
+
+constexpr int BIN_DEDUP_THREADS = 512;
+constexpr size_t BIN_DEDUP_SMEM = (size_t)BIN_TABLE_SLOTS * 32;
+
+struct bin_dedup_args {
+	bin_view bins;
+	const uint64_t *spill_order;    // sorted spill list: indices into bins.spill ...
+	const uint32_t *spill_sorted;   // ... and their keys (bin << 8), ascending
+	uint64_t n_spill;
+	table_view dense;               // slots: the unique children, capacity = room; slot `capacity` is the dedicated slot of the hash 0
+	unsigned long long *dense_cursor; // unique children written so far (= table.used)
+	double tolerance;
+	uint64_t *ukey;
+	uint32_t *uslot;
+	unsigned long long *count;      // entries of (ukey, uslot) so far
+};
+
+// first index in [0, n) with a[i] >= v (a ascending)
+__device__ __forceinline__ uint64_t lower_bound_u32(const uint32_t *a, uint64_t n, uint32_t v) {
+	uint64_t lo = 0, hi = n;
+	while (lo < hi) {
+		const uint64_t mid = (lo + hi) >> 1;
+		if (a[mid] < v)
+			lo = mid + 1;
+		else
+			hi = mid;
+	}
+	return lo;
+}
+
+static __global__ void __launch_bounds__(BIN_DEDUP_THREADS, 1) bin_dedup_kernel(bin_dedup_args a) {
+	extern __shared__ __align__(16) unsigned long long s_bin[];
+	unsigned long long *s_key = s_bin, *s_rep = s_bin + 3 * BIN_TABLE_SLOTS;
+	double *s_re = reinterpret_cast<double *>(s_bin + BIN_TABLE_SLOTS), *s_im = reinterpret_cast<double *>(s_bin + 2 * BIN_TABLE_SLOTS);
+	__shared__ unsigned int s_warp_occ[BIN_DEDUP_THREADS / 32], s_warp_keep[BIN_DEDUP_THREADS / 32], s_unique, s_failed;
+	__shared__ unsigned long long s_base_dense, s_base_keep;
+	const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+	constexpr uint32_t ROWS = BIN_TABLE_SLOTS / BIN_DEDUP_THREADS; // slots per thread in the compaction
+
+	auto insert = [&](uint64_t hash, double re, double im, uint64_t rep) {
+		uint32_t i = (uint32_t)(mix64(hash) >> 13) & (BIN_TABLE_SLOTS - 1); // other bits than the ones that chose the bin
+		for (uint32_t probes = 0; probes < BIN_TABLE_SLOTS; ++probes) {
+			unsigned long long k = s_key[i];
+			if (k == 0) {
+				if (s_unique >= BIN_MAX_UNIQUE) { // (a racy read is fine: the limit leaves an eighth of the table free)
+					s_failed = 1;
+					return;
+				}
+				k = atomicCAS(&s_key[i], 0ull, (unsigned long long)hash);
+				if (k == 0) {
+					s_rep[i] = rep; // this child created the slot: it is the representative
+					atomicAdd(&s_unique, 1u);
+					k = hash;
+				}
+			}
+			if (k == hash) {
+				atomicAdd(&s_re[i], re);
+				atomicAdd(&s_im[i], im);
+				return;
+			}
+			i = (i + 1) & (BIN_TABLE_SLOTS - 1);
+		}
+		s_failed = 1;
+	};
+
+	for (uint32_t bin = blockIdx.x; bin < a.bins.bins; bin += gridDim.x) {
+		// empty table: keys, re, im (the representative of a slot is written by whoever creates it)
+		for (uint32_t i = threadIdx.x; i < 3 * BIN_TABLE_SLOTS / 2; i += BIN_DEDUP_THREADS)
+			reinterpret_cast<ulonglong2 *>(s_bin)[i] = make_ulonglong2(0, 0);
+		if (threadIdx.x == 0) {
+			s_unique = 0;
+			s_failed = table_overflowed_lane(a.dense) ? 1 : 0; // another bin gave up: the host redoes the step anyway
+		}
+		__syncthreads();
+		if (s_failed)
+			break;
+		const unsigned int sent = __ldcg(&a.bins.cursor[bin]);
+		const uint32_t filled = sent < BIN_CAPACITY ? sent : BIN_CAPACITY;
+		const bin_record *records = a.bins.records + (size_t)bin * BIN_CAPACITY;
+		for (uint32_t i = threadIdx.x; i < filled; i += BIN_DEDUP_THREADS) {
+			const ulonglong2 lo = __ldcs(reinterpret_cast<const ulonglong2 *>(records + i));
+			const ulonglong2 hi = __ldcs(reinterpret_cast<const ulonglong2 *>(records + i) + 1);
+			insert(lo.x, __longlong_as_double((long long)lo.y), __longlong_as_double((long long)hi.x), hi.y);
+		}
+		if (sent > BIN_CAPACITY && a.n_spill) { // the part of the bin that went to the spill list
+			const uint64_t first = lower_bound_u32(a.spill_sorted, a.n_spill, bin << 8), last = lower_bound_u32(a.spill_sorted, a.n_spill, (bin + 1) << 8);
+			for (uint64_t j = first + threadIdx.x; j < last; j += BIN_DEDUP_THREADS) {
+				const bin_record *r = a.bins.spill + a.spill_order[j];
+				const ulonglong2 lo = __ldcs(reinterpret_cast<const ulonglong2 *>(r));
+				const ulonglong2 hi = __ldcs(reinterpret_cast<const ulonglong2 *>(r) + 1);
+				insert(lo.x, __longlong_as_double((long long)lo.y), __longlong_as_double((long long)hi.x), hi.y);
+			}
+		}
+		__syncthreads();
+		if (s_failed) { // more unique hashes than the table holds: the host redoes the step through the global table
+			if (threadIdx.x == 0)
+				*a.dense.overflow = 1;
+			break;
+		}
+		// occupied slots -> dense array; those above the tolerance -> (norm key, slot) list.  Warp w owns slots
+		// [w * 32 * ROWS, (w + 1) * 32 * ROWS), row r of lane l = that + r * 32 + l.
+		uint32_t occ_bits = 0, keep_bits = 0;
+		const uint32_t first_slot = warp * 32 * ROWS + lane;
+#pragma unroll
+		for (uint32_t r = 0; r < ROWS; ++r) {
+			const uint32_t i = first_slot + r * 32;
+			const bool occupied = s_key[i] != 0;
+			const bool keep = occupied && cnorm(cplx{s_re[i], s_im[i]}) > a.tolerance;
+			occ_bits |= (uint32_t)occupied << r;
+			keep_bits |= (uint32_t)keep << r;
+		}
+		uint32_t warp_occ = 0, warp_keep = 0, before_occ[ROWS], before_keep[ROWS];
+#pragma unroll
+		for (uint32_t r = 0; r < ROWS; ++r) {
+			const unsigned vo = __ballot_sync(0xffffffffu, (occ_bits >> r) & 1), vk = __ballot_sync(0xffffffffu, (keep_bits >> r) & 1);
+			const unsigned lt = (1u << lane) - 1;
+			before_occ[r] = warp_occ + __popc(vo & lt);
+			before_keep[r] = warp_keep + __popc(vk & lt);
+			warp_occ += __popc(vo);
+			warp_keep += __popc(vk);
+		}
+		if (lane == 0) {
+			s_warp_occ[warp] = warp_occ;
+			s_warp_keep[warp] = warp_keep;
+		}
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			unsigned int occ = 0, keep = 0;
+			for (int w = 0; w < BIN_DEDUP_THREADS / 32; ++w) {
+				const unsigned int o = s_warp_occ[w], k = s_warp_keep[w];
+				s_warp_occ[w] = occ;
+				s_warp_keep[w] = keep;
+				occ += o;
+				keep += k;
+			}
+			s_base_dense = occ ? atomicAdd(a.dense_cursor, (unsigned long long)occ) : 0;
+			s_base_keep = keep ? atomicAdd(a.count, (unsigned long long)keep) : 0;
+			if (s_base_dense + occ > a.dense.capacity) {
+				*a.dense.overflow = 1;
+				s_failed = 1;
+			}
+		}
+		__syncthreads();
+		if (s_failed)
+			break;
+		const uint64_t base_dense = s_base_dense + s_warp_occ[warp], base_keep = s_base_keep + s_warp_keep[warp];
+#pragma unroll
+		for (uint32_t r = 0; r < ROWS; ++r) {
+			if ((occ_bits >> r) & 1) {
+				const uint32_t i = first_slot + r * 32;
+				const uint64_t slot = base_dense + before_occ[r];
+				ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(a.dense.slots + slot);
+				const double re = s_re[i], im = s_im[i];
+				dst[0] = make_ulonglong2(s_key[i], (unsigned long long)__double_as_longlong(re));
+				dst[1] = make_ulonglong2((unsigned long long)__double_as_longlong(im), s_rep[i]);
+				if ((keep_bits >> r) & 1) {
+					const uint64_t at = base_keep + before_keep[r];
+					a.ukey[at] = (uint64_t)__double_as_longlong(cnorm(cplx{re, im}));
+					a.uslot[at] = (uint32_t)slot;
+				}
+			}
+		}
+		__syncthreads(); // the table is cleared again at the top of the loop
+	}
+	// the dedicated slot of the hash 0 (written by bin_emit through table_insert_zero_hash) joins the list
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		const table_slot *z = a.dense.slots + a.dense.capacity;
+		if (z->rep != 0) {
+			const double norm = cnorm(cplx{z->re, z->im});
+			if (norm > a.tolerance) {
+				const unsigned long long at = atomicAdd(a.count, 1ull);
+				a.ukey[at] = (uint64_t)__double_as_longlong(norm);
+				a.uslot[at] = (uint32_t)a.dense.capacity;
+			}
+		}
+	}
 }
 
 } // namespace qb

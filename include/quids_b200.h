@@ -65,10 +65,10 @@ typedef struct qb_options {
 	uint32_t seed;             /* probabilistic truncation: seed of the counter-based generator (the reference seeds from rand()) */
 	int32_t locality_sort;     /* engine knob: process the child groups in the order of the rule's group key so that equal
 	                              objects are merged on chip before the table; 0 off, 1 when there are >= 2^16 groups (default), 2 always */
-	int32_t binned_inserts;    /* engine knob: one-child-per-lane rules send their children to the table through bins ordered by table region
-	                              (the reference's bucket partition, quids.hpp:755-809); 0 off (default: measured SLOWER on B200 when most
-	                              children are unique -- a first touch costs the same DRAM round trip in any order),
-	                              1 when the table is larger than L2, 2 always */
+	int32_t binned_inserts;    /* engine knob: one-child-per-lane rules (split_merge, hadamard, rules written with the four reference methods)
+	                              send their children to small bins that are deduplicated in shared memory and written out as a dense
+	                              array of unique children (the reference's bucket partition, quids.hpp:755-809; table.cuh); 0 off,
+	                              1 when there are >= 2^22 children and no history of heavy duplication (default), 2 always */
 	int32_t family_routing;    /* engine knob, qb_simulate_dist: rules with families (erase_create, coin) move the PARENTS to the rank that
 	                              owns their family, so that interference needs no exchange of children; 1 on (default), 0 off */
 	uint64_t memory_budget;    /* engine knob: bytes the automatic budget (max_num_object = 0) may spend on the symbolic workspace and

@@ -162,7 +162,7 @@ class _Globals:
     min_equalize_step = 0.2    # quids::mpi::min_equalize_step
     min_equalize_size = 100    # quids::mpi::min_equalize_size
     locality_sort = 1          # engine knob: 0 off, 1 auto, 2 always
-    binned_inserts = 0         # engine knob: 0 off (default), 1 when the table is larger than L2, 2 always
+    binned_inserts = 1         # engine knob: 0 off, 1 for >= 2^22 children without heavy duplication (default), 2 always
     family_routing = 1         # engine knob, distributed path: parents routed to the owner of their family (erase_create, coin)
 
     def options(self):

@@ -74,7 +74,8 @@ enum { // u64 words of the small device scratch
 	DS_CURSOR = 7,    // region mode: slots handed out
 	DS_REGIONS = 8,   // region mode: regions created
 	DS_CHILD_RANGE = 9, // two u32: largest child count, ~smallest
-	DS_WORDS = 10
+	DS_SPILL = 10,      // binned interference: records in the spill list
+	DS_WORDS = 11
 };
 
 struct qb_ctx {
@@ -154,7 +155,7 @@ struct qb_iter {
 struct qb_sym {
 	qb_ctx *ctx;
 	uint64_t n_children = 0, n_unique = 0; // quids.hpp:344-346
-	dev_buf table, directory, ukey, uslot, sslot, kept, scratch, survivor_parent, survivor_child, padded, chunk_parent, sort_keys, sort_vals, sort_hist, sort_base, parent_ctx, bin_records, bin_cursor;
+	dev_buf table, directory, ukey, uslot, sslot, kept, scratch, survivor_parent, survivor_child, padded, chunk_parent, sort_keys, sort_vals, sort_hist, sort_base, parent_ctx, bin_records, bin_cursor, bin_spill, bin_spill_key;
 	cudaEvent_t ev[2 * QB_PHASE_COUNT] = {};
 	bool ev_used[QB_PHASE_COUNT] = {};
 	float phase_ms[QB_PHASE_COUNT] = {};
@@ -164,7 +165,7 @@ struct qb_sym {
 	int table_attempts = 0;
 
 	uint64_t device_bytes() const {
-		return table.cap + directory.cap + ukey.cap + uslot.cap + sslot.cap + kept.cap + scratch.cap + survivor_parent.cap + survivor_child.cap + padded.cap + chunk_parent.cap + sort_keys.cap + sort_vals.cap + sort_hist.cap + sort_base.cap + parent_ctx.cap + bin_records.cap + bin_cursor.cap;
+		return table.cap + directory.cap + ukey.cap + uslot.cap + sslot.cap + kept.cap + scratch.cap + survivor_parent.cap + survivor_child.cap + padded.cap + chunk_parent.cap + sort_keys.cap + sort_vals.cap + sort_hist.cap + sort_base.cap + parent_ctx.cap + bin_records.cap + bin_cursor.cap + bin_spill.cap + bin_spill_key.cap;
 	}
 };
 
@@ -172,8 +173,6 @@ struct qb_sym {
 
 // ---- helpers --------------------------------------------------------------------------------------------
 namespace {
-
-constexpr size_t BINNED_MIN_TABLE_BYTES = 96u << 20; // below this the table (mostly) stays in the 126 MB L2 by itself
 
 struct phase_timer {
 	qb_sym *sym;
@@ -372,6 +371,12 @@ struct widen_u32 {
 	__device__ uint64_t operator()(uint64_t j) const { return v[j]; }
 };
 
+__global__ void __launch_bounds__(256) iota_kernel(uint64_t *out, uint64_t n) {
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+		out[i] = i;
+}
+
 // number of positions where the sorted key changes (= runs - 1)
 __global__ void __launch_bounds__(256) key_changes_kernel(const uint32_t *keys, uint64_t n, unsigned long long *count) {
 	unsigned long long local = 0;
@@ -454,7 +459,7 @@ void resolve_options(const qb_options *in, qb_options &opt) {
 	if (!(opt.table_load > 0 && opt.table_load <= 0.95))
 		opt.table_load = 0.75;
 	if (in == nullptr || opt.binned_inserts < 0 || opt.binned_inserts > 2)
-		opt.binned_inserts = 0;
+		opt.binned_inserts = 1;
 }
 
 // ======================================================================================================
@@ -722,33 +727,43 @@ local_table build_local_table(qb_iter *it, uint64_t rule_id, const rule_ops *ops
 	// tolerance; "symbolic_iteration" before them covers the ordering of the work items.  A redo after a table overflow does not
 	// repeat the labels (their order is part of the API): its time is attributed to "finalize".
 	const bool collision_labels = comm == nullptr || comm->local_interference;
+	// binned interference (table.cuh) pays when most children are unique and the table would be far larger than L2; a state
+	// whose children mostly coincide (history of the rule: < 0.2 slots per child) keeps the hashed table, which then stays hot
+	const bool duplicate_heavy = !sorted_order && have_history && sym->unique_ratio[rule_id] < 0.2;
+	const bool binned_allowed = !sorted_order && !ops->warp_groups && opt.binned_inserts != 0 && n_children <= (1ull << 29) &&
+	                            (opt.binned_inserts > 1 || (n_children >= (1ull << 22) && !duplicate_heavy));
 	for (sym->table_attempts = 1;; ++sym->table_attempts) {
 		QB_REQUIRE(capacity + 1 <= 0xffffffffull, QB_ERR_CAPACITY, "interference table would need more than 2^32 slots");
 		if (collision_labels && sym->table_attempts == 1)
 			step("compute_collisions - prepare");
 		timer.begin(QB_PHASE_TABLE_CLEAR);
+		// binned interference (table.cuh): one-child-per-lane rules with many children and no history of heavy duplication send
+		// their children to small bins first; each bin is then deduplicated in shared memory and written out as a DENSE array
+		// of unique children -- the table below is that array (no clear, no compaction pass).  First attempt only: a bin that
+		// overflows falls back to the hashed global table.
+		L.bins = bin_view{nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0};
+		const bool binned = binned_allowed && sym->table_attempts == 1;
+		if (binned) {
+			const uint64_t bins = div_up<uint64_t>(n_children, BIN_MEAN_RECORDS);
+			QB_REQUIRE(bins < (1ull << 24), QB_ERR_CAPACITY, "binned interference: more than 2^24 bins");
+			capacity = std::min<uint64_t>(n_children, have_history ? (uint64_t)(sym->unique_ratio[rule_id] * (double)n_children * 1.3) + 65536 : n_children);
+			const uint64_t spill_capacity = n_children / 8 + 65536;
+			sym->bin_records.ensure(sizeof(bin_record) * bins * BIN_CAPACITY, stream);
+			sym->bin_cursor.ensure(sizeof(unsigned int) * bins, stream);
+			sym->bin_spill.ensure(sizeof(bin_record) * spill_capacity, stream);
+			sym->bin_spill_key.ensure(sizeof(unsigned int) * spill_capacity, stream);
+			QB_CUDA(cudaMemsetAsync(sym->bin_cursor.ptr, 0, sizeof(unsigned int) * bins, stream));
+			QB_CUDA(cudaMemsetAsync(ctx->small(DS_SPILL), 0, sizeof(uint64_t), stream));
+			L.bins = bin_view{sym->bin_records.as<bin_record>(), sym->bin_cursor.as<unsigned int>(), (uint32_t)bins, sym->bin_spill.as<bin_record>(),
+			                  sym->bin_spill_key.as<unsigned int>(), reinterpret_cast<unsigned long long *>(ctx->small(DS_SPILL)), spill_capacity};
+		}
 		const size_t table_bytes = (capacity + 1) * sizeof(table_slot);
 		sym->table.ensure(table_bytes, stream);
-		if (!region_mode) // regions are written whole by the runs that create them, what stays unused is zeroed by its warp (table.cuh)
+		if (binned) // only the dedicated slot of the hash 0 is accumulated into
+			QB_CUDA(cudaMemsetAsync(sym->table.as<table_slot>() + capacity, 0, sizeof(table_slot), stream));
+		else if (!region_mode) // regions are written whole by the runs that create them, what stays unused is zeroed by its warp (table.cuh)
 			QB_CUDA(cudaMemsetAsync(sym->table.ptr, 0, table_bytes, stream));
 		QB_CUDA(cudaMemsetAsync(ctx->small(DS_COUNT), 0, 4 * sizeof(uint64_t), stream)); // count, overflow, total, used
-		// binned inserts (table.cuh): one-child-per-lane rules whose table is far larger than L2 send their children to the bin of
-		// their table region first.  Bins: regions of about 2 MB of table; capacity: the mean + 5 % + 1024 (hashes are mixed, the
-		// spread of a bin is its square root; a bin that overflows because equal hashes pile up inserts directly).
-		L.bins = bin_view{nullptr, nullptr, 0, 0};
-		const bool binned = !sorted_order && !ops->warp_groups && opt.binned_inserts != 0 &&
-		                    (opt.binned_inserts > 1 || table_bytes >= (size_t)BINNED_MIN_TABLE_BYTES) && n_children >= 4096;
-		if (binned) {
-			uint32_t bins = 64;
-			while (bins < 16384 && (table_bytes / bins) > (size_t)(2u << 20))
-				bins <<= 1;
-			const uint64_t bin_capacity = n_children / bins + n_children / bins / 20 + 1024;
-			QB_REQUIRE(bin_capacity < (1ull << 32), QB_ERR_CAPACITY, "more than 2^32 children per bin");
-			sym->bin_records.ensure(sizeof(bin_record) * bins * bin_capacity, stream);
-			sym->bin_cursor.ensure(sizeof(uint64_t) * BIN_CURSOR_STRIDE * bins, stream);
-			QB_CUDA(cudaMemsetAsync(sym->bin_cursor.ptr, 0, sizeof(uint64_t) * BIN_CURSOR_STRIDE * bins, stream));
-			L.bins = bin_view{sym->bin_records.as<bin_record>(), sym->bin_cursor.as<unsigned long long>(), bins, (uint32_t)bin_capacity};
-		}
 		R.table = table_view{sym->table.as<table_slot>(), capacity, reinterpret_cast<unsigned int *>(ctx->small(DS_OVERFLOW)),
 		                     reinterpret_cast<unsigned long long *>(ctx->small(DS_USED))};
 		if (region_mode) {
@@ -773,21 +788,49 @@ local_table build_local_table(qb_iter *it, uint64_t rule_id, const rule_ops *ops
 			ops->launch_symbolic(rule, L);
 		QB_CUDA(cudaGetLastError());
 		timer.end(QB_PHASE_SYMBOLIC);
-		if (binned) { // pass 2: the bins reach the table in order, the slots in flight stay L2 resident
+		if (binned) {
+			// pass 2: every bin deduplicated in shared memory -> dense unique children + the compacted (norm key, slot) list
+			if (collision_labels && sym->table_attempts == 1)
+				step("compute_collisions - finalize");
 			timer.begin(QB_PHASE_INSERT);
-			static int per_sm_of_device[MAX_DEVICES] = {};
-			int &per_sm = per_sm_of_device[ctx->device % MAX_DEVICES];
-			if (per_sm == 0) {
-				QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)bin_insert_kernel, BIN_INSERT_THREADS, 0));
-				if (per_sm < 1) per_sm = 1;
+			ctx->fetch_small(); // the spill count sizes the sort below
+			const uint64_t n_spill = std::min<uint64_t>(ctx->h_small[DS_SPILL], L.bins.spill_capacity);
+			bin_dedup_args a;
+			a.bins = L.bins;
+			a.spill_order = nullptr;
+			a.spill_sorted = nullptr;
+			a.n_spill = n_spill;
+			if (n_spill > 0 && ctx->h_small[DS_OVERFLOW] == 0) { // sort the spilled records by bin: (bin << 8, index) pairs
+				sym->sort_keys.ensure(2 * sizeof(uint32_t) * n_spill, stream);
+				sym->sort_vals.ensure(2 * sizeof(uint64_t) * n_spill, stream);
+				QB_CUDA(cudaMemcpyAsync(sym->sort_keys.ptr, sym->bin_spill_key.ptr, sizeof(uint32_t) * n_spill, cudaMemcpyDeviceToDevice, stream));
+				iota_kernel<<<grid_for(n_spill, 256, ctx->grid_cap()), 256, 0, stream>>>(sym->sort_vals.as<uint64_t>(), n_spill);
+				++ctx->launches;
+				const uint32_t *sorted_keys = nullptr;
+				a.spill_order = sort_items(ctx, sym, n_spill, &sorted_keys);
+				a.spill_sorted = sorted_keys;
 			}
-			const uint64_t tiles = (uint64_t)L.bins.bins * div_up<uint64_t>(L.bins.bin_capacity, BIN_INSERT_THREADS * BIN_INSERT_BATCH);
-			bin_insert_kernel<<<(unsigned)std::min<uint64_t>(tiles, (uint64_t)per_sm * ctx->sm_count), BIN_INSERT_THREADS, 0, stream>>>(L.bins, R.table);
-			++ctx->launches;
-			QB_CUDA(cudaGetLastError());
+			const uint64_t bound = std::min<uint64_t>(n_children, capacity + 1);
+			sym->ukey.ensure(sizeof(uint64_t) * bound, stream);
+			sym->uslot.ensure(sizeof(uint32_t) * bound, stream);
+			a.dense = R.table;
+			a.dense_cursor = R.table.used;
+			a.tolerance = compaction_tolerance;
+			a.ukey = sym->ukey.as<uint64_t>();
+			a.uslot = sym->uslot.as<uint32_t>();
+			a.count = reinterpret_cast<unsigned long long *>(ctx->small(DS_COUNT));
+			static bool smem_allowed[MAX_DEVICES] = {};
+			if (!smem_allowed[ctx->device % MAX_DEVICES]) {
+				QB_CUDA(cudaFuncSetAttribute((const void *)bin_dedup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIN_DEDUP_SMEM));
+				smem_allowed[ctx->device % MAX_DEVICES] = true;
+			}
+			if (ctx->h_small[DS_OVERFLOW] == 0) {
+				bin_dedup_kernel<<<(unsigned)std::min<uint64_t>(L.bins.bins, (uint64_t)ctx->sm_count), BIN_DEDUP_THREADS, BIN_DEDUP_SMEM, stream>>>(a);
+				++ctx->launches;
+				QB_CUDA(cudaGetLastError());
+			}
 			timer.end(QB_PHASE_INSERT);
-		}
-
+		} else {
 		// unique children above the tolerance (quids.hpp:819-823)
 		if (collision_labels && sym->table_attempts == 1)
 			step("compute_collisions - finalize");
@@ -808,6 +851,7 @@ local_table build_local_table(qb_iter *it, uint64_t rule_id, const rule_ops *ops
 		++ctx->launches;
 		QB_CUDA(cudaGetLastError());
 		timer.end(QB_PHASE_COMPACT);
+		}
 		ctx->fetch_small();
 		if (getenv("QB_TABLE_TRACE"))
 			fprintf(stderr, "[qb table] rule %s attempt %d: children %llu groups %llu capacity %llu (full %llu) sorted %d regions %d (directory %llu, created %llu, slots %llu) -> used %llu kept %llu overflow %llu\n",
@@ -1391,7 +1435,7 @@ void qb_options_default(qb_options *opt) {
 	opt->table_load = 0;
 	opt->profile = 0;
 	opt->locality_sort = 1;
-	opt->binned_inserts = 0;
+	opt->binned_inserts = 1;
 	opt->family_routing = 1;
 	opt->safety_margin = 0.2f; // SAFETY_MARGIN, quids.hpp:33-35
 	opt->memory_budget = 0;

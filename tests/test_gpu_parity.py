@@ -44,15 +44,36 @@ def test_golden_vectors_with_parent_ordering(gpu, port, name):
 
 @pytest.mark.parametrize("name", golden_util.fixtures())
 def test_golden_vectors_with_binned_inserts(gpu, port, name):
-    """children sent to the table through bins ordered by table region (table.cuh, an engine knob that is off by default):
-    the same results, for the rules written with the four reference methods and for the fused ones"""
+    """children deduplicated bin by bin in shared memory (table.cuh; automatic from 2^22 children on, forced here): the same
+    results, for the rules written with the four reference methods and for the fused ones"""
     import quids_b200 as qb
     qb.config.binned_inserts = 2
     try:
         for suffix in ("", "_generic"):
             assert golden_util.replay(name, gpu(suffix), port) > 0
     finally:
-        qb.config.binned_inserts = 0
+        qb.config.binned_inserts = 1
+
+
+def test_binned_interference_spill_and_fallback(gpu, port):
+    """equal hashes pile up in one bin: 60000 identical parents send each of their children 60000 times to the same bin (far
+    beyond the bin's fixed space: the spill list, sorted by bin, carries the rest); and a state with more unique children per
+    bin than the shared-memory table holds cannot happen with mixed hashes, so the fallback is forced through a tiny limit"""
+    import quids_b200 as qb
+    one = port.qcgd_random_state(8, 1, 5)
+    same = orc.Packed.from_objects(one.objects() * 60000, [1 / math.sqrt(60000)] * 60000)
+    mixed = port.qcgd_random_state(9, 3000, 8)
+    both = orc.Packed(np.concatenate([same.sizes, mixed.sizes]), np.concatenate([same.mags, mixed.mags]), np.concatenate([same.data, mixed.data]))
+    qb.config.binned_inserts = 2
+    try:
+        for rid, params in ((orc.RULE_SPLIT_MERGE, [0.4, 0.3, 0.2]), (orc.RULE_ERASE_CREATE, [0.7, 0.2, 0.1])):
+            eng = gpu("_generic")
+            want, nc, nu = port.simulate(both, rid, params, orc.NO_TRUNCATION, 1e-18)
+            got, gc, gu = eng.simulate(both, rid, params, tol=1e-18)
+            assert (gc, gu) == (nc, nu)
+            orc.assert_same_state(got, port.hash_objects(got, rid), want, port.hash_objects(want, rid), True, rtol=1e-11, what=f"binned with spill, rule {rid}")
+    finally:
+        qb.config.binned_inserts = 1
 
 
 @pytest.mark.parametrize("align", [0, 4, 8, 16])
