@@ -286,9 +286,9 @@ __device__ __forceinline__ bool slot_occupied(const table_slot &s, bool is_zero_
 //   B  (this one) bins small enough that a bin's interference table fits in SHARED memory:
 //   pass 1  the child-generation kernel does not touch any table: a child's (hash, magnitude, representative) record goes to
 //           bin = mulhi(mix64(hash), bins): one L2 atomic on the bin's cursor and one 32-byte store, fire and forget -- the
-//           kernel is bound by the rule's own arithmetic.  ~1500 records per bin; the bins' open cache lines (one per bin) stay
+//           kernel is bound by the rule's own arithmetic.  ~770 records per bin; the bins' open cache lines (one per bin) stay
 //           in L2, which merges the 32-byte stores into full lines before they reach DRAM;
-//   pass 2  bin_dedup_kernel: one CTA per bin builds the bin's table in 128 KB of shared memory (shared-memory atomics, no
+//   pass 2  bin_dedup_kernel: one CTA per bin builds the bin's table in 64 KB of shared memory (shared-memory atomics, no
 //           DRAM traffic at all), then writes the UNIQUE children as a dense array of table slots together with the compacted
 //           (norm key, slot) list of those above the tolerance: no table clear, no compaction pass, every byte streamed once.
 // Equal hashes always land in the same bin, so a bin can receive any number of records; what does not fit its fixed space goes
@@ -299,9 +299,9 @@ struct __align__(32) bin_record {
 	double re, im;
 	unsigned long long rep;
 };
-constexpr uint32_t BIN_TABLE_SLOTS = 4096;                                  // shared-memory table of one bin (4 arrays of 8 bytes: 128 KB)
-constexpr uint32_t BIN_MEAN_RECORDS = 1536;                                 // records per bin the bin count aims at (load 0.375 if all unique)
-constexpr uint32_t BIN_CAPACITY = BIN_MEAN_RECORDS + 8 * 40 + 64;           // mean + 8 sigma of a Poisson(1536) + slack
+constexpr uint32_t BIN_TABLE_SLOTS = 2048;                                  // shared-memory table of one bin (4 arrays of 8 bytes: 64 KB, three CTAs per SM)
+constexpr uint32_t BIN_MEAN_RECORDS = 768;                                  // records per bin the bin count aims at (load 0.375 if all unique)
+constexpr uint32_t BIN_CAPACITY = BIN_MEAN_RECORDS + 8 * 28 + 64;           // mean + 8 sigma of a Poisson(768) + slack
 constexpr uint32_t BIN_MAX_UNIQUE = BIN_TABLE_SLOTS - BIN_TABLE_SLOTS / 8;  // beyond this load the bin gives up
 
 struct bin_view {
@@ -340,7 +340,8 @@ __device__ __forceinline__ bool bin_emit(const bin_view &b, const table_view &t,
 	return false;
 }
 
-constexpr int BIN_DEDUP_THREADS = 512;
+constexpr int BIN_DEDUP_THREADS = 256;
+constexpr int BIN_DEDUP_BLOCKS_PER_SM = 3; // phases of different bins overlap (clear / load + insert / write out)
 constexpr size_t BIN_DEDUP_SMEM = (size_t)BIN_TABLE_SLOTS * 32;
 
 struct bin_dedup_args {
@@ -369,7 +370,7 @@ __device__ __forceinline__ uint64_t lower_bound_u32(const uint32_t *a, uint64_t 
 	return lo;
 }
 
-static __global__ void __launch_bounds__(BIN_DEDUP_THREADS, 1) bin_dedup_kernel(bin_dedup_args a) {
+static __global__ void __launch_bounds__(BIN_DEDUP_THREADS, BIN_DEDUP_BLOCKS_PER_SM) bin_dedup_kernel(bin_dedup_args a) {
 	extern __shared__ __align__(16) unsigned long long s_bin[];
 	unsigned long long *s_key = s_bin, *s_rep = s_bin + 3 * BIN_TABLE_SLOTS;
 	double *s_re = reinterpret_cast<double *>(s_bin + BIN_TABLE_SLOTS), *s_im = reinterpret_cast<double *>(s_bin + 2 * BIN_TABLE_SLOTS);
@@ -418,10 +419,23 @@ static __global__ void __launch_bounds__(BIN_DEDUP_THREADS, 1) bin_dedup_kernel(
 		const unsigned int sent = __ldcg(&a.bins.cursor[bin]);
 		const uint32_t filled = sent < BIN_CAPACITY ? sent : BIN_CAPACITY;
 		const bin_record *records = a.bins.records + (size_t)bin * BIN_CAPACITY;
-		for (uint32_t i = threadIdx.x; i < filled; i += BIN_DEDUP_THREADS) {
-			const ulonglong2 lo = __ldcs(reinterpret_cast<const ulonglong2 *>(records + i));
-			const ulonglong2 hi = __ldcs(reinterpret_cast<const ulonglong2 *>(records + i) + 1);
-			insert(lo.x, __longlong_as_double((long long)lo.y), __longlong_as_double((long long)hi.x), hi.y);
+		// four records per thread in flight: all their loads are issued before the first insert (the shared-memory atomics of an
+		// insert would otherwise fence every load behind them: one DRAM latency per record instead of one per batch)
+		constexpr int BATCH = 4;
+		for (uint32_t i0 = threadIdx.x; i0 < filled; i0 += BATCH * BIN_DEDUP_THREADS) {
+			ulonglong2 lo[BATCH], hi[BATCH];
+#pragma unroll
+			for (int q = 0; q < BATCH; ++q) {
+				const uint32_t i = i0 + q * BIN_DEDUP_THREADS;
+				if (i < filled) {
+					lo[q] = __ldcs(reinterpret_cast<const ulonglong2 *>(records + i));
+					hi[q] = __ldcs(reinterpret_cast<const ulonglong2 *>(records + i) + 1);
+				}
+			}
+#pragma unroll
+			for (int q = 0; q < BATCH; ++q)
+				if (i0 + q * BIN_DEDUP_THREADS < filled)
+					insert(lo[q].x, __longlong_as_double((long long)lo[q].y), __longlong_as_double((long long)hi[q].x), hi[q].y);
 		}
 		if (sent > BIN_CAPACITY && a.n_spill) { // the part of the bin that went to the spill list
 			const uint64_t first = lower_bound_u32(a.spill_sorted, a.n_spill, bin << 8), last = lower_bound_u32(a.spill_sorted, a.n_spill, (bin + 1) << 8);

@@ -746,7 +746,7 @@ local_table build_local_table(qb_iter *it, uint64_t rule_id, const rule_ops *ops
 		if (binned) {
 			const uint64_t bins = div_up<uint64_t>(n_children, BIN_MEAN_RECORDS);
 			QB_REQUIRE(bins < (1ull << 24), QB_ERR_CAPACITY, "binned interference: more than 2^24 bins");
-			capacity = std::min<uint64_t>(n_children, have_history ? (uint64_t)(sym->unique_ratio[rule_id] * (double)n_children * 1.3) + 65536 : n_children);
+			capacity = n_children; // room for "every child is unique": the dense array is neither cleared nor scanned, room costs nothing
 			const uint64_t spill_capacity = n_children / 8 + 65536;
 			sym->bin_records.ensure(sizeof(bin_record) * bins * BIN_CAPACITY, stream);
 			sym->bin_cursor.ensure(sizeof(unsigned int) * bins, stream);
@@ -825,7 +825,7 @@ local_table build_local_table(qb_iter *it, uint64_t rule_id, const rule_ops *ops
 				smem_allowed[ctx->device % MAX_DEVICES] = true;
 			}
 			if (ctx->h_small[DS_OVERFLOW] == 0) {
-				bin_dedup_kernel<<<(unsigned)std::min<uint64_t>(L.bins.bins, (uint64_t)ctx->sm_count), BIN_DEDUP_THREADS, BIN_DEDUP_SMEM, stream>>>(a);
+				bin_dedup_kernel<<<(unsigned)std::min<uint64_t>(L.bins.bins, (uint64_t)ctx->sm_count * BIN_DEDUP_BLOCKS_PER_SM), BIN_DEDUP_THREADS, BIN_DEDUP_SMEM, stream>>>(a);
 				++ctx->launches;
 				QB_CUDA(cudaGetLastError());
 			}
