@@ -465,14 +465,17 @@ def run_ours(args):
     host = [p.numpy() for p in pinned]
     host[1], host[2] = host[1].view(np.uint64), host[2].view(np.uint32)
     del objects, begin, size, mag
-    ins, mids = [qb.Iteration(ctx), qb.Iteration(ctx)], b
+    # three states in rotation: while step i computes, the input of step i+1 is uploaded into one and the result of step i-1
+    # is downloaded from another, so that the two directions of the host link run at the same time
+    ROT = 3
+    ins, mids = [qb.Iteration(ctx) for _ in range(ROT)], b
 
     def pinned_result(cap_n, cap_b):
         return [torch.empty(cap_b, dtype=torch.uint8).pin_memory().numpy(), torch.empty(cap_n + 1, dtype=torch.int64).pin_memory().numpy().view(np.uint64),
                 torch.empty(cap_n, dtype=torch.int32).pin_memory().numpy().view(np.uint32), torch.empty(cap_n * 2, dtype=torch.float64).pin_memory().numpy()]
 
     n1, nb1, _ = a._counts_noflush()
-    out_host = [pinned_result(int(n1 * 1.5) + 4096, int(nb1 * 1.5) + 4096) for _ in range(2)]
+    out_host = [pinned_result(int(n1 * 1.5) + 4096, int(nb1 * 1.5) + 4096) for _ in range(ROT)]
     d2h_total, e2e_children = 0, 0
 
     def e2e_run(steps):
@@ -480,14 +483,15 @@ def run_ours(args):
         d2h_total = e2e_children = 0
         ins[0].upload_async(*host)
         for i in range(steps):
-            cur = i % 2
+            cur = i % ROT
             if i + 1 < steps:
-                ins[1 - cur].upload_async(*host)  # overlaps this step's rule iterations (ordered after the download of its previous result)
+                ins[(i + 1) % ROT].upload_async(*host)  # overlaps this step's rule iterations and the download of the previous result
             rec = []
             loop_pass(ins[cur], mids, rec)  # the result of the pass is back in ins[cur]
             e2e_children += sum(c["N_c"] for c in rec)
             n2, nb2, _ = ins[cur]._counts_noflush()
             if nb2 > out_host[cur][0].nbytes or n2 + 1 > out_host[cur][1].shape[0]:
+                ins[cur].wait()
                 out_host[cur] = pinned_result(int(n2 * 1.5) + 4096, int(nb2 * 1.5) + 4096)
             ins[cur].download_async(*out_host[cur])  # overlaps the next step
             d2h_total += nb2 + 8 * (n2 + 1) + 4 * n2 + 16 * n2
@@ -495,14 +499,14 @@ def run_ours(args):
             it.wait()
 
     e2e_steps = max(2, min(args.steps, 10))
-    e2e_run(2)  # untimed: allocations
+    e2e_run(ROT)  # untimed: allocations
     barrier()
     t0 = time.perf_counter()
     e2e_run(e2e_steps)
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
     d2h = d2h_total // e2e_steps
-    last = (e2e_steps - 1) % 2
+    last = (e2e_steps - 1) % ROT
     check = ins[last].download()
     n_last = check[2].shape[0]
     assert np.array_equal(check[3].reshape(-1), out_host[last][3][:2 * n_last]) and np.array_equal(check[2], out_host[last][2][:n_last]) and \
@@ -605,8 +609,8 @@ def run_ours(args):
             "per_rule": per_rule, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "how": "per step: qb_iter_upload_async of the saturated input state from pinned host memory, one pass of the loop (2 x qb_apply_modifier, 2 x qb_simulate), "
-                           "qb_iter_download_async of the result state into pinned host memory; double-buffered on the library's copy streams, wall clock over all steps incl. "
-                           "the first upload and the last download"},
+                           "qb_iter_download_async of the result state into pinned host memory; three states in rotation on the library's copy streams (upload of step i+1 and "
+                           "download of step i-1 overlap the rule iterations of step i), wall clock over all steps incl. the first upload and the last download"},
             "gpu_launches": int(launches), "best_case": best}
     print(json.dumps(line), flush=True)
     if dist is not None:
