@@ -165,6 +165,7 @@ struct flip_workspace_t {
 	// what the accumulators hold: family (eligible nodes, particles elsewhere, names) and target of the group
 	uint64_t run_eligible, run_fixed, run_names;
 	uint32_t run_n, run_target, run_leaves, run_valid;
+	uint32_t run_patterns[FLIP_BLOCK / 32]; // which parent patterns (accumulator indices) have received a root in this run
 	cplx amp[4]; // the rule's four amplitudes, index = taken * 2 + conjugated: one 16-byte shared load per factor
 	// region mode: the group that opened the run, kept so that the run can still write the objects' hashes and
 	// representatives if it turns out to be the one that creates their region
@@ -273,6 +274,7 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 	// this lane's group has the identity of the run that is open: its root joins the sum of its parent pattern
 	template <class WS>
 	__device__ void continue_run(const flip_ctx &ctx, const flip_root &root, WS &ws) const {
+		atomicOr(&ws.run_patterns[ctx.tree_bits >> 5], 1u << (ctx.tree_bits & 31));
 		atomicAdd(&ws.acc_re[ctx.tree_bits], root.mag.re);
 		atomicAdd(&ws.acc_im[ctx.tree_bits], root.mag.im);
 	}
@@ -495,6 +497,42 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 		const uint32_t lane = lane_id();
 		const uint32_t leaves = ws.run_leaves;
 		const cplx a00 = ws.amp[0], a01 = ws.amp[1], a10 = ws.amp[2], a11 = ws.amp[3]; // index = taken * 2 + parent's bit
+		// ONE parent pattern in the run (the usual case once a state has grown: about one group per region): the objects'
+		// magnitudes are root * prod_l amp[s_l xor t_l][t_l], a binary tree of 2^levels - 1 complex products instead of the
+		// levels * 2^(levels - 1) butterflies below (127 against 448 x 4 products for a full group).  Same values: a
+		// butterfly with one zero input is the same rounded product plus an exact zero.
+		uint32_t patterns = 0, t0 = 0;
+#pragma unroll
+		for (int w = 0; w < FLIP_BLOCK / 32; ++w) {
+			const uint32_t m = ws.run_patterns[w];
+			patterns += __popc(m);
+			if (m)
+				t0 = w * 32 + (__ffs(m) - 1);
+		}
+		if (patterns == 1) {
+			if (lane == 0 && t0 != 0) {
+				ws.acc_re[0] = ws.acc_re[t0];
+				ws.acc_im[0] = ws.acc_im[t0];
+				ws.acc_re[t0] = 0;
+				ws.acc_im[t0] = 0;
+			}
+			__syncwarp();
+			for (uint32_t bit = 1; bit < leaves; bit <<= 1) {
+				const bool parent_bit = (t0 & bit) != 0;
+				// object bit 0 / 1 on this node: taken = object bit xor parent's bit
+				const cplx f0 = parent_bit ? a11 : a00, f1 = parent_bit ? a01 : a10;
+				for (uint32_t i = lane; i < bit; i += 32) {
+					const cplx m{ws.acc_re[i], ws.acc_im[i]};
+					const cplx y0 = cmul(m, f0), y1 = cmul(m, f1);
+					ws.acc_re[i] = y0.re;
+					ws.acc_im[i] = y0.im;
+					ws.acc_re[i + bit] = y1.re;
+					ws.acc_im[i + bit] = y1.im;
+				}
+				__syncwarp();
+			}
+			return;
+		}
 		for (uint32_t bit = 1; bit < leaves; bit <<= 1) {
 			for (uint32_t b = lane; b < leaves / 2; b += 32) {
 				const uint32_t i0 = ((b & ~(bit - 1)) << 1) | (b & (bit - 1)), i1 = i0 | bit;
@@ -669,6 +707,10 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 			ws.run_target = target;
 			ws.run_leaves = leaves;
 			ws.run_valid = 1;
+#pragma unroll
+			for (int w = 0; w < FLIP_BLOCK / 32; ++w)
+				ws.run_patterns[w] = 0;
+			ws.run_patterns[tree_bits >> 5] = 1u << (tree_bits & 31);
 		}
 		if (emit.table.dir) { // region mode: hashes and representatives are only needed if this run creates the region (flush_warp)
 			if (lane == 0) {
@@ -744,6 +786,7 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 			}
 			// the objects of this group are already in the accumulators: its root joins the sum of its pattern
 			if (lane == 0) {
+				ws.run_patterns[ctx.tree_bits >> 5] |= 1u << (ctx.tree_bits & 31);
 				ws.acc_re[ctx.tree_bits] += root.mag.re;
 				ws.acc_im[ctx.tree_bits] += root.mag.im;
 			}
