@@ -320,10 +320,8 @@ __device__ __forceinline__ void bin_store(bin_record *dst, uint64_t hash, cplx m
 	__stcg(d + 1, make_ulonglong2((unsigned long long)__double_as_longlong(mag.im), rep));
 }
 
-// returns true when the record created a slot right away (only the dedicated slot of the hash 0 does)
-__device__ __forceinline__ bool bin_emit(const bin_view &b, const table_view &t, uint64_t hash, cplx mag, uint64_t rep) {
-	if (hash == 0) // 0 marks an empty slot of the shared-memory tables: the hash 0 keeps its dedicated global slot
-		return table_insert_zero_hash(t, mag, rep);
+// a record with a non-zero hash goes to its bin, or to the spill list when the bin's fixed space is full
+__device__ __forceinline__ void bin_put(const bin_view &b, unsigned int *overflow, uint64_t hash, cplx mag, uint64_t rep) {
 	const uint32_t bin = (uint32_t)__umul64hi(mix64(hash), (uint64_t)b.bins);
 	const unsigned int at = atomicAdd(&b.cursor[bin], 1u);
 	if (at < BIN_CAPACITY) {
@@ -334,9 +332,16 @@ __device__ __forceinline__ bool bin_emit(const bin_view &b, const table_view &t,
 			bin_store(b.spill + s, hash, mag, rep);
 			b.spill_bin[s] = bin << 8;
 		} else {
-			*t.overflow = 1;
+			*overflow = 1;
 		}
 	}
+}
+
+// returns true when the record created a slot right away (only the dedicated slot of the hash 0 does)
+__device__ __forceinline__ bool bin_emit(const bin_view &b, const table_view &t, uint64_t hash, cplx mag, uint64_t rep) {
+	if (hash == 0) // 0 marks an empty slot of the shared-memory tables: the hash 0 keeps its dedicated global slot
+		return table_insert_zero_hash(t, mag, rep);
+	bin_put(b, t.overflow, hash, mag, rep);
 	return false;
 }
 
@@ -355,6 +360,8 @@ struct bin_dedup_args {
 	uint64_t *ukey;
 	uint32_t *uslot;
 	unsigned long long *count;      // entries of (ukey, uslot) so far
+	int max_rep;                    // 0: the record that creates a slot is its representative; 1: the record with the largest `rep`
+	                                // (the owner side of the distributed exchange packs a pseudo-random byte on top: a fair choice)
 };
 
 // first index in [0, n) with a[i] >= v (a ascending)
@@ -390,7 +397,8 @@ static __global__ void __launch_bounds__(BIN_DEDUP_THREADS, BIN_DEDUP_BLOCKS_PER
 				}
 				k = atomicCAS(&s_key[i], 0ull, (unsigned long long)hash);
 				if (k == 0) {
-					s_rep[i] = rep; // this child created the slot: it is the representative
+					if (!a.max_rep)
+						s_rep[i] = rep; // this child created the slot: it is the representative
 					atomicAdd(&s_unique, 1u);
 					k = hash;
 				}
@@ -398,6 +406,8 @@ static __global__ void __launch_bounds__(BIN_DEDUP_THREADS, BIN_DEDUP_BLOCKS_PER
 			if (k == hash) {
 				atomicAdd(&s_re[i], re);
 				atomicAdd(&s_im[i], im);
+				if (a.max_rep)
+					atomicMax(&s_rep[i], (unsigned long long)rep);
 				return;
 			}
 			i = (i + 1) & (BIN_TABLE_SLOTS - 1);
@@ -407,7 +417,7 @@ static __global__ void __launch_bounds__(BIN_DEDUP_THREADS, BIN_DEDUP_BLOCKS_PER
 
 	for (uint32_t bin = blockIdx.x; bin < a.bins.bins; bin += gridDim.x) {
 		// empty table: keys, re, im (the representative of a slot is written by whoever creates it)
-		for (uint32_t i = threadIdx.x; i < 3 * BIN_TABLE_SLOTS / 2; i += BIN_DEDUP_THREADS)
+		for (uint32_t i = threadIdx.x; i < (a.max_rep ? 4 : 3) * BIN_TABLE_SLOTS / 2; i += BIN_DEDUP_THREADS)
 			reinterpret_cast<ulonglong2 *>(s_bin)[i] = make_ulonglong2(0, 0);
 		if (threadIdx.x == 0) {
 			s_unique = 0;

@@ -420,6 +420,64 @@ const uint64_t *sort_items(qb_ctx *ctx, qb_sym *sym, uint64_t n, const uint32_t 
 	return vals[src];
 }
 
+// ---- binned interference (table.cuh), host side: bins for n records in the given buffers ...
+struct bin_buffers {
+	dev_buf *records, *cursor, *spill, *spill_key;
+};
+bin_view make_bins(qb_ctx *ctx, const bin_buffers &buf, uint64_t n_records, unsigned long long *spill_cursor) {
+	cudaStream_t stream = ctx->stream;
+	const uint64_t bins = div_up<uint64_t>(std::max<uint64_t>(n_records, 1), BIN_MEAN_RECORDS);
+	QB_REQUIRE(bins < (1ull << 24), QB_ERR_CAPACITY, "binned interference: more than 2^24 bins");
+	const uint64_t spill_capacity = n_records / 8 + 65536;
+	buf.records->ensure(sizeof(bin_record) * bins * BIN_CAPACITY, stream);
+	buf.cursor->ensure(sizeof(unsigned int) * bins, stream);
+	buf.spill->ensure(sizeof(bin_record) * spill_capacity, stream);
+	buf.spill_key->ensure(sizeof(unsigned int) * spill_capacity, stream);
+	QB_CUDA(cudaMemsetAsync(buf.cursor->ptr, 0, sizeof(unsigned int) * bins, stream));
+	QB_CUDA(cudaMemsetAsync(spill_cursor, 0, sizeof(uint64_t), stream));
+	return bin_view{buf.records->as<bin_record>(), buf.cursor->as<unsigned int>(), (uint32_t)bins, buf.spill->as<bin_record>(), buf.spill_key->as<unsigned int>(),
+	                spill_cursor, spill_capacity};
+}
+
+// ... and pass 2: every bin deduplicated in shared memory -> dense unique entries + the compacted (norm key, slot) list.
+// Drains the stream once (the spill count sizes the sort of the spill list).  Nothing is launched if pass 1 raised the overflow flag.
+void launch_bin_dedup(qb_ctx *ctx, qb_sym *sym, const bin_view &bins, const table_view &dense, double tolerance, uint64_t *ukey, uint32_t *uslot, bool max_rep) {
+	cudaStream_t stream = ctx->stream;
+	ctx->fetch_small();
+	if (ctx->h_small[DS_OVERFLOW] != 0)
+		return;
+	bin_dedup_args a;
+	a.bins = bins;
+	a.spill_order = nullptr;
+	a.spill_sorted = nullptr;
+	a.n_spill = std::min<uint64_t>(ctx->h_small[DS_SPILL], bins.spill_capacity);
+	if (a.n_spill > 0) { // sort the spilled records by bin: (bin << 8, index) pairs
+		sym->sort_keys.ensure(2 * sizeof(uint32_t) * a.n_spill, stream);
+		sym->sort_vals.ensure(2 * sizeof(uint64_t) * a.n_spill, stream);
+		QB_CUDA(cudaMemcpyAsync(sym->sort_keys.ptr, bins.spill_bin, sizeof(uint32_t) * a.n_spill, cudaMemcpyDeviceToDevice, stream));
+		iota_kernel<<<grid_for(a.n_spill, 256, ctx->grid_cap()), 256, 0, stream>>>(sym->sort_vals.as<uint64_t>(), a.n_spill);
+		++ctx->launches;
+		const uint32_t *sorted_keys = nullptr;
+		a.spill_order = sort_items(ctx, sym, a.n_spill, &sorted_keys);
+		a.spill_sorted = sorted_keys;
+	}
+	a.dense = dense;
+	a.dense_cursor = dense.used;
+	a.tolerance = tolerance;
+	a.ukey = ukey;
+	a.uslot = uslot;
+	a.count = reinterpret_cast<unsigned long long *>(ctx->small(DS_COUNT));
+	a.max_rep = max_rep ? 1 : 0;
+	static bool smem_allowed[MAX_DEVICES] = {};
+	if (!smem_allowed[ctx->device % MAX_DEVICES]) {
+		QB_CUDA(cudaFuncSetAttribute((const void *)bin_dedup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIN_DEDUP_SMEM));
+		smem_allowed[ctx->device % MAX_DEVICES] = true;
+	}
+	bin_dedup_kernel<<<(unsigned)std::min<uint64_t>(bins.bins, (uint64_t)ctx->sm_count * BIN_DEDUP_BLOCKS_PER_SM), BIN_DEDUP_THREADS, BIN_DEDUP_SMEM, stream>>>(a);
+	++ctx->launches;
+	QB_CUDA(cudaGetLastError());
+}
+
 double reduce_norm_total(qb_ctx *ctx, const cplx *mag, uint64_t n) {
 	const int grid = grid_for(n, SCAN_THREADS, ctx->grid_cap());
 	ctx->partials.ensure(sizeof(double) * (size_t)ctx->grid_cap(), ctx->stream);
@@ -744,18 +802,9 @@ local_table build_local_table(qb_iter *it, uint64_t rule_id, const rule_ops *ops
 		L.bins = bin_view{nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0};
 		const bool binned = binned_allowed && sym->table_attempts == 1;
 		if (binned) {
-			const uint64_t bins = div_up<uint64_t>(n_children, BIN_MEAN_RECORDS);
-			QB_REQUIRE(bins < (1ull << 24), QB_ERR_CAPACITY, "binned interference: more than 2^24 bins");
 			capacity = n_children; // room for "every child is unique": the dense array is neither cleared nor scanned, room costs nothing
-			const uint64_t spill_capacity = n_children / 8 + 65536;
-			sym->bin_records.ensure(sizeof(bin_record) * bins * BIN_CAPACITY, stream);
-			sym->bin_cursor.ensure(sizeof(unsigned int) * bins, stream);
-			sym->bin_spill.ensure(sizeof(bin_record) * spill_capacity, stream);
-			sym->bin_spill_key.ensure(sizeof(unsigned int) * spill_capacity, stream);
-			QB_CUDA(cudaMemsetAsync(sym->bin_cursor.ptr, 0, sizeof(unsigned int) * bins, stream));
-			QB_CUDA(cudaMemsetAsync(ctx->small(DS_SPILL), 0, sizeof(uint64_t), stream));
-			L.bins = bin_view{sym->bin_records.as<bin_record>(), sym->bin_cursor.as<unsigned int>(), (uint32_t)bins, sym->bin_spill.as<bin_record>(),
-			                  sym->bin_spill_key.as<unsigned int>(), reinterpret_cast<unsigned long long *>(ctx->small(DS_SPILL)), spill_capacity};
+			L.bins = make_bins(ctx, bin_buffers{&sym->bin_records, &sym->bin_cursor, &sym->bin_spill, &sym->bin_spill_key}, n_children,
+			                   reinterpret_cast<unsigned long long *>(ctx->small(DS_SPILL)));
 		}
 		const size_t table_bytes = (capacity + 1) * sizeof(table_slot);
 		sym->table.ensure(table_bytes, stream);
@@ -793,42 +842,10 @@ local_table build_local_table(qb_iter *it, uint64_t rule_id, const rule_ops *ops
 			if (collision_labels && sym->table_attempts == 1)
 				step("compute_collisions - finalize");
 			timer.begin(QB_PHASE_INSERT);
-			ctx->fetch_small(); // the spill count sizes the sort below
-			const uint64_t n_spill = std::min<uint64_t>(ctx->h_small[DS_SPILL], L.bins.spill_capacity);
-			bin_dedup_args a;
-			a.bins = L.bins;
-			a.spill_order = nullptr;
-			a.spill_sorted = nullptr;
-			a.n_spill = n_spill;
-			if (n_spill > 0 && ctx->h_small[DS_OVERFLOW] == 0) { // sort the spilled records by bin: (bin << 8, index) pairs
-				sym->sort_keys.ensure(2 * sizeof(uint32_t) * n_spill, stream);
-				sym->sort_vals.ensure(2 * sizeof(uint64_t) * n_spill, stream);
-				QB_CUDA(cudaMemcpyAsync(sym->sort_keys.ptr, sym->bin_spill_key.ptr, sizeof(uint32_t) * n_spill, cudaMemcpyDeviceToDevice, stream));
-				iota_kernel<<<grid_for(n_spill, 256, ctx->grid_cap()), 256, 0, stream>>>(sym->sort_vals.as<uint64_t>(), n_spill);
-				++ctx->launches;
-				const uint32_t *sorted_keys = nullptr;
-				a.spill_order = sort_items(ctx, sym, n_spill, &sorted_keys);
-				a.spill_sorted = sorted_keys;
-			}
 			const uint64_t bound = std::min<uint64_t>(n_children, capacity + 1);
 			sym->ukey.ensure(sizeof(uint64_t) * bound, stream);
 			sym->uslot.ensure(sizeof(uint32_t) * bound, stream);
-			a.dense = R.table;
-			a.dense_cursor = R.table.used;
-			a.tolerance = compaction_tolerance;
-			a.ukey = sym->ukey.as<uint64_t>();
-			a.uslot = sym->uslot.as<uint32_t>();
-			a.count = reinterpret_cast<unsigned long long *>(ctx->small(DS_COUNT));
-			static bool smem_allowed[MAX_DEVICES] = {};
-			if (!smem_allowed[ctx->device % MAX_DEVICES]) {
-				QB_CUDA(cudaFuncSetAttribute((const void *)bin_dedup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIN_DEDUP_SMEM));
-				smem_allowed[ctx->device % MAX_DEVICES] = true;
-			}
-			if (ctx->h_small[DS_OVERFLOW] == 0) {
-				bin_dedup_kernel<<<(unsigned)std::min<uint64_t>(L.bins.bins, (uint64_t)ctx->sm_count * BIN_DEDUP_BLOCKS_PER_SM), BIN_DEDUP_THREADS, BIN_DEDUP_SMEM, stream>>>(a);
-				++ctx->launches;
-				QB_CUDA(cudaGetLastError());
-			}
+			launch_bin_dedup(ctx, sym, L.bins, R.table, compaction_tolerance, sym->ukey.as<uint64_t>(), sym->uslot.as<uint32_t>(), false);
 			timer.end(QB_PHASE_INSERT);
 		} else {
 		// unique children above the tolerance (quids.hpp:819-823)
@@ -1235,7 +1252,9 @@ void simulate_dist(qb_iter *it, uint64_t rule_id, const rule_ops *ops, const voi
 	// 2. partition the locally unique children by owner
 	timer.begin(QB_PHASE_OWNER);
 	const uint64_t n_local = err.ok() ? R.n_unique : 0;
-	const uint32_t sub = owner_sub_buckets(world), bins = world * sub; // records grouped by (owner, region of the owner's table)
+	// records grouped by (owner, region of the owner's hashed table); a large exchange is merged through bins on the owner's
+	// side (below), where the order of arrival does not matter: plain grouping by owner then
+	const uint32_t sub = (opt.binned_inserts != 0 && n_local >= (1ull << 21)) ? 1u : owner_sub_buckets(world), bins = world * sub;
 	unsigned long long *counts = nullptr, *cursor = nullptr;
 	std::vector<uint64_t> send_counts(world, 0);
 	err.run([&] {
@@ -1297,8 +1316,29 @@ void simulate_dist(qb_iter *it, uint64_t rule_id, const rule_ops *ops, const voi
 		if (cm->owner_unique_ratio > 0)
 			capacity = std::min<uint64_t>(full_capacity, std::max<uint64_t>(1024, (uint64_t)((cm->owner_unique_ratio * 1.25 * (double)n_recv + 1024) / 0.5)));
 		QB_REQUIRE(full_capacity + 1 <= 0xffffffffull, QB_ERR_CAPACITY, "owner table would need more than 2^32 slots");
-		cm->okey.ensure(sizeof(uint64_t) * n_recv, stream);
-		cm->oslot.ensure(sizeof(uint32_t) * n_recv, stream);
+		cm->okey.ensure(sizeof(uint64_t) * (n_recv + 1), stream);
+		cm->oslot.ensure(sizeof(uint32_t) * (n_recv + 1), stream);
+		// binned owner merge (table.cuh): the records are streamed into bins and every bin is deduplicated in shared memory --
+		// the owner's "table" is then the dense array of the unique objects; a bin that overflows falls back to the hashed table
+		if (opt.binned_inserts != 0 && (opt.binned_inserts > 1 || n_recv >= (1ull << 22)) && n_recv <= (1ull << 29)) {
+			capacity = n_recv;
+			cm->owner_table.ensure((capacity + 1) * sizeof(table_slot), stream);
+			QB_CUDA(cudaMemsetAsync(cm->owner_table.as<table_slot>() + capacity, 0, sizeof(table_slot), stream));
+			QB_CUDA(cudaMemsetAsync(ctx->small(DS_COUNT), 0, 4 * sizeof(uint64_t), stream));
+			owner = table_view{cm->owner_table.as<table_slot>(), capacity, reinterpret_cast<unsigned int *>(ctx->small(DS_OVERFLOW)),
+			                   reinterpret_cast<unsigned long long *>(ctx->small(DS_USED))};
+			const bin_view ob = make_bins(ctx, bin_buffers{&cm->obin_records, &cm->obin_cursor, &cm->obin_spill, &cm->obin_spill_key}, n_recv,
+			                              reinterpret_cast<unsigned long long *>(ctx->small(DS_SPILL)));
+			record_bin_kernel<<<grid_for(n_recv, 256, ctx->grid_cap()), 256, 0, stream>>>(ob, owner, cm->recv.as<exchange_record>(), n_recv);
+			++ctx->launches;
+			launch_bin_dedup(ctx, sym, ob, owner, opt.tolerance, cm->okey.as<uint64_t>(), cm->oslot.as<uint32_t>(), true);
+			ctx->fetch_small();
+			if (ctx->h_small[DS_OVERFLOW] == 0) {
+				n_owner_unique = ctx->h_small[DS_COUNT];
+				return;
+			}
+			capacity = full_capacity; // fall back to the hashed table below
+		}
 		for (int attempt = 0;; ++attempt) {
 			cm->owner_table.ensure((capacity + 1) * sizeof(table_slot), stream);
 			QB_CUDA(cudaMemsetAsync(cm->owner_table.ptr, 0, (capacity + 1) * sizeof(table_slot), stream));

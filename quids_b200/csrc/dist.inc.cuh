@@ -89,6 +89,7 @@ struct qb_comm {
 	ncclComm_t nccl = nullptr;
 	dev_buf scratch; // small device staging for host-value collectives
 	dev_buf send, recv, owner_table, okey, oslot, ret_send, ret_recv, cursors, recv_begin;
+	dev_buf obin_records, obin_cursor, obin_spill, obin_spill_key; // owner side: the received records binned for the shared-memory deduplication (table.cuh)
 	double owner_unique_ratio = 0; // slots created / records received by the owner table of the last call (0 = no call yet)
 	route_buffers *route = nullptr; // route.inc.cuh: parents grouped by family owner, and what arrived (created on first use)
 };
@@ -421,6 +422,27 @@ __global__ void __launch_bounds__(256) record_insert_kernel(table_view t, const 
 	created = (unsigned int)warp_sum((uint64_t)created);
 	if (lane_id() == 0 && created)
 		atomicAdd(t.used, (unsigned long long)created);
+}
+
+// owner side, binned (table.cuh): every received record goes to the bin of its hash with the POSITION it arrived at as its
+// representative (plus the pseudo-random byte of owner_rep_pack: bin_dedup_kernel keeps the largest, a fair choice between
+// the ranks); one streaming pass, no table
+__global__ void __launch_bounds__(256) record_bin_kernel(bin_view b, table_view t, const exchange_record *records, uint64_t n) {
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+		const ulonglong2 lo = __ldcs(reinterpret_cast<const ulonglong2 *>(records + i));
+		const ulonglong2 hi = __ldcs(reinterpret_cast<const ulonglong2 *>(records + i) + 1);
+		const uint64_t hash = lo.x;
+		const cplx mag{__longlong_as_double((long long)lo.y), __longlong_as_double((long long)hi.x)};
+		if (hash == 0) { // the dedicated slot
+			table_slot *s = t.slots + t.capacity;
+			atomicAdd(&s->re, mag.re);
+			atomicAdd(&s->im, mag.im);
+			atomicMax(&s->rep, (unsigned long long)owner_rep_pack(i, 0));
+		} else {
+			bin_put(b, t.overflow, hash, mag, owner_rep_pack(i, hash));
+		}
+	}
 }
 
 // survivors (owner slots) -> which rank their representative came from; counts per rank

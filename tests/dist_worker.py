@@ -139,12 +139,13 @@ def want_tail(p: orc.Packed, n):
     return multiset(sizes, mags, p.data[begin:])
 
 
-def run_case(comm, port, state, rid, params, k, tol, qcgd, what, share=share, equalize=0, family_routing=1, big=False):
+def run_case(comm, port, state, rid, params, k, tol, qcgd, what, share=share, equalize=0, family_routing=1, big=False, binned=1):
     rank, world = dist.get_rank(), dist.get_world_size()
     qb.config.tolerance = tol
     qb.config.align_byte_length = 8
     qb.config.equalize = equalize
     qb.config.family_routing = family_routing
+    qb.config.binned_inserts = binned
     mine = share(state, rank, world)
     it, nxt, sym = qb.Iteration(), qb.Iteration(), qb.SymbolicIteration()
     it.upload_packed(mine.sizes, mine.mags, mine.data)
@@ -268,6 +269,10 @@ def main():
         if rid != orc.RULE_SPLIT_MERGE:  # erase_create / coin went through the family routing above: the record exchange must agree
             run_case(comm, port, state, rid, p, 900, 1e-18, True, f"rule {rid} children truncated, record exchange", family_routing=0)
             run_case(comm, port, state, rid, p, 250, 1e-18, True, f"rule {rid} parents and children truncated, record exchange", family_routing=0)
+    # binned interference forced on both sides of the record exchange (local bins, owner-side bins with the fair representative)
+    for rid in orc.QCGD_RULES:
+        run_case(comm, port, state, rid, p, orc.NO_TRUNCATION, 1e-18, True, f"rule {rid} no truncation, bins on both sides", family_routing=0, binned=2)
+        run_case(comm, port, state, rid, p, 250, 1e-18, True, f"rule {rid} parents and children truncated, bins on both sides", family_routing=0, binned=2)
     # a ragged grown state (names of many shapes, nodes merged and split): families must still be closed under erase_create / coin
     grown, _, _ = port.simulate(port.qcgd_random_state(9, 2000, 8), orc.RULE_SPLIT_MERGE, [0.4, 0.3, 0.2], orc.NO_TRUNCATION, 1e-18)
     gm = np.random.default_rng(3).normal(size=(grown.n, 2))
@@ -291,6 +296,7 @@ def main():
     run_case(comm, port, state, orc.RULE_ERASE_CREATE, p, 900, 1e-18, True, "skewed shares, equalize by objects, children truncated", share=skewed_share,
              equalize=1)
     migration_cases(comm, port)
+    run_case(comm, port, grown, orc.RULE_SPLIT_MERGE, p, 30000, 1e-18, True, "split_merge on a grown state, bins on both sides, truncated", binned=2, big=True)
     failure_cases(comm, port, state)
     automatic_budget_cases(comm, port, state)
     # one rank empty: fewer objects than ranks
