@@ -168,6 +168,14 @@ struct dev_buf {
 		ptr = nullptr;
 		cap = 0;
 	}
+	// give the block back to the pool, ordered after everything enqueued on `stream` so far: scratch that is dead until the
+	// next call of its kind lets another buffer grow into the same memory (the pool serves the next ensure() from its cache)
+	void free_async(cudaStream_t stream) {
+		if (ptr)
+			cudaFreeAsync(ptr, stream);
+		ptr = nullptr;
+		cap = 0;
+	}
 	void ensure(size_t bytes, cudaStream_t stream, bool keep = false, size_t keep_bytes = 0) {
 		if (bytes <= cap)
 			return;

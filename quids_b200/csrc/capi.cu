@@ -807,6 +807,12 @@ local_table build_local_table(qb_iter *it, uint64_t rule_id, const rule_ops *ops
 			                   reinterpret_cast<unsigned long long *>(ctx->small(DS_SPILL)));
 		}
 		const size_t table_bytes = (capacity + 1) * sizeof(table_slot);
+		if (!binned && table_bytes > sym->table.cap && table_bytes > ((size_t)4 << 30)) {
+			// a table of many GB has to grow: what the binned path of another rule left behind is dead weight until that rule runs again
+			sym->bin_records.free_async(stream);
+			sym->bin_spill.free_async(stream);
+			sym->bin_spill_key.free_async(stream);
+		}
 		sym->table.ensure(table_bytes, stream);
 		if (binned) // only the dedicated slot of the hash 0 is accumulated into
 			QB_CUDA(cudaMemsetAsync(sym->table.as<table_slot>() + capacity, 0, sizeof(table_slot), stream));
@@ -1304,6 +1310,8 @@ void simulate_dist(qb_iter *it, uint64_t rule_id, const rule_ops *ops, const voi
 	timer.begin(QB_PHASE_OWNER);
 	table_view owner{};
 	uint64_t n_owner_unique = 0;
+	uint64_t *owner_keys = nullptr;  // compacted (norm key, slot) lists of the owner's unique objects
+	uint32_t *owner_slots = nullptr;
 	err.run([&] {
 		injected("owner");
 		if (n_recv == 0)
@@ -1316,29 +1324,37 @@ void simulate_dist(qb_iter *it, uint64_t rule_id, const rule_ops *ops, const voi
 		if (cm->owner_unique_ratio > 0)
 			capacity = std::min<uint64_t>(full_capacity, std::max<uint64_t>(1024, (uint64_t)((cm->owner_unique_ratio * 1.25 * (double)n_recv + 1024) / 0.5)));
 		QB_REQUIRE(full_capacity + 1 <= 0xffffffffull, QB_ERR_CAPACITY, "owner table would need more than 2^32 slots");
-		cm->okey.ensure(sizeof(uint64_t) * (n_recv + 1), stream);
-		cm->oslot.ensure(sizeof(uint32_t) * (n_recv + 1), stream);
 		// binned owner merge (table.cuh): the records are streamed into bins and every bin is deduplicated in shared memory --
 		// the owner's "table" is then the dense array of the unique objects; a bin that overflows falls back to the hashed table
 		if (opt.binned_inserts != 0 && (opt.binned_inserts > 1 || n_recv >= (1ull << 22)) && n_recv <= (1ull << 29)) {
+			// The local table, its (key, slot) lists and the local bins are dead once the records are in the send buffer: the
+			// owner's dense array, lists and bins take their memory (at 1e7 parents per GPU that is 19 GB not allocated twice)
 			capacity = n_recv;
-			cm->owner_table.ensure((capacity + 1) * sizeof(table_slot), stream);
-			QB_CUDA(cudaMemsetAsync(cm->owner_table.as<table_slot>() + capacity, 0, sizeof(table_slot), stream));
+			sym->table.ensure((capacity + 1) * sizeof(table_slot), stream);
+			sym->ukey.ensure(sizeof(uint64_t) * (n_recv + 1), stream);
+			sym->uslot.ensure(sizeof(uint32_t) * (n_recv + 1), stream);
+			QB_CUDA(cudaMemsetAsync(sym->table.as<table_slot>() + capacity, 0, sizeof(table_slot), stream));
 			QB_CUDA(cudaMemsetAsync(ctx->small(DS_COUNT), 0, 4 * sizeof(uint64_t), stream));
-			owner = table_view{cm->owner_table.as<table_slot>(), capacity, reinterpret_cast<unsigned int *>(ctx->small(DS_OVERFLOW)),
+			owner = table_view{sym->table.as<table_slot>(), capacity, reinterpret_cast<unsigned int *>(ctx->small(DS_OVERFLOW)),
 			                   reinterpret_cast<unsigned long long *>(ctx->small(DS_USED))};
-			const bin_view ob = make_bins(ctx, bin_buffers{&cm->obin_records, &cm->obin_cursor, &cm->obin_spill, &cm->obin_spill_key}, n_recv,
+			const bin_view ob = make_bins(ctx, bin_buffers{&sym->bin_records, &sym->bin_cursor, &sym->bin_spill, &sym->bin_spill_key}, n_recv,
 			                              reinterpret_cast<unsigned long long *>(ctx->small(DS_SPILL)));
 			record_bin_kernel<<<grid_for(n_recv, 256, ctx->grid_cap()), 256, 0, stream>>>(ob, owner, cm->recv.as<exchange_record>(), n_recv);
 			++ctx->launches;
-			launch_bin_dedup(ctx, sym, ob, owner, opt.tolerance, cm->okey.as<uint64_t>(), cm->oslot.as<uint32_t>(), true);
+			launch_bin_dedup(ctx, sym, ob, owner, opt.tolerance, sym->ukey.as<uint64_t>(), sym->uslot.as<uint32_t>(), true);
 			ctx->fetch_small();
 			if (ctx->h_small[DS_OVERFLOW] == 0) {
 				n_owner_unique = ctx->h_small[DS_COUNT];
+				owner_keys = sym->ukey.as<uint64_t>();
+				owner_slots = sym->uslot.as<uint32_t>();
 				return;
 			}
 			capacity = full_capacity; // fall back to the hashed table below
 		}
+		cm->okey.ensure(sizeof(uint64_t) * (n_recv + 1), stream);
+		cm->oslot.ensure(sizeof(uint32_t) * (n_recv + 1), stream);
+		owner_keys = cm->okey.as<uint64_t>();
+		owner_slots = cm->oslot.as<uint32_t>();
 		for (int attempt = 0;; ++attempt) {
 			cm->owner_table.ensure((capacity + 1) * sizeof(table_slot), stream);
 			QB_CUDA(cudaMemsetAsync(cm->owner_table.ptr, 0, (capacity + 1) * sizeof(table_slot), stream));
@@ -1393,18 +1409,18 @@ void simulate_dist(qb_iter *it, uint64_t rule_id, const rule_ops *ops, const voi
 	step("truncate - prepare");
 	step("truncate");
 	uint64_t n_owner_survivors = n_owner_unique;
-	const uint32_t *owner_survivor_slot = cm->oslot.as<uint32_t>();
+	const uint32_t *owner_survivor_slot = owner_slots;
 	if (max_num_object < n_unique_global) {
 		timer.begin(QB_PHASE_TRUNCATE);
 		sym->sslot.ensure(sizeof(uint32_t) * std::max<uint64_t>(1, std::min<uint64_t>(n_owner_unique, max_num_object)), stream);
 		if (!opt.simple_truncation && n_owner_unique > 0) {
-			randomize_keys_kernel<<<grid_for(n_owner_unique, 256, ctx->grid_cap()), 256, 0, stream>>>(cm->okey.as<uint64_t>(), owner, cm->oslot.as<uint32_t>(),
+			randomize_keys_kernel<<<grid_for(n_owner_unique, 256, ctx->grid_cap()), 256, 0, stream>>>(owner_keys, owner, owner_slots,
 			                                                                                         n_owner_unique, opt.seed);
 			++ctx->launches;
 		}
-		key_from_array keys{cm->okey.as<uint64_t>()};
+		key_from_array keys{owner_keys};
 		select_threshold(ctx, &comm, keys, n_owner_unique, max_num_object);
-		n_owner_survivors = select_keep(ctx, &comm, keys, n_owner_unique, out_gather_u32{sym->sslot.as<uint32_t>(), cm->oslot.as<uint32_t>()});
+		n_owner_survivors = select_keep(ctx, &comm, keys, n_owner_unique, out_gather_u32{sym->sslot.as<uint32_t>(), owner_slots});
 		owner_survivor_slot = sym->sslot.as<uint32_t>();
 		timer.end(QB_PHASE_TRUNCATE);
 	}

@@ -89,7 +89,6 @@ struct qb_comm {
 	ncclComm_t nccl = nullptr;
 	dev_buf scratch; // small device staging for host-value collectives
 	dev_buf send, recv, owner_table, okey, oslot, ret_send, ret_recv, cursors, recv_begin;
-	dev_buf obin_records, obin_cursor, obin_spill, obin_spill_key; // owner side: the received records binned for the shared-memory deduplication (table.cuh)
 	double owner_unique_ratio = 0; // slots created / records received by the owner table of the last call (0 = no call yet)
 	route_buffers *route = nullptr; // route.inc.cuh: parents grouped by family owner, and what arrived (created on first use)
 };
