@@ -121,18 +121,18 @@ __device__ __forceinline__ void stage_init(warp_stage &st) {
 	__syncwarp();
 }
 
-// copies [src, src + nbytes) (nbytes <= STAGE_BYTES) and returns the shared-memory address of src[0]; `phase` is the
-// caller's phase bit of this stage (starts at 0, flipped here)
-__device__ __forceinline__ const uint8_t *stage_range(warp_stage &st, const uint8_t *src, uint32_t nbytes, uint32_t &phase) {
+// copies [src, src + nbytes) into `bytes` (room for nbytes + 32) and returns the shared-memory address of src[0]; `phase` is
+// the caller's phase bit of this stage's barrier (starts at 0, flipped here)
+__device__ __forceinline__ const uint8_t *stage_range_to(uint8_t *bytes, unsigned long long *mbar, const uint8_t *src, uint32_t nbytes, uint32_t &phase) {
 	const uint32_t lead = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15);
 	const uint32_t total = (lead + nbytes + 15u) & ~15u;
-	const uint32_t bar = smem_addr(&st.mbar);
+	const uint32_t bar = smem_addr(mbar);
 	// what the lanes read from the stage before must not be overtaken by the asynchronous writes of this copy
 	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 	__syncwarp();
 	if (lane_id() == 0) {
 		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
-		asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(st.bytes)), "l"(src - lead),
+		asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(bytes)), "l"(src - lead),
 		             "r"(total), "r"(bar)
 		             : "memory");
 	}
@@ -140,7 +140,11 @@ __device__ __forceinline__ const uint8_t *stage_range(warp_stage &st, const uint
 	while (!done)
 		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(phase) : "memory");
 	phase ^= 1;
-	return st.bytes + lead;
+	return bytes + lead;
+}
+// (nbytes <= STAGE_BYTES)
+__device__ __forceinline__ const uint8_t *stage_range(warp_stage &st, const uint8_t *src, uint32_t nbytes, uint32_t &phase) {
+	return stage_range_to(st.bytes, &st.mbar, src, nbytes, phase);
 }
 
 // ---- growable device buffer (stands for utils::fast_vector, utils/vector.hpp:36-160) -----------

@@ -157,6 +157,21 @@ __global__ void __launch_bounds__(SYMBOLIC_THREADS, 5) symbolic_kernel(const Rul
 	__shared__ typename Rule::workspace_t s_workspace[ENGINE_WARPS];
 	warp_slice &s = s_slices[threadIdx.x >> 5];
 	const unsigned lane = lane_id();
+	// stage of the batch's parent bytes (rules with warp_prepare and prepare_stage_bytes)
+	constexpr uint32_t PREPARE_STAGE = Rule::warp_prepare ? Rule::prepare_stage_bytes : 0;
+	struct __align__(16) prepare_stage_t {
+		uint8_t bytes[PREPARE_STAGE ? PREPARE_STAGE + 32 : 16];
+		unsigned long long mbar, pad_;
+	};
+	__shared__ prepare_stage_t s_prepare_stage[PREPARE_STAGE ? ENGINE_WARPS : 1];
+	uint32_t stage_phase = 0;
+	if constexpr (PREPARE_STAGE > 0) {
+		if (lane == 0) {
+			asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&s_prepare_stage[threadIdx.x >> 5].mbar)));
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		}
+		__syncwarp();
+	}
 
 	uint8_t *scratch = Rule::needs_scratch ? L.scratch + ((size_t)blockIdx.x * SYMBOLIC_THREADS + threadIdx.x) * L.scratch_stride : nullptr;
 	uint32_t created = 0;
@@ -180,11 +195,13 @@ __global__ void __launch_bounds__(SYMBOLIC_THREADS, 5) symbolic_kernel(const Rul
 
 		for (uint64_t g0 = p_lo; g0 <= p_hi; g0 += BATCH) {
 			const uint32_t count = (uint32_t)min((uint64_t)BATCH, p_hi + 1 - g0);
+			uint64_t off = 0;
+			uint32_t sz = 0;
 			if (lane < count) {
 				const uint64_t p = g0 + lane;
 				const uint64_t oid = L.kept ? L.kept[p] : p;
-				const uint64_t off = L.it.begin[oid];
-				const uint32_t sz = L.it.size[oid];
+				off = L.it.begin[oid];
+				sz = L.it.size[oid];
 				const uint64_t gb = L.group_begin[p];
 				s.group_begin[lane] = gb;
 				s.child_begin[lane] = L.child_begin[p];
@@ -198,9 +215,21 @@ __global__ void __launch_bounds__(SYMBOLIC_THREADS, 5) symbolic_kernel(const Rul
 				s.group_begin[count] = L.group_begin[g0 + count];
 			__syncwarp();
 			if constexpr (Rule::warp_prepare) { // contexts built by the whole warp, one parent after the other
+				const uint8_t *staged = nullptr; // shared-memory copy of the batch's bytes, which start at offset `staged_from` of the state
+				uint64_t staged_from = 0;
+				if constexpr (PREPARE_STAGE > 0) {
+					if (!L.kept) { // storage order: the batch is the byte range [begin of the first, end of the last]
+						staged_from = __shfl_sync(0xffffffffu, off, 0);
+						const uint64_t end = __shfl_sync(0xffffffffu, off + sz, count - 1);
+						if (end - staged_from <= PREPARE_STAGE) {
+							prepare_stage_t &st = s_prepare_stage[threadIdx.x >> 5];
+							staged = stage_range_to(st.bytes, &st.mbar, L.it.objects + staged_from, (uint32_t)(end - staged_from), stage_phase);
+						}
+					}
+				}
 				for (uint32_t j = 0; j < count; ++j)
 					if (s.group_begin[j + 1] > s.group_begin[j])
-						rule.prepare_warp(L.it.objects + s.object[j], s.size[j], s.ctx[j]);
+						rule.prepare_warp(staged ? staged + (s.object[j] - staged_from) : L.it.objects + s.object[j], s.size[j], s.ctx[j]);
 				__syncwarp();
 			}
 
@@ -764,6 +793,7 @@ struct rule_glue {
 	static void symbolic(const void *rule, const engine_launch &L) {
 		constexpr int chunk = Rule::warp_groups ? 32 : SYMBOLIC_CHUNK;
 		const uint64_t warps = div_up<uint64_t>(L.n_groups, chunk);
+		Rule::prepare_device(L.stream);
 		chunk_parent_kernel<<<(unsigned)div_up<uint64_t>(warps + 1, ENGINE_THREADS), ENGINE_THREADS, 0, L.stream>>>(
 		    L.group_begin, L.n_parents, L.n_groups, chunk, warps, const_cast<uint64_t *>(L.chunk_parent));
 		++*L.launch_counter;
@@ -781,6 +811,7 @@ struct rule_glue {
 	static void symbolic_items(const void *rule, const engine_launch &L) {
 		if constexpr (Rule::has_group_key) {
 			const uint64_t warps = div_up<uint64_t>(L.n_groups, ITEM_CHUNK);
+			Rule::prepare_device(L.stream);
 			// occupancy target: the register budget follows from it (5 CTAs of 4 warps: 96 registers).  QB_ITEMS_BLOCKS is a developer
 			// knob for A/B runs (4: 128 registers, no spills; 6: 80 registers)
 			static const int blocks = getenv("QB_ITEMS_BLOCKS") ? atoi(getenv("QB_ITEMS_BLOCKS")) : ITEMS_BLOCKS_PER_SM;

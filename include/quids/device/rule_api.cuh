@@ -79,6 +79,10 @@ struct rule_base {
 	// 32 lanes with the same arguments after prepare() -- and, for large contexts, fewer parents are staged at a time
 	static constexpr bool warp_prepare = false;
 	static constexpr int parents_per_batch = 32;
+	// with warp_prepare: the parents of a batch (consecutive in the state) are first copied to shared memory in one bulk copy
+	// when they fit in this many bytes, and prepare_warp reads them there: its chains of dependent loads (node count -> name
+	// offsets -> atoms) then cost shared-memory latency instead of one DRAM round trip per link and parent.  0 = no staging
+	static constexpr uint32_t prepare_stage_bytes = 0;
 
 	__device__ uint64_t hasher(const uint8_t *object, uint32_t size) const { return murmur_bytes(object, size); }
 
@@ -162,6 +166,9 @@ struct rule_base {
 	// optional: called once per warp when the sorted-order kernel ends (after the last flush_warp)
 	template <class WS, class Emit>
 	__device__ void finish_warp(WS &, Emit &) const {}
+	// optional, HOST side: called before the symbolic kernels of this rule type are launched on `stream` (the device is
+	// current): device-resident tables the rule's kernels read, built once per device, ordered before the launch by the stream
+	static void prepare_device(cudaStream_t) {}
 };
 
 // ---- modifiers: f(begin, end, mag&) in place (quids.hpp:86,973-980) as a device functor

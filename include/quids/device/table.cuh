@@ -200,37 +200,52 @@ __device__ __forceinline__ unsigned long long load_acquire(const unsigned long l
 	return v;
 }
 
-// The region of the objects identified by `key` (`leaves` consecutive slots).  ONE lane calls this per run.
-__device__ __forceinline__ region_grant region_acquire(const table_view &t, region_chunk &mine, uint64_t key, uint32_t leaves) {
+// The region of the objects identified by `key` (`leaves` consecutive slots).  ONE lane calls this per run, in two halves so
+// that the round trip of the first probe overlaps whatever the warp computes in between: region_probe_begin claims the home
+// entry of the directory blindly (the result of the compare-and-swap is not looked at), region_acquire_finish reads it.
+struct region_probe {
+	uint64_t key, index;
+	unsigned long long seen; // what the home entry held before the compare-and-swap (0 = this run claimed it)
+};
+__device__ __forceinline__ region_probe region_probe_begin(const table_view &t, uint64_t key) {
+	region_probe p;
+	p.key = key ? key : 1;
+	p.index = __umul64hi(mix64(p.key), t.dir_capacity);
+	p.seen = atomicCAS(&t.dir[p.index].key, 0ull, (unsigned long long)p.key);
+	return p;
+}
+
+__device__ __forceinline__ region_grant region_acquire_finish(const table_view &t, region_chunk &mine, const region_probe &p, uint32_t leaves) {
 	region_grant g{~0ull, nullptr, 0, 0, false};
-	if (key == 0)
-		key = 1;
-	uint64_t i = __umul64hi(mix64(key), t.dir_capacity);
+	const uint64_t key = p.key;
+	uint64_t i = p.index;
+	unsigned long long seen = p.seen;
 	for (uint32_t probes = 0; probes <= TABLE_MAX_PROBES; ++probes) {
 		region_entry *e = t.dir + i;
-		unsigned long long seen = __ldcg(&e->key);
-		if (seen == 0) {
-			seen = atomicCAS(&e->key, 0ull, (unsigned long long)key);
-			if (seen == 0) { // this run creates the region
-				if (mine.next + leaves > mine.end) { // what is left of the old chunk stays empty
-					g.retire_from = mine.next;
-					g.retire_count = mine.end - mine.next;
-					const unsigned long long want = leaves > REGION_CHUNK ? leaves : REGION_CHUNK;
-					mine.next = atomicAdd(t.cursor, want);
-					mine.end = mine.next + want;
-					if (mine.end > t.capacity) { // the new chunk does not fit: nothing of it may be touched
-						mine.end = mine.next;
-						*t.overflow = 1;
-						atomicExch(&e->base, ~0ull); // whoever waits for this region gives up too
-						return g;
-					}
+		if (probes) {
+			seen = __ldcg(&e->key);
+			if (seen == 0)
+				seen = atomicCAS(&e->key, 0ull, (unsigned long long)key);
+		}
+		if (seen == 0) { // this run creates the region
+			if (mine.next + leaves > mine.end) { // what is left of the old chunk stays empty
+				g.retire_from = mine.next;
+				g.retire_count = mine.end - mine.next;
+				const unsigned long long want = leaves > REGION_CHUNK ? leaves : REGION_CHUNK;
+				mine.next = atomicAdd(t.cursor, want);
+				mine.end = mine.next + want;
+				if (mine.end > t.capacity) { // the new chunk does not fit: nothing of it may be touched
+					mine.end = mine.next;
+					*t.overflow = 1;
+					atomicExch(&e->base, ~0ull); // whoever waits for this region gives up too
+					return g;
 				}
-				g.base = mine.next;
-				mine.next += leaves;
-				g.entry = e;
-				g.created = true;
-				return g;
 			}
+			g.base = mine.next;
+			mine.next += leaves;
+			g.entry = e;
+			g.created = true;
+			return g;
 		}
 		if (seen == key) {
 			unsigned long long base;
@@ -248,6 +263,10 @@ __device__ __forceinline__ region_grant region_acquire(const table_view &t, regi
 	}
 	*t.overflow = 1;
 	return g;
+}
+
+__device__ __forceinline__ region_grant region_acquire(const table_view &t, region_chunk &mine, uint64_t key, uint32_t leaves) {
+	return region_acquire_finish(t, mine, region_probe_begin(t, key), leaves);
 }
 
 // the creator's slots are written: let the other runs of the same objects in (one lane, after a __syncwarp of the writers)

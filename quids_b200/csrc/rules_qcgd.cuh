@@ -40,6 +40,36 @@ __host__ __device__ __forceinline__ uint64_t hash_combine_index(uint64_t seed, u
 	return ((seed * MUL2) ^ (uint64_t)index) * MURMUR_MUL + 0xe6546b64ull;
 }
 
+// FOLD TABLE.  hash_graph's two particle hashes are folds of hash_combine over the INDICES of the nodes that hold a particle,
+// in increasing order: a function of the particle mask alone.  For graphs of at most FOLD_TABLE_BITS nodes the fold of every
+// mask is tabulated once per device (512 KB, L2 resident): the hash of a child whose particle masks are known costs two
+// loads and the two final folds instead of one dependent chain of 64-bit multiplications per node.
+constexpr uint32_t FOLD_TABLE_BITS = 16;
+static __device__ uint64_t g_particle_fold[1u << FOLD_TABLE_BITS];
+
+static __global__ void __launch_bounds__(256) particle_fold_init_kernel() {
+	const uint32_t mask = blockIdx.x * blockDim.x + threadIdx.x;
+	uint64_t h = 0;
+	for (uint32_t i = 0; i < FOLD_TABLE_BITS; ++i)
+		if ((mask >> i) & 1)
+			h = hash_combine_index(h, i);
+	g_particle_fold[mask] = h;
+}
+
+// host: the table of the current device is filled by a kernel on `stream` the first time a rule that reads it is launched there
+inline void particle_fold_prepare(cudaStream_t stream) {
+	static bool ready[64] = {};
+	int device = 0;
+	QB_CUDA(cudaGetDevice(&device));
+	if (ready[device & 63])
+		return;
+	particle_fold_init_kernel<<<(1u << FOLD_TABLE_BITS) / 256, 256, 0, stream>>>();
+	QB_CUDA(cudaGetLastError());
+	ready[device & 63] = true;
+}
+
+__device__ __forceinline__ uint64_t particle_fold(uint32_t mask) { return __ldg(&g_particle_fold[mask]); }
+
 struct atom {
 	int hmlz; // "has most-left zero" flag / element + 1   (qcgd.hpp:36,40-42)
 	int kind;
@@ -228,6 +258,7 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 	// sorted order with table regions needs every parent to go through the mask-based path (n <= 64 nodes); an object
 	// of fewer bytes than the smallest 65-node graph (4 + 4 n + 16 per name atom) cannot have more nodes
 	static constexpr uint32_t region_size_limit = 4 + 20 * 65;
+	static void prepare_device(cudaStream_t stream) { particle_fold_prepare(stream); }
 
 	// what makes two groups produce the same objects: family (eligible nodes, particles elsewhere, names, size) and target
 	struct run_id_t {
@@ -493,7 +524,7 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 	// instead of one product chain per child.  Same value as summing the children one by one up to rounding
 	// (the interference table adds them in no particular order either).
 	template <class WS>
-	__device__ __forceinline__ void spread_run(WS &ws) const {
+	__device__ __noinline__ void spread_run(WS &ws) const {
 		const uint32_t lane = lane_id();
 		const uint32_t leaves = ws.run_leaves;
 		const cplx a00 = ws.amp[0], a01 = ws.amp[1], a10 = ws.amp[2], a11 = ws.amp[3]; // index = taken * 2 + parent's bit
@@ -554,11 +585,174 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 		return mix64(eligible ^ mix64(fixed + 0x9e3779b97f4a7c15ull * (target + 1ull)) ^ mix64(names ^ (0xc2b2ae3d27d4eb4full * n)));
 	}
 
-	// the objects of the current run go to the global table, four per lane at a time
+	// Region mode, graphs of at most FOLD_TABLE_BITS nodes (the fold table applies): the run goes to its region WITHOUT the
+	// shared-memory trees.  Every lane owns the objects lane, lane + 32, ... of the run and computes, in registers,
+	//   * their magnitudes: one product chain per parent pattern of the run (same factors in the same order as the reference's
+	//     child by child products), summed over the patterns -- up to two patterns; more go through the butterflies of spread_run;
+	//   * if this run creates the region, their hashes: particle masks = the opening group's masks with the group's and the
+	//     object's toggles, two lookups in the fold table, two folds.
+	// The first probe of the directory is issued before the arithmetic and read after it.
 	template <class WS, class Emit>
-	__device__ void flush_warp(WS &ws, Emit &emit) const {
+	__device__ __forceinline__ void flush_region_direct(WS &ws, Emit &emit) const {
+		constexpr int PER_LANE = FLIP_BLOCK / 32;
+		const uint32_t lane = lane_id(), leaves = ws.run_leaves;
+		const uint32_t levels = ws.open_ctx.levels;
+		region_probe probe{};
+		if (lane == 0)
+			probe = region_probe_begin(emit.table, region_key(ws.run_eligible, ws.run_fixed, ws.run_target, ws.run_names, ws.run_n));
+		// parent patterns of the run
+		uint32_t patterns = 0, t0 = 0, t1 = 0;
+#pragma unroll
+		for (int w = 0; w < FLIP_BLOCK / 32; ++w) {
+			uint32_t m = ws.run_patterns[w];
+			if (m) {
+				if (patterns == 0) {
+					t0 = w * 32 + (__ffs(m) - 1);
+					if (m & (m - 1))
+						t1 = w * 32 + (__ffs(m & (m - 1)) - 1);
+				} else if (patterns == 1) {
+					t1 = w * 32 + (__ffs(m) - 1);
+				}
+				patterns += __popc(m);
+			}
+		}
+		cplx mag[PER_LANE];
+		if (patterns <= 2) {
+			// amp index = taken * 2 + parent's bit, taken = object's bit xor parent's bit
+			auto chain = [&](uint32_t t, cplx (&out)[PER_LANE]) {
+				cplx m{ws.acc_re[t], ws.acc_im[t]};
+				const uint32_t low = levels < 5 ? levels : 5;
+				for (uint32_t l = 0; l < low; ++l) {
+					const uint32_t tb = (t >> l) & 1, sb = (lane >> l) & 1;
+					m = cmul(m, ws.amp[((sb ^ tb) << 1) | tb]);
+				}
+#pragma unroll
+				for (int q = 0; q < PER_LANE; ++q) {
+					cplx mq = m;
+#pragma unroll
+					for (int l = 5; l < FLIP_LEVELS; ++l)
+						if ((uint32_t)l < levels) {
+							const uint32_t tb = (t >> l) & 1, sb = ((uint32_t)q >> (l - 5)) & 1;
+							mq = cmul(mq, ws.amp[((sb ^ tb) << 1) | tb]);
+						}
+					out[q] = mq;
+				}
+			};
+			chain(t0, mag);
+			if (patterns == 2) {
+				cplx other[PER_LANE];
+				chain(t1, other);
+#pragma unroll
+				for (int q = 0; q < PER_LANE; ++q)
+					mag[q] = cadd(mag[q], other[q]);
+			}
+		} else {
+			spread_run(ws);
+#pragma unroll
+			for (int q = 0; q < PER_LANE; ++q) {
+				const uint32_t slot = lane + 32 * q;
+				mag[q] = slot < leaves ? cplx{ws.acc_re[slot], ws.acc_im[slot]} : cplx{0, 0};
+			}
+		}
+		region_grant grant{~0ull, nullptr, 0, 0, false};
+		if (lane == 0) {
+			grant = region_acquire_finish(emit.table, ws.chunk, probe, leaves);
+			emit.regions += grant.created;
+		}
+		const unsigned long long base = __shfl_sync(0xffffffffu, grant.base, 0);
+		const int made = __shfl_sync(0xffffffffu, (int)grant.created, 0);
+		const unsigned long long retire_from = __shfl_sync(0xffffffffu, grant.retire_from, 0), retire_count = __shfl_sync(0xffffffffu, grant.retire_count, 0);
+		if (retire_count)
+			region_retire(emit.table, retire_from, retire_count);
+		if (base == ~0ull)
+			return;
+		table_slot *slots = emit.table.slots + base;
+		if (!made) {
+#pragma unroll
+			for (int q = 0; q < PER_LANE; ++q) {
+				const uint32_t slot = lane + 32 * q;
+				if (slot < leaves) {
+					atomicAdd(&slots[slot].re, mag[q].re); // results unused -> RED.ADD.F64 on consecutive sectors
+					atomicAdd(&slots[slot].im, mag[q].im);
+				}
+			}
+			return;
+		}
+		// first run of these objects anywhere: it writes the slots WHOLE -- hash, summed magnitude, representative: one full
+		// 32-byte sector per object -- then publishes the region
+		const uint32_t left = (uint32_t)ws.open_ctx.left, right = (uint32_t)ws.open_ctx.right;
+		const uint32_t tree_bits = ws.open_ctx.tree_bits, group = ws.open_group;
+		const uint32_t shift = ws.open_ctx.eligible - levels; // child_id = group | leaf << shift
+		uint32_t toggles = 0;
+		{ // the group index decides the first `shift` eligible nodes
+			uint32_t e = (uint32_t)ws.run_eligible;
+			for (uint32_t b = 0; b < shift; ++b) {
+				const uint32_t i = __ffs(e) - 1;
+				e &= e - 1;
+				toggles |= ((group >> b) & 1) << i;
+			}
+		}
+		{ // tree levels 0-4: the lane's bits of the object, xor the opening parent's own
+			const uint32_t leaf_low = (lane ^ tree_bits) & 31, low = levels < 5 ? levels : 5;
+			for (uint32_t l = 0; l < low; ++l)
+				toggles |= ((leaf_low >> l) & 1) << ws.open_ctx.pos[l];
+		}
+		const uint64_t names_hash = ws.open_ctx.names_hash, first_child = ws.open_first_child;
+		const uint32_t size = ws.open_size;
+		uint64_t hl[PER_LANE], hr[PER_LANE];
+#pragma unroll
+		for (int q = 0; q < PER_LANE; ++q) {
+			const uint32_t slot = lane + 32 * q;
+			if (slot < leaves) {
+				uint32_t t = toggles;
+#pragma unroll
+				for (int l = 5; l < FLIP_LEVELS; ++l)
+					if ((uint32_t)l < levels)
+						t |= ((((uint32_t)q >> (l - 5)) ^ (tree_bits >> l)) & 1) << ws.open_ctx.pos[l];
+				hl[q] = particle_fold(left ^ t);
+				hr[q] = particle_fold(right ^ t);
+			}
+		}
+#pragma unroll
+		for (int q = 0; q < PER_LANE; ++q) {
+			const uint32_t slot = lane + 32 * q;
+			if (slot < leaves) {
+				const uint32_t leaf = slot ^ tree_bits;
+				const unsigned long long key = hash_combine(hash_combine(names_hash, hl[q]), hr[q]);
+				const unsigned long long rep = rep_pack(first_child + (group | (leaf << shift)), size);
+				ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(slots + slot);
+				dst[0] = make_ulonglong2(key, (unsigned long long)__double_as_longlong(mag[q].re));
+				dst[1] = make_ulonglong2((unsigned long long)__double_as_longlong(mag[q].im), rep);
+			}
+		}
 		__syncwarp();
-		if (ws.run_valid && emit.table.dir) {
+		if (lane == 0) {
+			region_publish(grant);
+			emit.created += leaves;
+		}
+	}
+
+	// the objects of the current run go to the global table
+	template <class WS, class Emit>
+	__device__ __forceinline__ void flush_warp(WS &ws, Emit &emit) const {
+		__syncwarp();
+		if (ws.run_valid) {
+			if (emit.table.dir && ws.run_n <= FOLD_TABLE_BITS)
+				flush_region_direct(ws, emit);
+			else
+				flush_general(ws, emit);
+		}
+		__syncwarp();
+		if (lane_id() == 0)
+			ws.run_valid = 0;
+		__syncwarp();
+	}
+
+	// wide graphs in region mode (shared-memory trees), and the hashed table: four objects per lane at a time.  Out of line:
+	// rare next to flush_region_direct, whose registers it would otherwise compete for
+	template <class WS, class Emit>
+	__device__ __noinline__ void flush_general(WS &ws, Emit &emit) const {
+		if (emit.table.dir) {
 			// region mode: one directory probe for the whole run, then the run's objects land on consecutive slots
 			const uint32_t lane = lane_id(), leaves = ws.run_leaves;
 			spread_run(ws);
@@ -601,7 +795,7 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 					}
 				}
 			}
-		} else if (ws.run_valid) {
+		} else {
 			const uint32_t leaves = ws.run_leaves;
 			spread_run(ws);
 			for (uint32_t base = lane_id(); base < leaves; base += 128) {
@@ -618,10 +812,6 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 				    [&ws, base](int q) { return ws.hr[base + q * 32]; });
 			}
 		}
-		__syncwarp();
-		if (lane_id() == 0)
-			ws.run_valid = 0;
-		__syncwarp();
 	}
 
 	// the warp is done: what it did not use of its last range of table slots must read as empty (table.cuh, region_retire)
@@ -1101,7 +1291,9 @@ struct split_merge_fused : split_merge {
 	static constexpr bool needs_scratch = false;
 	typedef split_merge_ctx ctx_t;
 	static constexpr bool warp_prepare = true;
-	static constexpr int parents_per_batch = 8; // 1 KB of context per parent
+	static constexpr int parents_per_batch = 4; // 1 KB of context per parent
+	static constexpr uint32_t prepare_stage_bytes = 2048; // 4 graphs of up to 500 bytes
+	static void prepare_device(cudaStream_t stream) { particle_fold_prepare(stream); }
 
 	__device__ void prepare(const uint8_t *, uint32_t, split_merge_ctx &ctx) const { ctx.n = 0; }
 
@@ -1169,15 +1361,16 @@ struct split_merge_fused : split_merge {
 			return out.hash();
 		}
 		const uint32_t left = ctx.left, right = ctx.right, split = ctx.split, merge = ctx.merge;
-		uint64_t hn = 0, hl = 0, hr = 0;
+		uint64_t hn = 0;
+		uint64_t child_left = 0, child_right = 0; // particle masks of the child (at most 2 n <= 64 nodes)
 		uint32_t index = 0, atoms = 0, bits = child_id;
 		// one node of the child: selects, no branches (the lanes of a warp are different children of the same few parents
 		// and would take every path of a branchy walk one after the other: 2560 instructions per child, ncu
-		// profiles/split_merge_sym_r1i, against ~800 this way)
+		// profiles/split_merge_sym_r1i, against ~800 this way).  The particles only set a bit: their two hashes are folds over
+		// the node indices, looked up in the fold table at the end (two 64-bit multiplication chains per node less)
 		auto node = [&](bool l, bool r, uint32_t which, uint32_t i) {
-			const uint64_t with_l = hash_combine_index(hl, index), with_r = hash_combine_index(hr, index);
-			hl = l ? with_l : hl;
-			hr = r ? with_r : hr;
+			child_left |= (uint64_t)l << index;
+			child_right |= (uint64_t)r << index;
 			hn = hash_combine(hn, ctx.hash[which][i]);
 			atoms += ctx.len[which][i];
 			++index;
@@ -1224,6 +1417,16 @@ struct split_merge_fused : split_merge {
 		if (overflow)
 			node(true, false, 1, 0);
 		size = 4 + 4 * index + 16 * atoms;
+		uint64_t hl = 0, hr = 0;
+		if (index <= FOLD_TABLE_BITS) {
+			hl = particle_fold((uint32_t)child_left);
+			hr = particle_fold((uint32_t)child_right);
+		} else {
+			for (uint64_t m = child_left; m; m &= m - 1)
+				hl = hash_combine_index(hl, (uint32_t)__ffsll((long long)m) - 1);
+			for (uint64_t m = child_right; m; m &= m - 1)
+				hr = hash_combine_index(hr, (uint32_t)__ffsll((long long)m) - 1);
+		}
 		return hash_combine(hash_combine(hn, hl), hr);
 	}
 };
