@@ -459,6 +459,71 @@ __global__ void __launch_bounds__(SYMBOLIC_THREADS, BLOCKS_PER_SM) symbolic_item
 		atomicAdd(L.table.regions, (unsigned long long)regions);
 }
 
+// BATCH mode of the sorted order (rules with has_region_batch, region mode, short runs): a warp takes 32 items at a time, one
+// lane per item gathers its parent record and the root magnitude of its group, then the rule handles the whole batch
+// (rule.region_batch: all directory probes of the batch in flight together, one slot allocation, one publication).
+template <class Rule, int BLOCKS_PER_SM>
+__global__ void __launch_bounds__(SYMBOLIC_THREADS, BLOCKS_PER_SM) symbolic_items_batch_kernel(const Rule rule, const engine_launch L) {
+	if constexpr (Rule::has_region_batch) {
+		typedef typename Rule::ctx_t ctx_t;
+		struct warp_slice {
+			ctx_t ctx[32];
+			cplx root[32];
+			uint64_t child_begin[32];
+			uint32_t size[32];
+			uint32_t group[32];
+		};
+		__shared__ warp_slice s_slices[ENGINE_WARPS];
+		__shared__ typename Rule::items_workspace_t s_workspace[ENGINE_WARPS];
+		warp_slice &s = s_slices[threadIdx.x >> 5];
+		typename Rule::items_workspace_t &ws = s_workspace[threadIdx.x >> 5];
+		const unsigned lane = lane_id();
+		uint32_t created = 0, regions = 0;
+		rule.init_warp(ws);
+		__syncwarp();
+
+		const item_parent<Rule> *parents = static_cast<const item_parent<Rule> *>(L.parent_ctx);
+		const uint64_t num_chunks = div_up<uint64_t>(L.n_groups, ITEM_CHUNK);
+		const uint64_t warp_stride = (uint64_t)gridDim.x * ENGINE_WARPS;
+		for (uint64_t chunk = (uint64_t)blockIdx.x * ENGINE_WARPS + (threadIdx.x >> 5); chunk < num_chunks; chunk += warp_stride) {
+			if (table_overflowed(L.table))
+				break;
+			const uint64_t c0 = chunk * ITEM_CHUNK, c1 = min(c0 + (uint64_t)ITEM_CHUNK, L.n_groups);
+			uint64_t next_item = c0 + lane < c1 ? L.items[c0 + lane] : 0;
+			for (uint64_t b = c0; b < c1; b += 32) {
+				const uint32_t count = (uint32_t)min((uint64_t)32, c1 - b);
+				// the next batch's item is requested before this batch is processed, and its parent record is pulled into L2
+				const uint64_t item = next_item;
+				next_item = b + 32 + lane < c1 ? L.items[b + 32 + lane] : 0;
+				if (b + 32 + lane < c1) {
+					const char *ahead = reinterpret_cast<const char *>(parents + (next_item >> ITEM_GROUP_BITS));
+					prefetch_l2(ahead);
+					prefetch_l2(ahead + sizeof(item_parent<Rule>) - 1);
+				}
+				if (lane < count) {
+					const uint64_t p = item >> ITEM_GROUP_BITS;
+					const uint32_t group = (uint32_t)(item & ((1u << ITEM_GROUP_BITS) - 1));
+					const item_parent<Rule> &record = parents[p];
+					s.ctx[lane] = record.ctx;
+					s.child_begin[lane] = record.child_begin;
+					s.size[lane] = record.size;
+					s.group[lane] = group;
+					s.root[lane] = rule.root_magnitude(s.ctx[lane], group, record.mag);
+				}
+				__syncwarp();
+				rule.region_batch(s.ctx, s.root, s.child_begin, s.size, s.group, count, ws, L.table, created, regions);
+				__syncwarp();
+			}
+		}
+		created = (uint32_t)warp_sum((uint64_t)created);
+		regions = (uint32_t)warp_sum((uint64_t)regions);
+		if (lane == 0 && created)
+			atomicAdd(L.table.used, (unsigned long long)created);
+		if (lane == 0 && regions)
+			atomicAdd(L.table.regions, (unsigned long long)regions);
+	}
+}
+
 // parent holding the first group of every chunk (one binary search per chunk, all in parallel, instead of
 // a chain of dependent loads at the head of every chunk of the symbolic kernel)
 static __global__ void __launch_bounds__(ENGINE_THREADS) chunk_parent_kernel(const uint64_t *group_begin, uint64_t n_parents, uint64_t n_groups, uint32_t chunk,
@@ -828,6 +893,16 @@ struct rule_glue {
 			++*L.launch_counter;
 		}
 	}
+	static void symbolic_items_batch(const void *rule, const engine_launch &L) {
+		if constexpr (Rule::has_group_key && Rule::has_region_batch) {
+			const uint64_t warps = div_up<uint64_t>(L.n_groups, ITEM_CHUNK);
+			Rule::prepare_device(L.stream);
+			auto kernel = symbolic_items_batch_kernel<Rule, ITEMS_BLOCKS_PER_SM>;
+			int grid = grid_for(warps * 32, SYMBOLIC_THREADS, resident_grid((const void *)kernel, SYMBOLIC_THREADS, L.sm_count));
+			kernel<<<grid, SYMBOLIC_THREADS, 0, L.stream>>>(*static_cast<const Rule *>(rule), L);
+			++*L.launch_counter;
+		}
+	}
 	static void populate(const void *rule, const engine_launch &L) {
 		if constexpr (Rule::has_edit_child) {
 			int grid = grid_for(L.n_survivors, ENGINE_THREADS, resident_grid((const void *)populate_kernel<Rule>, ENGINE_THREADS, L.sm_count));
@@ -878,6 +953,8 @@ struct rule_glue {
 		o.group_capacity = Rule::group_capacity;
 		o.launch_group_items = group_items;
 		o.launch_symbolic_items = symbolic_items;
+		o.has_region_batch = Rule::has_group_key && Rule::has_region_batch;
+		o.launch_symbolic_items_batch = symbolic_items_batch;
 		o.has_family = Rule::has_family;
 		o.launch_family = family;
 		o.symbolic_grid = symbolic_grid;

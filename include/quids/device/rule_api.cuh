@@ -148,6 +148,11 @@ struct rule_base {
 	// optional, with has_run_identity: the rule can send a run to a REGION of the table (table.cuh: region_acquire) when
 	// every object of the state is smaller than this many bytes (0 = the rule does not use regions)
 	static constexpr uint32_t region_size_limit = 0;
+	// optional, with regions: BATCH mode for states whose runs are short (the host picks it from the run lengths it sees).  The
+	// rule handles 32 consecutive items of the sorted order at once, one lane per item for the bookkeeping:
+	//     cplx root_magnitude(ctx, group, parent_mag)                 one lane per item
+	//     region_batch(ctx[32], root[32], child_begin[32], size[32], group[32], count, workspace&, table, created&, regions&)   all lanes
+	static constexpr bool has_region_batch = false;
 
 	// optional, distributed path: a FAMILY is a set of objects closed under the rule -- every child of a member is a member --
 	// so that objects of different families never interfere.  family_key(parent, size) gives equal keys to the members of a
@@ -203,6 +208,8 @@ struct rule_ops {
 	size_t ctx_bytes;
 	void (*launch_group_items)(const void *rule, const engine_launch &L);
 	void (*launch_symbolic_items)(const void *rule, const engine_launch &L);
+	bool has_region_batch;
+	void (*launch_symbolic_items_batch)(const void *rule, const engine_launch &L); // region mode, short runs
 	bool has_family;
 	void (*launch_family)(const void *rule, const engine_launch &L); // L.hashes[i] = family_key of object i
 	int (*symbolic_grid)(int sm_count); // CTAs the symbolic kernel is launched with at most (sizes the scratch)

@@ -75,7 +75,8 @@ enum { // u64 words of the small device scratch
 	DS_REGIONS = 8,   // region mode: regions created
 	DS_CHILD_RANGE = 9, // two u32: largest child count, ~smallest
 	DS_SPILL = 10,      // binned interference: records in the spill list
-	DS_WORDS = 11
+	DS_KEPT = 11,       // filtered compaction: children above the tolerance (the list itself holds fewer)
+	DS_WORDS = 12
 };
 
 struct qb_ctx {
@@ -155,7 +156,7 @@ struct qb_iter {
 struct qb_sym {
 	qb_ctx *ctx;
 	uint64_t n_children = 0, n_unique = 0; // quids.hpp:344-346
-	dev_buf table, directory, ukey, uslot, sslot, kept, scratch, survivor_parent, survivor_child, padded, chunk_parent, sort_keys, sort_vals, sort_hist, sort_base, parent_ctx, bin_records, bin_cursor, bin_spill, bin_spill_key;
+	dev_buf table, directory, ukey, uslot, sslot, kept, scratch, survivor_parent, survivor_child, padded, chunk_parent, sort_keys, sort_vals, sort_hist, sort_base, parent_ctx, bin_records, bin_cursor, bin_spill, bin_spill_key, sample_keys;
 	cudaEvent_t ev[2 * QB_PHASE_COUNT] = {};
 	bool ev_used[QB_PHASE_COUNT] = {};
 	float phase_ms[QB_PHASE_COUNT] = {};
@@ -165,7 +166,7 @@ struct qb_sym {
 	int table_attempts = 0;
 
 	uint64_t device_bytes() const {
-		return table.cap + directory.cap + ukey.cap + uslot.cap + sslot.cap + kept.cap + scratch.cap + survivor_parent.cap + survivor_child.cap + padded.cap + chunk_parent.cap + sort_keys.cap + sort_vals.cap + sort_hist.cap + sort_base.cap + parent_ctx.cap + bin_records.cap + bin_cursor.cap + bin_spill.cap + bin_spill_key.cap;
+		return table.cap + directory.cap + ukey.cap + uslot.cap + sslot.cap + kept.cap + scratch.cap + survivor_parent.cap + survivor_child.cap + padded.cap + chunk_parent.cap + sort_keys.cap + sort_vals.cap + sort_hist.cap + sort_base.cap + parent_ctx.cap + bin_records.cap + bin_cursor.cap + bin_spill.cap + bin_spill_key.cap + sample_keys.cap;
 	}
 };
 
@@ -552,7 +553,8 @@ struct local_table {
 	uint32_t max_child_size = 0;
 	uint32_t uniform_fanout = 0; // != 0: every parent of the state has this many children
 	double workspace = 0; // automatic budget: bytes the symbolic workspace of the kept parents was counted for
-	uint64_t n_unique = 0; // entries kept by the compaction
+	uint64_t n_unique = 0; // unique children above the tolerance (N_u)
+	uint64_t n_listed = 0; // entries of the (norm key, slot) list: n_unique, or fewer when the compaction was filtered (pipeline.cuh)
 	table_view table{};
 	int empty_from = -1; // >= 0: nothing to do from label `empty_from` on (no parents / no children)
 };
@@ -705,6 +707,7 @@ local_table build_local_table(qb_iter *it, uint64_t rule_id, const rule_ops *ops
 	uint64_t full_capacity = std::max<uint64_t>(1024, (uint64_t)std::ceil((double)n_children / opt.table_load));
 	uint64_t capacity = full_capacity, directory = 0, full_directory = 0;
 	bool have_history = false, region_mode = false;
+	double expected_runs = 0; // region mode: runs of equal work items (= regions) the sorted order is expected to hold
 	{
 		auto hint = sym->unique_ratio.find(rule_id);
 		have_history = hint != sym->unique_ratio.end();
@@ -755,6 +758,7 @@ local_table build_local_table(qb_iter *it, uint64_t rule_id, const rule_ops *ops
 			if (have_history) {
 				capacity = std::min<uint64_t>(full_capacity, (uint64_t)(hint->second.first * (double)n_children * 1.3) + 4096);
 				directory = std::min<uint64_t>(full_directory, (uint64_t)(hint->second.second * (double)n_children * 2.6) + 1024);
+				expected_runs = hint->second.second * (double)n_children;
 			} else {
 				capacity = full_capacity;
 				directory = full_directory;
@@ -770,6 +774,7 @@ local_table build_local_table(qb_iter *it, uint64_t rule_id, const rule_ops *ops
 			++ctx->launches;
 			ctx->fetch_small();
 			const double flushes = 1.25 * (double)(ctx->h_small[DS_COUNT] + 1 + div_up<uint64_t>(n_groups, ITEM_CHUNK)) + 4096;
+			expected_runs = (double)(ctx->h_small[DS_COUNT] + 1);
 			if (region_mode) {
 				const uint64_t chunk_slack = std::min<uint64_t>(div_up<uint64_t>(n_groups, ITEM_CHUNK), (uint64_t)ctx->sm_count * 32) * REGION_CHUNK;
 				capacity = std::min<uint64_t>(full_capacity, std::max<uint64_t>(1024, (uint64_t)(flushes * ops->group_capacity * 1.15) + chunk_slack));
@@ -790,6 +795,7 @@ local_table build_local_table(qb_iter *it, uint64_t rule_id, const rule_ops *ops
 	const bool duplicate_heavy = !sorted_order && have_history && sym->unique_ratio[rule_id] < 0.2;
 	const bool binned_allowed = !sorted_order && !ops->warp_groups && opt.binned_inserts != 0 && n_children <= (1ull << 29) &&
 	                            (opt.binned_inserts > 1 || (n_children >= (1ull << 22) && !duplicate_heavy));
+	bool compaction_filtered = false;
 	for (sym->table_attempts = 1;; ++sym->table_attempts) {
 		QB_REQUIRE(capacity + 1 <= 0xffffffffull, QB_ERR_CAPACITY, "interference table would need more than 2^32 slots");
 		if (collision_labels && sym->table_attempts == 1)
@@ -837,7 +843,14 @@ local_table build_local_table(qb_iter *it, uint64_t rule_id, const rule_ops *ops
 			step("compute_collisions - insert");
 		timer.begin(QB_PHASE_SYMBOLIC);
 		L.table = R.table;
-		if (sorted_order)
+		// short runs (a grown state: about one group per region) go through the batch kernel, long runs (many parents of one
+		// family) through the accumulating one; QB_ITEMS_BATCH = 0 / 1 forces the choice (developer knob for A/B runs)
+		bool batch_mode = region_mode && ops->has_region_batch && (double)n_groups <= 3.0 * expected_runs;
+		if (const char *force = getenv("QB_ITEMS_BATCH"))
+			batch_mode = region_mode && ops->has_region_batch && atoi(force) != 0;
+		if (sorted_order && batch_mode)
+			ops->launch_symbolic_items_batch(rule, L);
+		else if (sorted_order)
 			ops->launch_symbolic_items(rule, L);
 		else
 			ops->launch_symbolic(rule, L);
@@ -869,9 +882,42 @@ local_table build_local_table(qb_iter *it, uint64_t rule_id, const rule_ops *ops
 		// hashed table: every slot + the dedicated slot of the hash 0; regions: exactly the slots handed out (nothing beyond was written or zeroed)
 		const uint64_t scan_n = region_mode ? scan_slots : scan_slots + 1;
 		const uint64_t tiles = div_up<uint64_t>(std::max<uint64_t>(scan_n, 1), COMPACT_TILE);
-		table_compact_kernel<<<(unsigned)std::min<uint64_t>(tiles, (uint64_t)ctx->sm_count * 16), SCAN_THREADS, 0, stream>>>(
-		    R.table, scan_n, compaction_tolerance, sym->ukey.as<uint64_t>(), sym->uslot.as<uint32_t>(), reinterpret_cast<unsigned long long *>(ctx->small(DS_COUNT)));
-		++ctx->launches;
+		const unsigned compact_grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)ctx->sm_count * 16);
+		unsigned long long *listed = reinterpret_cast<unsigned long long *>(ctx->small(DS_COUNT)), *kept = reinterpret_cast<unsigned long long *>(ctx->small(DS_KEPT));
+		// filtered compaction (pipeline.cuh): when the step keeps k survivors out of far more slots, a lower bound of the k-th
+		// largest key is taken from a random sample of the slots first, and only the entries above it are listed
+		constexpr uint32_t SAMPLES = 1u << 20;
+		const bool simple_topk = !comm && !automatic && opt.simple_truncation && max_num_object != QB_NO_TRUNCATION;
+		bool filtered = false;
+		if (simple_topk && scan_n >= (1ull << 24) && max_num_object < scan_n / 8 && !getenv("QB_NO_COMPACT_FILTER")) {
+			const double expected = (double)max_num_object * SAMPLES / (double)scan_n; // sample keys at or above the k-th largest key
+			const uint64_t rank = (uint64_t)(expected + 6.0 * std::sqrt(expected) + 16.0);
+			if (rank < SAMPLES / 2) {
+				sym->sample_keys.ensure(sizeof(uint64_t) * SAMPLES, stream);
+				sample_norm_keys_kernel<<<SAMPLES / 256, 256, 0, stream>>>(R.table, scan_n, compaction_tolerance, sym->sample_keys.as<uint64_t>(), SAMPLES,
+				                                                           0x51ed270b0a3f2c1dull * (sym->table_attempts + 1));
+				++ctx->launches;
+				select_threshold(ctx, nullptr, key_from_array{sym->sample_keys.as<uint64_t>()}, SAMPLES, rank); // -> ctx->select->prefix (device)
+				filtered = true;
+			}
+		}
+		if (filtered) {
+			QB_CUDA(cudaMemsetAsync(kept, 0, sizeof(uint64_t), stream));
+			table_compact_kernel<true><<<compact_grid, SCAN_THREADS, 0, stream>>>(R.table, scan_n, compaction_tolerance, sym->ukey.as<uint64_t>(),
+			                                                                     sym->uslot.as<uint32_t>(), listed, ctx->select.as<select_state>(), kept);
+			++ctx->launches;
+			ctx->fetch_small();
+			if (ctx->h_small[DS_COUNT] < std::min<uint64_t>(max_num_object, ctx->h_small[DS_KEPT])) { // the sample misled (6 sigma): the full list after all
+				filtered = false;
+				QB_CUDA(cudaMemsetAsync(listed, 0, sizeof(uint64_t), stream));
+			}
+		}
+		if (!filtered) {
+			table_compact_kernel<false><<<compact_grid, SCAN_THREADS, 0, stream>>>(R.table, scan_n, compaction_tolerance, sym->ukey.as<uint64_t>(),
+			                                                                      sym->uslot.as<uint32_t>(), listed, nullptr, nullptr);
+			++ctx->launches;
+		}
+		compaction_filtered = filtered;
 		QB_CUDA(cudaGetLastError());
 		timer.end(QB_PHASE_COMPACT);
 		}
@@ -890,7 +936,8 @@ local_table build_local_table(qb_iter *it, uint64_t rule_id, const rule_ops *ops
 		for (int p : {QB_PHASE_TABLE_CLEAR, QB_PHASE_SYMBOLIC, QB_PHASE_INSERT, QB_PHASE_COMPACT})
 			timer.restart(p); // report the attempt that counted
 	}
-	R.n_unique = ctx->h_small[DS_COUNT];
+	R.n_listed = ctx->h_small[DS_COUNT];
+	R.n_unique = compaction_filtered ? ctx->h_small[DS_KEPT] : R.n_listed;
 	sym->table_capacity = capacity;
 	if (region_mode)
 		sym->region_ratio[rule_id] = std::make_pair((double)ctx->h_small[DS_CURSOR] / (double)n_children, (double)ctx->h_small[DS_REGIONS] / (double)n_children);
@@ -1020,15 +1067,15 @@ void simulate(qb_iter *it, uint64_t rule_id, const rule_ops *ops, const void *ru
 	src.slot = sym->uslot.as<uint32_t>();
 	if (max_num_object < n_unique_global) {
 		timer.begin(QB_PHASE_TRUNCATE);
-		sym->sslot.ensure(sizeof(uint32_t) * std::max<uint64_t>(1, std::min<uint64_t>(R.n_unique, max_num_object)), stream);
+		sym->sslot.ensure(sizeof(uint32_t) * std::max<uint64_t>(1, std::min<uint64_t>(R.n_listed, max_num_object)), stream);
 		if (!opt.simple_truncation && R.n_unique > 0) {
 			randomize_keys_kernel<<<grid_for(R.n_unique, 256, ctx->grid_cap()), 256, 0, stream>>>(sym->ukey.as<uint64_t>(), R.table, sym->uslot.as<uint32_t>(),
 			                                                                                    R.n_unique, opt.seed);
 			++ctx->launches;
 		}
 		key_from_array keys{sym->ukey.as<uint64_t>()};
-		select_threshold(ctx, comm, keys, R.n_unique, max_num_object);
-		n_survivors = select_keep(ctx, comm, keys, R.n_unique, out_gather_u32{sym->sslot.as<uint32_t>(), sym->uslot.as<uint32_t>()});
+		select_threshold(ctx, comm, keys, R.n_listed, max_num_object);
+		n_survivors = select_keep(ctx, comm, keys, R.n_listed, out_gather_u32{sym->sslot.as<uint32_t>(), sym->uslot.as<uint32_t>()});
 		src.slot = sym->sslot.as<uint32_t>();
 		timer.end(QB_PHASE_TRUNCATE);
 	}
@@ -1364,8 +1411,9 @@ void simulate_dist(qb_iter *it, uint64_t rule_id, const rule_ops *ops, const voi
 			record_insert_kernel<<<grid_for(n_recv, 256, ctx->grid_cap()), 256, 0, stream>>>(owner, cm->recv.as<exchange_record>(), n_recv);
 			++ctx->launches;
 			const uint64_t tiles = div_up<uint64_t>(capacity + 1, COMPACT_TILE);
-			table_compact_kernel<<<(unsigned)std::min<uint64_t>(tiles, (uint64_t)ctx->sm_count * 16), SCAN_THREADS, 0, stream>>>(
-			    owner, capacity + 1, opt.tolerance, cm->okey.as<uint64_t>(), cm->oslot.as<uint32_t>(), reinterpret_cast<unsigned long long *>(ctx->small(DS_COUNT)));
+			table_compact_kernel<false><<<(unsigned)std::min<uint64_t>(tiles, (uint64_t)ctx->sm_count * 16), SCAN_THREADS, 0, stream>>>(
+			    owner, capacity + 1, opt.tolerance, cm->okey.as<uint64_t>(), cm->oslot.as<uint32_t>(), reinterpret_cast<unsigned long long *>(ctx->small(DS_COUNT)),
+			    nullptr, nullptr);
 			++ctx->launches;
 			QB_CUDA(cudaGetLastError());
 			ctx->fetch_small();

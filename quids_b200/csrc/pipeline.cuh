@@ -23,11 +23,20 @@ __device__ __forceinline__ uint64_t key_of_norm(double norm) { return (uint64_t)
 // Round 1 ranked the tiles with a decoupled look-back instead (stable order): the look-back chain advances about 8e7
 // tiles/s, and a table of 1.3e9 slots has 6.5e5 tiles of 2048 -- 8 ms of pure serialisation out of 16 ms for the kernel.
 // `n` = slots to scan (a hashed table: capacity + 1 with the dedicated slot of the hash 0; regions: the slots handed out).
+//
+// FILTER (single GPU, simple truncation to k survivors with k far below the number of slots): only the entries whose key is at
+// least `floor->prefix` are listed -- a lower bound of the k-th largest key, taken from a random sample of the slots
+// (sample_norm_keys_kernel) with 6 sigma of margin -- so that the list holds little more than k entries instead of every
+// unique child, and the selection after it reads megabytes instead of gigabytes.  `count_kept` still counts every child
+// above the tolerance (N_u); the host checks that at least min(k, N_u) entries were listed and redoes the pass unfiltered
+// otherwise (never seen: 1e-9 per call).
+template <bool FILTER>
 __global__ void __launch_bounds__(SCAN_THREADS) table_compact_kernel(table_view t, uint64_t n, double tolerance, uint64_t *ukey, uint32_t *uslot,
-                                                                     unsigned long long *count) {
+                                                                     unsigned long long *count, const select_state *floor, unsigned long long *count_kept) {
 	__shared__ unsigned long long s_base;
+	[[maybe_unused]] const uint64_t floor_key = FILTER ? floor->prefix : 0;
 	for (uint64_t base = (uint64_t)blockIdx.x * COMPACT_TILE; base < n; base += (uint64_t)gridDim.x * COMPACT_TILE) {
-		bool keep[COMPACT_ITEMS];
+		bool keep[COMPACT_ITEMS], above[COMPACT_ITEMS];
 		uint64_t key[COMPACT_ITEMS];
 		ulonglong2 lo[COMPACT_ITEMS], hi[COMPACT_ITEMS];
 #pragma unroll
@@ -47,11 +56,17 @@ __global__ void __launch_bounds__(SCAN_THREADS) table_compact_kernel(table_view 
 			const double norm = cnorm(cplx{__longlong_as_double((long long)lo[j].y), __longlong_as_double((long long)hi[j].x)});
 			keep[j] = occupied && norm > tolerance;
 			key[j] = key_of_norm(norm);
+			above[j] = keep[j];
+			if constexpr (FILTER)
+				keep[j] = keep[j] && key[j] >= floor_key;
 		}
-		uint32_t rank[COMPACT_ITEMS], unused_rank[COMPACT_ITEMS], total, unused_total;
-		block_rank_warp_striped<COMPACT_ITEMS, false>(keep, keep, rank, unused_rank, total, unused_total);
-		if (threadIdx.x == 0)
+		uint32_t rank[COMPACT_ITEMS], unused_rank[COMPACT_ITEMS], total, total_above;
+		block_rank_warp_striped<COMPACT_ITEMS, FILTER>(keep, above, rank, unused_rank, total, total_above);
+		if (threadIdx.x == 0) {
 			s_base = total ? atomicAdd(count, (unsigned long long)total) : 0;
+			if (FILTER && total_above)
+				atomicAdd(count_kept, (unsigned long long)total_above);
+		}
 		__syncthreads();
 		const uint64_t before = s_base;
 #pragma unroll
@@ -63,6 +78,19 @@ __global__ void __launch_bounds__(SCAN_THREADS) table_compact_kernel(table_view 
 			}
 		__syncthreads(); // s_base is reused by the next tile
 	}
+}
+
+// norm keys of `samples` slots drawn at random (with replacement) from the first n slots of the table; empty slots and
+// children below the tolerance give key 0
+__global__ void __launch_bounds__(256) sample_norm_keys_kernel(table_view t, uint64_t n, double tolerance, uint64_t *keys, uint32_t samples, uint64_t seed) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= samples)
+		return;
+	const uint64_t at = __umul64hi(mix64(seed + (uint64_t)i * 0x9e3779b97f4a7c15ull), n);
+	const ulonglong2 lo = __ldcs(reinterpret_cast<const ulonglong2 *>(t.slots + at));
+	const ulonglong2 hi = __ldcs(reinterpret_cast<const ulonglong2 *>(t.slots + at) + 1);
+	const double norm = cnorm(cplx{__longlong_as_double((long long)lo.y), __longlong_as_double((long long)hi.x)});
+	keys[i] = hi.y != 0 && norm > tolerance ? key_of_norm(norm) : 0;
 }
 
 // ---- keep the elements selected by a finished radix select --------------------------------------------

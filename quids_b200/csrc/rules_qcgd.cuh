@@ -69,6 +69,13 @@ inline void particle_fold_prepare(cudaStream_t stream) {
 }
 
 __device__ __forceinline__ uint64_t particle_fold(uint32_t mask) { return __ldg(&g_particle_fold[mask]); }
+// any mask of up to 64 nodes: the nodes the table covers are looked up, the others folded one by one
+__device__ __forceinline__ uint64_t particle_fold_wide(uint64_t mask) {
+	uint64_t h = particle_fold((uint32_t)mask & ((1u << FOLD_TABLE_BITS) - 1));
+	for (uint64_t m = mask >> FOLD_TABLE_BITS; m; m &= m - 1)
+		h = hash_combine_index(h, FOLD_TABLE_BITS + (uint32_t)__ffsll((long long)m) - 1);
+	return h;
+}
 
 struct atom {
 	int hmlz; // "has most-left zero" flag / element + 1   (qcgd.hpp:36,40-42)
@@ -524,7 +531,7 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 	// instead of one product chain per child.  Same value as summing the children one by one up to rounding
 	// (the interference table adds them in no particular order either).
 	template <class WS>
-	__device__ __noinline__ void spread_run(WS &ws) const {
+	__device__ __forceinline__ void spread_run(WS &ws) const {
 		const uint32_t lane = lane_id();
 		const uint32_t leaves = ws.run_leaves;
 		const cplx a00 = ws.amp[0], a01 = ws.amp[1], a10 = ws.amp[2], a11 = ws.amp[3]; // index = taken * 2 + parent's bit
@@ -585,174 +592,267 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 		return mix64(eligible ^ mix64(fixed + 0x9e3779b97f4a7c15ull * (target + 1ull)) ^ mix64(names ^ (0xc2b2ae3d27d4eb4full * n)));
 	}
 
-	// Region mode, graphs of at most FOLD_TABLE_BITS nodes (the fold table applies): the run goes to its region WITHOUT the
-	// shared-memory trees.  Every lane owns the objects lane, lane + 32, ... of the run and computes, in registers,
-	//   * their magnitudes: one product chain per parent pattern of the run (same factors in the same order as the reference's
-	//     child by child products), summed over the patterns -- up to two patterns; more go through the butterflies of spread_run;
-	//   * if this run creates the region, their hashes: particle masks = the opening group's masks with the group's and the
-	//     object's toggles, two lookups in the fold table, two folds.
-	// The first probe of the directory is issued before the arithmetic and read after it.
-	template <class WS, class Emit>
-	__device__ __forceinline__ void flush_region_direct(WS &ws, Emit &emit) const {
+	// ---- BATCH mode of the sorted order (engine.cuh, symbolic_items_batch_kernel): states whose runs are short (about one
+	// group per region: a grown state).  The accumulating path above walks the runs one after the other, and every run pays
+	// its own directory probe, its own publication and a dozen single-lane bookkeeping steps while 31 lanes wait.  Here a warp
+	// takes 32 items at once:
+	//   1. one lane per item: run identity; the HEAD of every stretch of equal identities probes the directory (all probes of
+	//      the batch in flight together) and learns whether its stretch creates the region or adds to it;
+	//   2. the regions created by the batch get consecutive slots with ONE addition to the table's cursor (exact: no chunks,
+	//      no unused tails to zero);
+	//   3. stretch by stretch, all lanes: lane l owns objects l, l + 32, ... of the region.  Magnitudes = one product chain per
+	//      item of the stretch (same factors in the same order as the reference's child by child products), summed; a stretch
+	//      of many items goes through the butterflies of spread_run instead.  Hashes of a created region = particle masks of the
+	//      head's parent with the group's and the object's toggles -> fold table -> the two final folds.  Created regions are
+	//      written whole (one full sector per object), the others receive RED.F64 additions;
+	//   4. the creators publish their regions together (one release per lane, after all the slots of the batch).
+	// Creators never wait for anybody, and a stretch that adds is handled after the batch's own creators are published: a
+	// region created and extended inside one batch (equal 32-bit sort keys interleaved) cannot deadlock.
+	// A run that crosses a batch boundary is simply two stretches: the second one adds to the region the first one created.
+	static constexpr bool has_region_batch = true;
+	template <class WS>
+	__device__ __noinline__ void spread_run_out_of_line(WS &ws) const { spread_run(ws); }
+	static constexpr uint32_t BATCH_MAX_CHAINS = 6; // stretches of more items use the butterflies
+
+	// magnitude of a group's root: the parent's magnitude times the factors of the eligible nodes the group index decides
+	__device__ __forceinline__ cplx root_magnitude(const flip_ctx &ctx, uint32_t group, cplx mag) const {
+		const uint32_t prefix = ctx.eligible - ctx.levels;
+		for (uint32_t b = 0; b < prefix; ++b)
+			mag = cmul(mag, this->amp.get((group >> b) & 1, (ctx.prefix_bits >> b) & 1));
+		return mag;
+	}
+
+	template <class WS>
+	__device__ __forceinline__ void region_batch(const flip_ctx *ctx, const cplx *root, const uint64_t *child_begin, const uint32_t *size, const uint32_t *group,
+	                                             uint32_t count, WS &ws, const table_view &table, uint32_t &created, uint32_t &regions) const {
 		constexpr int PER_LANE = FLIP_BLOCK / 32;
-		const uint32_t lane = lane_id(), leaves = ws.run_leaves;
-		const uint32_t levels = ws.open_ctx.levels;
-		region_probe probe{};
-		if (lane == 0)
-			probe = region_probe_begin(emit.table, region_key(ws.run_eligible, ws.run_fixed, ws.run_target, ws.run_names, ws.run_n));
-		// parent patterns of the run
-		uint32_t patterns = 0, t0 = 0, t1 = 0;
-#pragma unroll
-		for (int w = 0; w < FLIP_BLOCK / 32; ++w) {
-			uint32_t m = ws.run_patterns[w];
-			if (m) {
-				if (patterns == 0) {
-					t0 = w * 32 + (__ffs(m) - 1);
-					if (m & (m - 1))
-						t1 = w * 32 + (__ffs(m & (m - 1)) - 1);
-				} else if (patterns == 1) {
-					t1 = w * 32 + (__ffs(m) - 1);
+		const uint32_t lane = lane_id();
+		const bool valid = lane < count;
+		// 1. stretches and their regions
+		run_id_t id{};
+		uint32_t my_levels = 0;
+		if (valid) {
+			id = run_identity(ctx[lane], group[lane]);
+			my_levels = ctx[lane].levels;
+		}
+		const run_id_t before = id.shuffle_up();
+		const bool head = valid && (lane == 0 || !(id == before));
+		const unsigned heads = __ballot_sync(0xffffffffu, head);
+		region_entry *entry = nullptr;
+		bool made = false, failed = false;
+		if (head) {
+			uint64_t key = region_key(id.eligible, id.fixed, id.target, id.names, id.n);
+			if (key == 0)
+				key = 1;
+			uint64_t i = __umul64hi(mix64(key), table.dir_capacity);
+			unsigned long long seen = atomicCAS(&table.dir[i].key, 0ull, (unsigned long long)key);
+			for (uint32_t probes = 0;; ++probes) {
+				if (seen == 0) {
+					made = true;
+					break;
 				}
-				patterns += __popc(m);
+				if (seen == key)
+					break;
+				if (probes > TABLE_MAX_PROBES || ((probes & 63) == 63 && table_overflowed_lane(table))) {
+					*table.overflow = 1;
+					failed = true;
+					break;
+				}
+				if (++i == table.dir_capacity)
+					i = 0;
+				seen = __ldcg(&table.dir[i].key);
+				if (seen == 0)
+					seen = atomicCAS(&table.dir[i].key, 0ull, (unsigned long long)key);
+			}
+			entry = table.dir + i;
+		}
+		// 2. slots of the regions this batch creates
+		const uint32_t want = head && made ? 1u << my_levels : 0u;
+		uint32_t incl = want;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= (uint32_t)o)
+				incl += up;
+		}
+		const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+		unsigned long long base = 0;
+		if (total) {
+			if (lane == 0)
+				base = atomicAdd(table.cursor, (unsigned long long)total);
+			base = __shfl_sync(0xffffffffu, base, 0);
+			if (base + total > table.capacity) { // the table is too small: nothing of it may be touched, whoever waits for these regions gives up too
+				if (lane == 0)
+					*table.overflow = 1;
+				if (head && made)
+					atomicExch(&entry->base, ~0ull);
+				failed = true;
 			}
 		}
-		cplx mag[PER_LANE];
-		if (patterns <= 2) {
-			// amp index = taken * 2 + parent's bit, taken = object's bit xor parent's bit
-			auto chain = [&](uint32_t t, cplx (&out)[PER_LANE]) {
-				cplx m{ws.acc_re[t], ws.acc_im[t]};
+		base += incl - want; // (heads that create)
+
+		// 3. one stretch: magnitudes of the lane's objects, then the region's slots
+		auto stretch = [&](uint32_t h, unsigned long long first_slot, bool creates) {
+			const unsigned later = heads & ~((2u << h) - 1u);
+			const uint32_t e = later ? (uint32_t)__ffs(later) - 1 : count;
+			const flip_ctx &c = ctx[h];
+			const uint32_t levels = c.levels, leaves = 1u << levels;
+			cplx mag[PER_LANE];
+#pragma unroll
+			for (int q = 0; q < PER_LANE; ++q)
+				mag[q] = cplx{0, 0};
+			if (e - h <= BATCH_MAX_CHAINS) {
 				const uint32_t low = levels < 5 ? levels : 5;
-				for (uint32_t l = 0; l < low; ++l) {
-					const uint32_t tb = (t >> l) & 1, sb = (lane >> l) & 1;
-					m = cmul(m, ws.amp[((sb ^ tb) << 1) | tb]);
+				for (uint32_t j = h; j < e; ++j) {
+					// amp index = taken * 2 + parent's bit, taken = object's bit xor parent's bit
+					const uint32_t t = ctx[j].tree_bits;
+					cplx m = root[j];
+					for (uint32_t l = 0; l < low; ++l) {
+						const uint32_t tb = (t >> l) & 1, sb = (lane >> l) & 1;
+						m = cmul(m, ws.amp[((sb ^ tb) << 1) | tb]);
+					}
+#pragma unroll
+					for (int q = 0; q < PER_LANE; ++q) {
+						cplx mq = m;
+#pragma unroll
+						for (int l = 5; l < FLIP_LEVELS; ++l)
+							if ((uint32_t)l < levels) {
+								const uint32_t tb = (t >> l) & 1, sb = ((uint32_t)q >> (l - 5)) & 1;
+								mq = cmul(mq, ws.amp[((sb ^ tb) << 1) | tb]);
+							}
+						mag[q] = j == h ? mq : cadd(mag[q], mq);
+					}
 				}
+			} else {
+				// many items: their roots are summed per parent pattern, then one Kronecker transform for all of them
+				__syncwarp();
+				for (uint32_t leaf = lane; leaf < leaves; leaf += 32)
+					ws.acc_re[leaf] = ws.acc_im[leaf] = 0.0;
+				if (lane < FLIP_BLOCK / 32)
+					ws.run_patterns[lane] = 0;
+				if (lane == 0)
+					ws.run_leaves = leaves;
+				__syncwarp();
+				if (lane >= h && lane < e) {
+					const uint32_t t = ctx[lane].tree_bits;
+					atomicOr(&ws.run_patterns[t >> 5], 1u << (t & 31));
+					atomicAdd(&ws.acc_re[t], root[lane].re);
+					atomicAdd(&ws.acc_im[t], root[lane].im);
+				}
+				__syncwarp();
+				spread_run_out_of_line(ws);
 #pragma unroll
 				for (int q = 0; q < PER_LANE; ++q) {
-					cplx mq = m;
-#pragma unroll
-					for (int l = 5; l < FLIP_LEVELS; ++l)
-						if ((uint32_t)l < levels) {
-							const uint32_t tb = (t >> l) & 1, sb = ((uint32_t)q >> (l - 5)) & 1;
-							mq = cmul(mq, ws.amp[((sb ^ tb) << 1) | tb]);
-						}
-					out[q] = mq;
+					const uint32_t slot = lane + 32 * q;
+					if (slot < leaves)
+						mag[q] = cplx{ws.acc_re[slot], ws.acc_im[slot]};
 				}
-			};
-			chain(t0, mag);
-			if (patterns == 2) {
-				cplx other[PER_LANE];
-				chain(t1, other);
-#pragma unroll
-				for (int q = 0; q < PER_LANE; ++q)
-					mag[q] = cadd(mag[q], other[q]);
+				__syncwarp();
 			}
-		} else {
-			spread_run(ws);
+			table_slot *slots = table.slots + first_slot;
+			if (!creates) {
 #pragma unroll
-			for (int q = 0; q < PER_LANE; ++q) {
-				const uint32_t slot = lane + 32 * q;
-				mag[q] = slot < leaves ? cplx{ws.acc_re[slot], ws.acc_im[slot]} : cplx{0, 0};
+				for (int q = 0; q < PER_LANE; ++q) {
+					const uint32_t slot = lane + 32 * q;
+					if (slot < leaves) {
+						atomicAdd(&slots[slot].re, mag[q].re); // results unused -> RED.ADD.F64 on consecutive sectors
+						atomicAdd(&slots[slot].im, mag[q].im);
+					}
+				}
+				return;
 			}
-		}
-		region_grant grant{~0ull, nullptr, 0, 0, false};
-		if (lane == 0) {
-			grant = region_acquire_finish(emit.table, ws.chunk, probe, leaves);
-			emit.regions += grant.created;
-		}
-		const unsigned long long base = __shfl_sync(0xffffffffu, grant.base, 0);
-		const int made = __shfl_sync(0xffffffffu, (int)grant.created, 0);
-		const unsigned long long retire_from = __shfl_sync(0xffffffffu, grant.retire_from, 0), retire_count = __shfl_sync(0xffffffffu, grant.retire_count, 0);
-		if (retire_count)
-			region_retire(emit.table, retire_from, retire_count);
-		if (base == ~0ull)
-			return;
-		table_slot *slots = emit.table.slots + base;
-		if (!made) {
+			// the region is new: hash, summed magnitude and representative of every object, one full 32-byte sector each
+			const uint64_t left = c.left, right = c.right;
+			const uint32_t tree_bits = c.tree_bits, g = group[h];
+			const uint32_t shift = c.eligible - levels; // child_id = group | leaf << shift
+			uint64_t toggles = 0;
+			{ // the group index decides the first `shift` eligible nodes
+				const uint64_t all = c.n >= 64 ? ~0ull : ((1ull << c.n) - 1);
+				uint64_t el = (WANT_EQUAL ? ~(left ^ right) : (left ^ right)) & all;
+				for (uint32_t b = 0; b < shift; ++b) {
+					const uint32_t i = (uint32_t)__ffsll((long long)el) - 1;
+					el &= el - 1;
+					toggles |= (uint64_t)((g >> b) & 1) << i;
+				}
+			}
+			{ // tree levels 0-4: the lane's bits of the object, xor the head parent's own
+				const uint32_t leaf_low = (lane ^ tree_bits) & 31, low = levels < 5 ? levels : 5;
+				for (uint32_t l = 0; l < low; ++l)
+					toggles |= (uint64_t)((leaf_low >> l) & 1) << c.pos[l];
+			}
+			const bool narrow = c.n <= FOLD_TABLE_BITS;
+			uint64_t hl[PER_LANE], hr[PER_LANE];
 #pragma unroll
 			for (int q = 0; q < PER_LANE; ++q) {
 				const uint32_t slot = lane + 32 * q;
 				if (slot < leaves) {
-					atomicAdd(&slots[slot].re, mag[q].re); // results unused -> RED.ADD.F64 on consecutive sectors
-					atomicAdd(&slots[slot].im, mag[q].im);
+					uint64_t t = toggles;
+#pragma unroll
+					for (int l = 5; l < FLIP_LEVELS; ++l)
+						if ((uint32_t)l < levels)
+							t |= (uint64_t)((((uint32_t)q >> (l - 5)) ^ (tree_bits >> l)) & 1) << c.pos[l];
+					if (narrow) {
+						hl[q] = particle_fold((uint32_t)(left ^ t));
+						hr[q] = particle_fold((uint32_t)(right ^ t));
+					} else {
+						hl[q] = particle_fold_wide(left ^ t);
+						hr[q] = particle_fold_wide(right ^ t);
+					}
 				}
 			}
-			return;
-		}
-		// first run of these objects anywhere: it writes the slots WHOLE -- hash, summed magnitude, representative: one full
-		// 32-byte sector per object -- then publishes the region
-		const uint32_t left = (uint32_t)ws.open_ctx.left, right = (uint32_t)ws.open_ctx.right;
-		const uint32_t tree_bits = ws.open_ctx.tree_bits, group = ws.open_group;
-		const uint32_t shift = ws.open_ctx.eligible - levels; // child_id = group | leaf << shift
-		uint32_t toggles = 0;
-		{ // the group index decides the first `shift` eligible nodes
-			uint32_t e = (uint32_t)ws.run_eligible;
-			for (uint32_t b = 0; b < shift; ++b) {
-				const uint32_t i = __ffs(e) - 1;
-				e &= e - 1;
-				toggles |= ((group >> b) & 1) << i;
-			}
-		}
-		{ // tree levels 0-4: the lane's bits of the object, xor the opening parent's own
-			const uint32_t leaf_low = (lane ^ tree_bits) & 31, low = levels < 5 ? levels : 5;
-			for (uint32_t l = 0; l < low; ++l)
-				toggles |= ((leaf_low >> l) & 1) << ws.open_ctx.pos[l];
-		}
-		const uint64_t names_hash = ws.open_ctx.names_hash, first_child = ws.open_first_child;
-		const uint32_t size = ws.open_size;
-		uint64_t hl[PER_LANE], hr[PER_LANE];
+			const uint64_t names_hash = c.names_hash, first_child = child_begin[h];
+			const uint32_t bytes = size[h];
 #pragma unroll
-		for (int q = 0; q < PER_LANE; ++q) {
-			const uint32_t slot = lane + 32 * q;
-			if (slot < leaves) {
-				uint32_t t = toggles;
-#pragma unroll
-				for (int l = 5; l < FLIP_LEVELS; ++l)
-					if ((uint32_t)l < levels)
-						t |= ((((uint32_t)q >> (l - 5)) ^ (tree_bits >> l)) & 1) << ws.open_ctx.pos[l];
-				hl[q] = particle_fold(left ^ t);
-				hr[q] = particle_fold(right ^ t);
+			for (int q = 0; q < PER_LANE; ++q) {
+				const uint32_t slot = lane + 32 * q;
+				if (slot < leaves) {
+					const uint32_t leaf = slot ^ tree_bits;
+					const unsigned long long key = hash_combine(hash_combine(names_hash, hl[q]), hr[q]);
+					const unsigned long long rep = rep_pack(first_child + (g | (leaf << shift)), bytes);
+					ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(slots + slot);
+					dst[0] = make_ulonglong2(key, (unsigned long long)__double_as_longlong(mag[q].re));
+					dst[1] = make_ulonglong2((unsigned long long)__double_as_longlong(mag[q].im), rep);
+				}
 			}
+		};
+
+		const bool creates = head && made && !failed;
+		for (unsigned todo = __ballot_sync(0xffffffffu, creates); todo; todo &= todo - 1) {
+			const uint32_t h = (uint32_t)__ffs(todo) - 1;
+			stretch(h, __shfl_sync(0xffffffffu, base, h), true);
 		}
-#pragma unroll
-		for (int q = 0; q < PER_LANE; ++q) {
-			const uint32_t slot = lane + 32 * q;
-			if (slot < leaves) {
-				const uint32_t leaf = slot ^ tree_bits;
-				const unsigned long long key = hash_combine(hash_combine(names_hash, hl[q]), hr[q]);
-				const unsigned long long rep = rep_pack(first_child + (group | (leaf << shift)), size);
-				ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(slots + slot);
-				dst[0] = make_ulonglong2(key, (unsigned long long)__double_as_longlong(mag[q].re));
-				dst[1] = make_ulonglong2((unsigned long long)__double_as_longlong(mag[q].im), rep);
-			}
-		}
+		// 4. the batch's regions become visible to the other runs of the same objects
 		__syncwarp();
-		if (lane == 0) {
-			region_publish(grant);
-			emit.created += leaves;
+		if (creates) {
+			// st.release.gpu: the warp's slot writes (ordered before this lane by __syncwarp) become visible before the base does
+			asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(&entry->base), "l"(base + 1) : "memory");
+			created += want;
+			regions += 1;
+		}
+		for (unsigned todo = __ballot_sync(0xffffffffu, head && !made && !failed); todo; todo &= todo - 1) {
+			const uint32_t h = (uint32_t)__ffs(todo) - 1;
+			unsigned long long at = ~0ull;
+			if (lane == h) {
+				// published (release) once the creator has written the slots; the acquire load orders this stretch's additions after them
+				while ((at = load_acquire(&entry->base)) == 0)
+					if (table_overflowed_lane(table)) {
+						at = ~0ull;
+						break;
+					}
+				if (at != ~0ull)
+					at -= 1;
+			}
+			at = __shfl_sync(0xffffffffu, at, h);
+			if (at != ~0ull)
+				stretch(h, at, false);
 		}
 	}
 
-	// the objects of the current run go to the global table
+	// the objects of the current run go to the global table, four per lane at a time
 	template <class WS, class Emit>
-	__device__ __forceinline__ void flush_warp(WS &ws, Emit &emit) const {
+	__device__ void flush_warp(WS &ws, Emit &emit) const {
 		__syncwarp();
-		if (ws.run_valid) {
-			if (emit.table.dir && ws.run_n <= FOLD_TABLE_BITS)
-				flush_region_direct(ws, emit);
-			else
-				flush_general(ws, emit);
-		}
-		__syncwarp();
-		if (lane_id() == 0)
-			ws.run_valid = 0;
-		__syncwarp();
-	}
-
-	// wide graphs in region mode (shared-memory trees), and the hashed table: four objects per lane at a time.  Out of line:
-	// rare next to flush_region_direct, whose registers it would otherwise compete for
-	template <class WS, class Emit>
-	__device__ __noinline__ void flush_general(WS &ws, Emit &emit) const {
-		if (emit.table.dir) {
+		if (ws.run_valid && emit.table.dir) {
 			// region mode: one directory probe for the whole run, then the run's objects land on consecutive slots
 			const uint32_t lane = lane_id(), leaves = ws.run_leaves;
 			spread_run(ws);
@@ -795,7 +895,7 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 					}
 				}
 			}
-		} else {
+		} else if (ws.run_valid) {
 			const uint32_t leaves = ws.run_leaves;
 			spread_run(ws);
 			for (uint32_t base = lane_id(); base < leaves; base += 128) {
@@ -812,6 +912,10 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 				    [&ws, base](int q) { return ws.hr[base + q * 32]; });
 			}
 		}
+		__syncwarp();
+		if (lane_id() == 0)
+			ws.run_valid = 0;
+		__syncwarp();
 	}
 
 	// the warp is done: what it did not use of its last range of table slots must read as empty (table.cuh, region_retire)
@@ -1282,6 +1386,10 @@ struct split_merge_ctx {
 	uint32_t n; // 0: not prepared (more than 32 nodes): the children walk the object itself
 	uint32_t left, right, split, merge;
 	uint32_t most_left_zero; // qcgd.hpp:709-749: where the left half of a first split goes
+	// the sites in the order they consume the bits of child_id (a wrap-around merge first, then node order): their number, and
+	// for bit b whether its site is a merge.  The magnitude of child c is the parent's times amp(bit b of c, site b is a merge)
+	// for b = 0, 1, ... in this order (qcgd.hpp:647-700) -- it does not depend on the walk
+	uint32_t num_sites, site_is_merge;
 	// [0] the node's own name; [1] split site: left half, merge site (and node n-1): the merged name; [2] split site: right half
 	uint64_t hash[3][SPLIT_MERGE_MAX_NODES]; // first hash of the name
 	uint16_t len[3][SPLIT_MERGE_MAX_NODES];  // its number of atoms
@@ -1291,8 +1399,8 @@ struct split_merge_fused : split_merge {
 	static constexpr bool needs_scratch = false;
 	typedef split_merge_ctx ctx_t;
 	static constexpr bool warp_prepare = true;
-	static constexpr int parents_per_batch = 4; // 1 KB of context per parent
-	static constexpr uint32_t prepare_stage_bytes = 2048; // 4 graphs of up to 500 bytes
+	static constexpr int parents_per_batch = 6; // 1 KB of context per parent
+	static constexpr uint32_t prepare_stage_bytes = 3072; // 6 graphs of up to 500 bytes
 	static void prepare_device(cudaStream_t stream) { particle_fold_prepare(stream); }
 
 	__device__ void prepare(const uint8_t *, uint32_t, split_merge_ctx &ctx) const { ctx.n = 0; }
@@ -1318,6 +1426,13 @@ struct split_merge_fused : split_merge {
 			ctx.split = split;
 			ctx.merge = merge;
 			ctx.most_left_zero = !(g.get(0).kind >= 0 && g.get(1).hmlz > 0);
+			uint32_t count = wrap_merge ? 1 : 0, types = wrap_merge ? 1 : 0;
+			for (uint32_t sites = split | merge; sites; sites &= sites - 1) {
+				types |= ((merge >> (__ffs(sites) - 1)) & 1) << count;
+				++count;
+			}
+			ctx.num_sites = count;
+			ctx.site_is_merge = types;
 		}
 		if (!here)
 			return;
@@ -1379,8 +1494,10 @@ struct split_merge_fused : split_merge {
 		const bool first_split = (split & 1) && (bits & 1);
 		bool last_merge = !(split & 1) && n > 1 && (right & 1) && ((left >> (n - 1)) & 1) && !((right >> (n - 1)) & 1);
 		bool overflow = false;
+		// magnitude: one factor per site, in bit order
+		for (uint32_t b = 0; b < ctx.num_sites; ++b)
+			mag = cmul(mag, amp.get((child_id >> b) & 1, (ctx.site_is_merge >> b) & 1));
 		if (first_split) {
-			mag = cmul(mag, amp.get(true, false));
 			bits >>= 1;
 			if (ctx.most_left_zero)
 				node(true, false, 1, 0);
@@ -1390,7 +1507,6 @@ struct split_merge_fused : split_merge {
 		}
 		if (last_merge) {
 			last_merge = bits & 1;
-			mag = cmul(mag, amp.get(last_merge, true));
 			bits >>= 1;
 			if (last_merge)
 				node(true, true, 1, n - 1);
@@ -1403,10 +1519,7 @@ struct split_merge_fused : split_merge {
 			const bool is_split = (split >> i) & 1, is_merge = (merge >> i) & 1;
 			const bool site = (is_split || is_merge) && !pending;
 			const bool taken = site && (bits & 1);
-			if (site) {
-				mag = cmul(mag, amp.get(taken, is_merge));
-				bits >>= 1;
-			}
+			bits >>= site ? 1 : 0;
 			const bool l = pending ? false : (taken ? true : (bool)((left >> i) & 1));
 			const bool r = pending ? true : (taken ? is_merge : (bool)((right >> i) & 1));
 			node(l, r, pending ? 2u : (taken ? 1u : 0u), i);

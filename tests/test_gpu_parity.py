@@ -143,6 +143,60 @@ def test_qcgd_parent_ordering_and_groups_vs_oracle(gpu, port, rule_id):
         qb.config.locality_sort = 1
 
 
+_region_cases = {}  # (states, the oracle's results per rule): computed once, used by both kernels
+
+
+@pytest.mark.parametrize("batch", ["0", "1"])
+@pytest.mark.parametrize("rule_id", [orc.RULE_ERASE_CREATE, orc.RULE_COIN])
+def test_region_kernels_vs_oracle(gpu, port, rule_id, batch, monkeypatch):
+    """sorted order with table regions, both kernels forced in turn (QB_ITEMS_BATCH): the accumulating one (long runs) and the
+    batch one (32 items at a time, short runs) -- on states with one group per region, with many parents per family (several
+    parent patterns per run: product chains and, beyond 6 items, the butterflies), with identical parents (stretches of 32),
+    with graphs wider than the fold table (17-30 nodes), with and without truncation"""
+    import quids_b200 as qb
+    monkeypatch.setenv("QB_ITEMS_BATCH", batch)
+    params = [0.37, 0.21, -0.4]
+    rng = np.random.default_rng(5)
+
+    def with_random_magnitudes(state):
+        mags = rng.normal(size=(state.n, 2))
+        return orc.Packed(state.sizes, mags / np.sqrt((mags ** 2).sum()), state.data)
+
+    if "states" not in _region_cases:
+        one = port.qcgd_random_state(9, 1, 5)
+        grown, _, _ = port.simulate(port.qcgd_random_state(9, 800, 8), orc.RULE_SPLIT_MERGE, [0.4, 0.3, 0.2], orc.NO_TRUNCATION, 1e-18)
+        _region_cases["states"] = {
+            "12 nodes, distinct families": with_random_magnitudes(port.qcgd_random_state(12, 300, 21)),
+            "6 nodes, every family many times": with_random_magnitudes(port.qcgd_random_state(6, 3000, 3)),
+            "identical parents": orc.Packed.from_objects(one.objects() * 500, [1 / math.sqrt(500)] * 500),
+            "grown state (ragged sizes and node counts)": with_random_magnitudes(grown),
+            "wider than the fold table": port.qcgd_random_state(21, 12, 4),  # (its own uniform magnitudes keep total_proba's summation error small)
+        }
+    states = _region_cases["states"]
+    qb.config.locality_sort = 2
+    try:
+        for what, state in states.items():
+            if (rule_id, what) not in _region_cases:
+                _region_cases[(rule_id, what)] = port.simulate(state, rule_id, params, tolerance=1e-18)
+            want, nc, nu = _region_cases[(rule_id, what)]
+            got, gc, gu = gpu().simulate(state, rule_id, params, tol=1e-18)
+            assert (gc, gu) == (nc, nu), what
+            # random complex magnitudes of several parents add up with partial cancellation: the rounding error is 1e-16 of the
+            # largest term, i.e. up to a few 1e-12 of the sum (the summation order differs from the reference's)
+            orc.assert_same_state(got, port.hash_objects(got, rule_id), want, port.hash_objects(want, rule_id), True, rtol=1e-11,
+                                  what=f"{what}, batch={batch}")
+        state = states["12 nodes, distinct families"]
+        k = 5000
+        full, _, _ = port.simulate(state, rule_id, params, tolerance=1e-18)
+        assert full.n > k
+        want, wc, wu = port.simulate(state, rule_id, params, k, 1e-18)
+        got, gc, gu = gpu().simulate(state, rule_id, params, k, 1e-18)
+        assert (gc, gu) == (wc, wu)
+        orc.assert_same_truncated(got, port.hash_objects(got, rule_id), want, port.hash_objects(want, rule_id), full, port.hash_objects(full, rule_id), k, True)
+    finally:
+        qb.config.locality_sort = 1
+
+
 def test_qcgd_wide_graphs_vs_oracle(gpu, port):
     # more than 64 nodes: the bit-mask fast path of erase_create / coin does not apply
     base = port.qcgd_random_state(70, 2, 1, 1.0)
