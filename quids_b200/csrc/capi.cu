@@ -76,7 +76,8 @@ enum { // u64 words of the small device scratch
 	DS_CHILD_RANGE = 9, // two u32: largest child count, ~smallest
 	DS_SPILL = 10,      // binned interference: records in the spill list
 	DS_KEPT = 11,       // filtered compaction: children above the tolerance (the list itself holds fewer)
-	DS_WORDS = 12
+	DS_FLOOR = 12,      // filtered compaction: the key below which nothing was listed
+	DS_WORDS = 13
 };
 
 struct qb_ctx {
@@ -555,6 +556,10 @@ struct local_table {
 	double workspace = 0; // automatic budget: bytes the symbolic workspace of the kept parents was counted for
 	uint64_t n_unique = 0; // unique children above the tolerance (N_u)
 	uint64_t n_listed = 0; // entries of the (norm key, slot) list: n_unique, or fewer when the compaction was filtered (pipeline.cuh)
+	bool filtered = false; // the list only holds the entries whose key is at least `floor_key`
+	uint64_t floor_key = 0;
+	uint64_t scan_n = 0;   // slots the compaction scans (0: the list was not made by table_compact_kernel)
+	double compaction_tolerance = 0;
 	table_view table{};
 	int empty_from = -1; // >= 0: nothing to do from label `empty_from` on (no parents / no children)
 };
@@ -886,28 +891,40 @@ local_table build_local_table(qb_iter *it, uint64_t rule_id, const rule_ops *ops
 		unsigned long long *listed = reinterpret_cast<unsigned long long *>(ctx->small(DS_COUNT)), *kept = reinterpret_cast<unsigned long long *>(ctx->small(DS_KEPT));
 		// filtered compaction (pipeline.cuh): when the step keeps k survivors out of far more slots, a lower bound of the k-th
 		// largest key is taken from a random sample of the slots first, and only the entries above it are listed
+		// Distributed path with the parents routed by family: the top-k is global, but a rank only has to list what can be among
+		// the global survivors.  Families are spread by hash, so a rank holds about k / world of them: its floor is taken at
+		// 1.5 k / world of ITS keys, and simulate() checks it against the global threshold once that is known (and redoes the
+		// list of a rank whose floor turned out too high).
 		constexpr uint32_t SAMPLES = 1u << 20;
-		const bool simple_topk = !comm && !automatic && opt.simple_truncation && max_num_object != QB_NO_TRUNCATION;
+		const bool routed = comm && comm->local_interference;
+		const bool simple_topk = (!comm || routed) && !automatic && opt.simple_truncation && max_num_object != QB_NO_TRUNCATION;
+		const uint64_t filter_min = getenv("QB_COMPACT_FILTER_MIN") ? strtoull(getenv("QB_COMPACT_FILTER_MIN"), nullptr, 10) : (1ull << 24); // (test knob)
+		uint64_t local_k = max_num_object;
+		if (routed && simple_topk) {
+			const double factor = getenv("QB_DIST_FLOOR_FACTOR") ? atof(getenv("QB_DIST_FLOOR_FACTOR")) : 1.5; // (test knob: a small factor forces the redo)
+			local_k = (uint64_t)(factor * (double)max_num_object / comm->world()) + 1024;
+		}
 		bool filtered = false;
-		if (simple_topk && scan_n >= (1ull << 24) && max_num_object < scan_n / 8 && !getenv("QB_NO_COMPACT_FILTER")) {
-			const double expected = (double)max_num_object * SAMPLES / (double)scan_n; // sample keys at or above the k-th largest key
+		if (simple_topk && scan_n >= filter_min && local_k < scan_n / 8 && !getenv("QB_NO_COMPACT_FILTER")) {
+			const double expected = (double)local_k * SAMPLES / (double)scan_n; // sample keys at or above the k-th largest key
 			const uint64_t rank = (uint64_t)(expected + 6.0 * std::sqrt(expected) + 16.0);
 			if (rank < SAMPLES / 2) {
 				sym->sample_keys.ensure(sizeof(uint64_t) * SAMPLES, stream);
 				sample_norm_keys_kernel<<<SAMPLES / 256, 256, 0, stream>>>(R.table, scan_n, compaction_tolerance, sym->sample_keys.as<uint64_t>(), SAMPLES,
 				                                                           0x51ed270b0a3f2c1dull * (sym->table_attempts + 1));
 				++ctx->launches;
-				select_threshold(ctx, nullptr, key_from_array{sym->sample_keys.as<uint64_t>()}, SAMPLES, rank); // -> ctx->select->prefix (device)
+				select_threshold(ctx, nullptr, key_from_array{sym->sample_keys.as<uint64_t>()}, SAMPLES, rank);
+				QB_CUDA(cudaMemcpyAsync(ctx->small(DS_FLOOR), &ctx->select.as<select_state>()->prefix, sizeof(uint64_t), cudaMemcpyDeviceToDevice, stream));
 				filtered = true;
 			}
 		}
 		if (filtered) {
 			QB_CUDA(cudaMemsetAsync(kept, 0, sizeof(uint64_t), stream));
 			table_compact_kernel<true><<<compact_grid, SCAN_THREADS, 0, stream>>>(R.table, scan_n, compaction_tolerance, sym->ukey.as<uint64_t>(),
-			                                                                     sym->uslot.as<uint32_t>(), listed, ctx->select.as<select_state>(), kept);
+			                                                                     sym->uslot.as<uint32_t>(), listed, ctx->small(DS_FLOOR), kept);
 			++ctx->launches;
 			ctx->fetch_small();
-			if (ctx->h_small[DS_COUNT] < std::min<uint64_t>(max_num_object, ctx->h_small[DS_KEPT])) { // the sample misled (6 sigma): the full list after all
+			if (ctx->h_small[DS_COUNT] < std::min<uint64_t>(local_k, ctx->h_small[DS_KEPT])) { // the sample misled (6 sigma): the full list after all
 				filtered = false;
 				QB_CUDA(cudaMemsetAsync(listed, 0, sizeof(uint64_t), stream));
 			}
@@ -917,6 +934,7 @@ local_table build_local_table(qb_iter *it, uint64_t rule_id, const rule_ops *ops
 			                                                                      sym->uslot.as<uint32_t>(), listed, nullptr, nullptr);
 			++ctx->launches;
 		}
+		R.scan_n = scan_n;
 		compaction_filtered = filtered;
 		QB_CUDA(cudaGetLastError());
 		timer.end(QB_PHASE_COMPACT);
@@ -938,6 +956,9 @@ local_table build_local_table(qb_iter *it, uint64_t rule_id, const rule_ops *ops
 	}
 	R.n_listed = ctx->h_small[DS_COUNT];
 	R.n_unique = compaction_filtered ? ctx->h_small[DS_KEPT] : R.n_listed;
+	R.filtered = compaction_filtered;
+	R.floor_key = compaction_filtered ? ctx->h_small[DS_FLOOR] : 0;
+	R.compaction_tolerance = compaction_tolerance;
 	sym->table_capacity = capacity;
 	if (region_mode)
 		sym->region_ratio[rule_id] = std::make_pair((double)ctx->h_small[DS_CURSOR] / (double)n_children, (double)ctx->h_small[DS_REGIONS] / (double)n_children);
@@ -979,6 +1000,23 @@ void inject_failure(int rank, const char *phase) {
 	const char *inject = getenv("QB_DIST_INJECT_FAILURE");
 	if (inject && atoi(inject) == rank && strchr(inject, ':') && !strcmp(strchr(inject, ':') + 1, phase))
 		throw qb::error(QB_ERR_CAPACITY, std::string("injected failure in phase ") + phase);
+}
+
+// the complete (norm key, slot) list of a table whose compaction was filtered (the floor turned out to be too high, or nothing
+// is truncated after all)
+void compact_unfiltered(qb_ctx *ctx, qb_sym *sym, local_table &R) {
+	cudaStream_t stream = ctx->stream;
+	unsigned long long *listed = reinterpret_cast<unsigned long long *>(ctx->small(DS_COUNT));
+	QB_CUDA(cudaMemsetAsync(listed, 0, sizeof(uint64_t), stream));
+	const uint64_t tiles = div_up<uint64_t>(std::max<uint64_t>(R.scan_n, 1), COMPACT_TILE);
+	table_compact_kernel<false><<<(unsigned)std::min<uint64_t>(tiles, (uint64_t)ctx->sm_count * 16), SCAN_THREADS, 0, stream>>>(
+	    R.table, R.scan_n, R.compaction_tolerance, sym->ukey.as<uint64_t>(), sym->uslot.as<uint32_t>(), listed, nullptr, nullptr);
+	++ctx->launches;
+	QB_CUDA(cudaGetLastError());
+	ctx->fetch_small();
+	R.n_listed = ctx->h_small[DS_COUNT];
+	R.filtered = false;
+	R.floor_key = 0;
 }
 
 // One rule iteration with the interference complete on this GPU: the single-GPU path (comm = nullptr), and the distributed path
@@ -1061,20 +1099,35 @@ void simulate(qb_iter *it, uint64_t rule_id, const rule_ops *ops, const void *ru
 	}
 	step("truncate - prepare");
 	step("truncate");
+	if (R.filtered && !(max_num_object < n_unique_global)) // nothing is truncated after all (the other ranks hold fewer children than expected): the whole list
+		compact_unfiltered(ctx, sym, R);
 	uint64_t n_survivors = R.n_unique;
 	survivor_source src;
 	src.table = R.table;
 	src.slot = sym->uslot.as<uint32_t>();
 	if (max_num_object < n_unique_global) {
 		timer.begin(QB_PHASE_TRUNCATE);
-		sym->sslot.ensure(sizeof(uint32_t) * std::max<uint64_t>(1, std::min<uint64_t>(R.n_listed, max_num_object)), stream);
 		if (!opt.simple_truncation && R.n_unique > 0) {
 			randomize_keys_kernel<<<grid_for(R.n_unique, 256, ctx->grid_cap()), 256, 0, stream>>>(sym->ukey.as<uint64_t>(), R.table, sym->uslot.as<uint32_t>(),
 			                                                                                    R.n_unique, opt.seed);
 			++ctx->launches;
 		}
 		key_from_array keys{sym->ukey.as<uint64_t>()};
-		select_threshold(ctx, comm, keys, R.n_listed, max_num_object);
+		for (;;) {
+			select_threshold(ctx, comm, keys, R.n_listed, max_num_object);
+			if (!comm)
+				break; // one GPU: the floor was checked against the counts when the list was made
+			// routed by family: every rank listed its keys above ITS floor; the global threshold must not lie below any of them
+			uint64_t threshold = 0;
+			QB_CUDA(cudaMemcpyAsync(&threshold, &ctx->select.as<select_state>()->prefix, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+			ctx->sync();
+			const uint64_t too_high = R.filtered && R.floor_key > threshold ? 1 : 0;
+			if (comm->sum_u64(too_high) == 0)
+				break;
+			if (too_high)
+				compact_unfiltered(ctx, sym, R);
+		}
+		sym->sslot.ensure(sizeof(uint32_t) * std::max<uint64_t>(1, std::min<uint64_t>(R.n_listed, max_num_object)), stream);
 		n_survivors = select_keep(ctx, comm, keys, R.n_listed, out_gather_u32{sym->sslot.as<uint32_t>(), sym->uslot.as<uint32_t>()});
 		src.slot = sym->sslot.as<uint32_t>();
 		timer.end(QB_PHASE_TRUNCATE);

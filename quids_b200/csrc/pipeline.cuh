@@ -24,17 +24,17 @@ __device__ __forceinline__ uint64_t key_of_norm(double norm) { return (uint64_t)
 // tiles/s, and a table of 1.3e9 slots has 6.5e5 tiles of 2048 -- 8 ms of pure serialisation out of 16 ms for the kernel.
 // `n` = slots to scan (a hashed table: capacity + 1 with the dedicated slot of the hash 0; regions: the slots handed out).
 //
-// FILTER (single GPU, simple truncation to k survivors with k far below the number of slots): only the entries whose key is at
-// least `floor->prefix` are listed -- a lower bound of the k-th largest key, taken from a random sample of the slots
+// FILTER (simple truncation to k survivors with k far below the number of slots): only the entries whose key is at
+// least `*floor` are listed -- a lower bound of the k-th largest key, taken from a random sample of the slots
 // (sample_norm_keys_kernel) with 6 sigma of margin -- so that the list holds little more than k entries instead of every
 // unique child, and the selection after it reads megabytes instead of gigabytes.  `count_kept` still counts every child
 // above the tolerance (N_u); the host checks that at least min(k, N_u) entries were listed and redoes the pass unfiltered
 // otherwise (never seen: 1e-9 per call).
 template <bool FILTER>
 __global__ void __launch_bounds__(SCAN_THREADS) table_compact_kernel(table_view t, uint64_t n, double tolerance, uint64_t *ukey, uint32_t *uslot,
-                                                                     unsigned long long *count, const select_state *floor, unsigned long long *count_kept) {
+                                                                     unsigned long long *count, const uint64_t *floor, unsigned long long *count_kept) {
 	__shared__ unsigned long long s_base;
-	[[maybe_unused]] const uint64_t floor_key = FILTER ? floor->prefix : 0;
+	[[maybe_unused]] const uint64_t floor_key = FILTER ? *floor : 0;
 	for (uint64_t base = (uint64_t)blockIdx.x * COMPACT_TILE; base < n; base += (uint64_t)gridDim.x * COMPACT_TILE) {
 		bool keep[COMPACT_ITEMS], above[COMPACT_ITEMS];
 		uint64_t key[COMPACT_ITEMS];

@@ -628,22 +628,24 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 		constexpr int PER_LANE = FLIP_BLOCK / 32;
 		const uint32_t lane = lane_id();
 		const bool valid = lane < count;
-		// 1. stretches and their regions
-		run_id_t id{};
+		// 1. runs inside the batch and their regions.  The items are sorted by 24 bits of a key: the items of one run are
+		// close to each other but not always neighbours (another run with the same 24 bits may sit in between), so the members
+		// of a run are found by matching the region keys of all 32 items, not by comparing neighbours
+		uint64_t key = 0;
 		uint32_t my_levels = 0;
 		if (valid) {
-			id = run_identity(ctx[lane], group[lane]);
+			const run_id_t id = run_identity(ctx[lane], group[lane]);
+			key = region_key(id.eligible, id.fixed, id.target, id.names, id.n);
+			if (key == 0)
+				key = 1;
 			my_levels = ctx[lane].levels;
 		}
-		const run_id_t before = id.shuffle_up();
-		const bool head = valid && (lane == 0 || !(id == before));
-		const unsigned heads = __ballot_sync(0xffffffffu, head);
+		const unsigned in_batch = __ballot_sync(0xffffffffu, valid);
+		const unsigned members = valid ? __match_any_sync(in_batch, (unsigned long long)key) : 0u; // the items of this lane's run
+		const bool head = valid && (uint32_t)__ffs(members) - 1 == lane;
 		region_entry *entry = nullptr;
 		bool made = false, failed = false;
 		if (head) {
-			uint64_t key = region_key(id.eligible, id.fixed, id.target, id.names, id.n);
-			if (key == 0)
-				key = 1;
 			uint64_t i = __umul64hi(mix64(key), table.dir_capacity);
 			unsigned long long seen = atomicCAS(&table.dir[i].key, 0ull, (unsigned long long)key);
 			for (uint32_t probes = 0;; ++probes) {
@@ -693,17 +695,59 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 
 		// 3. one stretch: magnitudes of the lane's objects, then the region's slots
 		auto stretch = [&](uint32_t h, unsigned long long first_slot, bool creates) {
-			const unsigned later = heads & ~((2u << h) - 1u);
-			const uint32_t e = later ? (uint32_t)__ffs(later) - 1 : count;
+			const unsigned run = __shfl_sync(0xffffffffu, members, h); // the items of the run (h is the first)
 			const flip_ctx &c = ctx[h];
 			const uint32_t levels = c.levels, leaves = 1u << levels;
+			const uint32_t tree_bits = c.tree_bits;
+			// a new region: the particle masks of its objects are known before their magnitudes -- the lookups in the fold table
+			// are issued first and their latency hides behind the product chains
+			uint64_t hl[PER_LANE], hr[PER_LANE];
+			if (creates) {
+				const uint64_t left = c.left, right = c.right;
+				const uint32_t g = group[h], shift = c.eligible - levels; // child_id = group | leaf << shift
+				uint64_t toggles = 0;
+				{ // the group index decides the first `shift` eligible nodes
+					const uint64_t all = c.n >= 64 ? ~0ull : ((1ull << c.n) - 1);
+					uint64_t el = (WANT_EQUAL ? ~(left ^ right) : (left ^ right)) & all;
+					for (uint32_t b = 0; b < shift; ++b) {
+						const uint32_t i = (uint32_t)__ffsll((long long)el) - 1;
+						el &= el - 1;
+						toggles |= (uint64_t)((g >> b) & 1) << i;
+					}
+				}
+				{ // tree levels 0-4: the lane's bits of the object, xor the head parent's own
+					const uint32_t leaf_low = (lane ^ tree_bits) & 31, low = levels < 5 ? levels : 5;
+					for (uint32_t l = 0; l < low; ++l)
+						toggles |= (uint64_t)((leaf_low >> l) & 1) << c.pos[l];
+				}
+				const bool narrow = c.n <= FOLD_TABLE_BITS;
+#pragma unroll
+				for (int q = 0; q < PER_LANE; ++q) {
+					const uint32_t slot = lane + 32 * q;
+					if (slot < leaves) {
+						uint64_t t = toggles;
+#pragma unroll
+						for (int l = 5; l < FLIP_LEVELS; ++l)
+							if ((uint32_t)l < levels)
+								t |= (uint64_t)((((uint32_t)q >> (l - 5)) ^ (tree_bits >> l)) & 1) << c.pos[l];
+						if (narrow) {
+							hl[q] = particle_fold((uint32_t)(left ^ t));
+							hr[q] = particle_fold((uint32_t)(right ^ t));
+						} else {
+							hl[q] = particle_fold_wide(left ^ t);
+							hr[q] = particle_fold_wide(right ^ t);
+						}
+					}
+				}
+			}
 			cplx mag[PER_LANE];
 #pragma unroll
 			for (int q = 0; q < PER_LANE; ++q)
 				mag[q] = cplx{0, 0};
-			if (e - h <= BATCH_MAX_CHAINS) {
+			if ((uint32_t)__popc(run) <= BATCH_MAX_CHAINS) {
 				const uint32_t low = levels < 5 ? levels : 5;
-				for (uint32_t j = h; j < e; ++j) {
+				for (unsigned todo = run; todo; todo &= todo - 1) {
+					const uint32_t j = (uint32_t)__ffs(todo) - 1;
 					// amp index = taken * 2 + parent's bit, taken = object's bit xor parent's bit
 					const uint32_t t = ctx[j].tree_bits;
 					cplx m = root[j];
@@ -733,7 +777,7 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 				if (lane == 0)
 					ws.run_leaves = leaves;
 				__syncwarp();
-				if (lane >= h && lane < e) {
+				if ((run >> lane) & 1) {
 					const uint32_t t = ctx[lane].tree_bits;
 					atomicOr(&ws.run_patterns[t >> 5], 1u << (t & 31));
 					atomicAdd(&ws.acc_re[t], root[lane].re);
@@ -762,44 +806,7 @@ struct flip_rule_fused : flip_rule<WANT_EQUAL> {
 				return;
 			}
 			// the region is new: hash, summed magnitude and representative of every object, one full 32-byte sector each
-			const uint64_t left = c.left, right = c.right;
-			const uint32_t tree_bits = c.tree_bits, g = group[h];
-			const uint32_t shift = c.eligible - levels; // child_id = group | leaf << shift
-			uint64_t toggles = 0;
-			{ // the group index decides the first `shift` eligible nodes
-				const uint64_t all = c.n >= 64 ? ~0ull : ((1ull << c.n) - 1);
-				uint64_t el = (WANT_EQUAL ? ~(left ^ right) : (left ^ right)) & all;
-				for (uint32_t b = 0; b < shift; ++b) {
-					const uint32_t i = (uint32_t)__ffsll((long long)el) - 1;
-					el &= el - 1;
-					toggles |= (uint64_t)((g >> b) & 1) << i;
-				}
-			}
-			{ // tree levels 0-4: the lane's bits of the object, xor the head parent's own
-				const uint32_t leaf_low = (lane ^ tree_bits) & 31, low = levels < 5 ? levels : 5;
-				for (uint32_t l = 0; l < low; ++l)
-					toggles |= (uint64_t)((leaf_low >> l) & 1) << c.pos[l];
-			}
-			const bool narrow = c.n <= FOLD_TABLE_BITS;
-			uint64_t hl[PER_LANE], hr[PER_LANE];
-#pragma unroll
-			for (int q = 0; q < PER_LANE; ++q) {
-				const uint32_t slot = lane + 32 * q;
-				if (slot < leaves) {
-					uint64_t t = toggles;
-#pragma unroll
-					for (int l = 5; l < FLIP_LEVELS; ++l)
-						if ((uint32_t)l < levels)
-							t |= (uint64_t)((((uint32_t)q >> (l - 5)) ^ (tree_bits >> l)) & 1) << c.pos[l];
-					if (narrow) {
-						hl[q] = particle_fold((uint32_t)(left ^ t));
-						hr[q] = particle_fold((uint32_t)(right ^ t));
-					} else {
-						hl[q] = particle_fold_wide(left ^ t);
-						hr[q] = particle_fold_wide(right ^ t);
-					}
-				}
-			}
+			const uint32_t g = group[h], shift = c.eligible - levels;
 			const uint64_t names_hash = c.names_hash, first_child = child_begin[h];
 			const uint32_t bytes = size[h];
 #pragma unroll

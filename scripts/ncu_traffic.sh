@@ -8,6 +8,6 @@
 set -e
 PARENTS=${PARENTS:-10000000}
 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
-    -k regex:"symbolic_items_kernel|symbolic_kernel|bin_dedup_kernel|table_compact_kernel" --launch-skip 12 --launch-count 4 \
+    -k regex:"symbolic_items|symbolic_kernel|bin_dedup_kernel|table_compact_kernel" --launch-skip 12 --launch-count 4 \
     --csv --log-file gpurun_out/r2_traffic.csv python scripts/loop_probe.py --parents $PARENTS --passes 4 --skip 4
 tail -8 gpurun_out/r2_traffic.csv

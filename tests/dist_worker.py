@@ -252,6 +252,9 @@ def automatic_budget_cases(comm, port, state):
 
 
 def main():
+    # the compaction of the family-routed path lists only the entries above a rank-local floor (default: tables of 2^24 slots and
+    # more; here every table), and simulate() checks the floors against the global threshold
+    os.environ["QB_COMPACT_FILTER_MIN"] = "0"
     dist.init_process_group("gloo")
     rank = dist.get_rank()
     port = orc.Oracle(orc.PORT_SO)
@@ -290,6 +293,11 @@ def main():
     big = orc.Packed(big.sizes, big_mags / np.sqrt((big_mags ** 2).sum()), big.data)
     run_case(comm, port, big, orc.RULE_ERASE_CREATE, [math.pi / 4, 0.1, 0.2], 100000, 1e-18, True, "global select at scale")
     run_case(comm, port, port.qcgd_random_state(12, 6000, 3), orc.RULE_ERASE_CREATE, [math.pi / 4, 0, 0], 100000, 1e-18, True, "global select at scale, ties")
+    # a floor taken far too high on every rank (5 % of a rank's share of k): the check against the global threshold must catch it and redo the lists
+    os.environ["QB_DIST_FLOOR_FACTOR"] = "0.05"
+    run_case(comm, port, big, orc.RULE_ERASE_CREATE, [math.pi / 4, 0.1, 0.2], 100000, 1e-18, True, "global select at scale, floors too high")
+    run_case(comm, port, big, orc.RULE_COIN, [math.pi / 4, 0.1, 0.2], 40000, 1e-18, True, "global select at scale, floors too high, coin")
+    del os.environ["QB_DIST_FLOOR_FACTOR"]
     # load balancing at the head of mpi::simulate (quids_mpi.hpp:442-500): skewed shares, same result
     for rid in orc.QCGD_RULES:
         run_case(comm, port, state, rid, p, orc.NO_TRUNCATION, 1e-18, True, f"rule {rid} skewed shares, equalize by children", share=skewed_share, equalize=2)

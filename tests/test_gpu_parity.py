@@ -164,13 +164,13 @@ def test_region_kernels_vs_oracle(gpu, port, rule_id, batch, monkeypatch):
 
     if "states" not in _region_cases:
         one = port.qcgd_random_state(9, 1, 5)
-        grown, _, _ = port.simulate(port.qcgd_random_state(9, 800, 8), orc.RULE_SPLIT_MERGE, [0.4, 0.3, 0.2], orc.NO_TRUNCATION, 1e-18)
+        grown, _, _ = port.simulate(port.qcgd_random_state(9, 400, 8), orc.RULE_SPLIT_MERGE, [0.4, 0.3, 0.2], orc.NO_TRUNCATION, 1e-18)
         _region_cases["states"] = {
             "12 nodes, distinct families": with_random_magnitudes(port.qcgd_random_state(12, 300, 21)),
-            "6 nodes, every family many times": with_random_magnitudes(port.qcgd_random_state(6, 3000, 3)),
+            "6 nodes, every family many times": with_random_magnitudes(port.qcgd_random_state(6, 1500, 3)),
             "identical parents": orc.Packed.from_objects(one.objects() * 500, [1 / math.sqrt(500)] * 500),
             "grown state (ragged sizes and node counts)": with_random_magnitudes(grown),
-            "wider than the fold table": port.qcgd_random_state(21, 12, 4),  # (its own uniform magnitudes keep total_proba's summation error small)
+            "wider than the fold table": port.qcgd_random_state(21, 6, 4),  # (its own uniform magnitudes keep total_proba's summation error small)
         }
     states = _region_cases["states"]
     qb.config.locality_sort = 2
@@ -251,7 +251,10 @@ def test_modifiers_vs_oracle(gpu, port):
         g = want
 
 
-def test_truncation_band_vs_oracle(gpu, port):
+@pytest.mark.parametrize("filtered_list", [False, True])
+def test_truncation_band_vs_oracle(gpu, port, filtered_list, monkeypatch):
+    if filtered_list:  # the compaction lists only the entries above a sampled lower bound of the k-th key (default: tables of 2^24 slots and more)
+        monkeypatch.setenv("QB_COMPACT_FILTER_MIN", "0")
     base = port.qcgd_random_state(7, 300, 13, 1.0)
     rng = np.random.default_rng(6)
     mags = rng.normal(size=(300, 2))
@@ -267,7 +270,10 @@ def test_truncation_band_vs_oracle(gpu, port):
                                   min(k, full.n), True, what=f"truncated rule {rid}")
 
 
-def test_truncation_with_exact_ties(gpu, port):
+@pytest.mark.parametrize("filtered_list", [False, True])
+def test_truncation_with_exact_ties(gpu, port, filtered_list, monkeypatch):
+    if filtered_list:  # the compaction lists only the entries above a sampled lower bound of the k-th key (default: tables of 2^24 slots and more)
+        monkeypatch.setenv("QB_COMPACT_FILTER_MIN", "0")
     # equal magnitudes everywhere: any k objects of the tied set are a legal answer, the count is not negotiable
     st = port.qcgd_random_state(6, 64, 3)
     k = 500
@@ -283,7 +289,10 @@ def test_truncation_with_exact_ties(gpu, port):
         assert abs(kf[h][1]) ** 2 >= probs[k - 1] * (1 - 1e-12)
 
 
-def test_parent_pretruncation(gpu, port):
+@pytest.mark.parametrize("filtered_list", [False, True])
+def test_parent_pretruncation(gpu, port, filtered_list, monkeypatch):
+    if filtered_list:  # the compaction lists only the entries above a sampled lower bound of the k-th key (default: tables of 2^24 slots and more)
+        monkeypatch.setenv("QB_COMPACT_FILTER_MIN", "0")
     st0 = port.qcgd_random_state(6, 200, 17, 1.0)
     rng = np.random.default_rng(8)
     mags = rng.normal(size=(200, 2))
