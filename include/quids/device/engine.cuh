@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS) num_child_kernel(const Rule ru
 		const uint32_t size = it.size[i];
 		rule.get_num_child(parent, size, count, bound);
 		num_childs[i] = count;
-		if (Rule::warp_groups)
+		if (Rule::warp_groups || Rule::lane_groups)
 			num_groups[i] = rule.get_num_group(parent, size, count);
 		local_max = max(local_max, bound);
 		count_max = max(count_max, count);
@@ -227,9 +227,26 @@ __global__ void __launch_bounds__(SYMBOLIC_THREADS, 5) symbolic_kernel(const Rul
 						}
 					}
 				}
-				for (uint32_t j = 0; j < count; ++j)
-					if (s.group_begin[j + 1] > s.group_begin[j])
-						rule.prepare_warp(staged ? staged + (s.object[j] - staged_from) : L.it.objects + s.object[j], s.size[j], s.ctx[j]);
+				auto bytes_of = [&](uint32_t j) { return staged ? staged + (s.object[j] - staged_from) : L.it.objects + s.object[j]; };
+				if constexpr (Rule::warp_prepare_pairs) {
+					// two parents at a time, one per half warp, when both are small enough for 16 lanes
+					for (uint32_t j0 = 0; j0 < count; j0 += 2) {
+						const uint32_t j = min(j0 + (lane >> 4), count - 1);
+						const bool active = j0 + (lane >> 4) < count && s.group_begin[j + 1] > s.group_begin[j];
+						const uint8_t *bytes = bytes_of(j);
+						if (__all_sync(0xffffffffu, !active || Rule::fits_half_warp(bytes))) {
+							rule.prepare_half_warp(bytes, s.ctx[j], active);
+						} else {
+							for (uint32_t k = j0; k < min(j0 + 2, count); ++k)
+								if (s.group_begin[k + 1] > s.group_begin[k])
+									rule.prepare_warp(bytes_of(k), s.size[k], s.ctx[k]);
+						}
+					}
+				} else {
+					for (uint32_t j = 0; j < count; ++j)
+						if (s.group_begin[j + 1] > s.group_begin[j])
+							rule.prepare_warp(bytes_of(j), s.size[j], s.ctx[j]);
+				}
 				__syncwarp();
 			}
 
@@ -250,6 +267,19 @@ __global__ void __launch_bounds__(SYMBOLIC_THREADS, 5) symbolic_kernel(const Rul
 					rule.template symbolic_warp<false>(L.it.objects + s.object[j], s.size[j], s.ctx[j], (uint32_t)(c - s.group_begin[j]), s.group_ctx[c - lo],
 					                   s_workspace[threadIdx.x >> 5], emit);
 					created += emit.created;
+				}
+			} else if constexpr (Rule::lane_groups) {
+				// one FAN per lane: a few children of one parent that share most of their work (rule_api.cuh)
+				for (uint64_t c = lo + lane; c < hi; c += 32) {
+					const uint32_t j = (uint32_t)upper_bound_u64(s.group_begin, count + 1, c) - 1;
+					const uint64_t first_child = s.child_begin[j];
+					rule.symbolic_fan(L.it.objects + s.object[j], s.size[j], s.ctx[j], (uint32_t)(c - s.group_begin[j]), s.mag[j], scratch,
+					                  [&](uint32_t child_id, uint64_t hash, uint32_t size, cplx mag) {
+						                  if (L.bins.records)
+							                  created += bin_emit(L.bins, L.table, hash, mag, rep_pack(first_child + child_id, size));
+						                  else
+							                  created += table_insert(L.table, hash, mag, rep_pack(first_child + child_id, size));
+					                  });
 				}
 			} else {
 				// one child per lane: the loop body of quids.hpp:705-719.  (Collecting a lane's 4 children and inserting them as one
@@ -652,8 +682,12 @@ __global__ void __launch_bounds__(ENGINE_THREADS) populate_kernel(const Rule rul
 //   3. writes the children -- consecutive in the next state, hence ONE contiguous byte range -- with a single bulk
 //      store (cp.async.bulk shared -> global; the < 16-byte head and tail by the lanes).
 // A child or parent too large for a stage is built in place by one lane.
-constexpr uint32_t POPULATE_PARENT_STAGE = 8704;  // 32 parents of 256 bytes (widened to 16-byte bounds) at a stride of 272
-constexpr uint32_t POPULATE_CHILD_STAGE = 9728;
+// Stage sizes: a round handles the survivors whose parents AND children fit; 32 grown 12-node graphs (300-330 bytes each, slots
+// of 336) need 10.75 KB on either side -- with 8.5 KB stages every batch of 32 took two rounds (27 + 5 lanes busy).  Three
+// warps per CTA: 3 x 21.5 KB = 64.6 KB, three CTAs per SM.
+constexpr uint32_t POPULATE_PARENT_STAGE = 10752;
+constexpr uint32_t POPULATE_CHILD_STAGE = 10752;
+constexpr int POPULATE_THREADS = 96;
 struct __align__(16) populate_stage {
 	uint8_t parents[POPULATE_PARENT_STAGE];
 	uint8_t children[POPULATE_CHILD_STAGE];
@@ -673,7 +707,7 @@ __device__ __forceinline__ uint32_t warp_inclusive_sum(uint32_t v) {
 }
 
 template <class Rule>
-__global__ void __launch_bounds__(STAGED_THREADS) populate_staged_kernel(const Rule rule, const engine_launch L) {
+__global__ void __launch_bounds__(POPULATE_THREADS) populate_staged_kernel(const Rule rule, const engine_launch L) {
 	extern __shared__ __align__(16) uint8_t s_populate[];
 	populate_stage &st = reinterpret_cast<populate_stage *>(s_populate)[threadIdx.x >> 5];
 	const unsigned lane = lane_id();
@@ -908,7 +942,7 @@ struct rule_glue {
 			int grid = grid_for(L.n_survivors, ENGINE_THREADS, resident_grid((const void *)populate_kernel<Rule>, ENGINE_THREADS, L.sm_count));
 			populate_kernel<Rule><<<grid, ENGINE_THREADS, 0, L.stream>>>(*static_cast<const Rule *>(rule), L);
 		} else {
-			constexpr size_t smem = sizeof(populate_stage) * (STAGED_THREADS / 32);
+			constexpr size_t smem = sizeof(populate_stage) * (POPULATE_THREADS / 32);
 			// CTAs of this kernel one SM holds (shared-memory bound); the opt-in to more than 48 KB is a per-DEVICE attribute
 			static int per_sm_of_device[MAX_DEVICES] = {};
 			int device = 0;
@@ -916,12 +950,12 @@ struct rule_glue {
 			int &per_sm = per_sm_of_device[device % MAX_DEVICES];
 			if (per_sm == 0) {
 				QB_CUDA(cudaFuncSetAttribute((const void *)populate_staged_kernel<Rule>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-				QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)populate_staged_kernel<Rule>, STAGED_THREADS, smem));
+				QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)populate_staged_kernel<Rule>, POPULATE_THREADS, smem));
 				if (per_sm < 1)
 					per_sm = 1;
 			}
-			int grid = grid_for(L.n_survivors, STAGED_THREADS, per_sm * L.sm_count);
-			populate_staged_kernel<Rule><<<grid, STAGED_THREADS, smem, L.stream>>>(*static_cast<const Rule *>(rule), L);
+			int grid = grid_for(L.n_survivors, POPULATE_THREADS, per_sm * L.sm_count);
+			populate_staged_kernel<Rule><<<grid, POPULATE_THREADS, smem, L.stream>>>(*static_cast<const Rule *>(rule), L);
 		}
 		++*L.launch_counter;
 	}
@@ -947,6 +981,7 @@ struct rule_glue {
 		o.launch_hash = hash;
 		o.needs_scratch = Rule::needs_scratch;
 		o.warp_groups = Rule::warp_groups;
+		o.has_groups = Rule::warp_groups || Rule::lane_groups;
 		o.has_group_key = Rule::has_group_key;
 		o.region_size_limit = Rule::region_size_limit;
 		o.ctx_bytes = sizeof(item_parent<Rule>); // per kept parent in sorted order

@@ -79,6 +79,9 @@ struct rule_base {
 	// 32 lanes with the same arguments after prepare() -- and, for large contexts, fewer parents are staged at a time
 	static constexpr bool warp_prepare = false;
 	static constexpr int parents_per_batch = 32;
+	// with warp_prepare: the rule can also build TWO contexts at a time, one per half warp --
+	//     static bool fits_half_warp(parent);  prepare_half_warp(parent, ctx&, active)   (all 32 lanes, arguments of the lane's half)
+	static constexpr bool warp_prepare_pairs = false;
 	// with warp_prepare: the parents of a batch (consecutive in the state) are first copied to shared memory in one bulk copy
 	// when they fit in this many bytes, and prepare_warp reads them there: its chains of dependent loads (node count -> name
 	// offsets -> atoms) then cost shared-memory latency instead of one DRAM round trip per link and parent.  0 = no staging
@@ -109,6 +112,11 @@ struct rule_base {
 	// group must be emitted exactly once, by any lane: emit(child_id, hash, size, mag) or
 	// emit.batch<N>(count, hash[N], size, child_id_of(i), mag_of(i)).
 	static constexpr bool warp_groups = false;
+	// LANE groups ("fans"): a group is a few children of one parent produced by ONE lane that shares work between them (e.g.
+	// siblings that differ in their last choices share the walk over the parent up to there).  The rule provides
+	//     get_num_group(parent, parent_size, num_child) -> number of fans
+	//     symbolic_fan(parent, parent_size, ctx, fan, parent_mag, scratch, emit)     emit(child_id, hash, size, mag) once per child
+	static constexpr bool lane_groups = false;
 	struct workspace_t {};
 	typedef workspace_t items_workspace_t; // the sorted order may need less (or other) per-warp memory than the unsorted one
 	// per-group precomputation done by ONE lane per group, 32 groups at a time (whatever is the same
@@ -202,6 +210,7 @@ struct rule_ops {
 	void (*launch_hash)(const void *rule, const engine_launch &L);
 	bool needs_scratch;
 	bool warp_groups;
+	bool has_groups; // warp_groups or lane_groups: the groups are a second index space (num_groups, group_begin)
 	bool has_group_key;
 	uint32_t region_size_limit;
 	uint32_t group_capacity;

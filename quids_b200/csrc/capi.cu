@@ -586,7 +586,7 @@ local_table build_local_table(qb_iter *it, uint64_t rule_id, const rule_ops *ops
 		timer.begin(QB_PHASE_NUM_CHILD);
 		it->num_childs.ensure(sizeof(uint32_t) * it->n, stream);
 		L.num_childs = it->num_childs.as<uint32_t>();
-		if (ops->warp_groups) {
+		if (ops->has_groups) {
 			it->num_groups.ensure(sizeof(uint32_t) * it->n, stream);
 			L.num_groups = it->num_groups.as<uint32_t>();
 		}
@@ -604,7 +604,7 @@ local_table build_local_table(qb_iter *it, uint64_t rule_id, const rule_ops *ops
 		it->child_begin.ensure(sizeof(uint64_t) * (n_parents + 1), stream);
 		exclusive_scan(ctx, counts_through{it->num_childs.as<uint32_t>(), kept}, it->child_begin.as<uint64_t>(), n_parents);
 		group_begin = it->child_begin.as<uint64_t>();
-		if (ops->warp_groups) { // children are produced in groups that share work: a second index space
+		if (ops->has_groups) { // children are produced in groups that share work: a second index space
 			it->group_begin.ensure(sizeof(uint64_t) * (n_parents + 1), stream);
 			exclusive_scan(ctx, counts_through{it->num_groups.as<uint32_t>(), kept}, it->group_begin.as<uint64_t>(), n_parents);
 			group_begin = it->group_begin.as<uint64_t>();

@@ -151,7 +151,7 @@ uint64_t count_children(qb_iter *it, const rule_ops *ops, const void *rule) {
 	QB_CUDA(cudaMemsetAsync(ctx->d_small.ptr, 0, DS_WORDS * sizeof(uint64_t), stream));
 	it->num_childs.ensure(sizeof(uint32_t) * it->n, stream);
 	L.num_childs = it->num_childs.as<uint32_t>();
-	if (ops->warp_groups) {
+	if (ops->has_groups) {
 		it->num_groups.ensure(sizeof(uint32_t) * it->n, stream);
 		L.num_groups = it->num_groups.as<uint32_t>();
 	}

@@ -1413,16 +1413,30 @@ struct split_merge_fused : split_merge {
 	__device__ void prepare(const uint8_t *, uint32_t, split_merge_ctx &ctx) const { ctx.n = 0; }
 
 	// all 32 lanes, same arguments
-	__device__ void prepare_warp(const uint8_t *parent, uint32_t, split_merge_ctx &ctx) const {
-		const graph g(parent);
-		const uint32_t n = g.n, i = lane_id();
-		if (n == 0 || n > SPLIT_MERGE_MAX_NODES) {
-			if (i == 0)
+	__device__ void prepare_warp(const uint8_t *parent, uint32_t, split_merge_ctx &ctx) const { prepare_lanes<32>(parent, ctx, true); }
+
+	// TWO parents per warp (graphs of at most 16 nodes, the usual case): lanes 0-15 build the context of one parent, lanes 16-31
+	// that of the next -- the same instruction stream serves both, half the warp instructions per parent.  Called by all 32
+	// lanes; `parent` / `ctx` are those of the lane's half, `active` = the half has a parent
+	static constexpr bool warp_prepare_pairs = true;
+	__device__ static bool fits_half_warp(const uint8_t *parent) { return *reinterpret_cast<const uint16_t *>(parent) <= 16; }
+	__device__ void prepare_half_warp(const uint8_t *parent, split_merge_ctx &ctx, bool active) const { prepare_lanes<16>(parent, ctx, active); }
+
+	template <uint32_t WIDTH>
+	__device__ __forceinline__ void prepare_lanes(const uint8_t *parent, split_merge_ctx &ctx, bool active) const {
+		const uint32_t i = lane_id() & (WIDTH - 1), shift = lane_id() & ~(WIDTH - 1); // node of this lane, first lane of its group
+		const uint32_t n = active ? *reinterpret_cast<const uint16_t *>(parent) : 0;
+		const bool ok = n >= 1 && n <= (WIDTH < SPLIT_MERGE_MAX_NODES ? WIDTH : SPLIT_MERGE_MAX_NODES);
+		const graph g(ok ? parent : reinterpret_cast<const uint8_t *>(&ctx.n)); // (never dereferenced beyond n when !ok: n is taken as 0 below)
+		const bool here = ok && i < n;
+		const uint32_t group_mask = WIDTH == 32 ? 0xffffffffu : ((1u << WIDTH) - 1);
+		const uint32_t l = (__ballot_sync(0xffffffffu, here && parent[2 + i]) >> shift) & group_mask;
+		const uint32_t r = (__ballot_sync(0xffffffffu, here && parent[2 + n + i]) >> shift) & group_mask;
+		if (!ok) {
+			if (active && i == 0)
 				ctx.n = 0;
 			return;
 		}
-		const bool here = i < n;
-		const uint32_t l = __ballot_sync(0xffffffffu, here && g.left(i)), r = __ballot_sync(0xffffffffu, here && g.right(i));
 		const uint32_t split = l & r;
 		const uint32_t merge = ~split & l & (r >> 1) & ~(l >> 1) & (n > 1 ? (0xffffffffu >> (33 - n)) : 0u); // i + 1 < n
 		const bool wrap_merge = !(split & 1) && n > 1 && (r & 1) && ((l >> (n - 1)) & 1) && !((r >> (n - 1)) & 1);
@@ -1548,6 +1562,133 @@ struct split_merge_fused : split_merge {
 				hr = hash_combine_index(hr, (uint32_t)__ffsll((long long)m) - 1);
 		}
 		return hash_combine(hash_combine(hn, hl), hr);
+	}
+	// ---- FANS (rule_api.cuh, lane_groups).  The bits of child_id are consumed in walk order, so the children that differ only
+	// in their LAST choices share the walk over the parent up to the first of those sites.  One lane produces the 2^F children
+	// fan | x << (S - F) of a parent with S sites, F = min(2, S - 1): it walks to the (S - F)-th site once, forks there, and
+	// again at the last site -- about 1.8 walks for four children of a parent with four sites instead of four.  (Bit 0 is never
+	// forked: the wrap-around sites keep their place at the head of the walk.)
+	static constexpr bool lane_groups = true;
+	__device__ static uint32_t fork_bits(uint32_t sites) { return sites >= 3 ? 2u : (sites == 2 ? 1u : 0u); }
+	__device__ uint32_t get_num_group(const uint8_t *, uint32_t, uint32_t num_child) const {
+		const uint32_t sites = 31 - __clz(num_child);
+		return num_child >> fork_bits(sites);
+	}
+
+	struct walk_state {
+		uint64_t hn, left, right; // fold of the names, particle masks of the child so far
+		uint32_t index, atoms, i; // nodes and atoms of the child so far, next node of the parent
+		bool pending;             // the right half of a split is next
+	};
+
+	template <class Emit>
+	__device__ void symbolic_fan(const uint8_t *parent, uint32_t parent_size, const split_merge_ctx &ctx, uint32_t fan, cplx parent_mag, uint8_t *scratch,
+	                             Emit emit) const {
+		const uint32_t n = ctx.n;
+		if (n == 0) { // not prepared (more than 32 nodes): every child walks the object
+			uint32_t num_child, unused;
+			get_num_child(parent, parent_size, num_child, unused);
+			const uint32_t sites = 31 - __clz(num_child), forked = fork_bits(sites);
+			for (uint32_t x = 0; x < (1u << forked); ++x) {
+				const uint32_t child_id = fan | (x << (sites - forked));
+				cplx mag = parent_mag;
+				uint32_t size;
+				const uint64_t hash = symbolic(parent, parent_size, ctx, child_id, scratch, size, mag);
+				emit(child_id, hash, size, mag);
+			}
+			return;
+		}
+		const uint32_t left = ctx.left, right = ctx.right, split = ctx.split, merge = ctx.merge;
+		const uint32_t sites = ctx.num_sites, forked = fork_bits(sites), shared = sites - forked;
+		cplx mag = parent_mag; // factors of the shared choices, in bit order
+		for (uint32_t b = 0; b < shared; ++b)
+			mag = cmul(mag, amp.get((fan >> b) & 1, (ctx.site_is_merge >> b) & 1));
+
+		auto node = [&](walk_state &w, bool l, bool r, uint32_t which, uint32_t i) {
+			w.left |= (uint64_t)l << w.index;
+			w.right |= (uint64_t)r << w.index;
+			w.hn = hash_combine(w.hn, ctx.hash[which][i]);
+			w.atoms += ctx.len[which][i];
+			++w.index;
+		};
+		// the wrap-around sites first (qcgd.hpp:647-668); a first split that is not taken leaves its bit to the walk
+		walk_state st{0, 0, 0, 0, 0, 0, false};
+		uint32_t bits = fan, todo = shared; // choices of the shared part still to be consumed
+		const bool first_split = (split & 1) && (bits & 1);
+		bool last_merge = !(split & 1) && n > 1 && (right & 1) && ((left >> (n - 1)) & 1) && !((right >> (n - 1)) & 1);
+		bool overflow = false;
+		if (first_split) {
+			bits >>= 1;
+			--todo;
+			if (ctx.most_left_zero)
+				node(st, true, false, 1, 0);
+			else
+				overflow = true; // the left half goes to the end
+			node(st, false, true, 2, 0);
+		}
+		if (last_merge) {
+			last_merge = bits & 1;
+			bits >>= 1;
+			--todo;
+			if (last_merge)
+				node(st, true, true, 1, n - 1);
+		}
+		st.i = (uint32_t)first_split + last_merge;
+		const uint32_t end = n - last_merge;
+		// the general walk (see symbolic()): every iteration emits one node of the child; stops in front of a site when the
+		// choices given to it are used up
+		auto run = [&](walk_state &w, uint32_t choice_bits, uint32_t choices) {
+			while (w.i < end) {
+				const uint32_t i = w.i;
+				const bool is_split = (split >> i) & 1, is_merge = (merge >> i) & 1;
+				const bool site = (is_split || is_merge) && !w.pending;
+				if (site && choices == 0)
+					return;
+				const bool taken = site && (choice_bits & 1);
+				choice_bits >>= site ? 1 : 0;
+				choices -= site ? 1 : 0;
+				const bool l = w.pending ? false : (taken ? true : (bool)((left >> i) & 1));
+				const bool r = w.pending ? true : (taken ? is_merge : (bool)((right >> i) & 1));
+				node(w, l, r, w.pending ? 2u : (taken ? 1u : 0u), i);
+				const bool left_half = taken && is_split;
+				w.i = i + (left_half ? 0u : (taken ? 2u : 1u)); // a taken merge swallows node i + 1 (:816)
+				w.pending = left_half;
+			}
+		};
+		auto finish = [&](walk_state &w, cplx child_mag, uint32_t child_id) {
+			if (overflow)
+				node(w, true, false, 1, 0);
+			uint64_t hl = 0, hr = 0;
+			if (w.index <= FOLD_TABLE_BITS) {
+				hl = particle_fold((uint32_t)w.left);
+				hr = particle_fold((uint32_t)w.right);
+			} else {
+				for (uint64_t m = w.left; m; m &= m - 1)
+					hl = hash_combine_index(hl, (uint32_t)__ffsll((long long)m) - 1);
+				for (uint64_t m = w.right; m; m &= m - 1)
+					hr = hash_combine_index(hr, (uint32_t)__ffsll((long long)m) - 1);
+			}
+			emit(child_id, hash_combine(hash_combine(w.hn, hl), hr), 4 + 4 * w.index + 16 * w.atoms, child_mag);
+		};
+		run(st, bits, todo);
+		const uint32_t fan1 = forked >= 1 ? 2 : 1, fan2 = forked >= 2 ? 2 : 1;
+		for (uint32_t x1 = 0; x1 < fan1; ++x1) {
+			walk_state w1 = st;
+			cplx m1 = mag;
+			if (forked >= 1) {
+				m1 = cmul(mag, amp.get(x1, (ctx.site_is_merge >> shared) & 1));
+				run(w1, x1, 1);
+			}
+			for (uint32_t x2 = 0; x2 < fan2; ++x2) {
+				walk_state w2 = w1;
+				cplx m2 = m1;
+				if (forked >= 2) {
+					m2 = cmul(m1, amp.get(x2, (ctx.site_is_merge >> (shared + 1)) & 1));
+					run(w2, x2, 1);
+				}
+				finish(w2, m2, fan | (x1 << shared) | (x2 << (shared + 1)));
+			}
+		}
 	}
 };
 

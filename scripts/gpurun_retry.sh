@@ -1,8 +1,8 @@
 #!/bin/bash
 # developer helper: gpurun with retries while the pod answers "busy" (exit code 3: nothing charged)
-# usage: scripts/gpurun_retry.sh <timeout seconds> '<command>'
+# usage: [GPUS=N] scripts/gpurun_retry.sh <timeout seconds> '<command>'
 for attempt in $(seq 1 30); do
-	/usr/local/graft/bin/gpurun --timeout "$1" -- "$2"
+	/usr/local/graft/bin/gpurun ${GPUS:+--gpus $GPUS} --timeout "$1" -- "$2"
 	rc=$?
 	if [ $rc -ne 3 ]; then
 		exit $rc
