@@ -104,7 +104,7 @@ __device__ __forceinline__ uint64_t upper_bound_u64(const uint64_t *a, uint64_t 
 // One warp owns a stage: lane 0 arms the mbarrier with the byte count and issues the copy, all lanes wait on the
 // barrier's phase.  Source and destination must be 16-byte aligned and the size a multiple of 16: the range is widened
 // to those bounds (the callers' buffers start 256-byte aligned and carry 16 bytes of slack at the end).
-constexpr uint32_t STAGE_BYTES = 8192; // 32 objects of up to 256 bytes
+constexpr uint32_t STAGE_BYTES = 11264; // 32 objects of up to 352 bytes (grown 12-node graphs: 300-330)
 
 struct __align__(16) warp_stage {
 	uint8_t bytes[STAGE_BYTES + 32];

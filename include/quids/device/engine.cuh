@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(SYMBOLIC_THREADS, 5) symbolic_kernel(const Rul
 // ---- sorted order: work items = (parent, group), ordered by the rule's group key -------------------------
 constexpr int ITEM_GROUP_BITS = 24;
 constexpr int POPULATE_COPIES = 4;  // parent copies one warp keeps in flight in the finalisation
-constexpr int STAGED_THREADS = 128; // kernels whose warps stage their parents in shared memory: 4 stages of 8 KB per CTA
+constexpr int STAGED_THREADS = 96; // kernels whose warps stage their parents in shared memory: 3 stages of 11 KB per CTA
 constexpr int ITEMS_BLOCKS_PER_SM = 5; // occupancy target of the sorted-order kernel (latency bound: ncu shows 29 % issue utilisation at 5)
 constexpr int ITEM_CHUNK = 256; // items one warp takes at a time
 
@@ -720,20 +720,44 @@ __global__ void __launch_bounds__(POPULATE_THREADS) populate_staged_kernel(const
 	uint32_t phase = 0;
 	const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
 	const uint64_t batches = div_up<uint64_t>(L.n_survivors, 32);
-	for (uint64_t batch = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; batch < batches; batch += warps) {
+	// what a lane needs to know about its survivor: fetched one batch AHEAD (survivor -> parent -> offset and size of the
+	// parent is a chain of dependent round trips to DRAM; requested while the previous batch is built, it costs nothing)
+	struct survivor_meta {
+		uint64_t parent_begin, dst, dst_end;
+		uint32_t psize, csize, child_id;
+	};
+	auto fetch = [&](uint64_t batch) {
+		survivor_meta m{0, 0, 0, 0, 0, 0};
+		const uint64_t mine = batch * 32 + lane;
+		if (batch < batches && mine < L.n_survivors) {
+			const uint64_t oid = L.survivor_parent[mine];
+			m.parent_begin = L.it.begin[oid];
+			m.psize = L.it.size[oid];
+			m.dst = L.next_begin[mine];
+			m.dst_end = L.next_begin[mine + 1];
+			m.csize = L.next_size[mine];
+			m.child_id = L.survivor_child[mine];
+		}
+		return m;
+	};
+	bool store_in_flight = false; // a bulk store of the children stage may still be reading it
+	const uint64_t first_batch = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	survivor_meta ahead = fetch(first_batch);
+	for (uint64_t batch = first_batch; batch < batches; batch += warps) {
 		const uint64_t mine = batch * 32 + lane;
 		const bool valid = mine < L.n_survivors;
+		const survivor_meta meta = ahead;
+		ahead = fetch(batch + warps);
 		const uint8_t *parent = L.it.objects;
 		uint64_t dst = 0;
 		uint32_t psize = 0, csize = 0, cbytes = 0, child_id = 0, lead = 0, pbytes = 0, pslot = 0;
 		if (valid) {
-			const uint64_t oid = L.survivor_parent[mine];
-			parent = L.it.objects + L.it.begin[oid];
-			psize = L.it.size[oid];
-			dst = L.next_begin[mine];
-			cbytes = (uint32_t)(L.next_begin[mine + 1] - dst);
-			csize = L.next_size[mine];
-			child_id = L.survivor_child[mine];
+			parent = L.it.objects + meta.parent_begin;
+			psize = meta.psize;
+			dst = meta.dst;
+			cbytes = (uint32_t)(meta.dst_end - dst);
+			csize = meta.csize;
+			child_id = meta.child_id;
 			lead = (uint32_t)(reinterpret_cast<uintptr_t>(parent) & 15);
 			pbytes = (lead + psize + 15u) & ~15u;
 			// the lanes walk their parents in step: equal strides that are a multiple of 128 bytes (fresh 12-node graphs:
@@ -779,7 +803,13 @@ __global__ void __launch_bounds__(POPULATE_THREADS) populate_staged_kernel(const
 			while (!done)
 				asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(phase) : "memory");
 			phase ^= 1;
-			// 2. children built in shared memory
+			// 2. children built in shared memory (once the previous round's bulk store has read them out of the stage)
+			if (store_in_flight) {
+				if (lane == 0)
+					asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+				__syncwarp();
+				store_in_flight = false;
+			}
 			if (in) {
 				uint8_t *child = st.children + clead + (c_incl - cbytes - c0);
 				rule.populate_child_simple(staged + lead, psize, child, child_id);
@@ -800,8 +830,7 @@ __global__ void __launch_bounds__(POPULATE_THREADS) populate_staged_kernel(const
 				out[lane] = from[lane];
 			if (lane < tail)
 				out[head + body + lane] = from[head + body + lane];
-			if (lane == 0 && body)
-				asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // the stage may be overwritten
+			store_in_flight = body != 0; // waited for before the stage is written again: the store overlaps the next round's parent fetch
 			__syncwarp();
 			start = end;
 		}
