@@ -310,6 +310,7 @@ constexpr int ITEM_GROUP_BITS = 24;
 constexpr int POPULATE_COPIES = 4;  // parent copies one warp keeps in flight in the finalisation
 constexpr int STAGED_THREADS = 96; // kernels whose warps stage their parents in shared memory: 3 stages of 11 KB per CTA
 constexpr int ITEMS_BLOCKS_PER_SM = 5; // occupancy target of the sorted-order kernel (latency bound: ncu shows 29 % issue utilisation at 5)
+constexpr int BATCH_BLOCKS_PER_SM = 6; // the same for the batch kernel (80 registers)
 constexpr int ITEM_CHUNK = 256; // items one warp takes at a time
 
 // (Measured and dropped: building the contexts in the kernel that counts the children, so that the parents are read once
@@ -960,9 +961,20 @@ struct rule_glue {
 		if constexpr (Rule::has_group_key && Rule::has_region_batch) {
 			const uint64_t warps = div_up<uint64_t>(L.n_groups, ITEM_CHUNK);
 			Rule::prepare_device(L.stream);
-			auto kernel = symbolic_items_batch_kernel<Rule, ITEMS_BLOCKS_PER_SM>;
-			int grid = grid_for(warps * 32, SYMBOLIC_THREADS, resident_grid((const void *)kernel, SYMBOLIC_THREADS, L.sm_count));
-			kernel<<<grid, SYMBOLIC_THREADS, 0, L.stream>>>(*static_cast<const Rule *>(rule), L);
+			// CTAs per SM (the register budget follows): measured on the loop state at 1e7 parents, 4 -> 15.5 ms, 5 -> 14.8, 6 -> 14.0
+			static const int blocks = getenv("QB_ITEMS_BLOCKS") ? atoi(getenv("QB_ITEMS_BLOCKS")) : BATCH_BLOCKS_PER_SM; // (developer knob, as above)
+			auto launch = [&](auto kernel) {
+				int grid = grid_for(warps * 32, SYMBOLIC_THREADS, resident_grid((const void *)kernel, SYMBOLIC_THREADS, L.sm_count));
+				kernel<<<grid, SYMBOLIC_THREADS, 0, L.stream>>>(*static_cast<const Rule *>(rule), L);
+			};
+			if (blocks == 5)
+				launch(symbolic_items_batch_kernel<Rule, 5>);
+			else if (blocks == 7)
+				launch(symbolic_items_batch_kernel<Rule, 7>);
+			else if (blocks == 8)
+				launch(symbolic_items_batch_kernel<Rule, 8>);
+			else
+				launch(symbolic_items_batch_kernel<Rule, BATCH_BLOCKS_PER_SM>);
 			++*L.launch_counter;
 		}
 	}

@@ -1580,11 +1580,14 @@ struct split_merge_fused : split_merge {
 	}
 	// ---- FANS (rule_api.cuh, lane_groups).  The bits of child_id are consumed in walk order, so the children that differ only
 	// in their LAST choices share the walk over the parent up to the first of those sites.  One lane produces the 2^F children
-	// fan | x << (S - F) of a parent with S sites, F = min(2, S - 1): it walks to the (S - F)-th site once, forks there, and
-	// again at the last site -- about 1.8 walks for four children of a parent with four sites instead of four.  (Bit 0 is never
-	// forked: the wrap-around sites keep their place at the head of the walk.)
+	// fan | x << (S - F) of a parent with S sites, F = min(fork_max, S - 1): it walks to the (S - F)-th site once and forks there
+	// (and again at the last site when F = 2) -- 1.2 walks for two children of a parent with four sites instead of two.  (Bit 0
+	// is never forked: the wrap-around sites keep their place at the head of the walk.)
 	static constexpr bool lane_groups = true;
-	__device__ static uint32_t fork_bits(uint32_t sites) { return sites >= 3 ? 2u : (sites == 2 ? 1u : 0u); }
+	// children per fan = 2^fork_max at most.  Measured on the loop state (1e7 parents, child generation): 0 -> 15.2 ms, 1 -> 13.2 ms,
+	// 2 -> 15.2 ms: four children per lane share more of the walk, but a batch of six parents then fills only 21 lanes
+	uint32_t fork_max = 1; // (QB_SPLIT_MERGE_FORK = 0 / 1 / 2: developer knob for A/B runs)
+	__device__ uint32_t fork_bits(uint32_t sites) const { return min(fork_max, sites >= 3 ? 2u : (sites == 2 ? 1u : 0u)); }
 	__device__ uint32_t get_num_group(const uint8_t *, uint32_t, uint32_t num_child) const {
 		const uint32_t sites = 31 - __clz(num_child);
 		return num_child >> fork_bits(sites);
@@ -1708,10 +1711,18 @@ struct split_merge_fused : split_merge {
 };
 
 template <class Rule>
+inline void apply_developer_knobs(Rule &) {}
+inline void apply_developer_knobs(split_merge_fused &r) {
+	if (const char *fork = getenv("QB_SPLIT_MERGE_FORK"))
+		r.fork_max = (uint32_t)atoi(fork) > 2 ? 2u : (uint32_t)atoi(fork);
+}
+
+template <class Rule>
 inline int make_qcgd_rule(const double *params, uint32_t num_params, void *storage) {
 	if (num_params < 1)
 		return QB_ERR_ARG;
 	Rule r;
+	apply_developer_knobs(r);
 	r.amp.set(params[0], num_params > 1 ? params[1] : 0.0, num_params > 2 ? params[2] : 0.0);
 	memcpy(storage, &r, sizeof r);
 	return QB_OK;
