@@ -847,11 +847,34 @@ __global__ void __launch_bounds__(ENGINE_THREADS) hash_kernel(const Rule rule, i
 		hashes[i] = rule.hasher(it.objects + it.begin[i], it.size[i]);
 }
 
+// family keys of all objects (distributed path, route.inc.cuh).  A warp takes 32 consecutive objects: their bytes come to shared
+// memory with one bulk copy and every lane walks its object there (as in group_items_kernel: 32 lanes chasing 32 different
+// objects in global memory pay one L1 wavefront per lane and load)
 template <class Rule>
-__global__ void __launch_bounds__(ENGINE_THREADS) family_kernel(const Rule rule, iter_view it, uint64_t *family) {
-	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < it.n; i += stride)
-		family[i] = rule.family_key(it.objects + it.begin[i], it.size[i]);
+__global__ void __launch_bounds__(STAGED_THREADS) family_kernel(const Rule rule, iter_view it, uint64_t *family) {
+	__shared__ warp_stage s_stage[STAGED_THREADS / 32];
+	warp_stage &stage = s_stage[threadIdx.x >> 5];
+	stage_init(stage);
+	uint32_t phase = 0;
+	const unsigned lane = lane_id();
+	const uint64_t batches = div_up<uint64_t>(it.n, 32);
+	const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+	for (uint64_t batch = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; batch < batches; batch += warps) {
+		const uint64_t p0 = batch * 32, p = p0 + lane;
+		const uint32_t in_batch = (uint32_t)min((uint64_t)32, it.n - p0);
+		const bool valid = lane < in_batch;
+		const uint64_t off = valid ? it.begin[p] : 0;
+		const uint32_t size = valid ? it.size[p] : 0;
+		const uint8_t *object = it.objects + off;
+		const uint64_t lo = __shfl_sync(0xffffffffu, off, 0);
+		const uint64_t hi = __shfl_sync(0xffffffffu, off + size, in_batch - 1);
+		if (hi - lo <= STAGE_BYTES) {
+			const uint8_t *staged = stage_range(stage, it.objects + lo, (uint32_t)(hi - lo), phase);
+			object = staged + (off - lo);
+		}
+		if (valid)
+			family[p] = rule.family_key(object, size);
+	}
 }
 
 template <class Modifier>
@@ -1007,8 +1030,8 @@ struct rule_glue {
 	}
 	static void family(const void *rule, const engine_launch &L) {
 		if constexpr (Rule::has_family) {
-			int grid = grid_for(L.it.n, ENGINE_THREADS, resident_grid((const void *)family_kernel<Rule>, ENGINE_THREADS, L.sm_count));
-			family_kernel<Rule><<<grid, ENGINE_THREADS, 0, L.stream>>>(*static_cast<const Rule *>(rule), L.it, L.hashes);
+			int grid = grid_for(L.it.n, STAGED_THREADS, resident_grid((const void *)family_kernel<Rule>, STAGED_THREADS, L.sm_count));
+			family_kernel<Rule><<<grid, STAGED_THREADS, 0, L.stream>>>(*static_cast<const Rule *>(rule), L.it, L.hashes);
 			++*L.launch_counter;
 		}
 	}

@@ -126,6 +126,15 @@ bool route_by_family(qb_iter *it, qb_comm *cm, const rule_ops *ops, const void *
 	const uint64_t n = it->n;
 	comm_ops::pending_error err;
 	std::vector<uint64_t> mine(2 * world + 1, 0);
+	auto t_last = std::chrono::steady_clock::now();
+	auto mark = [&](const char *what) { // QB_DIST_TRACE: wall time of the routing's own phases
+		if (!trace)
+			return;
+		ctx->sync();
+		auto now = std::chrono::steady_clock::now();
+		fprintf(stderr, "[qb route rank %d]   %-34s %8.3f ms\n", cm->rank, what, std::chrono::duration<double, std::milli>(now - t_last).count());
+		t_last = now;
+	};
 	err.run([&] {
 		inject_failure(cm->rank, "route");
 		rb.counts.ensure(sizeof(uint64_t) * (2 * world + 1), stream);
@@ -149,9 +158,11 @@ bool route_by_family(qb_iter *it, qb_comm *cm, const rule_ops *ops, const void *
 		QB_CUDA(cudaMemcpyAsync(mine.data(), rb.counts.ptr, sizeof(uint64_t) * (2 * world + 1), cudaMemcpyDeviceToHost, stream));
 		ctx->sync();
 	});
+	mark("family keys + counts");
 	// matrix[src][0..world) objects for each owner, [world..2 world) bytes, [2 world] largest object of src
 	const uint32_t row = 2 * world + 1;
 	std::vector<uint64_t> matrix = comm.allgather_agreed(mine.data(), row, err, "the family count of the parents");
+	mark("count exchange");
 	uint64_t largest = 0;
 	for (uint32_t r = 0; r < world; ++r)
 		largest = std::max(largest, matrix[(size_t)r * row + 2 * world]);
@@ -202,34 +213,47 @@ bool route_by_family(qb_iter *it, qb_comm *cm, const rule_ops *ops, const void *
 		rb.r_begin.ensure(sizeof(uint64_t) * (n_recv + 1), stream);
 		rb.r_bytes.ensure(bytes_recv + 16, stream);
 	});
+	mark("grouping by owner (slots, scan, copy)");
 	comm.sum_u64_agreed(0, err, "the grouping of the parents by family owner"); // nothing is posted unless every rank is ready
+	mark("agreement");
 
-	// all-to-allv of the four arrays, one NCCL group; what stays here is a device copy
-	uint64_t so = 0, sb = 0, ro = 0, rbytes = 0;
-	QB_NCCL(nccl().GroupStart());
-	for (uint32_t r = 0; r < world; ++r) {
-		if ((int)r != cm->rank) {
-			if (send_obj[r]) {
-				QB_NCCL(nccl().Send(rb.s_size.as<uint32_t>() + so, send_obj[r], ncclUint32, r, cm->nccl, stream));
-				QB_NCCL(nccl().Send(rb.s_padded.as<uint32_t>() + so, send_obj[r], ncclUint32, r, cm->nccl, stream));
-				QB_NCCL(nccl().Send(rb.s_mag.as<cplx>() + so, send_obj[r] * sizeof(cplx), ncclUint8, r, cm->nccl, stream));
-				if (send_bytes[r])
-					QB_NCCL(nccl().Send(rb.s_bytes.as<uint8_t>() + sb, send_bytes[r], ncclUint8, r, cm->nccl, stream));
+	// all-to-allv of the four arrays; what stays here is a device copy.  Two NCCL groups: the object bytes alone first (one
+	// send and one receive per peer, 99 % of the volume), then the three small arrays -- with all four in one group the twelve
+	// operations per peer pair shared the channels and the exchange ran at 240 GB/s per GPU (4 GPUs, QB_DIST_TRACE), against
+	// 560 GB/s for the one-array exchange of the record path
+	for (int pass = 0; pass < 2; ++pass) {
+		uint64_t so = 0, sb = 0, ro = 0, rbytes = 0;
+		QB_NCCL(nccl().GroupStart());
+		for (uint32_t r = 0; r < world; ++r) {
+			if ((int)r != cm->rank) {
+				if (send_obj[r]) {
+					if (pass == 0) {
+						if (send_bytes[r])
+							QB_NCCL(nccl().Send(rb.s_bytes.as<uint8_t>() + sb, send_bytes[r], ncclUint8, r, cm->nccl, stream));
+					} else {
+						QB_NCCL(nccl().Send(rb.s_size.as<uint32_t>() + so, send_obj[r], ncclUint32, r, cm->nccl, stream));
+						QB_NCCL(nccl().Send(rb.s_padded.as<uint32_t>() + so, send_obj[r], ncclUint32, r, cm->nccl, stream));
+						QB_NCCL(nccl().Send(rb.s_mag.as<cplx>() + so, send_obj[r] * sizeof(cplx), ncclUint8, r, cm->nccl, stream));
+					}
+				}
+				if (recv_obj[r]) {
+					if (pass == 0) {
+						if (recv_bytes[r])
+							QB_NCCL(nccl().Recv(rb.r_bytes.as<uint8_t>() + rbytes, recv_bytes[r], ncclUint8, r, cm->nccl, stream));
+					} else {
+						QB_NCCL(nccl().Recv(rb.r_size.as<uint32_t>() + ro, recv_obj[r], ncclUint32, r, cm->nccl, stream));
+						QB_NCCL(nccl().Recv(rb.r_padded.as<uint32_t>() + ro, recv_obj[r], ncclUint32, r, cm->nccl, stream));
+						QB_NCCL(nccl().Recv(rb.r_mag.as<cplx>() + ro, recv_obj[r] * sizeof(cplx), ncclUint8, r, cm->nccl, stream));
+					}
+				}
 			}
-			if (recv_obj[r]) {
-				QB_NCCL(nccl().Recv(rb.r_size.as<uint32_t>() + ro, recv_obj[r], ncclUint32, r, cm->nccl, stream));
-				QB_NCCL(nccl().Recv(rb.r_padded.as<uint32_t>() + ro, recv_obj[r], ncclUint32, r, cm->nccl, stream));
-				QB_NCCL(nccl().Recv(rb.r_mag.as<cplx>() + ro, recv_obj[r] * sizeof(cplx), ncclUint8, r, cm->nccl, stream));
-				if (recv_bytes[r])
-					QB_NCCL(nccl().Recv(rb.r_bytes.as<uint8_t>() + rbytes, recv_bytes[r], ncclUint8, r, cm->nccl, stream));
-			}
+			so += send_obj[r];
+			sb += send_bytes[r];
+			ro += recv_obj[r];
+			rbytes += recv_bytes[r];
 		}
-		so += send_obj[r];
-		sb += send_bytes[r];
-		ro += recv_obj[r];
-		rbytes += recv_bytes[r];
+		QB_NCCL(nccl().GroupEnd());
 	}
-	QB_NCCL(nccl().GroupEnd());
 	{
 		uint64_t self_so = 0, self_sb = 0, self_ro = 0, self_rb = 0;
 		for (int r = 0; r < cm->rank; ++r) {
@@ -247,6 +271,7 @@ bool route_by_family(qb_iter *it, qb_comm *cm, const rule_ops *ops, const void *
 				QB_CUDA(cudaMemcpyAsync(rb.r_bytes.as<uint8_t>() + self_rb, rb.s_bytes.as<uint8_t>() + self_sb, send_bytes[cm->rank], cudaMemcpyDeviceToDevice, stream));
 		}
 	}
+	mark("all-to-allv of the four arrays");
 	// object_begin of what arrived: every segment carries its objects back to back with their padding
 	exclusive_scan(ctx, widen_u32{rb.r_padded.as<uint32_t>()}, rb.r_begin.as<uint64_t>(), n_recv);
 	// the arrays that arrived become the state (the old ones become next call's receive buffers)
