@@ -242,3 +242,31 @@ def model_equalize(objs, weight_of, max_rounds, min_size, inbalance_limit, min_s
         previous_diff = diff
         rounds += 1
     return objs, rounds
+
+
+def model_floored_topk(keys, k, factor=1.5, sample=None):
+    """family-routed path (capi.cu simulate(), pipeline.cuh filtered compaction): every rank lists only its keys at or above a
+    RANK-LOCAL floor (about the factor * k / world-th largest of its own keys, here exact or taken from `sample` keys), the
+    global k-th largest key is selected over the lists, and a rank whose floor turns out to lie above that threshold relists
+    everything (all ranks then select again).  Returns (threshold, this rank's keys at or above it, rounds)."""
+    world = dist.get_world_size()
+    keys = np.asarray(keys, dtype=np.uint64)
+    local_k = int(factor * k / world) + 1
+    basis = np.sort(np.asarray(sample if sample is not None else keys, dtype=np.uint64))[::-1]
+    rank_in_basis = min(len(basis), max(1, int(np.ceil(local_k * len(basis) / max(1, len(keys)))))) if len(basis) else 0
+    floor = int(basis[rank_in_basis - 1]) if rank_in_basis and local_k < len(keys) else 0
+    listed = keys[keys >= np.uint64(floor)]
+    rounds = 0
+    while True:
+        rounds += 1
+        everyone = [None] * world
+        dist.all_gather_object(everyone, listed)  # (the GPUs all-reduce digit histograms instead: same threshold)
+        union = np.sort(np.concatenate(everyone))[::-1]
+        threshold = int(union[k - 1]) if k <= len(union) else 0
+        too_high = floor > threshold
+        flags = [None] * world
+        dist.all_gather_object(flags, bool(too_high))
+        if not any(flags):
+            return threshold, np.sort(listed[listed >= np.uint64(threshold)]), rounds
+        if too_high:
+            floor, listed = 0, keys

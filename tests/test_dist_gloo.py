@@ -200,3 +200,47 @@ def test_two_rank_equalize_model():
     assert len({o for g in gathered for o in g[0]}) == 400
     assert gathered[0][2] >= 1 and abs(children[0] - children[1]) <= 200, children  # within one object's weight
     assert gathered[0][3] >= 1 and abs(objects[0] - objects[1]) <= 1, objects
+
+
+def _floor_worker(rank, world, port_number, results):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port_number))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(11)
+    out = []
+    k = 400
+    balanced = [rng.integers(1, 2 ** 40, size=5000, dtype=np.uint64) for _ in range(world)]
+    skewed = [np.concatenate([balanced[0] + np.uint64(2 ** 50), np.array([], dtype=np.uint64)]), balanced[1]]  # every survivor sits on rank 0
+    tied = [np.full(3000, 7, dtype=np.uint64) for _ in range(world)]
+    for name, shares, sample in (("balanced", balanced, None), ("skewed", skewed, None), ("tied", tied, None),
+                                 ("sampled floor", balanced, lambda keys: rng.choice(keys, size=300))):
+        mine = shares[rank]
+        threshold, kept, rounds = dist_model.model_floored_topk(mine, k, sample=sample(mine) if sample else None)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (kept, rounds))
+        if rank == 0:
+            everything = np.sort(np.concatenate(shares))[::-1]
+            out.append((name, threshold, int(everything[k - 1]), sum(len(g[0]) for g in gathered), int((everything >= everything[k - 1]).sum()), [g[1] for g in gathered]))
+    if rank == 0:
+        results.put(out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_rank_local_floors_give_the_global_threshold():
+    """the filtered lists of the family-routed path: whatever the floors, the threshold is the global k-th largest key and every key
+    at or above it is listed; a rank that holds more than its share of the survivors relists (second round)"""
+    ctx = mp.get_context("spawn")
+    results = ctx.Queue()
+    procs = [ctx.Process(target=_floor_worker, args=(r, 2, 29536, results)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = results.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+    assert all(p.exitcode == 0 for p in procs)
+    for name, threshold, want_threshold, kept, want_kept, rounds in out:
+        assert threshold == want_threshold, (name, threshold, want_threshold)
+        assert kept == want_kept, (name, kept, want_kept)
+        assert len(set(rounds)) == 1, (name, rounds)  # the ranks stay in step
+    by_name = {o[0]: o for o in out}
+    assert by_name["balanced"][5][0] == 1 and by_name["skewed"][5][0] == 2, out
