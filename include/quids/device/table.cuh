@@ -200,9 +200,10 @@ __device__ __forceinline__ unsigned long long load_acquire(const unsigned long l
 	return v;
 }
 
-// The region of the objects identified by `key` (`leaves` consecutive slots).  ONE lane calls this per run, in two halves so
-// that the round trip of the first probe overlaps whatever the warp computes in between: region_probe_begin claims the home
-// entry of the directory blindly (the result of the compare-and-swap is not looked at), region_acquire_finish reads it.
+// The region of the objects identified by `key` (`leaves` consecutive slots), accumulating kernel: ONE lane calls
+// region_acquire per run.  (Two halves -- region_probe_begin claims the home entry of the directory blindly, without looking at
+// the result of the compare-and-swap, region_acquire_finish reads it -- so that a caller may put work between them; the batch
+// kernel has its own probe, one lane per run of a 32-item batch, rules_qcgd.cuh region_batch.)
 struct region_probe {
 	uint64_t key, index;
 	unsigned long long seen; // what the home entry held before the compare-and-swap (0 = this run claimed it)
