@@ -80,6 +80,28 @@ enum { // u64 words of the small device scratch
 	DS_WORDS = 13
 };
 
+// Counters the host needs between two launches travel through MAPPED pinned memory, written by a one-block kernel on the
+// compute stream, not through cudaMemcpyAsync: a device-to-host copy shares the copy engine of its direction with the bulk
+// qb_iter_download_async transfers on the copy stream and would queue behind them (QB_PEEK_MEMCPY=1 restores the copies).
+struct peek_list {
+	uint64_t *dst[4];
+	const uint64_t *src[4];
+	uint32_t words[4];
+	uint32_t n = 0;
+	void add(uint64_t *host_mapped, const uint64_t *dev, uint32_t n_words = 1) {
+		dst[n] = host_mapped;
+		src[n] = dev;
+		words[n++] = n_words;
+	}
+};
+__global__ void peek_kernel(peek_list l) {
+#pragma unroll
+	for (uint32_t e = 0; e < 4; ++e)
+		if (e < l.n)
+			for (uint32_t i = threadIdx.x; i < l.words[e]; i += blockDim.x)
+				l.dst[e][i] = l.src[e][i];
+}
+
 struct qb_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr;
@@ -122,8 +144,22 @@ struct qb_ctx {
 		return st;
 	}
 	uint64_t *small(int word) { return d_small.as<uint64_t>() + word; }
+	// enqueue the fetch of up to four groups of words into h_small (visible to the host after the next sync())
+	void peek(const peek_list &l) {
+		static const bool by_copy = getenv("QB_PEEK_MEMCPY") != nullptr;
+		if (by_copy) {
+			for (uint32_t e = 0; e < l.n; ++e)
+				QB_CUDA(cudaMemcpyAsync(l.dst[e], l.src[e], l.words[e] * sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+			return;
+		}
+		peek_kernel<<<1, 32, 0, stream>>>(l);
+		QB_CUDA(cudaGetLastError());
+		++launches;
+	}
 	void fetch_small() {
-		QB_CUDA(cudaMemcpyAsync(h_small, d_small.ptr, DS_WORDS * sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+		peek_list l;
+		l.add(h_small, d_small.as<uint64_t>(), DS_WORDS);
+		peek(l);
 		sync();
 	}
 	int grid_cap() const { return sm_count * 8; }
@@ -609,10 +645,12 @@ local_table build_local_table(qb_iter *it, uint64_t rule_id, const rule_ops *ops
 			exclusive_scan(ctx, counts_through{it->num_groups.as<uint32_t>(), kept}, it->group_begin.as<uint64_t>(), n_parents);
 			group_begin = it->group_begin.as<uint64_t>();
 		}
-		QB_CUDA(cudaMemcpyAsync(&ctx->h_small[DS_COUNT], it->child_begin.as<uint64_t>() + n_parents, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
-		QB_CUDA(cudaMemcpyAsync(&ctx->h_small[DS_USED], group_begin + n_parents, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
-		QB_CUDA(cudaMemcpyAsync(&ctx->h_small[DS_MAX_CHILD_SIZE], ctx->small(DS_MAX_CHILD_SIZE), sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
-		QB_CUDA(cudaMemcpyAsync(&ctx->h_small[DS_CHILD_RANGE], ctx->small(DS_CHILD_RANGE), sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+		peek_list l;
+		l.add(&ctx->h_small[DS_COUNT], it->child_begin.as<uint64_t>() + n_parents);
+		l.add(&ctx->h_small[DS_USED], group_begin + n_parents);
+		l.add(&ctx->h_small[DS_MAX_CHILD_SIZE], ctx->small(DS_MAX_CHILD_SIZE));
+		l.add(&ctx->h_small[DS_CHILD_RANGE], ctx->small(DS_CHILD_RANGE));
+		ctx->peek(l);
 		ctx->sync();
 		{
 			const uint32_t largest = (uint32_t)ctx->h_small[DS_CHILD_RANGE], smallest = ~(uint32_t)(ctx->h_small[DS_CHILD_RANGE] >> 32);
@@ -1215,8 +1253,10 @@ void finalize_and_normalize(qb_iter *it, const rule_ops *ops, const void *rule, 
 		norm_total_kernel<<<1, SCAN_THREADS, 0, stream>>>(ctx->partials.as<double>(), meta_grid, reinterpret_cast<double *>(ctx->small(DS_TOTAL)));
 		ctx->launches += 2;
 		exclusive_scan(ctx, widen_u32{sym->padded.as<uint32_t>()}, next->begin.as<uint64_t>(), n_survivors);
-		QB_CUDA(cudaMemcpyAsync(&ctx->h_small[DS_COUNT], next->begin.as<uint64_t>() + n_survivors, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
-		QB_CUDA(cudaMemcpyAsync(&ctx->h_small[DS_TOTAL], ctx->small(DS_TOTAL), sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+		peek_list l;
+		l.add(&ctx->h_small[DS_COUNT], next->begin.as<uint64_t>() + n_survivors);
+		l.add(&ctx->h_small[DS_TOTAL], ctx->small(DS_TOTAL));
+		ctx->peek(l);
 		ctx->sync();
 		next->n_bytes = ctx->h_small[DS_COUNT];
 		memcpy(&local_total, &ctx->h_small[DS_TOTAL], sizeof local_total);
@@ -1641,7 +1681,7 @@ int qb_ctx_create(int device, qb_ctx **out) {
 			uint64_t keep = ~0ull;
 			QB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
 		}
-		QB_CUDA(cudaHostAlloc((void **)&ctx->h_small, DS_WORDS * sizeof(uint64_t), cudaHostAllocDefault));
+		QB_CUDA(cudaHostAlloc((void **)&ctx->h_small, DS_WORDS * sizeof(uint64_t), cudaHostAllocMapped));
 		ctx->d_small.ensure(DS_WORDS * sizeof(uint64_t), ctx->stream);
 		QB_CUDA(cudaMemsetAsync(ctx->d_small.ptr, 0, DS_WORDS * sizeof(uint64_t), ctx->stream));
 		ctx->sync();
@@ -1818,6 +1858,28 @@ int qb_iter_download_f32(const qb_iter *it, uint8_t *objects, uint64_t *object_b
 }
 
 // ---- transfers that overlap the rule iterations: pinned host memory <-> HBM on dedicated copy streams --------------
+// A copy engine runs one copy to completion before it looks at another stream: behind a 2.5 GB object array the 8-byte
+// counter fetches of the rule iteration running meanwhile (fetch_small and friends, on the compute stream, same engine
+// per direction) would wait for the whole array, and the iteration with them. Bulk transfers are therefore cut into
+// pieces between which the engine can serve the compute stream (QB_COPY_CHUNK_MB, default 8; 0 = one copy per array).
+static size_t copy_chunk_bytes() {
+	static const size_t bytes = [] {
+		const char *e = getenv("QB_COPY_CHUNK_MB");
+		const long mb = e ? atol(e) : 8;
+		return mb > 0 ? (size_t)mb << 20 : (size_t)0;
+	}();
+	return bytes;
+}
+static void copy_in_pieces(void *dst, const void *src, size_t bytes, cudaMemcpyKind kind, cudaStream_t s) {
+	const size_t piece = copy_chunk_bytes();
+	if (piece == 0 || bytes <= piece) {
+		QB_CUDA(cudaMemcpyAsync(dst, src, bytes, kind, s));
+		return;
+	}
+	for (size_t done = 0; done < bytes; done += piece)
+		QB_CUDA(cudaMemcpyAsync((char *)dst + done, (const char *)src + done, std::min(piece, bytes - done), kind, s));
+}
+
 static void transfer_events(qb_iter *it) {
 	it->ctx->copy_streams();
 	if (!it->uploaded) {
@@ -1845,11 +1907,11 @@ int qb_iter_upload_async(qb_iter *it, uint64_t n, const uint8_t *objects, uint64
 		ctx->order_after_compute(s);
 		if (it->download_pending)
 			QB_CUDA(cudaStreamWaitEvent(s, it->downloaded, 0));
-		if (num_bytes) QB_CUDA(cudaMemcpyAsync(it->objects.ptr, objects, num_bytes, cudaMemcpyHostToDevice, s));
+		if (num_bytes) copy_in_pieces(it->objects.ptr, objects, num_bytes, cudaMemcpyHostToDevice, s);
 		if (n) {
-			QB_CUDA(cudaMemcpyAsync(it->begin.ptr, object_begin, sizeof(uint64_t) * (n + 1), cudaMemcpyHostToDevice, s));
-			QB_CUDA(cudaMemcpyAsync(it->size.ptr, object_size, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, s));
-			QB_CUDA(cudaMemcpyAsync(it->mag.ptr, magnitude, sizeof(cplx) * n, cudaMemcpyHostToDevice, s));
+			copy_in_pieces(it->begin.ptr, object_begin, sizeof(uint64_t) * (n + 1), cudaMemcpyHostToDevice, s);
+			copy_in_pieces(it->size.ptr, object_size, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, s);
+			copy_in_pieces(it->mag.ptr, magnitude, sizeof(cplx) * n, cudaMemcpyHostToDevice, s);
 		} else {
 			QB_CUDA(cudaMemsetAsync(it->begin.ptr, 0, sizeof(uint64_t), s));
 		}
@@ -1872,10 +1934,10 @@ int qb_iter_download_async(const qb_iter *cit, uint8_t *objects, uint64_t *objec
 		ctx->order_after_compute(s); // the state as the calls made so far leave it
 		if (it->upload_pending)
 			QB_CUDA(cudaStreamWaitEvent(s, it->uploaded, 0));
-		if (objects && it->n_bytes) QB_CUDA(cudaMemcpyAsync(objects, it->objects.ptr, it->n_bytes, cudaMemcpyDeviceToHost, s));
-		if (object_begin) QB_CUDA(cudaMemcpyAsync(object_begin, it->begin.ptr, sizeof(uint64_t) * (it->n + 1), cudaMemcpyDeviceToHost, s));
-		if (object_size && it->n) QB_CUDA(cudaMemcpyAsync(object_size, it->size.ptr, sizeof(uint32_t) * it->n, cudaMemcpyDeviceToHost, s));
-		if (magnitude && it->n) QB_CUDA(cudaMemcpyAsync(magnitude, it->mag.ptr, sizeof(cplx) * it->n, cudaMemcpyDeviceToHost, s));
+		if (objects && it->n_bytes) copy_in_pieces(objects, it->objects.ptr, it->n_bytes, cudaMemcpyDeviceToHost, s);
+		if (object_begin) copy_in_pieces(object_begin, it->begin.ptr, sizeof(uint64_t) * (it->n + 1), cudaMemcpyDeviceToHost, s);
+		if (object_size && it->n) copy_in_pieces(object_size, it->size.ptr, sizeof(uint32_t) * it->n, cudaMemcpyDeviceToHost, s);
+		if (magnitude && it->n) copy_in_pieces(magnitude, it->mag.ptr, sizeof(cplx) * it->n, cudaMemcpyDeviceToHost, s);
 		QB_CUDA(cudaEventRecord(it->downloaded, s));
 		it->download_pending = true;
 	});
@@ -1983,7 +2045,9 @@ int qb_iter_pop(qb_iter *it, uint64_t n, int normalize) {
 		ctx->use();
 		it->settle();
 		it->n -= n;
-		QB_CUDA(cudaMemcpyAsync(&ctx->h_small[DS_COUNT], it->begin.as<uint64_t>() + it->n, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+		peek_list l;
+		l.add(&ctx->h_small[DS_COUNT], it->begin.as<uint64_t>() + it->n);
+		ctx->peek(l);
 		ctx->sync();
 		it->n_bytes = ctx->h_small[DS_COUNT];
 	});
