@@ -561,7 +561,6 @@ void resolve_options(const qb_options *in, qb_options &opt) {
 // ======================================================================================================
 // one rule iteration
 // ======================================================================================================
-// stages 1-6 of an iteration on THIS GPU: child counts, parent pre-truncation, index ranges, children ->
 // bytes the automatic budget (max_num_object = 0) may spend: what is free now + what `sym` (and `next`) already hold
 // and will reuse, minus the safety margin (quids.hpp:459-470 with cudaMemGetInfo in place of /proc/meminfo);
 // qb_options.memory_budget overrides the measurement (tests, or a share of a GPU)
@@ -582,7 +581,8 @@ double automatic_budget(qb_ctx *ctx, const qb_sym *sym, const qb_iter *next, con
 	return (double)free_bytes + reusable - (double)opt.safety_margin * (double)total_bytes;
 }
 
-// interference table, compaction of the table into (norm key, slot) lists
+// stages 1-6 of an iteration on THIS GPU: child counts, parent pre-truncation, index ranges, children -> interference
+// table (regions / bins / hashed), compaction of the table into (norm key, slot) lists
 struct local_table {
 	uint64_t n_parents = 0;
 	const uint64_t *kept = nullptr;
