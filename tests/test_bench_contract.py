@@ -39,3 +39,43 @@ def test_our_arm_needs_a_gpu():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
                          text=True, timeout=300, cwd=ROOT)
     assert out.returncode != 0 and out.stdout.strip() == "" and "no CUDA device" in out.stderr
+
+
+def test_pinned_buffers_are_allocated_near_the_gpu(monkeypatch):
+    """bench.near_gpu: the calling thread is bound to the CPUs NVML reports as local to the device while the pinned buffers of
+    the e2e leg are allocated, and gets its affinity back; without NVML nothing changes"""
+    import types
+    sys.path.insert(0, ROOT)
+    import bench
+    allowed = os.sched_getaffinity(0)
+    if len(allowed) < 2:
+        pytest.skip("one CPU: nothing to choose from")
+    local = set(sorted(allowed)[: len(allowed) // 2])
+    fake = types.ModuleType("pynvml")
+    fake.nvmlInit = lambda: None
+    fake.nvmlDeviceGetHandleByIndex = lambda i: i
+    seen = {}
+
+    def affinity(handle, n_words):
+        seen["words"] = n_words
+        return [sum(1 << (c - 64 * w) for c in local if 64 * w <= c < 64 * w + 64) for w in range(n_words)]
+
+    fake.nvmlDeviceGetCpuAffinity = affinity
+    monkeypatch.setitem(sys.modules, "pynvml", fake)
+    with bench.near_gpu(0) as n:
+        assert os.sched_getaffinity(0) == local
+        assert "local to the GPU" in n.placement
+    assert os.sched_getaffinity(0) == allowed
+    assert seen["words"] * 64 > max(allowed)
+    # a cpuset that excludes the GPU's CPUs, or a failing NVML: nothing changes
+    fake.nvmlDeviceGetCpuAffinity = lambda handle, n_words: [0] * n_words
+    with bench.near_gpu(0) as n:
+        assert os.sched_getaffinity(0) == allowed and n.placement == "default placement"
+
+    def broken(handle, n_words):
+        raise RuntimeError("no NVML")
+
+    fake.nvmlDeviceGetCpuAffinity = broken
+    with bench.near_gpu(0) as n:
+        assert os.sched_getaffinity(0) == allowed and n.placement == "default placement"
+    assert os.sched_getaffinity(0) == allowed
