@@ -345,7 +345,7 @@ class Iteration:
         assert objects.dtype == np.uint8 and object_begin.dtype == np.uint64 and object_size.dtype == np.uint32 and magnitude.dtype == np.float64
         assert object_begin.shape[0] == n + 1 and magnitude.size == 2 * n
         self._pending = []
-        self._async_refs = (objects, object_begin, object_size, magnitude)
+        self._async_refs = ((getattr(self, "_async_refs", None) or []) + [(objects, object_begin, object_size, magnitude)])[-4:]  # alive until wait() (or four transfers later)
         _check(lib().qb_iter_upload_async(self.handle, n, objects.ctypes.data, int(object_begin[n]) if n else 0, object_begin.ctypes.data,
                                           object_size.ctypes.data, magnitude.ctypes.data, total_proba))
 
@@ -353,7 +353,7 @@ class Iteration:
         """download into page-locked arrays on the copy stream; valid after wait() (qb_iter_download_async)"""
         n, nb, _ = self._counts_noflush()
         assert objects.nbytes >= nb and object_begin.shape[0] >= n + 1 and object_size.shape[0] >= n and magnitude.size >= 2 * n
-        self._async_refs = (objects, object_begin, object_size, magnitude)
+        self._async_refs = ((getattr(self, "_async_refs", None) or []) + [(objects, object_begin, object_size, magnitude)])[-4:]  # alive until wait() (or four transfers later)
         _check(lib().qb_iter_download_async(self.handle, objects.ctypes.data, object_begin.ctypes.data, object_size.ctypes.data, magnitude.ctypes.data))
         return n, nb
 
